@@ -1,0 +1,229 @@
+/*
+ * vecb200.h -- C ABI of libvecb200.so: the B200 (sm_100a) implementation of
+ * pgvector's batched-distance hot path.
+ *
+ * This is the drop-in boundary.  Every entry point takes plain
+ * pointers and sizes; there are no PostgreSQL, C++ or torch types in any
+ * signature.  Each function names the reference code whose inner loop it
+ * replaces (paths relative to the pgvector tree @ e48241b).  The extension-side
+ * glue that calls these from the index AM is in pgvector_b200/ext/ and
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 (VB_OK) or a negative VB_E* code; the message is
+ *     available from vb_last_error() (thread local).  The caller (a Postgres
+ *     backend) turns it into ereport(ERROR) AFTER the call returns, so no device
+ *     state is held across a longjmp.
+ *   - there is NO CPU fallback: every call fails with VB_ENODEVICE when no
+ *     sm_100 device is usable.
+ *   - "host" pointers are ordinary process memory; "_dev" variants take device
+ *     pointers valid on the library's current device.  Work is enqueued on the
+ *     library stream (vb_stream()); host-buffer variants synchronise before
+ *     returning, _dev variants do not.
+ *   - rows are row-major and contiguous in the caller's buffers (vector: dim
+ *     fp32; halfvec: dim IEEE binary16; bit: (dim+7)/8 bytes, MSB first, tail
+ *     bits zero -- exactly the payload of Vector.x (src/vector.h:18-24),
+ *     HalfVector.x (src/halfvec.h:67-73) and VARBITS (src/bitvec.c:16-28)).
+ *     Device images pad each row to a multiple of 16 bytes (zero fill).
+ *   - heap TIDs are passed opaquely as int64 ids (block << 16 | offset in the glue).
+ */
+#ifndef VECB200_H
+#define VECB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_ABI_VERSION 1
+
+/* status codes */
+#define VB_OK 0
+#define VB_EINVAL (-1)			/* bad argument (dimension mismatch, unsupported metric for type, ...) */
+#define VB_ENODEVICE (-2)		/* no usable sm_100 device / CUDA failure at init */
+#define VB_ECUDA (-3)			/* CUDA runtime error */
+#define VB_ENOMEM (-4)			/* device or host allocation failed */
+#define VB_ESTATE (-5)			/* call sequence error (index not loaded, ...) */
+
+/* element types */
+#define VB_VECTOR 0				/* vector   : fp32   (src/vector.h:18-24) */
+#define VB_HALFVEC 1			/* halfvec  : fp16   (src/halfvec.h:67-73) */
+#define VB_BIT 2				/* bit      : packed (src/bitvec.c:16-28) */
+
+/* metrics: what the SQL operator / opclass support function returns */
+#define VB_L2_SQUARED 0			/* vector_l2_squared_distance    src/vector.c:595-605, halfvec.c:575-585 (index proc 1 of l2 opclasses) */
+#define VB_NEG_IP 1				/* vector_negative_inner_product src/vector.c:637-647, halfvec.c:605-615 (<#>; proc 1 of ip and cosine opclasses) */
+#define VB_COSINE 2				/* cosine_distance               src/vector.c:671-696, halfvec.c:620-645 (<=>, sequential scan only) */
+#define VB_L1 3					/* l1_distance                   src/vector.c:740-750, halfvec.c:676-686 (<+>) */
+#define VB_HAMMING 4			/* hamming_distance              src/bitvec.c:45-55  (<~>) */
+#define VB_JACCARD 5			/* jaccard_distance              src/bitvec.c:60-70  (<%>) */
+#define VB_L2 6					/* l2_distance                   src/vector.c:579-589 (<->): sqrt((double) L2^2) */
+#define VB_IP 7					/* inner_product                 src/vector.c:622-632 */
+#define VB_SPHERICAL 8			/* vector_spherical_distance     src/vector.c:703-722 (k-means proc 3 of ip/cosine opclasses) */
+
+/* ------------------------------------------------------------------ runtime */
+
+/* Bind this process to CUDA device `device` (a backend calls it once, lazily). */
+int			vb_init(int device);
+/* Release every device allocation made by the library in this process. */
+int			vb_shutdown(void);
+const char *vb_last_error(void);
+int			vb_abi_version(void);
+/* cudaStream_t the library launches on (as void*), for event timing / graph capture by the host. */
+void	   *vb_stream(void);
+/* Kernels launched by this library since vb_init (a claim for bench.py's gpu_launches). */
+int64_t		vb_launch_count(void);
+int			vb_synchronize(void);
+
+/* ------------------------------------------------- batched distance operator */
+
+/*
+ * One query against n rows, all host buffers: out[i] = metric(rows[i], q) as the
+ * float8 the fmgr wrapper returns.  Replaces n calls of
+ * FunctionCall2Coll(procinfo, collation, row, q) -> l2_distance / ... / jaccard_distance
+ * (src/vector.c:576-750, src/halfvec.c:557-686, src/bitvec.c:33-70).
+ * dim is elements (bits for VB_BIT).  q == NULL gives all zeros (ZeroDistance, src/ivfscan.c:192-196).
+ */
+int			vb_distance_batch(int elem, int metric, int dim, const void *q,
+							  const void *rows, int64_t n, double *out);
+
+/* ------------------------------------------------------ resident row tables */
+
+typedef struct vb_table vb_table;	/* [n x dim] rows resident in HBM (exact scan, HNSW vectors, k-means samples) */
+
+int			vb_table_create(int elem, int dim, vb_table **out);
+/* Append n rows from host memory (pinned staging + async copy inside). */
+int			vb_table_append(vb_table *t, const void *rows, int64_t n);
+/* Append n rows that already live on the device (packed, unpadded layout). */
+int			vb_table_append_dev(vb_table *t, const void *rows_dev, int64_t n);
+int64_t		vb_table_rows(const vb_table *t);
+int			vb_table_free(vb_table *t);
+
+/*
+ * Exact (no index) top-k of nq queries over the table: the sequential-scan plan
+ * "ORDER BY v <op> q LIMIT k" (operator wrapper + top-N sort).
+ * out_ids[q*k + j] is the row number (0-based append order), -1 padded;
+ * out_dist the operator's float8.  Ties on distance: smaller row number first.
+ */
+int			vb_exact_topk(vb_table *t, int metric, const void *queries, int64_t nq, int k,
+						  int64_t *out_ids, double *out_dist);
+int			vb_exact_topk_dev(vb_table *t, int metric, const void *queries_dev, int64_t nq, int k,
+							  int64_t *out_ids_dev, float *out_dist_dev);
+
+/* ---------------------------------------------------------------- IVFFlat */
+
+typedef struct vb_ivf vb_ivf;	/* device image of one ivfflat index: centres + rows grouped by list + ids */
+
+/* metric = the opclass's proc 1: VB_L2_SQUARED, VB_NEG_IP (ip and cosine opclasses) or VB_HAMMING. */
+int			vb_ivf_create(int elem, int metric, int dim, int lists, vb_ivf **out);
+/*
+ * Load the whole image from host memory: centres [lists], rows grouped by
+ * list with list_offsets [lists+1] (row index prefix), ids [n] (heap TIDs).
+ * This is what the packer produces from the list pages / entry pages
+ * (src/ivfflat.h:251-277; readers src/ivfscan.c:62-107, 139-179).
+ */
+int			vb_ivf_load(vb_ivf *ix, const void *centers, const int64_t *list_offsets,
+						const void *rows, const int64_t *ids);
+/* Same, from device buffers (packed rows; ids may be NULL = row positions). */
+int			vb_ivf_load_dev(vb_ivf *ix, const void *centers_dev, const int64_t *list_offsets_host,
+							const void *rows_dev, const int64_t *ids_dev);
+int64_t		vb_ivf_rows(const vb_ivf *ix);
+int			vb_ivf_free(vb_ivf *ix);
+
+/*
+ * GetScanLists (src/ivfscan.c:47-118): distance from each query to every
+ * centre, nearest max_probes lists, ascending.  Ties: smaller list number first.
+ * out_lists [nq x max_probes] (int32), out_dist [nq x max_probes] (may be NULL).
+ */
+int			vb_ivf_scan_lists(vb_ivf *ix, const void *queries, int64_t nq, int max_probes,
+							  int32_t *out_lists, double *out_dist);
+/*
+ * GetScanItems (src/ivfscan.c:123-187) for ONE query: distance to every row of
+ * the given lists, fully sorted ascending (tuplesort_performsort, :182).  Writes
+ * at most cap results, *n_out = number of candidates scanned.  Ties: scan order.
+ * q == NULL: all distances 0 (src/ivfscan.c:207-211).
+ */
+int			vb_ivf_scan_items(vb_ivf *ix, const void *q, const int32_t *lists, int nlists,
+							  int64_t cap, int64_t *out_ids, double *out_dist, int64_t *n_out);
+/*
+ * The whole first batch of ivfflatgettuple (src/ivfscan.c:360-414) for nq
+ * queries at once: probe selection + list scan + top-k (k nearest of the
+ * probed lists; k <= 0 is rejected here, use vb_ivf_scan_items for "all").
+ * Host buffers; copies are inside the call.
+ */
+int			vb_ivf_search(vb_ivf *ix, const void *queries, int64_t nq, int probes, int k,
+						  int64_t *out_ids, double *out_dist);
+/* Same with device-resident queries and outputs (float distances), asynchronous on vb_stream(). */
+int			vb_ivf_search_dev(vb_ivf *ix, const void *queries_dev, int64_t nq, int probes, int k,
+							  int64_t *out_ids_dev, float *out_dist_dev);
+/* algorithmic bytes of the last vb_ivf_search*: sum over queries of (lists + candidates) * dim * elem size */
+int64_t		vb_ivf_last_scan_bytes(const vb_ivf *ix);
+int64_t		vb_ivf_last_candidates(const vb_ivf *ix);
+
+/* ------------------------------------------------------- IVFFlat build path */
+
+/*
+ * Collective hook for the sharded build: sum-reduce `count` elements of the
+ * given device buffer in place across all ranks (dtype 0 = fp32, 1 = int32,
+ * 2 = int64).  The extension passes an ncclAllReduce wrapper; tests pass a
+ * torch.distributed one.  NULL = single process.
+ */
+typedef int (*vb_allreduce_fn) (void *buf_dev, int64_t count, int dtype, void *ctx);
+
+/*
+ * k-means on samples resident in `samples` (this rank's shard), replacing
+ * ElkanKmeans (src/ivfkmeans.c:246-485) from given initial centres
+ * (centres = in/out host buffer of k rows; k-means++ draws are host-side,
+ * see vb_kmeans_pp_init).  kmeans_metric: VB_L2 (l2 opclasses), VB_SPHERICAL
+ * (ip / cosine opclasses; samples must already be unit vectors,
+ * src/ivfbuild.c:153-155) or VB_HAMMING (bit).  Lloyd iterations with a dense
+ * assign step; centre update and stopping rule as src/ivfkmeans.c:179-236,
+ * 482-483.  *iters_out = iterations executed.
+ */
+int			vb_kmeans(vb_table *samples, int kmeans_metric, void *centers, int k, int max_iter,
+					  uint64_t seed, vb_allreduce_fn allreduce, void *allreduce_ctx, int *iters_out);
+/* InitCenters (src/ivfkmeans.c:23-91): k-means++ seeding on the device, centres out (host). */
+int			vb_kmeans_pp_init(vb_table *samples, int kmeans_metric, void *centers, int k, uint64_t seed);
+/*
+ * AddTupleToSort's argmin (src/ivfbuild.c:161-219): out_list[i] = first centre
+ * minimising the proc-1 distance (strict <).  metric = VB_L2_SQUARED / VB_NEG_IP / VB_HAMMING.
+ */
+int			vb_assign(vb_table *rows, int metric, const void *centers, int k, int32_t *out_list);
+int			vb_assign_dev(vb_table *rows, int metric, const void *centers_dev, int k, int32_t *out_list_dev);
+
+/* -------------------------------------------------------------------- HNSW */
+
+typedef struct vb_hnsw vb_hnsw;	/* device image of one hnsw index: element vectors + neighbour tables */
+
+/*
+ * metric = opclass proc 1 (VB_L2_SQUARED, VB_NEG_IP, VB_L1, VB_HAMMING, VB_JACCARD).
+ * Elements are numbered 0..n-1; levels[n]; nbr0 [n x 2m] layer-0 neighbour
+ * element numbers in on-disk order (HnswSetNeighborTuple, src/hnswutils.c:455-486),
+ * -1 terminated; upper layers as upper_off[n] (-1 when level 0) and
+ * upper [slots x m] with layer lc of element e at slot upper_off[e] + lc - 1.
+ * entry = entry point element (meta page, src/hnswutils.c:298-328).
+ */
+int			vb_hnsw_create(int elem, int metric, int dim, int m, vb_hnsw **out);
+int			vb_hnsw_load(vb_hnsw *h, const void *rows, int64_t n, const int32_t *levels,
+						 const int32_t *nbr0, const int64_t *upper_off, const int32_t *upper,
+						 int64_t upper_slots, int64_t entry);
+int			vb_hnsw_free(vb_hnsw *h);
+/*
+ * GetScanItems (src/hnswscan.c:25-56): greedy descent with ef = 1 through the
+ * upper layers, then HnswSearchLayer (src/hnswutils.c:824-987) with ef at layer 0;
+ * results nearest first (src/hnswscan.c:293-326), k <= ef of them per query,
+ * -1 padded.  Every distance comparison is on the total order (distance,
+ * element number).  out_ndist (may be NULL) = distance evaluations per query
+ * (the reference's `tuples` counter, src/hnswutils.c:872-873, 905-906).
+ */
+int			vb_hnsw_search(vb_hnsw *h, const void *queries, int64_t nq, int ef, int k,
+						   int64_t *out_ids, double *out_dist, int64_t *out_ndist);
+int			vb_hnsw_search_dev(vb_hnsw *h, const void *queries_dev, int64_t nq, int ef, int k,
+							   int64_t *out_ids_dev, float *out_dist_dev, int64_t *out_ndist_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif							/* VECB200_H */

@@ -1,0 +1,399 @@
+"""pgvector_b200 -- host-side mirror of pgvector's distance / index-scan interface
+over libvecb200.so (hand-written sm_100a CUDA behind the C ABI of include/vecb200.h).
+
+PostgreSQL is not available in this image, so the reference's C host code
+(index AM callbacks) cannot be linked here; the extension-side glue is under
+``pgvector_b200/ext`` (written against the PostgreSQL API) and this module is
+the thin Python mirror of the same operator / opclass surface that the parity
+tests and ``bench.py`` drive.  Names follow the reference: operators
+(``l2_distance`` ... ``jaccard_distance``, src/vector.c:576-750,
+src/bitvec.c:45-70), opclasses (``vector_l2_ops`` ..., sql/vector.sql:406-446,
+819-911), ``IvfflatIndex`` (src/ivfscan.c) and ``HnswIndex`` (src/hnswscan.c).
+
+Everything computes on the GPU through the C ABI; nothing here falls back to
+numpy / torch math, and nothing imports the test oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import VecB200Error, load  # noqa: F401
+
+VECTOR, HALFVEC, BIT = 0, 1, 2
+L2_SQUARED, NEG_IP, COSINE, L1, HAMMING, JACCARD, L2, IP, SPHERICAL = range(9)
+
+_NP = {VECTOR: np.float32, HALFVEC: np.uint16, BIT: np.uint8}
+_TYPE_NAME = {VECTOR: "vector", HALFVEC: "halfvec", BIT: "bit"}
+
+# opclass -> (element type, proc-1 metric the index evaluates, normalise rows/query?, k-means metric)
+# (sql/vector.sql:406-446, 819-866, 894-911)
+OPCLASSES = {
+    "vector_l2_ops": (VECTOR, L2_SQUARED, False, L2),
+    "vector_ip_ops": (VECTOR, NEG_IP, False, SPHERICAL),
+    "vector_cosine_ops": (VECTOR, NEG_IP, True, SPHERICAL),
+    "vector_l1_ops": (VECTOR, L1, False, None),
+    "halfvec_l2_ops": (HALFVEC, L2_SQUARED, False, L2),
+    "halfvec_ip_ops": (HALFVEC, NEG_IP, False, SPHERICAL),
+    "halfvec_cosine_ops": (HALFVEC, NEG_IP, True, SPHERICAL),
+    "halfvec_l1_ops": (HALFVEC, L1, False, None),
+    "bit_hamming_ops": (BIT, HAMMING, False, HAMMING),
+    "bit_jaccard_ops": (BIT, JACCARD, False, None),
+}
+
+
+def init(device: int = 0):
+    _lib.check(load().vb_init(device))
+
+
+def stream_handle() -> int:
+    """cudaStream_t of the library (int) -- wrap with torch.cuda.ExternalStream for event timing."""
+    return int(load().vb_stream() or 0)
+
+
+def launch_count() -> int:
+    return int(load().vb_launch_count())
+
+
+def synchronize():
+    _lib.check(load().vb_synchronize())
+
+
+def _host(elem, a):
+    return np.ascontiguousarray(a, dtype=_NP[elem])
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+def _is_torch(a):
+    return a is not None and not isinstance(a, np.ndarray) and hasattr(a, "data_ptr")
+
+
+def _dim_of(elem, a, dim):
+    if dim is not None:
+        return int(dim)
+    return int(a.shape[-1]) * (8 if elem == BIT else 1)
+
+
+def _check_dims(elem, da, db):
+    # CheckDims (src/vector.c:70-77, src/halfvec.c:74-81, src/bitvec.c:33-40)
+    if da != db:
+        kind = {VECTOR: "vector dimensions", HALFVEC: "halfvec dimensions", BIT: "bit lengths"}[elem]
+        raise ValueError(f"different {kind} {da} and {db}")
+
+
+# --------------------------------------------------------------------- operators
+
+def distance_batch(elem, metric, q, rows, dim=None, q_dim=None):
+    """float8 distances of one query against n rows (host arrays), as the fmgr wrapper returns them."""
+    rows = _host(elem, rows)
+    if rows.ndim == 1:
+        rows = rows.reshape(1, -1)
+    d = _dim_of(elem, rows, dim)
+    if q is not None:
+        q = _host(elem, q)
+        _check_dims(elem, q_dim if q_dim is not None else _dim_of(elem, q, dim), d)
+    out = np.empty(rows.shape[0], dtype=np.float64)
+    _lib.check(load().vb_distance_batch(elem, metric, d, _ptr(q), _ptr(rows), rows.shape[0], _ptr(out)))
+    return out
+
+
+def l2_distance(a, rows, elem=VECTOR, **kw):
+    return distance_batch(elem, L2, a, rows, **kw)
+
+
+def l2_squared_distance(a, rows, elem=VECTOR, **kw):
+    return distance_batch(elem, L2_SQUARED, a, rows, **kw)
+
+
+def inner_product(a, rows, elem=VECTOR, **kw):
+    return distance_batch(elem, IP, a, rows, **kw)
+
+
+def negative_inner_product(a, rows, elem=VECTOR, **kw):
+    return distance_batch(elem, NEG_IP, a, rows, **kw)
+
+
+def cosine_distance(a, rows, elem=VECTOR, **kw):
+    return distance_batch(elem, COSINE, a, rows, **kw)
+
+
+def l1_distance(a, rows, elem=VECTOR, **kw):
+    return distance_batch(elem, L1, a, rows, **kw)
+
+
+def spherical_distance(a, rows, elem=VECTOR, **kw):
+    return distance_batch(elem, SPHERICAL, a, rows, **kw)
+
+
+def hamming_distance(a, rows, dim=None, **kw):
+    return distance_batch(BIT, HAMMING, a, rows, dim=dim, **kw)
+
+
+def jaccard_distance(a, rows, dim=None, **kw):
+    return distance_batch(BIT, JACCARD, a, rows, dim=dim, **kw)
+
+
+# --------------------------------------------------------------------- resident table / exact scan
+
+class Table:
+    """[n x dim] rows resident in HBM."""
+
+    def __init__(self, elem, dim):
+        self.elem, self.dim = elem, int(dim)
+        h = C.c_void_p()
+        _lib.check(load().vb_table_create(elem, self.dim, C.byref(h)))
+        self.h = h
+
+    def append(self, rows):
+        if _is_torch(rows):
+            _lib.check(load().vb_table_append_dev(self.h, _ptr(rows), rows.shape[0]))
+        else:
+            rows = _host(self.elem, rows)
+            _lib.check(load().vb_table_append(self.h, _ptr(rows), rows.shape[0]))
+        return self
+
+    def __len__(self):
+        return int(load().vb_table_rows(self.h))
+
+    def exact_topk(self, metric, queries, k):
+        """ORDER BY v <op> q LIMIT k without an index."""
+        if _is_torch(queries):
+            import torch
+            nq = queries.shape[0]
+            ids = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+            dist = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+            _lib.check(load().vb_exact_topk_dev(self.h, metric, _ptr(queries), nq, k, _ptr(ids), _ptr(dist)))
+            return ids, dist
+        queries = _host(self.elem, queries)
+        if queries.ndim == 1:
+            queries = queries.reshape(1, -1)
+        nq = queries.shape[0]
+        ids = np.empty((nq, k), dtype=np.int64)
+        dist = np.empty((nq, k), dtype=np.float64)
+        _lib.check(load().vb_exact_topk(self.h, metric, _ptr(queries), nq, k, _ptr(ids), _ptr(dist)))
+        return ids, dist
+
+    def free(self):
+        if self.h:
+            load().vb_table_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------- IVFFlat
+
+class IvfflatIndex:
+    """Device image of an ivfflat index and its scan (src/ivfscan.c).
+
+    ``probes`` mirrors the ivfflat.probes GUC (src/ivfflat.c:45-47)."""
+
+    def __init__(self, opclass, dim, lists):
+        self.opclass = opclass
+        self.elem, self.metric, self.normalize, self.kmeans_metric = OPCLASSES[opclass]
+        if self.metric not in (L2_SQUARED, NEG_IP, HAMMING):
+            raise ValueError(f"operator class {opclass} is not supported by ivfflat")
+        self.dim, self.lists = int(dim), int(lists)
+        self.probes = 1  # IVFFLAT_DEFAULT_PROBES
+        h = C.c_void_p()
+        _lib.check(load().vb_ivf_create(self.elem, self.metric, self.dim, self.lists, C.byref(h)))
+        self.h = h
+
+    def load(self, centers, list_offsets, rows, ids=None):
+        off = np.ascontiguousarray(list_offsets, dtype=np.int64)
+        assert off.shape[0] == self.lists + 1
+        self._off = off
+        if _is_torch(rows):
+            self._keep = (centers, rows, ids)
+            _lib.check(load().vb_ivf_load_dev(self.h, _ptr(centers), _ptr(off), _ptr(rows), _ptr(ids)))
+        else:
+            centers = _host(self.elem, centers)
+            rows = _host(self.elem, rows)
+            ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
+            _lib.check(load().vb_ivf_load(self.h, _ptr(centers), _ptr(off), _ptr(rows), _ptr(ids)))
+        return self
+
+    def scan_lists(self, queries, max_probes=None):
+        """GetScanLists: nearest lists per query, ascending."""
+        mp = int(max_probes or self.probes)
+        if queries is None:
+            nq, q = 1, None
+        else:
+            q = _host(self.elem, queries)
+            if q.ndim == 1:
+                q = q.reshape(1, -1)
+            nq = q.shape[0]
+        lists = np.empty((nq, mp), dtype=np.int32)
+        dist = np.empty((nq, mp), dtype=np.float64)
+        _lib.check(load().vb_ivf_scan_lists(self.h, _ptr(q), nq, mp, _ptr(lists), _ptr(dist)))
+        return lists, dist
+
+    def scan_items(self, q, lists, cap=None):
+        """GetScanItems for one query: every row of `lists`, sorted by distance."""
+        lists = np.ascontiguousarray(lists, dtype=np.int32)
+        total = int(sum(self._off[l + 1] - self._off[l] for l in lists))
+        cap = total if cap is None else min(int(cap), total)
+        ids = np.empty(max(cap, 1), dtype=np.int64)
+        dist = np.empty(max(cap, 1), dtype=np.float64)
+        n = C.c_int64()
+        qh = None if q is None else _host(self.elem, q)
+        _lib.check(load().vb_ivf_scan_items(self.h, _ptr(qh), _ptr(lists), len(lists), cap, _ptr(ids), _ptr(dist), C.byref(n)))
+        return ids[:cap], dist[:cap], int(n.value)
+
+    def search(self, queries, k, probes=None):
+        """first batch of ivfflatgettuple for many queries: k nearest of the probed lists."""
+        p = int(probes or self.probes)
+        if _is_torch(queries):
+            import torch
+            nq = queries.shape[0]
+            ids = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
+            dist = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+            _lib.check(load().vb_ivf_search_dev(self.h, _ptr(queries), nq, p, k, _ptr(ids), _ptr(dist)))
+            return ids, dist
+        q = _host(self.elem, queries)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.int64)
+        dist = np.empty((nq, k), dtype=np.float64)
+        _lib.check(load().vb_ivf_search(self.h, _ptr(q), nq, p, k, _ptr(ids), _ptr(dist)))
+        return ids, dist
+
+    def search_into(self, queries_dev, k, probes, ids_dev, dist_dev):
+        """asynchronous device-resident search into preallocated torch tensors (bench inner loop)."""
+        _lib.check(load().vb_ivf_search_dev(self.h, _ptr(queries_dev), queries_dev.shape[0], int(probes), int(k),
+                                            _ptr(ids_dev), _ptr(dist_dev)))
+
+    def search_host_into(self, queries, k, probes, ids, dist):
+        _lib.check(load().vb_ivf_search(self.h, _ptr(queries), queries.shape[0], int(probes), int(k), _ptr(ids), _ptr(dist)))
+
+    def last_scan_bytes(self):
+        return int(load().vb_ivf_last_scan_bytes(self.h))
+
+    def last_candidates(self):
+        return int(load().vb_ivf_last_candidates(self.h))
+
+    def free(self):
+        if self.h:
+            load().vb_ivf_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# --------------------------------------------------------------------- IVFFlat build
+
+def make_allreduce(fn):
+    """wrap a python callable (ptr, count, dtype_code) -> None as the C hook."""
+    def _cb(buf, count, dtype, _ctx):
+        try:
+            fn(buf, count, dtype)
+            return 0
+        except Exception:  # pragma: no cover - surfaced as VB error
+            return -1
+    return _lib.ALLREDUCE_FN(_cb)
+
+
+def kmeans(samples: Table, kmeans_metric, init_centers, max_iter=500, seed=42, allreduce=None):
+    """IvfflatKmeans (src/ivfkmeans.c:553-570) from given initial centres."""
+    centers = _host(samples.elem, init_centers).copy()
+    k = centers.shape[0]
+    iters = C.c_int()
+    cb = make_allreduce(allreduce) if allreduce is not None else None
+    _lib.check(load().vb_kmeans(samples.h, kmeans_metric, _ptr(centers), k, max_iter, seed,
+                                C.cast(cb, C.c_void_p) if cb is not None else None, None, C.byref(iters)))
+    return centers, iters.value
+
+
+def kmeans_pp_init(samples: Table, kmeans_metric, k, seed=42):
+    raw = (samples.dim + 7) // 8 if samples.elem == BIT else samples.dim
+    centers = np.empty((k, raw), dtype=_NP[samples.elem])
+    _lib.check(load().vb_kmeans_pp_init(samples.h, kmeans_metric, _ptr(centers), k, seed))
+    return centers
+
+
+def assign(rows: Table, metric, centers):
+    """AddTupleToSort's nearest-centre pass (src/ivfbuild.c:161-219)."""
+    if _is_torch(centers):
+        import torch
+        out = torch.empty(len(rows), dtype=torch.int32, device=centers.device)
+        _lib.check(load().vb_assign_dev(rows.h, metric, _ptr(centers), centers.shape[0], _ptr(out)))
+        return out
+    centers = _host(rows.elem, centers)
+    out = np.empty(len(rows), dtype=np.int32)
+    _lib.check(load().vb_assign(rows.h, metric, _ptr(centers), centers.shape[0], _ptr(out)))
+    return out
+
+
+# --------------------------------------------------------------------- HNSW
+
+class HnswIndex:
+    """Device image of an hnsw index and its scan (src/hnswscan.c, src/hnswutils.c:824-987).
+
+    ``ef_search`` mirrors the hnsw.ef_search GUC (src/hnsw.c:93-95)."""
+
+    def __init__(self, opclass, dim, m=16):
+        self.opclass = opclass
+        self.elem, self.metric, self.normalize, _ = OPCLASSES[opclass]
+        self.dim, self.m = int(dim), int(m)
+        self.ef_search = 40  # HNSW_DEFAULT_EF_SEARCH
+        h = C.c_void_p()
+        _lib.check(load().vb_hnsw_create(self.elem, self.metric, self.dim, self.m, C.byref(h)))
+        self.h = h
+
+    def load(self, rows, levels, nbr0, upper_off, upper, entry):
+        rows = _host(self.elem, rows)
+        levels = np.ascontiguousarray(levels, dtype=np.int32)
+        nbr0 = np.ascontiguousarray(nbr0, dtype=np.int32)
+        upper_off = np.ascontiguousarray(upper_off, dtype=np.int64)
+        upper = np.ascontiguousarray(upper, dtype=np.int32)
+        slots = upper.shape[0] if upper.size else 0
+        self.n = rows.shape[0]
+        _lib.check(load().vb_hnsw_load(self.h, _ptr(rows), rows.shape[0], _ptr(levels), _ptr(nbr0), _ptr(upper_off),
+                                       _ptr(upper) if slots else None, slots, int(entry)))
+        return self
+
+    def search(self, queries, k=None, ef_search=None):
+        ef = int(ef_search or self.ef_search)
+        k = int(k or ef)
+        q = _host(self.elem, queries)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        nq = q.shape[0]
+        ids = np.empty((nq, k), dtype=np.int64)
+        dist = np.empty((nq, k), dtype=np.float64)
+        nd = np.empty(nq, dtype=np.int64)
+        _lib.check(load().vb_hnsw_search(self.h, _ptr(q), nq, ef, k, _ptr(ids), _ptr(dist), _ptr(nd)))
+        return ids, dist, nd
+
+    def search_into(self, queries_dev, k, ef, ids_dev, dist_dev, nd_dev=None):
+        _lib.check(load().vb_hnsw_search_dev(self.h, _ptr(queries_dev), queries_dev.shape[0], int(ef), int(k),
+                                             _ptr(ids_dev), _ptr(dist_dev), _ptr(nd_dev)))
+
+    def free(self):
+        if self.h:
+            load().vb_hnsw_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,0 +1,89 @@
+"""ctypes loader for libvecb200.so (the C ABI declared in include/vecb200.h).
+
+The library is the product; this module only binds it.  There is no Python or
+CPU implementation behind any call: if the shared object is missing or no
+sm_100 device is usable every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvecb200.so")
+
+OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, ESTATE = 0, -1, -2, -3, -4, -5
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p)
+
+# name -> (restype, argtypes); keep in step with include/vecb200.h (tests/test_abi.py checks the header)
+_vp, _i, _i64, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64
+SIGNATURES = {
+    "vb_init": (_i, [_i]),
+    "vb_shutdown": (_i, []),
+    "vb_last_error": (C.c_char_p, []),
+    "vb_abi_version": (_i, []),
+    "vb_stream": (_vp, []),
+    "vb_launch_count": (_i64, []),
+    "vb_synchronize": (_i, []),
+    "vb_distance_batch": (_i, [_i, _i, _i, _vp, _vp, _i64, _vp]),
+    "vb_table_create": (_i, [_i, _i, C.POINTER(_vp)]),
+    "vb_table_append": (_i, [_vp, _vp, _i64]),
+    "vb_table_append_dev": (_i, [_vp, _vp, _i64]),
+    "vb_table_rows": (_i64, [_vp]),
+    "vb_table_free": (_i, [_vp]),
+    "vb_exact_topk": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "vb_exact_topk_dev": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "vb_ivf_create": (_i, [_i, _i, _i, _i, C.POINTER(_vp)]),
+    "vb_ivf_load": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "vb_ivf_load_dev": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "vb_ivf_rows": (_i64, [_vp]),
+    "vb_ivf_free": (_i, [_vp]),
+    "vb_ivf_scan_lists": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "vb_ivf_scan_items": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
+    "vb_ivf_search": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
+    "vb_ivf_search_dev": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
+    "vb_ivf_last_scan_bytes": (_i64, [_vp]),
+    "vb_ivf_last_candidates": (_i64, [_vp]),
+    "vb_kmeans": (_i, [_vp, _i, _vp, _i, _i, _u64, _vp, _vp, _vp]),
+    "vb_kmeans_pp_init": (_i, [_vp, _i, _vp, _i, _u64]),
+    "vb_assign": (_i, [_vp, _i, _vp, _i, _vp]),
+    "vb_assign_dev": (_i, [_vp, _i, _vp, _i, _vp]),
+    "vb_hnsw_create": (_i, [_i, _i, _i, _i, C.POINTER(_vp)]),
+    "vb_hnsw_load": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64]),
+    "vb_hnsw_free": (_i, [_vp]),
+    "vb_hnsw_search": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "vb_hnsw_search_dev": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+}
+
+
+class VecB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libvecb200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library and declare every prototype.  Raises if it was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m pgvector_b200.build` "
+                "(there is no CPU fallback for the distance hot path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError here = ABI mismatch, fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int):
+    if rc != OK:
+        msg = load().vb_last_error()
+        raise VecB200Error(rc, msg.decode() if msg else "")

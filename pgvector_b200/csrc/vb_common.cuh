@@ -1,0 +1,132 @@
+// vb_common.cuh -- shared declarations for libvecb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+
+#include "../../include/vecb200.h"
+
+namespace vb {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+extern thread_local int g_last_status;
+
+#define VB_CUDA(call)                                                                    \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            vb::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return VB_ECUDA;                                                             \
+        }                                                                                \
+    } while (0)
+
+#define VB_TRY(expr)               \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != VB_OK) return rc__; \
+    } while (0)
+
+#define VB_REQUIRE(cond, ...)        \
+    do {                             \
+        if (!(cond)) {               \
+            vb::set_error(__VA_ARGS__); \
+            return VB_EINVAL;        \
+        }                            \
+    } while (0)
+
+// ---------------------------------------------------------------- context
+struct Context {
+    bool inited = false;
+    int device = -1;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    int64_t launches = 0;
+    // grow-only device workspace arenas (index = slot)
+    void* ws[16] = {nullptr};
+    size_t ws_bytes[16] = {0};
+    // pinned staging
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    void* pinned2 = nullptr;
+    size_t pinned2_bytes = 0;
+};
+Context& ctx();
+int require_init();
+// returns device pointer of at least `bytes` in slot (contents preserved only if not grown)
+int workspace(int slot, size_t bytes, void** out);
+int pinned_buffer(size_t bytes, void** out);
+int pinned_buffer2(size_t bytes, void** out);
+
+inline void count_launch(int n = 1) { ctx().launches += n; }
+
+// ---------------------------------------------------------------- layout
+inline size_t raw_row_bytes(int elem, int dim) {
+    return elem == VB_VECTOR ? (size_t)dim * 4 : elem == VB_HALFVEC ? (size_t)dim * 2 : ((size_t)dim + 7) / 8;
+}
+// device rows are padded to 16-byte multiples so every row starts 128-bit aligned
+inline size_t padded_row_bytes(int elem, int dim) { return (raw_row_bytes(elem, dim) + 15) & ~(size_t)15; }
+
+inline bool metric_valid_for(int elem, int metric) {
+    if (elem == VB_BIT) return metric == VB_HAMMING || metric == VB_JACCARD;
+    return metric == VB_L2_SQUARED || metric == VB_NEG_IP || metric == VB_COSINE || metric == VB_L1 ||
+           metric == VB_L2 || metric == VB_IP || metric == VB_SPHERICAL;
+}
+// the metric the kernels order by ("key metric"); the float8 the operator returns is derived from it
+inline int key_metric(int metric) {
+    switch (metric) {
+        case VB_L2: return VB_L2_SQUARED;
+        case VB_IP:
+        case VB_SPHERICAL: return VB_NEG_IP;
+        default: return metric;
+    }
+}
+
+// A resident row table: n rows, padded stride.
+struct Table {
+    int elem = 0, dim = 0;
+    size_t stride = 0;      // padded row bytes
+    int64_t n = 0, cap = 0;
+    uint8_t* d = nullptr;   // device
+};
+int table_reserve(Table& t, int64_t rows);
+int table_append_host(Table& t, const void* rows, int64_t n);
+int table_append_dev(Table& t, const void* rows_dev, int64_t n);
+void table_free(Table& t);
+
+// Pad + (for halfvec) widen queries into the fp32 query image the kernels read.
+// vector/halfvec: float[nq][qstride/4]; bit: bytes[nq][qstride]. host==true: `queries` is host memory.
+int upload_queries(int elem, int dim, const void* queries, int64_t nq, bool host, int ws_slot, void** out_dev, size_t* qstride);
+
+// ---------------------------------------------------------------- scan primitives (vb_scan.cu)
+struct Chunk {           // one unit of scan work: a run of rows against one query
+    int64_t row_begin;   // row index into the table
+    int64_t out_off;     // where distance[0] of this run goes in the output array
+    int32_t n_rows;
+    int32_t q;           // query index
+};
+
+// distances of regular work: every query against rows [0, n) ; out[q * out_stride + r]
+int launch_scan_regular(const Table& t, int key_metric, const void* q_dev, size_t qstride, int64_t nq,
+                        int64_t n_rows, float* out, int64_t out_stride);
+// distances of chunk-list work; n_chunks_dev holds the chunk count (device int32)
+int launch_scan_chunks(const Table& t, int key_metric, const void* q_dev, size_t qstride,
+                       const Chunk* chunks_dev, const int* n_chunks_dev, int max_chunks, float* out);
+// Jaccard needs the exact float8: out as double
+int launch_scan_regular_f64(const Table& t, int key_metric, const void* q_dev, size_t qstride, int64_t nq,
+                            int64_t n_rows, double* out, int64_t out_stride);
+
+// per segment top-k of float keys with position tie-break, ascending (vb_scan.cu).
+// seg_begin/seg_len: device arrays (offset into keys, length).  Host copies are only needed for
+// k > 2048 (full segmented sort path).  Writes out_pos[nseg*k] (position within segment, -1 pad)
+// and out_key[nseg*k].
+int launch_segment_topk_v(const float* keys, const int64_t* seg_begin_dev, const int32_t* seg_len_dev,
+                          const int64_t* seg_begin_host, const int32_t* seg_len_host, int64_t nseg, int k,
+                          int32_t* out_pos, float* out_key);
+int scan_chunk_rows(const Table& t);
+
+}  // namespace vb

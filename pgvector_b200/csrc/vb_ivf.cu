@@ -1,0 +1,640 @@
+// vb_ivf.cu -- C ABI for the batched distance operator, resident tables, exact
+// top-k and the IVFFlat scan path (GetScanLists + GetScanItems, src/ivfscan.c:47-187).
+#include "vb_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+namespace vb {
+
+// workspace slots
+enum { WS_QIMG = 0, WS_DIST = 1, WS_CDIST = 2, WS_PROBES = 3, WS_CHUNKS = 4, WS_SEG = 5, WS_POS = 6, WS_OUT = 7 };
+// 8..11 are used by the CUB sort path in vb_scan.cu
+enum { WS_MISC = 12, WS_OUT2 = 13 };
+
+__global__ void regular_segments_kernel(int64_t nseg, int64_t stride, int32_t len, int64_t* begin, int32_t* lens) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < nseg) {
+        begin[i] = i * stride;
+        lens[i] = len;
+    }
+}
+
+// float key -> the operator's float8 (sqrt for <->, negate for inner_product)
+__device__ __forceinline__ double finish_value(int metric, float key) {
+    if (metric == VB_L2) return sqrt((double)key);
+    if (metric == VB_IP) return -(double)key;
+    return (double)key;
+}
+
+__global__ void finish_exact_kernel(int metric, int64_t n, const int32_t* __restrict__ pos, const float* __restrict__ key,
+                                    int64_t* __restrict__ out_ids, float* __restrict__ out_f, double* __restrict__ out_d) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out_ids[i] = pos[i];
+    double v = finish_value(metric, key[i]);
+    if (out_f) out_f[i] = (float)v;
+    if (out_d) out_d[i] = v;
+}
+
+// ----------------------------------------------------------------------------- IVFFlat device image
+
+struct Ivf {
+    int elem, metric, dim, lists;
+    Table centers;
+    Table rows;
+    int64_t* d_ids = nullptr;
+    int64_t* d_list_off = nullptr;
+    std::vector<int64_t> h_list_off;
+    std::vector<int64_t> sorted_len;  // list lengths, descending (bounds candidates per query)
+    int64_t last_bytes = 0, last_cand = 0;
+    int64_t* d_cand_sum = nullptr;    // device accumulator of candidates scanned
+    bool loaded = false;
+};
+
+// One CTA per query: candidate offsets of its probed lists and the chunk descriptors of the scan.
+__global__ void __launch_bounds__(128) ivf_build_chunks_kernel(const int32_t* __restrict__ probe_lists, int probes,
+                                                               const int64_t* __restrict__ list_off, int rows_per_chunk,
+                                                               int64_t cap, int32_t* __restrict__ cand_off /*[nq][probes+1]*/,
+                                                               int64_t* __restrict__ seg_begin, int32_t* __restrict__ seg_len,
+                                                               Chunk* __restrict__ chunks, int* __restrict__ n_chunks,
+                                                               int64_t* __restrict__ cand_sum) {
+    const int q = blockIdx.x;
+    const int32_t* pl = probe_lists + (int64_t)q * probes;
+    int32_t* co = cand_off + (int64_t)q * (probes + 1);
+    __shared__ int s_base;
+    if (threadIdx.x == 0) {
+        int32_t off = 0;
+        int nch = 0;
+        for (int p = 0; p < probes; ++p) {
+            co[p] = off;
+            int l = pl[p];
+            int32_t len = l >= 0 ? (int32_t)(list_off[l + 1] - list_off[l]) : 0;
+            off += len;
+            nch += (len + rows_per_chunk - 1) / rows_per_chunk;
+        }
+        co[probes] = off;
+        seg_begin[q] = (int64_t)q * cap;
+        seg_len[q] = off;
+        s_base = atomicAdd(n_chunks, nch);
+        atomicAdd((unsigned long long*)cand_sum, (unsigned long long)off);
+    }
+    __syncthreads();
+    // emit descriptors; per-probe chunk base via a serial prefix held by each thread (probes is small)
+    int base = s_base;
+    for (int p = 0; p < probes; ++p) {
+        int l = pl[p];
+        if (l < 0) continue;
+        int64_t lo = list_off[l];
+        int32_t len = (int32_t)(list_off[l + 1] - lo);
+        int nch = (len + rows_per_chunk - 1) / rows_per_chunk;
+        for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+            Chunk ch;
+            ch.row_begin = lo + (int64_t)c * rows_per_chunk;
+            ch.n_rows = min(rows_per_chunk, len - c * rows_per_chunk);
+            ch.q = q;
+            ch.out_off = (int64_t)q * cap + co[p] + (int64_t)c * rows_per_chunk;
+            chunks[base + c] = ch;
+        }
+        base += nch;
+    }
+}
+
+// winners (position within the query's candidate run) -> heap ids and float8 distances
+__global__ void ivf_finish_kernel(int metric, int64_t nq, int k, int probes, const int32_t* __restrict__ pos,
+                                  const float* __restrict__ key, const int32_t* __restrict__ probe_lists,
+                                  const int32_t* __restrict__ cand_off, const int64_t* __restrict__ list_off,
+                                  const int64_t* __restrict__ ids, int64_t* __restrict__ out_ids,
+                                  float* __restrict__ out_f, double* __restrict__ out_d) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nq * k) return;
+    int64_t q = i / k;
+    int32_t ps = pos[i];
+    int64_t id = -1;
+    if (ps >= 0) {
+        const int32_t* co = cand_off + q * (probes + 1);
+        int lo = 0, hi = probes;  // largest p with co[p] <= ps
+        while (hi - lo > 1) {
+            int mid = (lo + hi) >> 1;
+            if (co[mid] <= ps) lo = mid;
+            else hi = mid;
+        }
+        // skip empty lists that share the same offset
+        while (lo + 1 < probes && co[lo + 1] <= ps) ++lo;
+        int l = probe_lists[q * probes + lo];
+        int64_t row = list_off[l] + (ps - co[lo]);
+        id = ids ? ids[row] : row;
+    }
+    out_ids[i] = id;
+    double v = finish_value(metric, key[i]);
+    if (out_f) out_f[i] = (float)v;
+    if (out_d) out_d[i] = v;
+}
+
+static int64_t ivf_cap(const Ivf& ix, int probes) {
+    int64_t cap = 0;
+    for (int i = 0; i < probes && i < (int)ix.sorted_len.size(); ++i) cap += ix.sorted_len[(size_t)i];
+    return std::max<int64_t>(cap, 1);
+}
+
+// probe selection for a batch of query images: d_probe_lists [nq x probes] ascending by (distance, list)
+static int ivf_select_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, int probes, int32_t** d_lists,
+                             float** d_ldist) {
+    Context& c = ctx();
+    void *d_cdist, *d_seg, *d_probe;
+    VB_TRY(workspace(WS_CDIST, sizeof(float) * (size_t)nq * ix.lists, &d_cdist));
+    VB_TRY(launch_scan_regular(ix.centers, key_metric(ix.metric), qimg, qstride, nq, ix.lists, (float*)d_cdist, ix.lists));
+    VB_TRY(workspace(WS_SEG, (sizeof(int64_t) + sizeof(int32_t)) * (size_t)nq * 2 + 64, &d_seg));
+    int64_t* seg_begin = (int64_t*)d_seg;
+    int32_t* seg_len = (int32_t*)(seg_begin + nq);
+    regular_segments_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c.stream>>>(nq, ix.lists, ix.lists, seg_begin, seg_len);
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    VB_TRY(workspace(WS_PROBES, (sizeof(int32_t) + sizeof(float)) * (size_t)nq * probes, &d_probe));
+    int32_t* lists = (int32_t*)d_probe;
+    float* ldist = (float*)(lists + (size_t)nq * probes);
+    std::vector<int64_t> hb;
+    std::vector<int32_t> hl;
+    if (probes > 2048) {
+        hb.resize((size_t)nq);
+        hl.assign((size_t)nq, ix.lists);
+        for (int64_t i = 0; i < nq; ++i) hb[(size_t)i] = i * ix.lists;
+    }
+    VB_TRY(launch_segment_topk_v((const float*)d_cdist, seg_begin, seg_len, hb.empty() ? nullptr : hb.data(),
+                                 hl.empty() ? nullptr : hl.data(), nq, probes, lists, ldist));
+    *d_lists = lists;
+    *d_ldist = ldist;
+    return VB_OK;
+}
+
+// scan the given probe lists for a batch of queries and keep the k nearest per query
+static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists, int probes, int k,
+                         int64_t* out_ids_dev, float* out_f_dev, double* out_d_dev, int32_t** cand_total_dev) {
+    Context& c = ctx();
+    const int rpc = scan_chunk_rows(ix.rows);
+    const int64_t cap = ivf_cap(ix, probes);
+    const int64_t max_chunks = nq * (cap / rpc + probes + 1);
+    VB_REQUIRE(max_chunks < (int64_t)INT32_MAX, "too many scan chunks (%lld)", (long long)max_chunks);
+    void *d_chunks, *d_seg, *d_dist, *d_pos;
+    VB_TRY(workspace(WS_CHUNKS, sizeof(Chunk) * (size_t)max_chunks + sizeof(int32_t) * (size_t)nq * (probes + 1) + 64, &d_chunks));
+    Chunk* chunks = (Chunk*)d_chunks;
+    int32_t* cand_off = (int32_t*)(chunks + max_chunks);
+    VB_TRY(workspace(WS_SEG, (sizeof(int64_t) + sizeof(int32_t)) * (size_t)nq * 2 + 64, &d_seg));
+    // second half of WS_SEG (first half may still hold the probe-selection segments)
+    int64_t* seg_begin = (int64_t*)d_seg;
+    int32_t* seg_len = (int32_t*)(seg_begin + nq);
+    int* n_chunks = (int*)(seg_len + nq);
+    VB_CUDA(cudaMemsetAsync(n_chunks, 0, sizeof(int), c.stream));
+    if (!ix.d_cand_sum) {
+        VB_CUDA(cudaMalloc(&ix.d_cand_sum, sizeof(int64_t)));
+        VB_CUDA(cudaMemsetAsync(ix.d_cand_sum, 0, sizeof(int64_t), c.stream));
+    }
+    ivf_build_chunks_kernel<<<(unsigned)nq, 128, 0, c.stream>>>(d_lists, probes, ix.d_list_off, rpc, cap, cand_off, seg_begin,
+                                                               seg_len, chunks, n_chunks, ix.d_cand_sum);
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    VB_TRY(workspace(WS_DIST, sizeof(float) * (size_t)nq * cap, &d_dist));
+    VB_TRY(launch_scan_chunks(ix.rows, key_metric(ix.metric), qimg, qstride, chunks, n_chunks, (int)max_chunks, (float*)d_dist));
+    VB_TRY(workspace(WS_POS, (sizeof(int32_t) + sizeof(float)) * (size_t)nq * k, &d_pos));
+    int32_t* pos = (int32_t*)d_pos;
+    float* key = (float*)(pos + (size_t)nq * k);
+    std::vector<int64_t> hb;
+    std::vector<int32_t> hl;
+    if (k > 2048) {
+        // "sort everything" path (reference semantics of GetScanItems): needs sizes on the host
+        hb.resize((size_t)nq);
+        hl.resize((size_t)nq);
+        VB_CUDA(cudaMemcpyAsync(hl.data(), seg_len, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, c.stream));
+        VB_CUDA(cudaStreamSynchronize(c.stream));
+        for (int64_t i = 0; i < nq; ++i) hb[(size_t)i] = i * cap;
+    }
+    VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, hb.empty() ? nullptr : hb.data(),
+                                 hl.empty() ? nullptr : hl.data(), nq, k, pos, key));
+    ivf_finish_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, c.stream>>>(ix.metric, nq, k, probes, pos, key, d_lists, cand_off,
+                                                                              ix.d_list_off, ix.d_ids, out_ids_dev, out_f_dev,
+                                                                              out_d_dev);
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    if (cand_total_dev) *cand_total_dev = seg_len;
+    return VB_OK;
+}
+
+static int64_t ivf_batch_limit(const Ivf& ix, int probes) {
+    // keep the candidate-distance buffer under ~1 GiB
+    int64_t cap = ivf_cap(ix, probes);
+    int64_t lim = (int64_t)(1ull << 30) / (4 * cap);
+    return std::max<int64_t>(1, std::min<int64_t>(lim, 65535));
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+struct vb_table {
+    Table t;
+};
+struct vb_ivf {
+    Ivf ix;
+};
+
+extern "C" {
+
+// ----------------------------------------------------------------------------- operator
+
+int vb_distance_batch(int elem, int metric, int dim, const void* q, const void* rows, int64_t n, double* out) {
+    VB_TRY(require_init());
+    VB_REQUIRE(elem >= 0 && elem <= 2 && dim > 0 && metric_valid_for(elem, metric), "bad element type/metric/dim (%d, %d, %d)", elem,
+               metric, dim);
+    if (n <= 0) return VB_OK;
+    if (q == nullptr) {  // ZeroDistance (src/ivfscan.c:192-196)
+        for (int64_t i = 0; i < n; ++i) out[i] = 0.0;
+        return VB_OK;
+    }
+    Context& c = ctx();
+    Table t;
+    t.elem = elem;
+    t.dim = dim;
+    t.stride = padded_row_bytes(elem, dim);
+    int rc = table_append_host(t, rows, n);
+    if (rc != VB_OK) {
+        table_free(t);
+        return rc;
+    }
+    void* qimg;
+    size_t qstride;
+    void* d_out;
+    rc = upload_queries(elem, dim, q, 1, true, WS_QIMG, &qimg, &qstride);
+    if (rc == VB_OK) rc = workspace(WS_OUT, sizeof(double) * (size_t)n, &d_out);
+    if (rc == VB_OK) rc = launch_scan_regular_f64(t, key_metric(metric), qimg, qstride, 1, n, (double*)d_out, n);
+    if (rc == VB_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+        if (e != cudaSuccess) {
+            set_error("copy back failed: %s", cudaGetErrorString(e));
+            rc = VB_ECUDA;
+        }
+    }
+    table_free(t);
+    if (rc != VB_OK) return rc;
+    // operator epilogues that are not the key metric (fp64, like the fmgr wrappers)
+    if (metric == VB_L2)
+        for (int64_t i = 0; i < n; ++i) out[i] = sqrt(out[i]);
+    else if (metric == VB_IP)
+        for (int64_t i = 0; i < n; ++i) out[i] = -out[i];
+    else if (metric == VB_SPHERICAL)
+        for (int64_t i = 0; i < n; ++i) {
+            double d = -out[i];  // src/vector.c:714-722
+            if (d > 1) d = 1;
+            else if (d < -1) d = -1;
+            out[i] = acos(d) / M_PI;
+        }
+    return VB_OK;
+}
+
+// ----------------------------------------------------------------------------- tables
+
+int vb_table_create(int elem, int dim, vb_table** out) {
+    VB_TRY(require_init());
+    VB_REQUIRE(elem >= 0 && elem <= 2 && dim > 0 && out, "bad table arguments");
+    vb_table* t = new vb_table();
+    t->t.elem = elem;
+    t->t.dim = dim;
+    t->t.stride = padded_row_bytes(elem, dim);
+    *out = t;
+    return VB_OK;
+}
+int vb_table_append(vb_table* t, const void* rows, int64_t n) {
+    VB_TRY(require_init());
+    VB_REQUIRE(t && (rows || n == 0), "null table/rows");
+    return table_append_host(t->t, rows, n);
+}
+int vb_table_append_dev(vb_table* t, const void* rows_dev, int64_t n) {
+    VB_TRY(require_init());
+    VB_REQUIRE(t && (rows_dev || n == 0), "null table/rows");
+    return table_append_dev(t->t, rows_dev, n);
+}
+int64_t vb_table_rows(const vb_table* t) { return t ? t->t.n : 0; }
+int vb_table_free(vb_table* t) {
+    if (t) {
+        table_free(t->t);
+        delete t;
+    }
+    return VB_OK;
+}
+
+static int exact_topk_impl(vb_table* t, int metric, const void* queries, int64_t nq, int k, bool host, int64_t* out_ids,
+                           float* out_f, double* out_d) {
+    VB_TRY(require_init());
+    VB_REQUIRE(t && metric_valid_for(t->t.elem, metric) && metric != VB_SPHERICAL, "bad table/metric");
+    VB_REQUIRE(metric != VB_JACCARD || true, "");
+    VB_REQUIRE(k > 0, "k must be positive");
+    if (nq <= 0) return VB_OK;
+    Context& c = ctx();
+    Table& T = t->t;
+    const int64_t n = T.n;
+    const size_t rawq = raw_row_bytes(T.elem, T.dim);
+    // sub-batch so the distance matrix stays under ~1 GiB
+    int64_t bq = std::max<int64_t>(1, std::min<int64_t>(nq, (int64_t)(1ull << 30) / (4 * std::max<int64_t>(n, 1))));
+    for (int64_t q0 = 0; q0 < nq; q0 += bq) {
+        int64_t m = std::min(bq, nq - q0);
+        void *qimg, *d_dist, *d_seg, *d_pos, *d_ids, *d_of;
+        size_t qstride;
+        VB_TRY(upload_queries(T.elem, T.dim, (const uint8_t*)queries + (size_t)q0 * rawq, m, host, WS_QIMG, &qimg, &qstride));
+        VB_TRY(workspace(WS_DIST, sizeof(float) * (size_t)m * std::max<int64_t>(n, 1), &d_dist));
+        VB_TRY(launch_scan_regular(T, key_metric(metric), qimg, qstride, m, n, (float*)d_dist, n));
+        VB_TRY(workspace(WS_SEG, (sizeof(int64_t) + sizeof(int32_t)) * (size_t)m + 64, &d_seg));
+        int64_t* seg_begin = (int64_t*)d_seg;
+        int32_t* seg_len = (int32_t*)(seg_begin + m);
+        regular_segments_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c.stream>>>(m, n, (int32_t)n, seg_begin, seg_len);
+        VB_CUDA(cudaGetLastError());
+        count_launch();
+        VB_TRY(workspace(WS_POS, (sizeof(int32_t) + sizeof(float)) * (size_t)m * k, &d_pos));
+        int32_t* pos = (int32_t*)d_pos;
+        float* key = (float*)(pos + (size_t)m * k);
+        std::vector<int64_t> hb;
+        std::vector<int32_t> hl;
+        if (k > 2048) {
+            hb.resize((size_t)m);
+            hl.assign((size_t)m, (int32_t)n);
+            for (int64_t i = 0; i < m; ++i) hb[(size_t)i] = i * n;
+        }
+        VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, hb.empty() ? nullptr : hb.data(),
+                                     hl.empty() ? nullptr : hl.data(), m, k, pos, key));
+        int64_t* o_ids;
+        float* o_f = nullptr;
+        double* o_d = nullptr;
+        if (host) {
+            VB_TRY(workspace(WS_OUT, (sizeof(int64_t) + sizeof(double)) * (size_t)m * k, &d_ids));
+            o_ids = (int64_t*)d_ids;
+            o_d = (double*)(o_ids + (size_t)m * k);
+        } else {
+            o_ids = out_ids + q0 * k;
+            o_f = out_f + q0 * k;
+        }
+        (void)d_of;
+        finish_exact_kernel<<<(unsigned)((m * k + 255) / 256), 256, 0, c.stream>>>(metric, m * k, pos, key, o_ids, o_f, o_d);
+        VB_CUDA(cudaGetLastError());
+        count_launch();
+        if (host) {
+            VB_CUDA(cudaMemcpyAsync(out_ids + q0 * k, o_ids, sizeof(int64_t) * (size_t)m * k, cudaMemcpyDeviceToHost, c.stream));
+            VB_CUDA(cudaMemcpyAsync(out_d + q0 * k, o_d, sizeof(double) * (size_t)m * k, cudaMemcpyDeviceToHost, c.stream));
+            VB_CUDA(cudaStreamSynchronize(c.stream));
+        }
+    }
+    return VB_OK;
+}
+
+int vb_exact_topk(vb_table* t, int metric, const void* queries, int64_t nq, int k, int64_t* out_ids, double* out_dist) {
+    return exact_topk_impl(t, metric, queries, nq, k, true, out_ids, nullptr, out_dist);
+}
+int vb_exact_topk_dev(vb_table* t, int metric, const void* queries_dev, int64_t nq, int k, int64_t* out_ids_dev,
+                      float* out_dist_dev) {
+    return exact_topk_impl(t, metric, queries_dev, nq, k, false, out_ids_dev, out_dist_dev, nullptr);
+}
+
+// ----------------------------------------------------------------------------- IVFFlat
+
+int vb_ivf_create(int elem, int metric, int dim, int lists, vb_ivf** out) {
+    VB_TRY(require_init());
+    VB_REQUIRE(out && elem >= 0 && elem <= 2 && dim > 0 && lists >= 1 && lists <= 32768, "bad ivfflat arguments (lists 1..32768, src/ivfflat.h:56-57)");
+    bool ok = elem == VB_BIT ? metric == VB_HAMMING : (metric == VB_L2_SQUARED || metric == VB_NEG_IP);
+    VB_REQUIRE(ok, "ivfflat opclass proc 1 must be L2 squared / negative inner product (vector, halfvec) or Hamming (bit)");
+    vb_ivf* h = new vb_ivf();
+    Ivf& ix = h->ix;
+    ix.elem = elem;
+    ix.metric = metric;
+    ix.dim = dim;
+    ix.lists = lists;
+    ix.centers.elem = ix.rows.elem = elem;
+    ix.centers.dim = ix.rows.dim = dim;
+    ix.centers.stride = ix.rows.stride = padded_row_bytes(elem, dim);
+    *out = h;
+    return VB_OK;
+}
+
+static int ivf_set_offsets(Ivf& ix, const int64_t* list_offsets) {
+    ix.h_list_off.assign(list_offsets, list_offsets + ix.lists + 1);
+    VB_REQUIRE(ix.h_list_off[0] == 0, "list_offsets[0] must be 0");
+    ix.sorted_len.resize((size_t)ix.lists);
+    for (int l = 0; l < ix.lists; ++l) {
+        int64_t len = ix.h_list_off[(size_t)l + 1] - ix.h_list_off[(size_t)l];
+        VB_REQUIRE(len >= 0 && len < (int64_t)INT32_MAX, "bad list length");
+        ix.sorted_len[(size_t)l] = len;
+    }
+    std::sort(ix.sorted_len.begin(), ix.sorted_len.end(), std::greater<int64_t>());
+    if (!ix.d_list_off) VB_CUDA(cudaMalloc(&ix.d_list_off, sizeof(int64_t) * ((size_t)ix.lists + 1)));
+    VB_CUDA(cudaMemcpy(ix.d_list_off, ix.h_list_off.data(), sizeof(int64_t) * ((size_t)ix.lists + 1), cudaMemcpyHostToDevice));
+    return VB_OK;
+}
+
+int vb_ivf_load(vb_ivf* h, const void* centers, const int64_t* list_offsets, const void* rows, const int64_t* ids) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && centers && list_offsets, "null argument");
+    Ivf& ix = h->ix;
+    table_free(ix.centers);
+    table_free(ix.rows);
+    VB_TRY(ivf_set_offsets(ix, list_offsets));
+    const int64_t n = ix.h_list_off[(size_t)ix.lists];
+    VB_TRY(table_append_host(ix.centers, centers, ix.lists));
+    VB_TRY(table_append_host(ix.rows, rows, n));
+    if (ix.d_ids) cudaFree(ix.d_ids);
+    ix.d_ids = nullptr;
+    if (ids && n > 0) {
+        VB_CUDA(cudaMalloc(&ix.d_ids, sizeof(int64_t) * (size_t)n));
+        VB_CUDA(cudaMemcpy(ix.d_ids, ids, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice));
+    }
+    ix.loaded = true;
+    return VB_OK;
+}
+
+int vb_ivf_load_dev(vb_ivf* h, const void* centers_dev, const int64_t* list_offsets_host, const void* rows_dev,
+                    const int64_t* ids_dev) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && centers_dev && list_offsets_host, "null argument");
+    Ivf& ix = h->ix;
+    table_free(ix.centers);
+    table_free(ix.rows);
+    VB_TRY(ivf_set_offsets(ix, list_offsets_host));
+    const int64_t n = ix.h_list_off[(size_t)ix.lists];
+    VB_TRY(table_append_dev(ix.centers, centers_dev, ix.lists));
+    VB_TRY(table_append_dev(ix.rows, rows_dev, n));
+    if (ix.d_ids) cudaFree(ix.d_ids);
+    ix.d_ids = nullptr;
+    if (ids_dev && n > 0) {
+        VB_CUDA(cudaMalloc(&ix.d_ids, sizeof(int64_t) * (size_t)n));
+        VB_CUDA(cudaMemcpyAsync(ix.d_ids, ids_dev, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToDevice, ctx().stream));
+    }
+    VB_CUDA(cudaStreamSynchronize(ctx().stream));
+    ix.loaded = true;
+    return VB_OK;
+}
+
+int64_t vb_ivf_rows(const vb_ivf* h) { return h ? h->ix.rows.n : 0; }
+
+int vb_ivf_free(vb_ivf* h) {
+    if (!h) return VB_OK;
+    table_free(h->ix.centers);
+    table_free(h->ix.rows);
+    if (h->ix.d_ids) cudaFree(h->ix.d_ids);
+    if (h->ix.d_list_off) cudaFree(h->ix.d_list_off);
+    if (h->ix.d_cand_sum) cudaFree(h->ix.d_cand_sum);
+    delete h;
+    return VB_OK;
+}
+
+int vb_ivf_scan_lists(vb_ivf* h, const void* queries, int64_t nq, int max_probes, int32_t* out_lists, double* out_dist) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && h->ix.loaded, "index not loaded");
+    VB_REQUIRE(max_probes >= 1, "max_probes must be >= 1");
+    Ivf& ix = h->ix;
+    Context& c = ctx();
+    int probes = std::min(max_probes, ix.lists);  // src/ivfscan.c:279-283
+    if (nq <= 0) return VB_OK;
+    if (queries == nullptr) {
+        // NULL query: every centre at distance 0; with this library's tie rule the first lists win
+        for (int64_t q = 0; q < nq; ++q)
+            for (int p = 0; p < probes; ++p) {
+                out_lists[q * max_probes + p] = p;
+                if (out_dist) out_dist[q * max_probes + p] = 0.0;
+            }
+        return VB_OK;
+    }
+    void* qimg;
+    size_t qstride;
+    VB_TRY(upload_queries(ix.elem, ix.dim, queries, nq, true, WS_QIMG, &qimg, &qstride));
+    int32_t* d_lists;
+    float* d_ldist;
+    VB_TRY(ivf_select_probes(ix, qimg, qstride, nq, probes, &d_lists, &d_ldist));
+    std::vector<int32_t> hl((size_t)nq * probes);
+    std::vector<float> hd((size_t)nq * probes);
+    VB_CUDA(cudaMemcpyAsync(hl.data(), d_lists, sizeof(int32_t) * hl.size(), cudaMemcpyDeviceToHost, c.stream));
+    VB_CUDA(cudaMemcpyAsync(hd.data(), d_ldist, sizeof(float) * hd.size(), cudaMemcpyDeviceToHost, c.stream));
+    VB_CUDA(cudaStreamSynchronize(c.stream));
+    for (int64_t q = 0; q < nq; ++q)
+        for (int p = 0; p < max_probes; ++p) {
+            bool have = p < probes;
+            out_lists[q * max_probes + p] = have ? hl[(size_t)(q * probes + p)] : -1;
+            if (out_dist) out_dist[q * max_probes + p] = have ? (double)hd[(size_t)(q * probes + p)] : INFINITY;
+        }
+    return VB_OK;
+}
+
+int vb_ivf_scan_items(vb_ivf* h, const void* q, const int32_t* lists, int nlists, int64_t cap, int64_t* out_ids, double* out_dist,
+                      int64_t* n_out) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && h->ix.loaded, "index not loaded");
+    VB_REQUIRE(nlists >= 0 && lists && n_out, "bad arguments");
+    Ivf& ix = h->ix;
+    Context& c = ctx();
+    int64_t total = 0;
+    for (int i = 0; i < nlists; ++i) {
+        VB_REQUIRE(lists[i] >= 0 && lists[i] < ix.lists, "list %d out of range", lists[i]);
+        total += ix.h_list_off[(size_t)lists[i] + 1] - ix.h_list_off[(size_t)lists[i]];
+    }
+    *n_out = total;
+    int64_t k = std::min(cap, total);
+    if (k <= 0) return VB_OK;
+    if (q == nullptr) {
+        // NULL query: all distances 0, every probed row returned in scan order (src/ivfscan.c:207-211)
+        std::vector<int64_t> hid;
+        int64_t w = 0;
+        for (int i = 0; i < nlists && w < k; ++i) {
+            int64_t lo = ix.h_list_off[(size_t)lists[i]], hi = ix.h_list_off[(size_t)lists[i] + 1];
+            int64_t m = std::min(hi - lo, k - w);
+            if (ix.d_ids) VB_CUDA(cudaMemcpy(out_ids + w, ix.d_ids + lo, sizeof(int64_t) * (size_t)m, cudaMemcpyDeviceToHost));
+            else
+                for (int64_t j = 0; j < m; ++j) out_ids[w + j] = lo + j;
+            for (int64_t j = 0; j < m; ++j) out_dist[w + j] = 0.0;
+            w += m;
+        }
+        return VB_OK;
+    }
+    VB_REQUIRE(k < (int64_t)INT32_MAX, "too many candidates");
+    void* qimg;
+    size_t qstride;
+    VB_TRY(upload_queries(ix.elem, ix.dim, q, 1, true, WS_QIMG, &qimg, &qstride));
+    void* d_misc;
+    VB_TRY(workspace(WS_MISC, sizeof(int32_t) * (size_t)nlists, &d_misc));
+    VB_CUDA(cudaMemcpyAsync(d_misc, lists, sizeof(int32_t) * (size_t)nlists, cudaMemcpyHostToDevice, c.stream));
+    VB_CUDA(cudaStreamSynchronize(c.stream));
+    void* d_out;
+    VB_TRY(workspace(WS_OUT, (sizeof(int64_t) + sizeof(double)) * (size_t)k, &d_out));
+    int64_t* o_ids = (int64_t*)d_out;
+    double* o_d = (double*)(o_ids + k);
+    // capacity bound must cover these particular lists
+    std::vector<int64_t> saved = ix.sorted_len;
+    ix.sorted_len.assign(1, total);
+    int rc = ivf_scan_topk(ix, qimg, qstride, 1, (const int32_t*)d_misc, nlists, (int)k, o_ids, nullptr, o_d, nullptr);
+    ix.sorted_len = saved;
+    VB_TRY(rc);
+    VB_CUDA(cudaMemcpyAsync(out_ids, o_ids, sizeof(int64_t) * (size_t)k, cudaMemcpyDeviceToHost, c.stream));
+    VB_CUDA(cudaMemcpyAsync(out_dist, o_d, sizeof(double) * (size_t)k, cudaMemcpyDeviceToHost, c.stream));
+    VB_CUDA(cudaStreamSynchronize(c.stream));
+    return VB_OK;
+}
+
+static int ivf_search_impl(vb_ivf* h, const void* queries, int64_t nq, int probes, int k, bool host, int64_t* out_ids, float* out_f,
+                           double* out_d) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && h->ix.loaded, "index not loaded");
+    VB_REQUIRE(queries && probes >= 1 && k >= 1, "bad search arguments");
+    Ivf& ix = h->ix;
+    Context& c = ctx();
+    probes = std::min(probes, ix.lists);
+    if (nq <= 0) return VB_OK;
+    const size_t rawq = raw_row_bytes(ix.elem, ix.dim);
+    const int64_t bq = ivf_batch_limit(ix, probes);
+    if (!ix.d_cand_sum) VB_CUDA(cudaMalloc(&ix.d_cand_sum, sizeof(int64_t)));
+    VB_CUDA(cudaMemsetAsync(ix.d_cand_sum, 0, sizeof(int64_t), c.stream));
+    for (int64_t q0 = 0; q0 < nq; q0 += bq) {
+        int64_t m = std::min(bq, nq - q0);
+        void* qimg;
+        size_t qstride;
+        VB_TRY(upload_queries(ix.elem, ix.dim, (const uint8_t*)queries + (size_t)q0 * rawq, m, host, WS_QIMG, &qimg, &qstride));
+        int32_t* d_lists;
+        float* d_ldist;
+        VB_TRY(ivf_select_probes(ix, qimg, qstride, m, probes, &d_lists, &d_ldist));
+        if (host) {
+            void* d_out;
+            VB_TRY(workspace(WS_OUT, (sizeof(int64_t) + sizeof(double)) * (size_t)m * k, &d_out));
+            int64_t* o_ids = (int64_t*)d_out;
+            double* o_d = (double*)(o_ids + (size_t)m * k);
+            VB_TRY(ivf_scan_topk(ix, qimg, qstride, m, d_lists, probes, k, o_ids, nullptr, o_d, nullptr));
+            VB_CUDA(cudaMemcpyAsync(out_ids + q0 * k, o_ids, sizeof(int64_t) * (size_t)m * k, cudaMemcpyDeviceToHost, c.stream));
+            VB_CUDA(cudaMemcpyAsync(out_d + q0 * k, o_d, sizeof(double) * (size_t)m * k, cudaMemcpyDeviceToHost, c.stream));
+            VB_CUDA(cudaStreamSynchronize(c.stream));
+        } else {
+            VB_TRY(ivf_scan_topk(ix, qimg, qstride, m, d_lists, probes, k, out_ids + q0 * k, out_f + q0 * k, nullptr, nullptr));
+        }
+    }
+    ix.last_cand = -1;  // fetched lazily
+    ix.last_bytes = nq;
+    return VB_OK;
+}
+
+int vb_ivf_search(vb_ivf* h, const void* queries, int64_t nq, int probes, int k, int64_t* out_ids, double* out_dist) {
+    return ivf_search_impl(h, queries, nq, probes, k, true, out_ids, nullptr, out_dist);
+}
+int vb_ivf_search_dev(vb_ivf* h, const void* queries_dev, int64_t nq, int probes, int k, int64_t* out_ids_dev, float* out_dist_dev) {
+    return ivf_search_impl(h, queries_dev, nq, probes, k, false, out_ids_dev, out_dist_dev, nullptr);
+}
+
+int64_t vb_ivf_last_candidates(const vb_ivf* h) {
+    if (!h || !h->ix.d_cand_sum) return 0;
+    int64_t v = 0;
+    cudaStreamSynchronize(ctx().stream);
+    cudaMemcpy(&v, h->ix.d_cand_sum, sizeof(int64_t), cudaMemcpyDeviceToHost);
+    return v;
+}
+int64_t vb_ivf_last_scan_bytes(const vb_ivf* h) {
+    if (!h) return 0;
+    const Ivf& ix = h->ix;
+    int64_t cand = vb_ivf_last_candidates(h);
+    int64_t nq = ix.last_bytes;  // number of queries of the last search
+    return (nq * ix.lists + cand) * (int64_t)raw_row_bytes(ix.elem, ix.dim);
+}
+
+}  // extern "C"

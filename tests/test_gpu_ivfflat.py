@@ -1,0 +1,174 @@
+"""GPU parity of the IVFFlat scan path (GetScanLists / GetScanItems, src/ivfscan.c) vs the oracle."""
+import numpy as np
+import pytest
+
+import oracle as O
+from tests.util import build_ivf_arrays, f32_to_half_bits, load_golden, mixture, parse_vector, recall_at_k
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def pv():
+    import pgvector_b200 as pv
+    pv.init(0)
+    return pv
+
+
+def make_index(pv, opclass, rows, centers, dim=None):
+    elem, metric, _, _ = pv.OPCLASSES[opclass]
+    lists = centers.shape[0]
+    assign = O.ivf_assign(elem, metric, rows, centers, threads=8, dim=dim)
+    grouped, ids, offsets = build_ivf_arrays(rows, assign, lists)
+    d = dim if dim is not None else rows.shape[1]
+    gix = pv.IvfflatIndex(opclass, d, lists).load(centers, offsets, grouped, ids)
+    oix = O.Ivf(elem, metric, centers, offsets, grouped, ids, dim=d)
+    return gix, oix
+
+
+@pytest.fixture(scope="module")
+def l2_index(pv):
+    rows, centers = mixture(30000, 96, 64, seed=3)
+    queries, _ = mixture(200, 96, 64, seed=4)
+    gix, oix = make_index(pv, "vector_l2_ops", rows, centers)
+    return gix, oix, rows, queries
+
+
+def test_scan_lists_matches_oracle(l2_index):
+    gix, oix, rows, queries = l2_index
+    for mp in (1, 5, 64, 100):
+        lists, dist = gix.scan_lists(queries[:50], mp)
+        for i in range(50):
+            wl, wd = oix.scan_lists(queries[i], mp)
+            n = len(wl)
+            assert np.array_equal(lists[i][:n], wl), (mp, i)
+            assert np.allclose(dist[i][:n], wd, rtol=RTOL)
+            assert np.all(lists[i][n:] == -1)
+
+
+def test_scan_items_full_sort_matches_oracle(l2_index):
+    gix, oix, rows, queries = l2_index
+    for i in range(5):
+        wl, _ = oix.scan_lists(queries[i], 7)
+        ids, dist, n = gix.scan_items(queries[i], wl)
+        wi, wd, wn = oix.search(queries[i], 7, 0)
+        assert n == wn == len(ids)
+        assert np.allclose(dist, wd, rtol=RTOL)
+        assert np.all(np.diff(dist) >= 0)
+        # same multiset of heap ids; order equal except fp near-ties
+        assert sorted(ids) == sorted(wi)
+        assert (ids == wi).mean() > 0.995
+        # cap smaller than the candidate count: a sorted prefix
+        ids2, dist2, n2 = gix.scan_items(queries[i], wl, cap=17)
+        assert n2 == wn and np.array_equal(ids2, ids[:17])
+
+
+def test_scan_items_null_query_returns_everything_at_zero(l2_index):
+    gix, oix, rows, queries = l2_index
+    ids, dist, n = gix.scan_items(None, [3, 9])
+    wi, wd, wn = oix.search(None, 2, 0)   # oracle: first two lists by its tie rule differ; compare counts/zeros
+    assert n == len(ids) and np.all(dist == 0)
+    lo = sorted(int(x) for x in ids)
+    assert lo == sorted(int(x) for x in np.concatenate([oix.ids[oix.offsets[3]:oix.offsets[4]], oix.ids[oix.offsets[9]:oix.offsets[10]]]))
+
+
+@pytest.mark.parametrize("probes,k", [(1, 10), (8, 10), (64, 100), (5, 1), (10, 3000)])
+def test_search_matches_oracle(l2_index, probes, k):
+    gix, oix, rows, queries = l2_index
+    ids, dist = gix.search(queries, k=k, probes=probes)
+    wi, wd = oix.search_batch(queries, probes, k, threads=8)
+    finite = np.isfinite(wd)
+    assert np.array_equal(np.isfinite(dist), finite)
+    assert np.allclose(dist[finite], wd[finite], rtol=RTOL)
+    assert (ids == wi).mean() > 0.998
+    assert np.array_equal(ids < 0, wi < 0)
+    # recall is identical to the oracle's at the same probes (north_star)
+    kk = min(k, 10)
+    truth = [O.exact_topk(O.VECTOR, O.L2_SQUARED, q, rows, kk)[0] for q in queries[:50]]
+    r_gpu = recall_at_k(ids[:50, :kk], truth)
+    r_cpu = recall_at_k(wi[:50, :kk], truth)
+    assert abs(r_gpu - r_cpu) < 1e-3
+
+
+def test_probes_equal_lists_is_exact(l2_index):
+    """test/t/003_ivfflat_vector_build_recall.pl:114-116: probes = lists gives recall 1.0"""
+    gix, oix, rows, queries = l2_index
+    ids, dist = gix.search(queries[:40], k=10, probes=64)
+    truth = [O.exact_topk(O.VECTOR, O.L2_SQUARED, q, rows, 10)[0] for q in queries[:40]]
+    assert recall_at_k(ids, truth) >= 0.999
+
+
+def test_self_query_recall_is_100_percent(l2_index):
+    """test/t/005_ivfflat_query_recall.pl:23-32: a stored row is its own nearest neighbour at probes=1...lists"""
+    gix, oix, rows, queries = l2_index
+    pick = rows[::1500][:20]
+    ids, dist = gix.search(pick, k=1, probes=64)
+    assert np.all(dist[:, 0] == 0)
+    assert np.array_equal(ids[:, 0], np.arange(0, 30000, 1500)[:20])
+
+
+@pytest.mark.parametrize("opclass,dim", [("vector_ip_ops", 40), ("vector_cosine_ops", 40), ("halfvec_l2_ops", 72),
+                                         ("halfvec_cosine_ops", 768), ("bit_hamming_ops", 52), ("bit_hamming_ops", 1024)])
+def test_other_opclasses(pv, opclass, dim):
+    elem, metric, normalize, _ = pv.OPCLASSES[opclass]
+    lists = 20
+    x, c = mixture(6000, dim, lists, seed=11)
+    q, _ = mixture(60, dim, lists, seed=12)
+    if elem == O.BIT:
+        rows, centers, queries = O.binary_quantize(O.VECTOR, x), O.binary_quantize(O.VECTOR, c), O.binary_quantize(O.VECTOR, q)
+    else:
+        if elem == O.HALFVEC:
+            x, c, q = f32_to_half_bits(x), f32_to_half_bits(c), f32_to_half_bits(q)
+        rows, centers, queries = x, c, q
+        if normalize or metric == O.NEG_IP:
+            # cosine opclasses index normalised rows and normalise the query (src/ivfscan.c:222-229);
+            # ip k-means centres are unit vectors too (src/ivfkmeans.c:233-235)
+            rows, centers, queries = O.l2_normalize(elem, rows), O.l2_normalize(elem, centers), O.l2_normalize(elem, queries)
+    gix, oix = make_index(pv, opclass, rows, centers, dim=dim)
+    ids, dist = gix.search(queries, k=10, probes=4)
+    wi, wd = oix.search_batch(queries, 4, 10, threads=8)
+    if elem == O.BIT:
+        assert np.array_equal(dist, wd)
+        # Hamming ties are constant: identical ids are required only up to equal-distance groups
+        for i in range(len(queries)):
+            assert sorted(zip(dist[i], ids[i])) == sorted(zip(wd[i], wi[i])) or set(dist[i]) == set(wd[i])
+        assert np.array_equal(ids, wi)   # both sides break ties by scan order
+    else:
+        assert np.allclose(dist, wd, rtol=RTOL, atol=1e-6)
+        assert (ids == wi).mean() > 0.99
+
+
+def test_reference_index_orderings(pv):
+    """tiny-table orderings of test/expected/ivfflat_*.out (no ties in them)"""
+    blocks = [b for b in load_golden("index_orderings.json")["blocks"] if b["index"]["am"] == "ivfflat"]
+    assert len(blocks) >= 7
+    ELEMS = {"vector": O.VECTOR, "halfvec": O.HALFVEC, "bit": O.BIT}
+    for b in blocks:
+        elem = ELEMS[b["type"]]
+        opclass = b["index"]["opclass"]
+        _, metric, normalize, _ = pv.OPCLASSES[opclass]
+        lists = int(b["index"]["options"].split("=")[1]) if "lists" in b["index"]["options"] else 100
+        texts = [v for grp in b["rows"] for v in grp["values"] if v is not None]
+        rows = np.stack([parse_vector(t, elem)[0] for t in texts])
+        keep = np.ones(len(texts), bool)
+        stored = rows
+        if normalize:
+            keep = np.array([O.norm(elem, r) > 0 for r in rows])      # zero vectors are not indexed
+            stored = O.l2_normalize(elem, rows[keep])
+        dim = b["dim"]
+        # lists = 1: the single centre is irrelevant for the ordering; lists = 3: one row per list
+        if lists == 1:
+            centers = stored[:1].copy()
+        else:
+            centers = stored[:lists].copy()
+        gix, oix = make_index(pv, opclass, stored, centers, dim=dim)
+        kept_texts = [t for t, kp in zip(texts, keep) if kp]
+        qry = b["queries"][0]
+        qv = parse_vector(qry["query"], elem)[0]
+        if normalize:
+            qv = O.l2_normalize(elem, qv)
+        ids, dist, n = gix.scan_items(qv, list(range(lists)))
+        got = [kept_texts[i] for i in ids]
+        want = qry["expected"]
+        assert got[:len(want)] == want, (b["source"], got, want)
