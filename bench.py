@@ -1,0 +1,441 @@
+#!/usr/bin/env python3
+"""bench.py -- IVFFlat scan throughput (BASELINE.json metric) on B200.
+
+Workload (config B of BASELINE.json / SURVEY.md section 8d): 1,000,000 x 1536-d fp32 rows drawn from a
+1000-component Gaussian mixture (sigma 0.3, seed 3), ivfflat vector_l2_ops, lists = 1000,
+probes = 10, k = 10; 10,000 queries from the same mixture (seed 4).  A "step" is one batch
+of --batch queries through the hot path (probe selection + list scan + top-k).
+
+  value : queries/s with queries and outputs resident in HBM (device pointers, C ABI *_dev call)
+  e2e   : queries/s through vb_ivf_search with HOST buffers (H2D of the queries and D2H of
+          ids + distances inside the timed region); the index image stays resident in HBM
+          (it is uploaded once per index version, like shared_buffers; upload time reported
+          in config.index_upload_s)
+  roofline : algorithmic bytes of the list-scan kernel / its CUDA-event time, vs MEASURED_PEAKS.json
+  cpu_baseline : the oracle port of the same scan on the host cores (bounded sample)
+
+`--impl reference` times only the CPU arm (oracle port of src/ivfscan.c; PostgreSQL itself is
+not installable here).  Under torchrun every rank shards the lists
+(list l lives on rank l % N), all ranks see all queries, and per-query top-k lists are
+exchanged with one NCCL all-gather and merged on the GPU ("strong" scaling: same index).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000)
+    ap.add_argument("--dim", type=int, default=1536)
+    ap.add_argument("--lists", type=int, default=1000)
+    ap.add_argument("--probes", type=int, default=10)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--queries", type=int, default=10_000)
+    ap.add_argument("--batch", type=int, default=2048)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-recall", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- synthetic data + index build (setup, untimed)
+
+def make_dataset(args, device):
+    """mixture of `lists` Gaussians; generated in slabs to bound temporary memory"""
+    import torch
+    g = torch.Generator(device=device).manual_seed(3)
+    comp = torch.randn((args.lists, args.dim), generator=g, device=device, dtype=torch.float32)
+    rows = torch.empty((args.rows, args.dim), device=device, dtype=torch.float32)
+    slab = 65536
+    for lo in range(0, args.rows, slab):
+        hi = min(args.rows, lo + slab)
+        which = torch.randint(0, args.lists, (hi - lo,), generator=g, device=device)
+        rows[lo:hi] = comp[which] + 0.3 * torch.randn((hi - lo, args.dim), generator=g, device=device)
+    g2 = torch.Generator(device=device).manual_seed(4)
+    which = torch.randint(0, args.lists, (args.queries,), generator=g2, device=device)
+    queries = comp[which] + 0.3 * torch.randn((args.queries, args.dim), generator=g2, device=device)
+    return rows, queries
+
+
+def torch_assign(rows, centers, slab=32768):
+    """setup-only nearest-centre pass (fp32 matmul, TF32 disabled)"""
+    import torch
+    out = torch.empty(rows.shape[0], dtype=torch.int64, device=rows.device)
+    cn = (centers * centers).sum(1)
+    for lo in range(0, rows.shape[0], slab):
+        x = rows[lo:lo + slab]
+        d = cn[None, :] - 2.0 * (x @ centers.T)
+        out[lo:lo + slab] = d.argmin(1)
+    return out
+
+
+def build_index_arrays(args, rows, pv=None):
+    """k-means on a sample + assign + group by list.  Uses libvecb200's k-means/assign when built,
+    otherwise a torch fp32 Lloyd (setup only; the timed path never touches torch math)."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n = rows.shape[0]
+    g = torch.Generator(device=rows.device).manual_seed(42)
+    ns = min(n, max(args.lists * 50, 10000))          # src/ivfbuild.c:448-452
+    samp = rows[torch.randperm(n, generator=g, device=rows.device)[:ns]]
+    centers = samp[torch.randperm(ns, generator=g, device=rows.device)[:args.lists]].clone()
+    how = "torch-lloyd(setup)"
+    done = False
+    if pv is not None and os.environ.get("VB_BENCH_TORCH_BUILD") != "1":
+        try:
+            t = pv.Table(pv.VECTOR, args.dim).append(samp)
+            c_host, iters = pv.kmeans(t, pv.L2, centers.cpu().numpy(), max_iter=20)
+            centers = torch.from_numpy(c_host).to(rows.device)
+            t.free()
+            tr = pv.Table(pv.VECTOR, args.dim).append(rows)
+            assign = pv.assign(tr, pv.L2_SQUARED, centers).to(torch.int64)
+            tr.free()
+            how = f"vb_kmeans({iters} it)+vb_assign"
+            done = True
+        except pv.VecB200Error as e:
+            if e.code != -5:
+                raise
+    if not done:
+        for _ in range(10):
+            a = torch_assign(samp, centers)
+            sums = torch.zeros_like(centers).index_add_(0, a, samp)
+            cnt = torch.bincount(a, minlength=args.lists).clamp(min=1).to(torch.float32)
+            centers = sums / cnt[:, None]
+        assign = torch_assign(rows, centers)
+    order = torch.argsort(assign, stable=True)
+    counts = torch.bincount(assign, minlength=args.lists)
+    offsets = torch.zeros(args.lists + 1, dtype=torch.int64)
+    offsets[1:] = torch.cumsum(counts.cpu(), 0)
+    grouped = torch.empty_like(rows)
+    slab = 65536
+    for lo in range(0, n, slab):
+        grouped[lo:lo + slab] = rows[order[lo:lo + slab]]
+    return centers.contiguous(), offsets.numpy(), grouped, order.contiguous(), how
+
+
+# ----------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- CPU arm
+
+def cpu_arm(args, centers, offsets, grouped, ids, queries, seconds):
+    """oracle port of GetScanLists + GetScanItems + sort on all host cores; bounded sample"""
+    import oracle as O
+    cores = os.cpu_count() or 1
+    oix = O.Ivf(O.VECTOR, O.L2_SQUARED, centers, offsets, grouped, ids)
+    # calibrate on a few queries, then size the sample for ~`seconds`
+    t0 = time.perf_counter()
+    oix.search_batch(queries[:cores], args.probes, args.k, threads=cores)
+    dt = max(time.perf_counter() - t0, 1e-3)
+    nq = int(min(len(queries), max(cores, cores * seconds / dt)))
+    t0 = time.perf_counter()
+    ids_o, dist_o = oix.search_batch(queries[:nq], args.probes, args.k, threads=cores)
+    dt = time.perf_counter() - t0
+    # single backend figure (amcanparallel = false): one thread
+    n1 = max(4, min(nq, int(2.0 / (dt / nq * cores)) if dt > 0 else 4))
+    t1 = time.perf_counter()
+    oix.search_batch(queries[:n1], args.probes, args.k, threads=1)
+    dt1 = time.perf_counter() - t1
+    return {"value": nq / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{nq} queries of the same workload, one query per thread on {cores} threads "
+                      f"(oracle port of src/ivfscan.c:47-187 with the reference's compiler flags; no PostgreSQL "
+                      f"buffer-manager/fmgr/tuplesort overhead => optimistic)",
+            "single_thread_qps": n1 / dt1}, ids_o, dist_o, nq
+
+
+# ----------------------------------------------------------------------------- main
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+        rows, queries = make_dataset(args, dev)
+        centers, offsets, grouped, order, how = build_index_arrays(args, rows)
+        del rows
+        cb, _, _, nq = cpu_arm(args, centers.cpu().numpy(), offsets, grouped.cpu().numpy(), order.cpu().numpy(),
+                               queries.cpu().numpy(), max(args.cpu_seconds, 2.0) * max(1, args.steps) / 3.0)
+        line = {"impl": "reference", "metric": "IVFFlat 1Mx1536d queries/sec", "value": cb["value"], "unit": "queries/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1000.0 * args.batch / cb["value"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, how), "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    import pgvector_b200 as pv
+    pv.init(local)
+
+    # ---- setup (untimed): data, index, device image
+    rows, queries = make_dataset(args, dev)
+    centers, offsets, grouped, order, how = build_index_arrays(args, rows, pv)
+    del rows
+    torch.cuda.empty_cache()
+    full_offsets = offsets
+    if world > 1:
+        # list l lives on rank l % world; the others keep an empty list with the same number
+        keep = (torch.arange(args.lists) % world) == rank
+        lens = np.diff(offsets)
+        sel = torch.zeros(grouped.shape[0], dtype=torch.bool)
+        for l in range(args.lists):
+            if keep[l]:
+                sel[offsets[l]:offsets[l + 1]] = True
+        sel = sel.to(dev)
+        grouped_local = grouped[sel].contiguous()
+        order_local = order[sel].contiguous()
+        lens_local = np.where(keep.numpy(), lens, 0)
+        offsets = np.zeros(args.lists + 1, dtype=np.int64)
+        offsets[1:] = np.cumsum(lens_local)
+    else:
+        grouped_local, order_local = grouped, order
+
+    ix = pv.IvfflatIndex("vector_l2_ops", args.dim, args.lists)
+    t0 = time.perf_counter()
+    ix.load(centers, offsets, grouped_local, order_local)
+    pv.synchronize()
+    upload_s = time.perf_counter() - t0
+
+    stream = torch.cuda.ExternalStream(pv.stream_handle(), device=dev)
+    B, k = min(args.batch, args.queries), args.k
+    nb = max(1, args.queries // B)
+    qbatches = [queries[i * B:(i + 1) * B].contiguous() for i in range(nb)]
+    ids_dev = torch.empty((B, k), dtype=torch.int64, device=dev)
+    dist_dev = torch.empty((B, k), dtype=torch.float32, device=dev)
+    if world > 1:
+        g_ids = torch.empty((world, B, k), dtype=torch.int64, device=dev)
+        g_dist = torch.empty((world, B, k), dtype=torch.float32, device=dev)
+
+    def step_dev(i):
+        ix.search_into(qbatches[i % nb], k, args.probes, ids_dev, dist_dev)
+        if world > 1:
+            # the one exchange of the list-sharded scan: k (distance, id) pairs per rank, then a k-way merge
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(g_dist, dist_dev)
+                dist.all_gather_into_tensor(g_ids, ids_dev)
+                d = g_dist.permute(1, 0, 2).reshape(B, world * k)
+                ii = g_ids.permute(1, 0, 2).reshape(B, world * k)
+                top = torch.topk(d, k, dim=1, largest=False, sorted=True)
+                ids_dev.copy_(torch.gather(ii, 1, top.indices))
+                dist_dev.copy_(top.values)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    pv.prof_enable(True)
+    pv.prof_read(pv.PROF_SCAN_ITEMS)
+    pv.prof_read(pv.PROF_SCAN_LISTS)
+    pv.prof_read(pv.PROF_TOPK)
+    l0 = pv.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cand_total = 0
+    e0.record(stream)
+    for i in range(args.steps):
+        step_dev(args.warmup + i)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = pv.launch_count() - l0
+    scan_ms, scan_n = pv.prof_read(pv.PROF_SCAN_ITEMS)
+    lists_ms, lists_n = pv.prof_read(pv.PROF_SCAN_LISTS)
+    topk_ms, topk_n = pv.prof_read(pv.PROF_TOPK)
+    pv.prof_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    # candidates of the last step (same batch size every step; lists differ slightly per batch)
+    cand_last = ix.last_candidates()
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        c = torch.tensor([cand_last], device=dev, dtype=torch.int64)
+        dist.all_reduce(c)
+        cand_all = int(c.item())
+    else:
+        cand_all = cand_last
+    qps = args.steps * B / (ms / 1000.0)
+
+    # ---- end to end through the host-buffer C ABI call
+    q_host = [torch.empty((B, args.dim), dtype=torch.float32).pin_memory().copy_(qb.cpu()).numpy() for qb in qbatches[:4]]
+    ids_h = torch.empty((B, k), dtype=torch.int64).pin_memory().numpy()
+    dist_h = torch.empty((B, k), dtype=torch.float64).pin_memory().numpy()
+
+    def step_host(i):
+        ix.search_host_into(q_host[i % len(q_host)], k, args.probes, ids_h, dist_h)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dd = torch.from_numpy(dist_h).to(dev, non_blocking=True).float()
+                iid = torch.from_numpy(ids_h).to(dev, non_blocking=True)
+                dist.all_gather_into_tensor(g_dist, dd)
+                dist.all_gather_into_tensor(g_ids, iid)
+                d = g_dist.permute(1, 0, 2).reshape(B, world * k)
+                ii = g_ids.permute(1, 0, 2).reshape(B, world * k)
+                top = torch.topk(d, k, dim=1, largest=False, sorted=True)
+                res = torch.gather(ii, 1, top.indices).cpu()
+            stream.synchronize()
+            return res
+
+    for i in range(args.warmup):
+        step_host(i)
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record(stream)
+    for i in range(args.steps):
+        step_host(i)
+    h1.record(stream)
+    barrier()
+    ms_h = h0.elapsed_time(h1)
+    if world > 1:
+        t = torch.tensor([ms_h], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_h = float(t.item())
+    e2e_qps = args.steps * B / (ms_h / 1000.0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (list scan), from live CUDA events
+    elem_bytes = 4
+    cand_per_step = cand_last                         # this rank's candidates in one step
+    scan_bytes_per_launch = cand_per_step * args.dim * elem_bytes
+    peak, peak_src = measured_peaks()
+    scan_avg_ms = scan_ms / max(scan_n, 1)
+    achieved = scan_bytes_per_launch / (scan_avg_ms / 1000.0) / 1e9 if scan_avg_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "scan_kernel<vector,L2^2> (GetScanItems list scan)", "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "bytes_per_launch": scan_bytes_per_launch, "avg_launch_ms": scan_avg_ms,
+                "share_of_step": scan_ms / ms if ms > 0 else None,
+                "other_kernels_ms_per_step": {"centre_scan": lists_ms / max(lists_n, 1), "topk_select": topk_ms / max(topk_n, 1)},
+                "whole_step_algorithmic_gbs": (B * args.lists + cand_all) * args.dim * elem_bytes / (ms / args.steps / 1000.0) / 1e9}
+
+    # ---- recall@10 vs exact brute force (GPU exact scan) and CPU baseline
+    recall = None
+    cpu = None
+    if not args.no_recall and world == 1:
+        t = pv.Table(pv.VECTOR, args.dim).append(grouped)
+        nq_r = min(256, args.queries)
+        ex_ids, _ = t.exact_topk(pv.L2_SQUARED, queries[:nq_r].contiguous(), k)
+        ex_heap = order[ex_ids.clamp(min=0)]
+        got, _ = ix.search(queries[:nq_r].contiguous(), k=k, probes=args.probes)
+        hit = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(got.cpu(), ex_heap.cpu()))
+        recall = hit / (nq_r * k)
+        t.free()
+    if not args.no_cpu and world == 1:
+        cpu, ids_o, dist_o, nq_c = cpu_arm(args, centers.cpu().numpy(), full_offsets, grouped.cpu().numpy(),
+                                            order.cpu().numpy(), queries.cpu().numpy(), args.cpu_seconds)
+        # parity of the timed configuration against the oracle on the CPU sample
+        got, gd = ix.search(queries[:nq_c].contiguous(), k=k, probes=args.probes)
+        cpu["gpu_vs_oracle_id_agreement"] = float((got.cpu().numpy() == ids_o).mean())
+        cpu["gpu_vs_oracle_max_rel_dist_err"] = float(np.max(np.abs(gd.cpu().numpy() - dist_o) / np.maximum(np.abs(dist_o), 1e-30)))
+
+    line = {"metric": "IVFFlat 1Mx1536d queries/sec", "value": qps, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args, how), index_upload_s=upload_s,
+                           l2_policy="inputs larger than L2: every step streams ~%d MB of list rows" % (cand_all * args.dim * 4 // 2**20)),
+            "recall_at_10": recall, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * args.dim * 4,
+                    "d2h_bytes_per_step": B * k * 16, "ms_per_step": ms_h / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def workload_config(args, how):
+    return {"workload": f"IVFFlat L2 {args.rows}x{args.dim} fp32, lists={args.lists}, probes={args.probes}, k={args.k} "
+                        f"(BASELINE.json configs[1])", "queries": args.queries, "batch": args.batch,
+            "index_build": how, "parallelism": "lists sharded l % N, one NCCL all-gather of k results per rank"}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -77,6 +77,21 @@ void	   *vb_stream(void);
 int64_t		vb_launch_count(void);
 int			vb_synchronize(void);
 
+/*
+ * Optional per-kernel timing with CUDA events on vb_stream(), used by bench.py for the
+ * roofline of the dominant kernel (the events add ~1 us per bracketed launch).
+ * Kernels: 0 = list/candidate scan (GetScanItems), 1 = centre scan (GetScanLists),
+ * 2 = top-k select, 3 = k-means assign, 4 = HNSW search.
+ */
+#define VB_PROF_SCAN_ITEMS 0
+#define VB_PROF_SCAN_LISTS 1
+#define VB_PROF_TOPK 2
+#define VB_PROF_ASSIGN 3
+#define VB_PROF_HNSW 4
+int			vb_prof_enable(int on);
+/* Synchronises, then returns accumulated milliseconds and bracketed launches since the last read of `kernel`. */
+int			vb_prof_read(int kernel, double *total_ms, int64_t *launches);
+
 /* ------------------------------------------------- batched distance operator */
 
 /*

@@ -57,6 +57,20 @@ def launch_count() -> int:
     return int(load().vb_launch_count())
 
 
+PROF_SCAN_ITEMS, PROF_SCAN_LISTS, PROF_TOPK, PROF_ASSIGN, PROF_HNSW = range(5)
+
+
+def prof_enable(on=True):
+    _lib.check(load().vb_prof_enable(1 if on else 0))
+
+
+def prof_read(kernel):
+    """(total milliseconds, launches) of the bracketed kernel class since the last read."""
+    ms, n = C.c_double(), C.c_int64()
+    _lib.check(load().vb_prof_read(kernel, C.byref(ms), C.byref(n)))
+    return ms.value, n.value
+
+
 def synchronize():
     _lib.check(load().vb_synchronize())
 

@@ -26,6 +26,8 @@ SIGNATURES = {
     "vb_stream": (_vp, []),
     "vb_launch_count": (_i64, []),
     "vb_synchronize": (_i, []),
+    "vb_prof_enable": (_i, [_i]),
+    "vb_prof_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "vb_distance_batch": (_i, [_i, _i, _i, _vp, _vp, _i64, _vp]),
     "vb_table_create": (_i, [_i, _i, C.POINTER(_vp)]),
     "vb_table_append": (_i, [_vp, _vp, _i64]),

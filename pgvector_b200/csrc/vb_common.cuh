@@ -64,6 +64,10 @@ int pinned_buffer2(size_t bytes, void** out);
 
 inline void count_launch(int n = 1) { ctx().launches += n; }
 
+// optional event brackets around a kernel class (vb_prof_enable)
+void prof_begin(int which);
+void prof_end(int which);
+
 // ---------------------------------------------------------------- layout
 inline size_t raw_row_bytes(int elem, int dim) {
     return elem == VB_VECTOR ? (size_t)dim * 4 : elem == VB_HALFVEC ? (size_t)dim * 2 : ((size_t)dim + 7) / 8;
@@ -129,4 +133,14 @@ int launch_segment_topk_v(const float* keys, const int64_t* seg_begin_dev, const
                           int32_t* out_pos, float* out_key);
 int scan_chunk_rows(const Table& t);
 
+// exact fp32 nearest-centre assign (vb_kmeans.cu) and the default assign entry (tensor cores + exact re-check)
+int launch_assign_exact(const Table& X, int metric, const Table& Cn, int k, const int32_t* row_sel_dev, int64_t n_sel,
+                        int32_t* out_idx, float* out_val);
+int launch_assign(const Table& X, int metric, const Table& Cn, int k, int32_t* out_idx);
+
 }  // namespace vb
+
+// opaque handle types of the C ABI
+struct vb_table {
+    vb::Table t;
+};

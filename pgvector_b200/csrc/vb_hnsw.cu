@@ -1,0 +1,569 @@
+// vb_hnsw.cu -- HNSW search on the device: GetScanItems (src/hnswscan.c:25-56) =
+// greedy descent with ef = 1 through the upper layers, then HnswSearchLayer
+// (src/hnswutils.c:824-987) with ef at layer 0.  Many queries per launch, one warp per query.
+//
+// Formulation.  Every distance comparison of the reference is taken on the total order
+// (distance, element number).  Under a total order the two pairing heaps collapse into ONE
+// sorted array R of the best <= ef elements seen so far, each with an "expanded" flag:
+//   W (results)    = R;   f = R[len-1]
+//   C (candidates) = unexpanded elements of R  (anything evicted from W is > f for ever,
+//                    so the reference would break on it before expanding it)
+//   pop nearest(C) = first unexpanded element of R;  "c > f -> break" = no unexpanded left
+//   admit e        = e lands inside the first ef entries of merge(R, {e})
+// which is order independent, so the <= lm neighbours of one expansion are scored
+// together: one 128-byte neighbour-list read, lm independent row gathers in flight,
+// a warp bitonic sort of the batch and a parallel merge into R.
+//
+// Roofline: HBM (latency-bound random row gathers).  Algorithmic bytes per query =
+// n_dist * dim * element size + n_expand * lm * 4; n_dist is returned per query.
+#include "vb_common.cuh"
+#include "vb_distance.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace vb {
+
+struct HnswDev {
+    const uint8_t* rows;
+    size_t stride;
+    int V;                    // 16-byte vectors per row
+    const int32_t* levels;    // [n]
+    const int32_t* nbr0;      // [n][2m]
+    const int32_t* upper_off; // [n] slot index or -1
+    const int32_t* upper;     // [slots][m]
+    int m;
+    int64_t n;
+    int entry;
+    int entry_level;
+};
+
+struct Hnsw {
+    int elem, metric, dim, m;
+    Table rows;
+    int32_t *levels = nullptr, *nbr0 = nullptr, *upper_off = nullptr, *upper = nullptr;
+    int64_t n = 0, entry = -1;
+    int entry_level = -1;
+    bool loaded = false;
+    uint32_t* vis = nullptr;  // visited hash tables, one per resident warp
+    size_t vis_bytes = 0;
+};
+
+constexpr int HN_WARPS = 4;             // queries per CTA
+constexpr uint32_t VIS_EMPTY = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+
+// returns true when id was NOT in the set (and inserts it)
+__device__ __forceinline__ bool vis_insert(uint32_t* tab, uint32_t mask, uint32_t id) {
+    uint32_t h = hash_u32(id) & mask;
+    for (;;) {
+        uint32_t old = atomicCAS(&tab[h], VIS_EMPTY, id);
+        if (old == VIS_EMPTY) return true;
+        if (old == id) return false;
+        h = (h + 1) & mask;
+    }
+}
+
+struct Ent {
+    uint64_t key;   // orderable64(distance)
+    uint32_t id;    // element number, bit 31 = expanded
+};
+__device__ __forceinline__ bool ent_less(uint64_t ka, uint32_t ia, uint64_t kb, uint32_t ib) {
+    return ka < kb || (ka == kb && (ia & 0x7fffffffu) < (ib & 0x7fffffffu));
+}
+
+// One warp = one query at a time.
+template <int ELEM, int METRIC, int LPR>
+__global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswDev g, const uint8_t* __restrict__ queries, size_t qstride,
+                                                                    int64_t nq, int ef, int k, uint32_t* __restrict__ vis_all,
+                                                                    uint32_t vis_cap, uint32_t vis_upper, int64_t* __restrict__ out_ids,
+                                                                    float* __restrict__ out_f, double* __restrict__ out_d,
+                                                                    int64_t* __restrict__ out_ndist, int* __restrict__ overflow) {
+    extern __shared__ uint4 smem[];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int qvec = (int)(qstride / 16);
+    // per-warp carve-up: query image | keys A | keys B | ids A | ids B | batch keys | batch ids
+    const size_t per_warp = (size_t)qvec * 16 + (size_t)ef * 2 * 8 + (size_t)ef * 2 * 4 + 32 * 8 + 32 * 4;
+    const size_t per_warp_al = (per_warp + 15) & ~(size_t)15;
+    uint8_t* base = reinterpret_cast<uint8_t*>(smem) + (size_t)warp * per_warp_al;
+    uint4* sq = reinterpret_cast<uint4*>(base);
+    uint64_t* keyA = reinterpret_cast<uint64_t*>(base + (size_t)qvec * 16);
+    uint64_t* keyB = keyA + ef;
+    uint64_t* bkey = keyB + ef;
+    uint32_t* idA = reinterpret_cast<uint32_t*>(bkey + 32);
+    uint32_t* idB = idA + ef;
+    uint32_t* bid = idB + ef;
+
+    const int gwarp = blockIdx.x * HN_WARPS + warp;
+    const int nwarps = gridDim.x * HN_WARPS;
+    uint32_t* vis = vis_all + (size_t)gwarp * vis_cap;
+    constexpr int GROUPS = 32 / LPR;       // rows scored at once
+    const int grp = lane / LPR, gl = lane % LPR;
+
+    for (int64_t q = gwarp; q < nq; q += nwarps) {
+        const uint4* gq = reinterpret_cast<const uint4*>(queries + (size_t)q * qstride);
+        for (int i = lane; i < qvec; i += 32) sq[i] = gq[i];
+        __syncwarp();
+
+        uint64_t* rk = keyA;
+        uint32_t* ri = idA;
+        uint64_t* nk = keyB;
+        uint32_t* ni = idB;
+        int len = 0;
+        int64_t ndist = 0;
+        bool failed = false;
+
+        // entry point distance (HnswEntryCandidate, src/hnswutils.c:609-621)
+        {
+            Acc<ELEM, METRIC> acc;
+            const uint4* rp = reinterpret_cast<const uint4*>(g.rows + (size_t)g.entry * g.stride);
+            for (int v = lane; v < g.V; v += 32) acc.add(ldg_stream(rp + v), sq, v);
+            acc.template reduce<32>();
+            if (lane == 0) {
+                rk[0] = orderable_key64(acc.value());
+                ri[0] = (uint32_t)g.entry;
+            }
+            len = 1;
+            __syncwarp();
+        }
+
+        for (int lc = g.entry_level; lc >= 0 && !failed; --lc) {
+            const int efl = lc == 0 ? ef : 1;
+            const int lm = lc == 0 ? 2 * g.m : g.m;
+            // visited set of this layer (InitVisited, src/hnswutils.c:671-680)
+            // (the ef = 1 layers use a small region of their own so only it is cleared per layer)
+            uint32_t* tab = lc == 0 ? vis + vis_upper : vis;
+            const uint32_t cap = lc == 0 ? vis_cap - vis_upper : vis_upper;
+            const uint32_t mask = cap - 1;
+            for (uint32_t i = lane; i < cap; i += 32) tab[i] = VIS_EMPTY;
+            __syncwarp();
+            uint32_t inserted = 0;
+            // entry points: visited, unexpanded; they count towards `tuples` at layer 0 (src/hnswutils.c:866-873)
+            for (int i = lane; i < len; i += 32) {
+                ri[i] &= 0x7fffffffu;
+                vis_insert(tab, mask, ri[i]);
+            }
+            inserted += (uint32_t)len;
+            if (lc == 0) ndist += len;
+            if (len > efl) len = efl;   // cannot happen (len <= previous efl = 1), kept for safety
+            __syncwarp();
+
+            for (;;) {
+                // nearest unexpanded element of R
+                int first = 0x7fffffff;
+                for (int i = lane; i < len; i += 32)
+                    if (!(ri[i] & 0x80000000u)) {
+                        first = i;
+                        break;
+                    }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+                if (first == 0x7fffffff) break;
+                const uint32_t c = ri[first] & 0x7fffffffu;
+                __syncwarp();
+                if (lane == 0) ri[first] = c | 0x80000000u;
+                __syncwarp();
+
+                // neighbour list of c at layer lc, in on-disk order (HnswLoadNeighborTids, src/hnswutils.c:761-791)
+                const int32_t* nb = nullptr;
+                if (lc == 0) nb = g.nbr0 + (size_t)c * lm;
+                else if (g.levels[c] >= lc) nb = g.upper + ((size_t)g.upper_off[c] + (lc - 1)) * (size_t)lm;
+                if (nb == nullptr) continue;
+
+                for (int off = 0; off < lm; off += 32) {
+                    int nid = (off + lane < lm) ? nb[off + lane] : -1;
+                    bool valid = nid >= 0;
+                    // an invalid TID terminates the list (src/hnswutils.c:809-810)
+                    unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                    unsigned inval = ~vmask;
+                    int first_inval = inval ? __ffs(inval) - 1 : 32;
+                    valid = valid && lane < first_inval;
+                    bool fresh = valid && vis_insert(tab, mask, (uint32_t)nid);
+                    inserted += (uint32_t)__popc(__ballot_sync(0xffffffffu, fresh));
+                    // elements below this layer are skipped (src/hnswutils.c:949-950)
+                    if (fresh && lc > 0 && g.levels[nid] < lc) fresh = false;
+                    unsigned fm = __ballot_sync(0xffffffffu, fresh);
+                    const int cnt = __popc(fm);
+                    if (cnt == 0) {
+                        if (first_inval < 32) break;
+                        continue;
+                    }
+                    if (lc == 0) ndist += cnt;
+                    const int pos = __popc(fm & ((1u << lane) - 1u));
+                    if (fresh) bid[pos] = (uint32_t)nid;
+                    __syncwarp();
+
+                    // score the batch: GROUPS rows per pass, RPI passes in flight
+                    constexpr int RPI = (LPR == 32) ? 4 : 2;
+                    for (int b0 = 0; b0 < cnt; b0 += GROUPS * RPI) {
+                        Acc<ELEM, METRIC> acc[RPI];
+                        const uint4* rp[RPI];
+#pragma unroll
+                        for (int i = 0; i < RPI; ++i) {
+                            int bi = b0 + i * GROUPS + grp;
+                            uint32_t e = bid[min(bi, cnt - 1)];
+                            rp[i] = reinterpret_cast<const uint4*>(g.rows + (size_t)e * g.stride);
+                        }
+                        for (int v = gl; v < g.V; v += LPR) {
+                            uint4 x[RPI];
+#pragma unroll
+                            for (int i = 0; i < RPI; ++i) x[i] = ldg_stream(rp[i] + v);
+#pragma unroll
+                            for (int i = 0; i < RPI; ++i) acc[i].add(x[i], sq, v);
+                        }
+#pragma unroll
+                        for (int i = 0; i < RPI; ++i) {
+                            acc[i].template reduce<LPR>();
+                            int bi = b0 + i * GROUPS + grp;
+                            if (gl == 0 && bi < cnt) bkey[bi] = orderable_key64(acc[i].value());
+                        }
+                    }
+                    __syncwarp();
+
+                    // sort the batch by (key, id): bitonic over 32 lanes, empty lanes = +inf
+                    uint64_t mk = lane < cnt ? bkey[lane] : ~0ull;
+                    uint32_t mi = lane < cnt ? bid[lane] : 0x7fffffffu;
+#pragma unroll
+                    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+                        for (int st = size >> 1; st > 0; st >>= 1) {
+                            uint64_t ok = __shfl_xor_sync(0xffffffffu, mk, st);
+                            uint32_t oi = __shfl_xor_sync(0xffffffffu, mi, st);
+                            bool up = (lane & size) == 0;
+                            bool lower = (lane & st) == 0;
+                            bool other_less = ent_less(ok, oi, mk, mi);
+                            // keep min in the lower lane of an ascending pair, max otherwise
+                            bool take = (lower == up) ? other_less : !other_less;
+                            if (take) {
+                                mk = ok;
+                                mi = oi;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane < cnt) {
+                        bkey[lane] = mk;
+                        bid[lane] = mi;
+                    }
+                    __syncwarp();
+
+                    // merge R (len, sorted) with the batch (cnt, sorted) into the other buffer, keep efl
+                    for (int j = lane; j < len; j += 32) {
+                        uint64_t kj = rk[j];
+                        uint32_t ij = ri[j];
+                        int lo = 0, hi = cnt;   // number of batch elements < R[j]
+                        while (lo < hi) {
+                            int mid = (lo + hi) >> 1;
+                            if (ent_less(bkey[mid], bid[mid], kj, ij)) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        int np = j + lo;
+                        if (np < efl) {
+                            nk[np] = kj;
+                            ni[np] = ij;
+                        }
+                    }
+                    if (lane < cnt) {
+                        int lo = 0, hi = len;   // number of R elements < batch[lane]
+                        while (lo < hi) {
+                            int mid = (lo + hi) >> 1;
+                            if (ent_less(rk[mid], ri[mid], mk, mi)) lo = mid + 1;
+                            else hi = mid;
+                        }
+                        int np = lane + lo;
+                        if (np < efl) {
+                            nk[np] = mk;
+                            ni[np] = mi;     // unexpanded
+                        }
+                    }
+                    __syncwarp();
+                    len = min(efl, len + cnt);
+                    uint64_t* tk = rk;
+                    rk = nk;
+                    nk = tk;
+                    uint32_t* ti = ri;
+                    ri = ni;
+                    ni = ti;
+                    if (first_inval < 32) break;
+                }
+                // keep the table at most half full; otherwise report and let the host retry with a larger one
+                if (inserted > cap / 2) {
+                    failed = true;
+                    break;
+                }
+            }
+        }
+
+        if (failed && lane == 0) atomicExch(overflow, 1);
+        // results nearest first (src/hnswscan.c:293-326)
+        for (int i = lane; i < k; i += 32) {
+            bool have = i < len && !failed;
+            int64_t id = have ? (int64_t)(ri[i] & 0x7fffffffu) : -1;
+            double d = have ? key64_to_double(rk[i]) : (double)INFINITY;
+            out_ids[q * k + i] = id;
+            if (out_f) out_f[q * k + i] = (float)d;
+            if (out_d) out_d[q * k + i] = d;
+        }
+        if (out_ndist && lane == 0) out_ndist[q] = ndist;
+        __syncwarp();
+    }
+}
+
+template <int ELEM, int METRIC>
+static int hnsw_launch_t(const HnswDev& g, const void* qimg, size_t qstride, int64_t nq, int ef, int k, uint32_t* vis, uint32_t vis_cap,
+                         uint32_t vis_upper, int grid, int64_t* out_ids, float* out_f, double* out_d, int64_t* out_nd, int* overflow) {
+    const int qvec = (int)(qstride / 16);
+    size_t per_warp = (size_t)qvec * 16 + (size_t)ef * 2 * 8 + (size_t)ef * 2 * 4 + 32 * 8 + 32 * 4;
+    per_warp = (per_warp + 15) & ~(size_t)15;
+    const size_t smem = per_warp * HN_WARPS;
+    VB_REQUIRE(smem <= 200 * 1024, "ef_search %d with this dimension needs %zu bytes of shared memory per CTA", ef, smem);
+    cudaStream_t s = ctx().stream;
+#define VB_HL(LPR)                                                                                                        \
+    do {                                                                                                                  \
+        auto kern = hnsw_search_kernel<ELEM, METRIC, LPR>;                                                                \
+        if (smem > 48 * 1024) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, HN_WARPS * 32, smem, s>>>(g, (const uint8_t*)qimg, qstride, nq, ef, k, vis, vis_cap, vis_upper, out_ids, out_f, out_d, \
+                                               out_nd, overflow);                                                        \
+    } while (0)
+    if (g.V >= 32) VB_HL(32);
+    else if (g.V >= 16) VB_HL(16);
+    else if (g.V >= 8) VB_HL(8);
+    else if (g.V >= 4) VB_HL(4);
+    else if (g.V >= 2) VB_HL(2);
+    else VB_HL(1);
+#undef VB_HL
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    return VB_OK;
+}
+
+static int hnsw_launch(const Hnsw& h, const HnswDev& g, const void* qimg, size_t qstride, int64_t nq, int ef, int k, uint32_t* vis,
+                       uint32_t vis_cap, uint32_t vis_upper, int grid, int64_t* out_ids, float* out_f, double* out_d, int64_t* out_nd, int* overflow) {
+#define VB_HC(E, M) return hnsw_launch_t<E, M>(g, qimg, qstride, nq, ef, k, vis, vis_cap, vis_upper, grid, out_ids, out_f, out_d, out_nd, overflow)
+    if (h.elem == VB_VECTOR) {
+        switch (h.metric) {
+            case VB_L2_SQUARED: VB_HC(VB_VECTOR, VB_L2_SQUARED);
+            case VB_NEG_IP: VB_HC(VB_VECTOR, VB_NEG_IP);
+            case VB_L1: VB_HC(VB_VECTOR, VB_L1);
+        }
+    } else if (h.elem == VB_HALFVEC) {
+        switch (h.metric) {
+            case VB_L2_SQUARED: VB_HC(VB_HALFVEC, VB_L2_SQUARED);
+            case VB_NEG_IP: VB_HC(VB_HALFVEC, VB_NEG_IP);
+            case VB_L1: VB_HC(VB_HALFVEC, VB_L1);
+        }
+    } else {
+        switch (h.metric) {
+            case VB_HAMMING: VB_HC(VB_BIT, VB_HAMMING);
+            case VB_JACCARD: VB_HC(VB_BIT, VB_JACCARD);
+        }
+    }
+#undef VB_HC
+    set_error("hnsw: unsupported metric %d for element type %d", h.metric, h.elem);
+    return VB_EINVAL;
+}
+
+enum { WSH_QIMG = 0, WSH_OUT = 7, WSH_FLAG = 12 };
+
+static int hnsw_search_impl(Hnsw& h, const void* queries, int64_t nq, int ef, int k, bool host, int64_t* out_ids, float* out_f,
+                            double* out_d, int64_t* out_nd) {
+    VB_REQUIRE(h.loaded, "hnsw index not loaded");
+    VB_REQUIRE(ef >= 1 && ef <= 1000, "ef_search must be 1..1000 (src/hnsw.h:60-62)");
+    VB_REQUIRE(k >= 1 && k <= ef, "k must be 1..ef_search");
+    if (nq <= 0) return VB_OK;
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    if (h.entry < 0) {
+        // empty index: no results
+        std::vector<int64_t> ids((size_t)nq * k, -1);
+        if (host) {
+            memcpy(out_ids, ids.data(), sizeof(int64_t) * ids.size());
+            for (int64_t i = 0; i < nq * k; ++i) out_d[i] = INFINITY;
+            if (out_nd) memset(out_nd, 0, sizeof(int64_t) * (size_t)nq);
+        }
+        return VB_OK;
+    }
+    HnswDev g{};
+    g.rows = h.rows.d;
+    g.stride = h.rows.stride;
+    g.V = (int)(h.rows.stride / 16);
+    g.levels = h.levels;
+    g.nbr0 = h.nbr0;
+    g.upper_off = h.upper_off;
+    g.upper = h.upper;
+    g.m = h.m;
+    g.n = h.n;
+    g.entry = (int)h.entry;
+    g.entry_level = h.entry_level;
+
+    void* qimg;
+    size_t qstride;
+    VB_TRY(upload_queries(h.elem, h.dim, queries, nq, host, WSH_QIMG, &qimg, &qstride));
+
+    int64_t* d_ids = out_ids;
+    float* d_f = out_f;
+    double* d_d = nullptr;
+    int64_t* d_nd = out_nd;
+    if (host) {
+        void* d_out;
+        VB_TRY(workspace(WSH_OUT, (sizeof(int64_t) + sizeof(double)) * (size_t)nq * k + sizeof(int64_t) * (size_t)nq, &d_out));
+        d_ids = (int64_t*)d_out;
+        d_d = (double*)(d_ids + (size_t)nq * k);
+        d_nd = (int64_t*)(d_d + (size_t)nq * k);
+        d_f = nullptr;
+    }
+    void* d_flag;
+    VB_TRY(workspace(WSH_FLAG, 64, &d_flag));
+
+    // resident warps: a few CTAs per SM; every warp owns one visited table
+    const int64_t want_ctas = (nq + HN_WARPS - 1) / HN_WARPS;
+    const int grid = (int)std::min<int64_t>(want_ctas, (int64_t)c.sm_count * 6);
+    // layer-0 table: generous for ef * 2m insertions per expansion wave; grows on overflow
+    uint32_t cap = 1u << 14;
+    while (cap < (uint32_t)(ef * h.m * 16) && cap < (1u << 22)) cap <<= 1;
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        const uint32_t vis_upper = std::max<uint32_t>(2048u, cap / 8);
+        const uint32_t vis_cap = cap + vis_upper;
+        const size_t need = (size_t)grid * HN_WARPS * vis_cap * sizeof(uint32_t);
+        if (h.vis_bytes < need) {
+            if (h.vis) {
+                VB_CUDA(cudaStreamSynchronize(s));
+                cudaFree(h.vis);
+                h.vis = nullptr;
+                h.vis_bytes = 0;
+            }
+            if (cudaMalloc(&h.vis, need) != cudaSuccess) {
+                set_error("hnsw: visited tables (%zu bytes) do not fit", need);
+                return VB_ENOMEM;
+            }
+            h.vis_bytes = need;
+        }
+        VB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
+        prof_begin(VB_PROF_HNSW);
+        VB_TRY(hnsw_launch(h, g, qimg, qstride, nq, ef, k, h.vis, vis_cap, vis_upper, grid, d_ids, d_f, d_d, d_nd, (int*)d_flag));
+        prof_end(VB_PROF_HNSW);
+        if (!host && attempt == 0) {
+            // device variant stays asynchronous unless the table was too small; check lazily
+        }
+        int flag = 0;
+        VB_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+        VB_CUDA(cudaStreamSynchronize(s));
+        if (!flag) break;
+        cap <<= 2;   // visited table overflowed for some query: retry everything with a larger one
+        VB_REQUIRE(attempt < 5, "hnsw: visited set overflow");
+    }
+    if (host) {
+        VB_CUDA(cudaMemcpyAsync(out_ids, d_ids, sizeof(int64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, s));
+        VB_CUDA(cudaMemcpyAsync(out_d, d_d, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, s));
+        if (out_nd) VB_CUDA(cudaMemcpyAsync(out_nd, d_nd, sizeof(int64_t) * (size_t)nq, cudaMemcpyDeviceToHost, s));
+        VB_CUDA(cudaStreamSynchronize(s));
+    }
+    return VB_OK;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+struct vb_hnsw {
+    Hnsw h;
+};
+
+extern "C" {
+
+int vb_hnsw_create(int elem, int metric, int dim, int m, vb_hnsw** out) {
+    VB_TRY(require_init());
+    VB_REQUIRE(out && elem >= 0 && elem <= 2 && dim > 0, "bad hnsw arguments");
+    VB_REQUIRE(m >= 2 && m <= 100, "m must be 2..100 (src/hnsw.h:54-56)");
+    bool ok = elem == VB_BIT ? (metric == VB_HAMMING || metric == VB_JACCARD)
+                             : (metric == VB_L2_SQUARED || metric == VB_NEG_IP || metric == VB_L1);
+    VB_REQUIRE(ok, "hnsw opclass proc 1 must be L2 squared / negative inner product / L1 (vector, halfvec) or Hamming / Jaccard (bit)");
+    vb_hnsw* p = new vb_hnsw();
+    p->h.elem = elem;
+    p->h.metric = metric;
+    p->h.dim = dim;
+    p->h.m = m;
+    p->h.rows.elem = elem;
+    p->h.rows.dim = dim;
+    p->h.rows.stride = padded_row_bytes(elem, dim);
+    *out = p;
+    return VB_OK;
+}
+
+static void hnsw_release(Hnsw& h) {
+    table_free(h.rows);
+    cudaFree(h.levels);
+    cudaFree(h.nbr0);
+    cudaFree(h.upper_off);
+    cudaFree(h.upper);
+    cudaFree(h.vis);
+    h.levels = h.nbr0 = h.upper_off = h.upper = nullptr;
+    h.vis = nullptr;
+    h.vis_bytes = 0;
+    h.loaded = false;
+}
+
+int vb_hnsw_load(vb_hnsw* p, const void* rows, int64_t n, const int32_t* levels, const int32_t* nbr0, const int64_t* upper_off,
+                 const int32_t* upper, int64_t upper_slots, int64_t entry) {
+    VB_TRY(require_init());
+    VB_REQUIRE(p && n >= 0 && n < (int64_t)0x7fffffff, "bad hnsw load arguments");
+    Hnsw& h = p->h;
+    hnsw_release(h);
+    h.n = n;
+    h.entry = n > 0 ? entry : -1;
+    if (n == 0) {
+        h.loaded = true;
+        return VB_OK;
+    }
+    VB_REQUIRE(rows && levels && nbr0 && upper_off && entry >= 0 && entry < n, "null graph arrays / bad entry point");
+    VB_TRY(table_append_host(h.rows, rows, n));
+    const int lm0 = 2 * h.m;
+    std::vector<int32_t> uo((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        VB_REQUIRE(upper_off[i] < (int64_t)0x7fffffff, "upper slot overflow");
+        uo[(size_t)i] = (int32_t)upper_off[i];
+        VB_REQUIRE(levels[i] == 0 || upper_off[i] >= 0, "element %lld has level %d but no upper slot", (long long)i, levels[i]);
+    }
+    h.entry_level = levels[entry];
+    VB_CUDA(cudaMalloc(&h.levels, sizeof(int32_t) * (size_t)n));
+    VB_CUDA(cudaMalloc(&h.nbr0, sizeof(int32_t) * (size_t)n * lm0));
+    VB_CUDA(cudaMalloc(&h.upper_off, sizeof(int32_t) * (size_t)n));
+    VB_CUDA(cudaMalloc(&h.upper, sizeof(int32_t) * (size_t)std::max<int64_t>(upper_slots, 1) * h.m));
+    VB_CUDA(cudaMemcpy(h.levels, levels, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
+    VB_CUDA(cudaMemcpy(h.nbr0, nbr0, sizeof(int32_t) * (size_t)n * lm0, cudaMemcpyHostToDevice));
+    VB_CUDA(cudaMemcpy(h.upper_off, uo.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
+    if (upper_slots > 0) VB_CUDA(cudaMemcpy(h.upper, upper, sizeof(int32_t) * (size_t)upper_slots * h.m, cudaMemcpyHostToDevice));
+    h.loaded = true;
+    return VB_OK;
+}
+
+int vb_hnsw_free(vb_hnsw* p) {
+    if (p) {
+        hnsw_release(p->h);
+        delete p;
+    }
+    return VB_OK;
+}
+
+int vb_hnsw_search(vb_hnsw* p, const void* queries, int64_t nq, int ef, int k, int64_t* out_ids, double* out_dist, int64_t* out_ndist) {
+    VB_TRY(require_init());
+    VB_REQUIRE(p && queries && out_ids && out_dist, "null argument");
+    return hnsw_search_impl(p->h, queries, nq, ef, k, true, out_ids, nullptr, out_dist, out_ndist);
+}
+
+int vb_hnsw_search_dev(vb_hnsw* p, const void* queries_dev, int64_t nq, int ef, int k, int64_t* out_ids_dev, float* out_dist_dev,
+                       int64_t* out_ndist_dev) {
+    VB_TRY(require_init());
+    VB_REQUIRE(p && queries_dev && out_ids_dev && out_dist_dev, "null argument");
+    return hnsw_search_impl(p->h, queries_dev, nq, ef, k, false, out_ids_dev, out_dist_dev, nullptr, out_ndist_dev);
+}
+
+}  // extern "C"

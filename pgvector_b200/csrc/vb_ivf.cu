@@ -146,7 +146,9 @@ static int ivf_select_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t 
     Context& c = ctx();
     void *d_cdist, *d_seg, *d_probe;
     VB_TRY(workspace(WS_CDIST, sizeof(float) * (size_t)nq * ix.lists, &d_cdist));
+    prof_begin(VB_PROF_SCAN_LISTS);
     VB_TRY(launch_scan_regular(ix.centers, key_metric(ix.metric), qimg, qstride, nq, ix.lists, (float*)d_cdist, ix.lists));
+    prof_end(VB_PROF_SCAN_LISTS);
     VB_TRY(workspace(WS_SEG, (sizeof(int64_t) + sizeof(int32_t)) * (size_t)nq * 2 + 64, &d_seg));
     int64_t* seg_begin = (int64_t*)d_seg;
     int32_t* seg_len = (int32_t*)(seg_begin + nq);
@@ -197,7 +199,9 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
     VB_CUDA(cudaGetLastError());
     count_launch();
     VB_TRY(workspace(WS_DIST, sizeof(float) * (size_t)nq * cap, &d_dist));
+    prof_begin(VB_PROF_SCAN_ITEMS);
     VB_TRY(launch_scan_chunks(ix.rows, key_metric(ix.metric), qimg, qstride, chunks, n_chunks, (int)max_chunks, (float*)d_dist));
+    prof_end(VB_PROF_SCAN_ITEMS);
     VB_TRY(workspace(WS_POS, (sizeof(int32_t) + sizeof(float)) * (size_t)nq * k, &d_pos));
     int32_t* pos = (int32_t*)d_pos;
     float* key = (float*)(pos + (size_t)nq * k);
@@ -211,8 +215,10 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
         VB_CUDA(cudaStreamSynchronize(c.stream));
         for (int64_t i = 0; i < nq; ++i) hb[(size_t)i] = i * cap;
     }
+    prof_begin(VB_PROF_TOPK);
     VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, hb.empty() ? nullptr : hb.data(),
                                  hl.empty() ? nullptr : hl.data(), nq, k, pos, key));
+    prof_end(VB_PROF_TOPK);
     ivf_finish_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, c.stream>>>(ix.metric, nq, k, probes, pos, key, d_lists, cand_off,
                                                                               ix.d_list_off, ix.d_ids, out_ids_dev, out_f_dev,
                                                                               out_d_dev);
@@ -233,9 +239,6 @@ static int64_t ivf_batch_limit(const Ivf& ix, int probes) {
 
 using namespace vb;
 
-struct vb_table {
-    Table t;
-};
 struct vb_ivf {
     Ivf ix;
 };

@@ -1,0 +1,651 @@
+// vb_kmeans.cu -- IVFFlat build path on the device: nearest-centre assign (AddTupleToSort,
+// src/ivfbuild.c:161-219), Lloyd k-means with the reference's centre-update rules
+// (ComputeNewCenters, src/ivfkmeans.c:179-236) and k-means++ seeding (InitCenters, :23-91).
+//
+// This file holds the EXACT fp32 assign kernel: distances are accumulated as
+// sum((x - c)^2) / sum(x * c) / popcount(x ^ c) in fp32 / integer, the same arithmetic
+// as the reference's proc-1 functions, so argmin decisions match the CPU path up to
+// fp32 reassociation.  It is compute bound on the CUDA cores (2 ops per element for L2);
+// the tensor-core (tcgen05) assign in vb_assign_tc.cu uses it to re-check near ties.
+#include "vb_common.cuh"
+
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace vb {
+
+enum { WSK_QIMG = 0, WSK_DIST = 1, WSK_A = 2, WSK_B = 3, WSK_C = 4, WSK_D = 5, WSK_E = 6, WSK_F = 7, WSK_G = 12, WSK_H = 13, WSK_I = 14, WSK_J = 15 };
+
+// ----------------------------------------------------------------------------- exact assign
+
+constexpr int AT_M = 128, AT_N = 128, AT_K = 16, AT_THREADS = 256;
+
+// four consecutive 32-bit "words" of a row starting at word w (w % 4 == 0): fp32 values, widened halves, or raw bit words
+template <int ELEM>
+__device__ __forceinline__ uint4 load_words4(const uint8_t* row, int w, int words) {
+    if (w >= words) return make_uint4(0, 0, 0, 0);
+    if (ELEM == VB_HALFVEC) {
+        uint2 h = *reinterpret_cast<const uint2*>(row + (size_t)w * 2);
+        float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
+        float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+        return make_uint4(__float_as_uint(a.x), __float_as_uint(a.y), __float_as_uint(b.x), __float_as_uint(b.y));
+    }
+    return *reinterpret_cast<const uint4*>(row + (size_t)w * 4);
+}
+
+// KIND 0: sum (x-c)^2   1: -sum x*c   2: popcount(x ^ c)
+template <int ELEM, int KIND>
+__global__ void __launch_bounds__(AT_THREADS) assign_exact_kernel(const uint8_t* __restrict__ X, size_t xstride, int64_t n,
+                                                                   const int32_t* __restrict__ row_sel, int64_t n_sel,
+                                                                   const uint8_t* __restrict__ Cn, size_t cstride, int k, int words,
+                                                                   int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+    __shared__ uint32_t Xs[AT_K][AT_M + 4];
+    __shared__ uint32_t Cs[AT_K][AT_N + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % 16, ty = tid / 16;
+    const int64_t total = row_sel ? n_sel : n;
+    const int64_t m0 = (int64_t)blockIdx.x * AT_M;
+
+    float best_v[8];
+    int best_i[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        best_v[i] = INFINITY;
+        best_i[i] = 0x7fffffff;
+    }
+    // the two rows / centres this thread stages per K step
+    const int lr = tid / 4;        // 0..63 (+64)
+    const int lw = (tid % 4) * 4;  // word offset within the K step
+    const uint8_t* xrow[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        int64_t r = m0 + lr + h * 64;
+        if (r >= total) r = total - 1;
+        if (row_sel) r = row_sel[r];
+        xrow[h] = X + (size_t)r * xstride;
+    }
+
+    for (int n0 = 0; n0 < k; n0 += AT_N) {
+        const uint8_t* crow[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            int c = n0 + lr + h * 64;
+            if (c >= k) c = k - 1;
+            crow[h] = Cn + (size_t)c * cstride;
+        }
+        float acc[8][8];
+        uint32_t uacc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[i][j] = 0.f;
+                uacc[i][j] = 0;
+            }
+        for (int k0 = 0; k0 < words; k0 += AT_K) {
+            uint4 xv[2], cv[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                xv[h] = load_words4<ELEM>(xrow[h], k0 + lw, words);
+                cv[h] = load_words4<ELEM>(crow[h], k0 + lw, words);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int r = lr + h * 64;
+                Xs[lw + 0][r] = xv[h].x;
+                Xs[lw + 1][r] = xv[h].y;
+                Xs[lw + 2][r] = xv[h].z;
+                Xs[lw + 3][r] = xv[h].w;
+                Cs[lw + 0][r] = cv[h].x;
+                Cs[lw + 1][r] = cv[h].y;
+                Cs[lw + 2][r] = cv[h].z;
+                Cs[lw + 3][r] = cv[h].w;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < AT_K; ++kk) {
+                uint32_t a[8], b[8];
+                *reinterpret_cast<uint4*>(&a[0]) = *reinterpret_cast<const uint4*>(&Xs[kk][ty * 8]);
+                *reinterpret_cast<uint4*>(&a[4]) = *reinterpret_cast<const uint4*>(&Xs[kk][ty * 8 + 4]);
+                *reinterpret_cast<uint4*>(&b[0]) = *reinterpret_cast<const uint4*>(&Cs[kk][tx * 8]);
+                *reinterpret_cast<uint4*>(&b[4]) = *reinterpret_cast<const uint4*>(&Cs[kk][tx * 8 + 4]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (KIND == 0) {
+                            float d = __uint_as_float(a[i]) - __uint_as_float(b[j]);
+                            acc[i][j] = fmaf(d, d, acc[i][j]);
+                        } else if (KIND == 1) {
+                            acc[i][j] = fmaf(__uint_as_float(a[i]), __uint_as_float(b[j]), acc[i][j]);
+                        } else {
+                            uacc[i][j] += __popc(a[i] ^ b[j]);
+                        }
+                    }
+            }
+        }
+        // fold this centre tile into the running argmin: strict <, first minimum wins (src/ivfbuild.c:183-192)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float v = INFINITY;
+            int vi = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int c = n0 + tx * 8 + j;
+                float d = KIND == 0 ? acc[i][j] : KIND == 1 ? -acc[i][j] : (float)uacc[i][j];
+                if (c < k && d < v) {  // NaN / +Inf never win a strict <
+                    v = d;
+                    vi = c;
+                }
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                float ov = __shfl_xor_sync(0xffffffffu, v, o);
+                int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+                if (ov < v || (ov == v && oi < vi)) {
+                    v = ov;
+                    vi = oi;
+                }
+            }
+            if (v < best_v[i]) {
+                best_v[i] = v;
+                best_i[i] = vi;
+            }
+        }
+    }
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int64_t r = m0 + ty * 8 + i;
+            if (r < total) {
+                int64_t dst = row_sel ? row_sel[r] : r;
+                // all-NaN / all-inf rows: closestCenter stays 0 like the reference (minDistance = DBL_MAX start)
+                out_idx[dst] = best_i[i] == 0x7fffffff ? 0 : best_i[i];
+                if (out_val) out_val[dst] = best_v[i];
+            }
+        }
+    }
+}
+
+static int assign_kind(int metric) {
+    switch (key_metric(metric)) {
+        case VB_L2_SQUARED: return 0;
+        case VB_NEG_IP: return 1;
+        case VB_HAMMING: return 2;
+    }
+    return -1;
+}
+
+// exact assign of all rows of X (or of the rows listed in row_sel) against k centres
+int launch_assign_exact(const Table& X, int metric, const Table& Cn, int k, const int32_t* row_sel_dev, int64_t n_sel,
+                        int32_t* out_idx, float* out_val) {
+    const int kind = assign_kind(metric);
+    VB_REQUIRE(kind >= 0, "assign: unsupported metric %d", metric);
+    const int64_t total = row_sel_dev ? n_sel : X.n;
+    if (total <= 0 || k <= 0) return VB_OK;
+    const int words = (int)(X.elem == VB_HALFVEC ? X.stride / 2 : X.stride / 4);
+    const unsigned grid = (unsigned)((total + AT_M - 1) / AT_M);
+    cudaStream_t s = ctx().stream;
+#define VB_ASSIGN(E, K) \
+    assign_exact_kernel<E, K><<<grid, AT_THREADS, 0, s>>>(X.d, X.stride, X.n, row_sel_dev, n_sel, Cn.d, Cn.stride, k, words, out_idx, out_val)
+    if (X.elem == VB_VECTOR) {
+        if (kind == 0) VB_ASSIGN(VB_VECTOR, 0);
+        else if (kind == 1) VB_ASSIGN(VB_VECTOR, 1);
+        else VB_REQUIRE(false, "assign: Hamming needs bit rows");
+    } else if (X.elem == VB_HALFVEC) {
+        if (kind == 0) VB_ASSIGN(VB_HALFVEC, 0);
+        else if (kind == 1) VB_ASSIGN(VB_HALFVEC, 1);
+        else VB_REQUIRE(false, "assign: Hamming needs bit rows");
+    } else {
+        VB_REQUIRE(kind == 2, "assign: bit rows need the Hamming metric");
+        VB_ASSIGN(VB_BIT, 2);
+    }
+#undef VB_ASSIGN
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    return VB_OK;
+}
+
+// ----------------------------------------------------------------------------- centre update
+
+__global__ void count_and_diff_kernel(const int32_t* __restrict__ closest, int32_t* __restrict__ prev, int64_t n,
+                                      int32_t* __restrict__ counts, int* __restrict__ changes, int first) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = closest[i];
+    atomicAdd(&counts[c], 1);
+    if (!first && prev[i] != c) atomicAdd(changes, 1);
+    prev[i] = c;
+}
+
+// stable counting sort of sample ids by cluster: position = start[c] + rank among equal c in index order.
+// One thread per cluster walks the (small) assignment array; k threads x n reads is fine for k-means samples
+// (n = 50 * k), and keeps member order = ascending sample index = the reference's summation order.
+__global__ void members_kernel(const int32_t* __restrict__ closest, int64_t n, int k, const int32_t* __restrict__ start,
+                               int32_t* __restrict__ members) {
+    // warp per cluster: ballot-compaction keeps index order
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    const int lane = threadIdx.x % 32;
+    if (warp >= k) return;
+    int pos = start[warp];
+    for (int64_t base = 0; base < n; base += 32) {
+        int64_t i = base + lane;
+        bool mine = i < n && closest[i] == warp;
+        unsigned m = __ballot_sync(0xffffffffu, mine);
+        if (mine) members[pos + __popc(m & ((1u << lane) - 1))] = (int32_t)i;
+        pos += __popc(m);
+    }
+}
+
+// agg[c][j] = sum over members in ascending sample order of x[j] (fp32, sequential like SumCenters, src/ivfkmeans.c:151-160)
+template <int ELEM>
+__global__ void sum_centers_kernel(const uint8_t* __restrict__ X, size_t xstride, int dim, const int32_t* __restrict__ members,
+                                   const int32_t* __restrict__ start, const int32_t* __restrict__ counts,
+                                   float* __restrict__ agg) {
+    const int c = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= dim) return;
+    const int32_t* mem = members + start[c];
+    const int cnt = counts[c];
+    float s = 0.f;
+    for (int t = 0; t < cnt; ++t) {
+        const uint8_t* row = X + (size_t)mem[t] * xstride;
+        float v;
+        if (ELEM == VB_VECTOR) v = reinterpret_cast<const float*>(row)[j];
+        else if (ELEM == VB_HALFVEC) v = __half2float(reinterpret_cast<const __half*>(row)[j]);
+        else v = (float)((row[j >> 3] >> (7 - (j & 7))) & 1);   // BitSumCenter (src/ivfutils.c:363-370)
+        s += v;
+    }
+    agg[(size_t)c * dim + j] = s;
+}
+
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t a, uint64_t b) {
+    // counter-based stand-in for RandomDouble() (pg_prng is PostgreSQL core; stream not reproduced)
+    uint64_t z = seed + 0x9e3779b97f4a7c15ULL * (a * 0x100000001b3ULL + b + 1);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    z ^= z >> 31;
+    return (float)((double)(z >> 11) * (1.0 / 9007199254740992.0));
+}
+
+// divide by count, clamp +-Inf, re-seed empty clusters (src/ivfkmeans.c:203-228)
+__global__ void finish_centers_kernel(float* __restrict__ agg, const int32_t* __restrict__ counts, int k, int dim,
+                                      uint64_t seed, int iteration) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)k * dim) return;
+    int c = (int)(i / dim), j = (int)(i % dim);
+    int cnt = counts[c];
+    float x = agg[i];
+    if (cnt > 0) {
+        if (isinf(x)) x = x > 0 ? 3.402823466e+38f : -3.402823466e+38f;
+        x /= (float)cnt;
+    } else {
+        x = hash_uniform(seed, (uint64_t)iteration * k + c, j);
+    }
+    agg[i] = x;
+}
+
+// typed centre rows from fp32 aggregates (+ spherical renormalisation):
+// {Vector,Halfvec,Bit}UpdateCenter (src/ivfutils.c:301-339), l2_normalize (src/vector.c:785-819, src/halfvec.c:725-759)
+template <int ELEM>
+__global__ void write_centers_kernel(const float* __restrict__ agg, int k, int dim, int spherical, uint8_t* __restrict__ Cn,
+                                     size_t cstride) {
+    const int c = blockIdx.x;
+    const float* a = agg + (size_t)c * dim;
+    uint8_t* row = Cn + (size_t)c * cstride;
+    __shared__ double s_norm;
+    __shared__ double red[32];
+    if (ELEM == VB_BIT) {
+        for (int b = threadIdx.x; b < (int)cstride; b += blockDim.x) {
+            uint8_t v = 0;
+            for (int t = 0; t < 8; ++t) {
+                int j = b * 8 + t;
+                if (j < dim && a[j] > 0.5f) v |= (uint8_t)(1u << (7 - t));
+            }
+            row[b] = v;
+        }
+        return;
+    }
+    double norm = 1.0;
+    if (spherical) {
+        // typed value first (half centres are rounded before normalising), norm accumulated in double
+        double p = 0;
+        for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+            float v = ELEM == VB_HALFVEC ? __half2float(__float2half_rn(a[j])) : a[j];
+            p += (double)v * (double)v;
+        }
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = p;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0;
+            for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+            s_norm = sqrt(t);
+        }
+        __syncthreads();
+        norm = s_norm;
+    }
+    const int padded = ELEM == VB_VECTOR ? (int)(cstride / 4) : (int)(cstride / 2);
+    for (int j = threadIdx.x; j < padded; j += blockDim.x) {
+        float v = j < dim ? a[j] : 0.f;
+        if (ELEM == VB_HALFVEC) {
+            __half h = __float2half_rn(v);
+            if (spherical && j < dim) {
+                // zero vector stays zero (src/halfvec.c:745)
+                h = norm > 0 ? __float2half_rn((float)((double)__half2float(h) / norm)) : __float2half_rn(0.f);
+            }
+            reinterpret_cast<__half*>(row)[j] = h;
+        } else {
+            if (spherical && j < dim) v = norm > 0 ? (float)((double)v / norm) : 0.f;
+            reinterpret_cast<float*>(row)[j] = v;
+        }
+    }
+}
+
+// device working set of one k-means run
+struct KmeansState {
+    Table centers;           // typed centre rows (padded)
+    int32_t *closest = nullptr, *prev = nullptr, *counts = nullptr, *start = nullptr, *members = nullptr;
+    float* agg = nullptr;
+    int* changes = nullptr;
+    void* scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
+};
+
+static int kmeans_update_centers(const Table& X, KmeansState& st, int k, bool spherical, uint64_t seed, int iteration,
+                                 vb_allreduce_fn allreduce, void* actx) {
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    const int dim = X.dim;
+    // member lists in ascending sample order
+    VB_CUDA(cub::DeviceScan::ExclusiveSum(st.scan_tmp, st.scan_tmp_bytes, st.counts, st.start, k, s));
+    count_launch();
+    if (X.n > 0) {
+        members_kernel<<<(unsigned)((k * 32 + 255) / 256), 256, 0, s>>>(st.closest, X.n, k, st.start, st.members);
+        VB_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    dim3 grid((unsigned)((dim + 127) / 128), (unsigned)k);
+    if (X.elem == VB_VECTOR) sum_centers_kernel<VB_VECTOR><<<grid, 128, 0, s>>>(X.d, X.stride, dim, st.members, st.start, st.counts, st.agg);
+    else if (X.elem == VB_HALFVEC) sum_centers_kernel<VB_HALFVEC><<<grid, 128, 0, s>>>(X.d, X.stride, dim, st.members, st.start, st.counts, st.agg);
+    else sum_centers_kernel<VB_BIT><<<grid, 128, 0, s>>>(X.d, X.stride, dim, st.members, st.start, st.counts, st.agg);
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    if (allreduce) {
+        // sharded build: partial sums and counts of every rank are added (the only collective of the build)
+        VB_CUDA(cudaStreamSynchronize(s));
+        if (allreduce(st.agg, (int64_t)k * dim, 0, actx) != 0 || allreduce(st.counts, k, 1, actx) != 0) {
+            set_error("allreduce hook failed");
+            return VB_ESTATE;
+        }
+    }
+    finish_centers_kernel<<<(unsigned)(((int64_t)k * dim + 255) / 256), 256, 0, s>>>(st.agg, st.counts, k, dim, seed, iteration);
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    if (X.elem == VB_VECTOR) write_centers_kernel<VB_VECTOR><<<k, 256, 0, s>>>(st.agg, k, dim, spherical, st.centers.d, st.centers.stride);
+    else if (X.elem == VB_HALFVEC) write_centers_kernel<VB_HALFVEC><<<k, 256, 0, s>>>(st.agg, k, dim, spherical, st.centers.d, st.centers.stride);
+    else write_centers_kernel<VB_BIT><<<k, 256, 0, s>>>(st.agg, k, dim, 0, st.centers.d, st.centers.stride);
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    return VB_OK;
+}
+
+
+static int kmeans_run(const Table& X, int kmeans_metric, void* centers_host, int k, int max_iter, uint64_t seed,
+                      vb_allreduce_fn allreduce, void* actx, int* iters_out) {
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    const bool spherical = kmeans_metric == VB_SPHERICAL;
+    int proc1;
+    if (kmeans_metric == VB_L2) proc1 = VB_L2_SQUARED;           // argmin of sqrt(d2) == argmin of d2
+    else if (kmeans_metric == VB_SPHERICAL) proc1 = VB_NEG_IP;   // acos(ip)/pi is decreasing in ip
+    else if (kmeans_metric == VB_HAMMING) proc1 = VB_HAMMING;
+    else VB_REQUIRE(false, "k-means distance must be L2, spherical or Hamming (opclass proc 3)");
+    VB_REQUIRE((X.elem == VB_BIT) == (kmeans_metric == VB_HAMMING), "metric does not fit the element type");
+    if (max_iter <= 0 || max_iter > 500) max_iter = 500;        // src/ivfkmeans.c:347
+
+    KmeansState st;
+    st.centers.elem = X.elem;
+    st.centers.dim = X.dim;
+    st.centers.stride = X.stride;
+    int rc = table_append_host(st.centers, centers_host, k);
+    const int64_t n = X.n;
+    auto cleanup = [&]() {
+        table_free(st.centers);
+        cudaFree(st.closest);
+        cudaFree(st.prev);
+        cudaFree(st.counts);
+        cudaFree(st.start);
+        cudaFree(st.members);
+        cudaFree(st.agg);
+        cudaFree(st.changes);
+        cudaFree(st.scan_tmp);
+    };
+    if (rc != VB_OK) {
+        cleanup();
+        return rc;
+    }
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 16));
+    };
+    alloc((void**)&st.closest, sizeof(int32_t) * (size_t)n);
+    alloc((void**)&st.prev, sizeof(int32_t) * (size_t)n);
+    alloc((void**)&st.counts, sizeof(int32_t) * (size_t)k);
+    alloc((void**)&st.start, sizeof(int32_t) * (size_t)k);
+    alloc((void**)&st.members, sizeof(int32_t) * (size_t)n);
+    alloc((void**)&st.agg, sizeof(float) * (size_t)k * X.dim);
+    alloc((void**)&st.changes, sizeof(int));
+    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, st.scan_tmp_bytes, st.counts, st.start, k, s);
+    alloc(&st.scan_tmp, st.scan_tmp_bytes);
+    if (e != cudaSuccess) {
+        set_error("k-means allocation failed: %s", cudaGetErrorString(e));
+        cleanup();
+        return VB_ENOMEM;
+    }
+
+    int iteration = 0;
+    rc = VB_OK;
+    for (; iteration < max_iter; ++iteration) {
+        prof_begin(VB_PROF_ASSIGN);
+        rc = launch_assign(X, proc1, st.centers, k, st.closest);
+        prof_end(VB_PROF_ASSIGN);
+        if (rc != VB_OK) break;
+        cudaMemsetAsync(st.counts, 0, sizeof(int32_t) * (size_t)k, s);
+        cudaMemsetAsync(st.changes, 0, sizeof(int), s);
+        if (n > 0) {
+            count_and_diff_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(st.closest, st.prev, n, st.counts, st.changes, iteration == 0);
+            count_launch();
+        }
+        rc = kmeans_update_centers(X, st, k, spherical, seed, iteration, allreduce, actx);
+        if (rc != VB_OK) break;
+        int changes = 0;
+        if (cudaMemcpyAsync(&changes, st.changes, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess) {
+            set_error("k-means: reading the change counter failed");
+            rc = VB_ECUDA;
+            break;
+        }
+        if (allreduce) {
+            // every rank must take the same branch: sum the change counters
+            if (cudaMemcpy(st.changes, &changes, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+                allreduce(st.changes, 1, 1, actx) != 0 ||
+                cudaMemcpy(&changes, st.changes, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+                set_error("k-means: change-counter allreduce failed");
+                rc = VB_ESTATE;
+                break;
+            }
+        }
+        // src/ivfkmeans.c:482-483 (iteration 0 here = initial assignment + first pass of the reference)
+        if (changes == 0 && iteration != 0) {
+            ++iteration;
+            break;
+        }
+    }
+    if (rc == VB_OK) {
+        const size_t raw = raw_row_bytes(X.elem, X.dim);
+        cudaError_t ce = cudaMemcpy2DAsync(centers_host, raw, st.centers.d, st.centers.stride, raw, (size_t)k, cudaMemcpyDeviceToHost, s);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s);
+        if (ce != cudaSuccess) {
+            set_error("k-means: copying centres back failed: %s", cudaGetErrorString(ce));
+            rc = VB_ECUDA;
+        }
+    }
+    if (iters_out) *iters_out = iteration;
+    cleanup();
+    return rc;
+}
+
+// ----------------------------------------------------------------------------- k-means++ seeding
+
+// weight[j] = min(weight[j], d^2) with the reference's types (src/ivfkmeans.c:59-69); also emits the weights as double for the scan
+__global__ void pp_weight_kernel(const float* __restrict__ key, int kmeans_metric, int64_t n, float* __restrict__ weight,
+                                 double* __restrict__ wd) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double distance;
+    if (kmeans_metric == VB_L2) distance = sqrt((double)key[j]);
+    else if (kmeans_metric == VB_SPHERICAL) {
+        double d = -(double)key[j];
+        if (d > 1) d = 1;
+        else if (d < -1) d = -1;
+        distance = acos(d) / 3.14159265358979323846;
+    } else distance = (double)key[j];
+    distance *= distance;
+    float w = weight[j];
+    if (distance < (double)w) w = (float)distance;
+    weight[j] = w;
+    wd[j] = (double)w;
+}
+
+// first j in [0, n-1) with choice - cumsum(w)[j] <= 0, else n-1 (src/ivfkmeans.c:77-83)
+__global__ void pp_pick_kernel(const double* __restrict__ cum, int64_t n, double u, int64_t* __restrict__ picked) {
+    if (blockIdx.x || threadIdx.x) return;
+    double choice = cum[n - 1] * u;
+    int64_t lo = 0, hi = n - 1;  // smallest j with cum[j] >= choice
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (cum[mid] >= choice) hi = mid;
+        else lo = mid + 1;
+    }
+    *picked = lo;
+}
+
+static double host_uniform(uint64_t* st) {
+    uint64_t z = (*st += 0x9e3779b97f4a7c15ULL);
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    z ^= z >> 31;
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+static int kmeans_pp(const Table& X, int kmeans_metric, void* centers_host, int k, uint64_t seed) {
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    const int64_t n = X.n;
+    VB_REQUIRE(n > 0 && k > 0, "k-means++ needs samples");
+    VB_REQUIRE(kmeans_metric == VB_L2 || kmeans_metric == VB_SPHERICAL || kmeans_metric == VB_HAMMING, "bad k-means metric");
+    const int km = kmeans_metric == VB_L2 ? VB_L2_SQUARED : kmeans_metric == VB_SPHERICAL ? VB_NEG_IP : VB_HAMMING;
+    const size_t raw = raw_row_bytes(X.elem, X.dim);
+    void *d_key, *d_w, *d_wd, *d_cum, *d_pick, *d_tmp, *d_q;
+    VB_TRY(workspace(WSK_DIST, sizeof(float) * (size_t)n, &d_key));
+    VB_TRY(workspace(WSK_A, sizeof(float) * (size_t)n, &d_w));
+    VB_TRY(workspace(WSK_B, sizeof(double) * (size_t)n, &d_wd));
+    VB_TRY(workspace(WSK_C, sizeof(double) * (size_t)n, &d_cum));
+    VB_TRY(workspace(WSK_D, 64, &d_pick));
+    size_t tmp_bytes = 0;
+    VB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, (double*)d_wd, (double*)d_cum, (int)n, s));
+    VB_TRY(workspace(WSK_E, tmp_bytes, &d_tmp));
+    // FLT_MAX start (src/ivfkmeans.c:39-40)
+    std::vector<float> w0((size_t)n, 3.402823466e+38f);
+    VB_CUDA(cudaMemcpyAsync(d_w, w0.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s));
+    VB_CUDA(cudaStreamSynchronize(s));
+    uint64_t rs = seed ^ 0x5851f42d4c957f2dULL;
+    int64_t cur = (int64_t)(host_uniform(&rs) * (double)n);
+    if (cur >= n) cur = n - 1;
+    uint8_t* out = (uint8_t*)centers_host;
+    for (int i = 0; i < k; ++i) {
+        VB_CUDA(cudaMemcpyAsync(out + (size_t)i * raw, X.d + (size_t)cur * X.stride, raw, cudaMemcpyDeviceToHost, s));
+        if (i + 1 == k) break;
+        // distance of every sample to the new centre: the scan kernel with the centre as the query
+        size_t qstride;
+        VB_TRY(upload_queries(X.elem, X.dim, X.d + (size_t)cur * X.stride, 1, false, WSK_QIMG, &d_q, &qstride));
+        VB_TRY(launch_scan_regular(X, km, d_q, qstride, 1, n, (float*)d_key, n));
+        pp_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)d_key, kmeans_metric, n, (float*)d_w, (double*)d_wd);
+        VB_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, (double*)d_wd, (double*)d_cum, (int)n, s));
+        pp_pick_kernel<<<1, 1, 0, s>>>((const double*)d_cum, n, host_uniform(&rs), (int64_t*)d_pick);
+        count_launch(3);
+        VB_CUDA(cudaMemcpyAsync(&cur, d_pick, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        VB_CUDA(cudaStreamSynchronize(s));
+    }
+    VB_CUDA(cudaStreamSynchronize(s));
+    return VB_OK;
+}
+
+}  // namespace vb
+
+using namespace vb;
+
+extern "C" {
+
+int vb_kmeans(vb_table* samples, int kmeans_metric, void* centers, int k, int max_iter, uint64_t seed, vb_allreduce_fn allreduce,
+              void* allreduce_ctx, int* iters_out) {
+    VB_TRY(require_init());
+    VB_REQUIRE(samples && centers && k >= 1, "bad k-means arguments");
+    return kmeans_run(samples->t, kmeans_metric, centers, k, max_iter, seed, allreduce, allreduce_ctx, iters_out);
+}
+
+int vb_kmeans_pp_init(vb_table* samples, int kmeans_metric, void* centers, int k, uint64_t seed) {
+    VB_TRY(require_init());
+    VB_REQUIRE(samples && centers && k >= 1, "bad k-means++ arguments");
+    return kmeans_pp(samples->t, kmeans_metric, centers, k, seed);
+}
+
+static int assign_impl(vb_table* rows, int metric, const void* centers, int k, bool host, int32_t* out) {
+    VB_TRY(require_init());
+    VB_REQUIRE(rows && centers && k >= 1 && out, "bad assign arguments");
+    const Table& X = rows->t;
+    VB_REQUIRE(metric == VB_L2_SQUARED || metric == VB_NEG_IP || metric == VB_HAMMING, "assign metric must be the opclass proc 1");
+    VB_REQUIRE((X.elem == VB_BIT) == (metric == VB_HAMMING), "metric does not fit the element type");
+    Table Cn;
+    Cn.elem = X.elem;
+    Cn.dim = X.dim;
+    Cn.stride = X.stride;
+    int rc = host ? table_append_host(Cn, centers, k) : table_append_dev(Cn, centers, k);
+    int32_t* d_out = out;
+    void* ws = nullptr;
+    if (rc == VB_OK && host) {
+        rc = workspace(WSK_F, sizeof(int32_t) * (size_t)std::max<int64_t>(X.n, 1), &ws);
+        d_out = (int32_t*)ws;
+    }
+    if (rc == VB_OK) {
+        prof_begin(VB_PROF_ASSIGN);
+        rc = launch_assign(X, metric, Cn, k, d_out);
+        prof_end(VB_PROF_ASSIGN);
+    }
+    if (rc == VB_OK && host && X.n > 0) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(int32_t) * (size_t)X.n, cudaMemcpyDeviceToHost, ctx().stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx().stream);
+        if (e != cudaSuccess) {
+            set_error("assign: copy back failed: %s", cudaGetErrorString(e));
+            rc = VB_ECUDA;
+        }
+    }
+    if (rc == VB_OK && !host) cudaStreamSynchronize(ctx().stream);  // Cn is freed below
+    table_free(Cn);
+    return rc;
+}
+
+int vb_assign(vb_table* rows, int metric, const void* centers, int k, int32_t* out_list) {
+    return assign_impl(rows, metric, centers, k, true, out_list);
+}
+int vb_assign_dev(vb_table* rows, int metric, const void* centers_dev, int k, int32_t* out_list_dev) {
+    return assign_impl(rows, metric, centers_dev, k, false, out_list_dev);
+}
+
+}  // extern "C"

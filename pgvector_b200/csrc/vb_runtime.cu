@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <vector>
 
 namespace vb {
 
@@ -19,6 +20,8 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* last_error() { return g_err; }
+int prof_read(int which, double* total_ms, int64_t* launches);
+void prof_set(bool on);
 
 Context& ctx() {
     static Context c;
@@ -209,6 +212,64 @@ int upload_queries(int elem, int dim, const void* queries, int64_t nq, bool host
 
 const char* last_error();
 
+// ----------------------------------------------------------------------------- profiling brackets
+struct ProfSpan {
+    int which;
+    cudaEvent_t a, b;
+};
+static bool g_prof_on = false;
+static std::vector<ProfSpan> g_spans;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t prof_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+void prof_begin(int which) {
+    if (!g_prof_on) return;
+    ProfSpan s{which, prof_event(), prof_event()};
+    cudaEventRecord(s.a, ctx().stream);
+    g_spans.push_back(s);
+}
+void prof_end(int which) {
+    if (!g_prof_on) return;
+    for (size_t i = g_spans.size(); i-- > 0;)
+        if (g_spans[i].which == which) {
+            cudaEventRecord(g_spans[i].b, ctx().stream);
+            return;
+        }
+}
+int prof_read(int which, double* total_ms, int64_t* launches) {
+    VB_CUDA(cudaStreamSynchronize(ctx().stream));
+    double ms = 0;
+    int64_t n = 0;
+    std::vector<ProfSpan> keep;
+    for (auto& s : g_spans) {
+        if (s.which != which) {
+            keep.push_back(s);
+            continue;
+        }
+        float f = 0;
+        if (cudaEventElapsedTime(&f, s.a, s.b) == cudaSuccess) {
+            ms += f;
+            ++n;
+        }
+        g_event_pool.push_back(s.a);
+        g_event_pool.push_back(s.b);
+    }
+    g_spans.swap(keep);
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    return VB_OK;
+}
+void prof_set(bool on) { g_prof_on = on; }
+
 }  // namespace vb
 
 // ----------------------------------------------------------------------------- C ABI: runtime
@@ -274,6 +335,15 @@ int vb_shutdown(void) {
 }
 
 void* vb_stream(void) { return (void*)vb::ctx().stream; }
+
+int vb_prof_enable(int on) {
+    vb::prof_set(on != 0);
+    return VB_OK;
+}
+int vb_prof_read(int kernel, double* total_ms, int64_t* launches) {
+    VB_TRY(vb::require_init());
+    return vb::prof_read(kernel, total_ms, launches);
+}
 int64_t vb_launch_count(void) { return vb::ctx().launches; }
 
 int vb_synchronize(void) {
