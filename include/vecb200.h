@@ -207,6 +207,15 @@ int			vb_kmeans_pp_init(vb_table *samples, int kmeans_metric, void *centers, int
  */
 int			vb_assign(vb_table *rows, int metric, const void *centers, int k, int32_t *out_list);
 int			vb_assign_dev(vb_table *rows, int metric, const void *centers_dev, int k, int32_t *out_list_dev);
+/*
+ * The assign step runs on the tensor cores (tcgen05, split-bf16 GEMM with a fused row argmin)
+ * and re-checks rows whose best/second-best margin is inside the error bound with the exact
+ * fp32 kernel.  vb_set_tensor_cores(0) forces the exact CUDA-core kernel for everything
+ * (used by the parity tests); vb_last_assign_rechecked() = rows the last assign re-checked
+ * (-1 when the exact kernel did all the work).
+ */
+int			vb_set_tensor_cores(int on);
+int64_t		vb_last_assign_rechecked(void);
 
 /* -------------------------------------------------------------------- HNSW */
 

@@ -411,3 +411,12 @@ class HnswIndex:
             self.free()
         except Exception:
             pass
+
+
+def set_tensor_cores(on: bool):
+    """False forces the exact fp32 CUDA-core assign kernel (parity tests); True (default) uses tcgen05."""
+    _lib.check(load().vb_set_tensor_cores(1 if on else 0))
+
+
+def last_assign_rechecked() -> int:
+    return int(load().vb_last_assign_rechecked())

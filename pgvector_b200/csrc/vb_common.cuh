@@ -46,6 +46,7 @@ struct Context {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     int64_t launches = 0;
+    int64_t last_assign_flagged = -1;  // rows re-checked by the exact kernel in the last tensor-core assign (-1: exact path)
     // grow-only device workspace arenas (index = slot)
     void* ws[16] = {nullptr};
     size_t ws_bytes[16] = {0};
@@ -137,6 +138,7 @@ int scan_chunk_rows(const Table& t);
 int launch_assign_exact(const Table& X, int metric, const Table& Cn, int k, const int32_t* row_sel_dev, int64_t n_sel,
                         int32_t* out_idx, float* out_val);
 int launch_assign(const Table& X, int metric, const Table& Cn, int k, int32_t* out_idx);
+void set_tc_enabled(bool on);
 
 }  // namespace vb
 

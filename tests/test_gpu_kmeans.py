@@ -1,0 +1,145 @@
+"""GPU parity of the IVFFlat build path: nearest-centre assign (src/ivfbuild.c:161-219), Lloyd k-means
+with the reference's centre rules (src/ivfkmeans.c:179-236, 246-485) and k-means++ seeding (:23-91)."""
+import numpy as np
+import pytest
+
+import oracle as O
+from tests.util import f32_to_half_bits, mixture
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pv():
+    import pgvector_b200 as pv
+    pv.init(0)
+    return pv
+
+
+def _data(elem, n, dim, k, seed, unit=False):
+    x, c = mixture(n, dim, k, seed=seed)
+    if elem == O.BIT:
+        return O.binary_quantize(O.VECTOR, x), O.binary_quantize(O.VECTOR, c)
+    if elem == O.HALFVEC:
+        x, c = f32_to_half_bits(x), f32_to_half_bits(c)
+    if unit:
+        x, c = O.l2_normalize(elem, x), O.l2_normalize(elem, c)
+    return x, c
+
+
+def _assign_agreement(elem, metric, rows, centers, got, dim=None):
+    want = O.ivf_assign(elem, metric, rows, centers, threads=8, dim=dim)
+    diff = np.nonzero(got != want)[0]
+    # any disagreement must be a genuine fp32 near-tie between the two chosen centres
+    for i in diff[:50]:
+        d_g = O.distance(elem, metric, rows[i], centers[got[i]], dim=dim, f64=True)
+        d_w = O.distance(elem, metric, rows[i], centers[want[i]], dim=dim, f64=True)
+        assert abs(d_g - d_w) <= 1e-5 * max(abs(d_w), 1.0), (i, d_g, d_w)
+    return 1.0 - len(diff) / len(want)
+
+
+@pytest.mark.parametrize("tensor_cores", [False, True])
+@pytest.mark.parametrize("elem,metric,n,dim,k", [
+    (O.VECTOR, O.L2_SQUARED, 5000, 96, 37),
+    (O.VECTOR, O.L2_SQUARED, 20000, 1536, 300),
+    (O.VECTOR, O.NEG_IP, 6000, 64, 100),
+    (O.HALFVEC, O.L2_SQUARED, 6000, 200, 129),
+    (O.HALFVEC, O.NEG_IP, 4000, 768, 64),
+    (O.VECTOR, O.L2_SQUARED, 3000, 3, 100),       # the reference's own test shape (3-d, lists=100): tiny margins
+    (O.BIT, O.HAMMING, 5000, 1024, 50),
+    (O.BIT, O.HAMMING, 3000, 52, 20),
+])
+def test_assign_matches_oracle(pv, tensor_cores, elem, metric, n, dim, k):
+    if dim == 3:
+        rng = np.random.default_rng(3)
+        rows, centers = rng.random((n, 3)).astype(np.float32), rng.random((k, 3)).astype(np.float32)
+    else:
+        rows, centers = _data(elem, n, dim, k, seed=n + k, unit=(metric == O.NEG_IP))
+    pv.set_tensor_cores(tensor_cores)
+    try:
+        t = pv.Table(elem, dim).append(rows)
+        got = pv.assign(t, metric, centers)
+        rechecked = pv.last_assign_rechecked()
+    finally:
+        pv.set_tensor_cores(True)
+    agree = _assign_agreement(elem, metric, rows, centers, got, dim=dim)
+    assert agree >= (1.0 if elem == O.BIT else 0.9995), agree
+    if tensor_cores and elem != O.BIT and n >= 1024 and k >= 16:
+        assert rechecked >= 0            # the tcgen05 path ran
+        assert rechecked <= 0.2 * n      # and only a minority of rows needed the exact kernel
+    else:
+        assert rechecked == -1
+
+
+def test_assign_first_minimum_wins_on_exact_ties(pv):
+    """duplicate centres: strict < keeps the first (src/ivfbuild.c:186-190)"""
+    rng = np.random.default_rng(0)
+    c = rng.standard_normal((40, 16)).astype(np.float32)
+    centers = np.concatenate([c, c])          # centre i == centre i + 40
+    rows = (c[rng.integers(0, 40, 3000)] + 0.01 * rng.standard_normal((3000, 16))).astype(np.float32)
+    for tc in (False, True):
+        pv.set_tensor_cores(tc)
+        got = pv.assign(pv.Table(O.VECTOR, 16).append(rows), O.L2_SQUARED, centers)
+        pv.set_tensor_cores(True)
+        assert got.max() < 40
+        assert np.array_equal(got, O.ivf_assign(O.VECTOR, O.L2_SQUARED, rows, centers))
+
+
+@pytest.mark.parametrize("elem,km,dim,k,unit", [(O.VECTOR, O.L2, 24, 20, False), (O.HALFVEC, O.L2, 40, 16, False),
+                                                (O.VECTOR, O.SPHERICAL, 32, 12, True), (O.BIT, O.HAMMING, 128, 10, False)])
+def test_kmeans_matches_elkan_oracle_from_shared_centres(pv, elem, km, dim, k, unit):
+    rows, _ = _data(elem, 4000, dim, k, seed=77, unit=unit)
+    init = O.kmeans_pp_init(elem, km, rows, k, seed=5, dim=dim)
+    want_c, want_a, want_it = O.kmeans(elem, km, rows, init, algo="elkan", dim=dim)
+    t = pv.Table(elem, dim).append(rows)
+    got_c, got_it = pv.kmeans(t, km, init)
+    proc1 = {O.L2: O.L2_SQUARED, O.SPHERICAL: O.NEG_IP, O.HAMMING: O.HAMMING}[km]
+    got_a = pv.assign(t, proc1, got_c)
+    assert abs(got_it - want_it) <= 2
+    assert (got_a == want_a).mean() > 0.995
+    if elem == O.BIT:
+        assert (np.unpackbits(got_c) != np.unpackbits(want_c)).mean() < 0.01
+    elif elem == O.HALFVEC:
+        a, b = got_c.view(np.float16).astype(np.float32), want_c.view(np.float16).astype(np.float32)
+        assert np.allclose(a, b, rtol=2e-3, atol=2e-3)
+    else:
+        assert np.allclose(got_c, want_c, rtol=1e-4, atol=1e-4)
+        if unit:
+            assert np.allclose(np.linalg.norm(got_c, axis=1), 1.0, atol=1e-6)
+
+
+def test_kmeans_single_iteration_centres_are_bit_identical_sums(pv):
+    """one Lloyd step: per-cluster fp32 sums are accumulated in ascending sample order like SumCenters"""
+    rows, _ = _data(O.VECTOR, 3000, 20, 8, seed=9)
+    init = rows[:8].copy()
+    got_c, it = pv.kmeans(pv.Table(O.VECTOR, 20).append(rows), O.L2, init, max_iter=1)
+    want_c, _, _ = O.kmeans(O.VECTOR, O.L2, rows, init, max_iter=1, algo="lloyd")
+    assert it == 1
+    assert np.array_equal(got_c, want_c)
+
+
+def test_kmeans_pp_init_picks_samples_and_spreads(pv):
+    rows, true_c = _data(O.VECTOR, 5000, 16, 25, seed=13)
+    t = pv.Table(O.VECTOR, 16).append(rows)
+    c = pv.kmeans_pp_init(t, O.L2, 25, seed=1)
+    # every centre is one of the samples
+    for ci in c:
+        assert np.any(np.all(rows == ci, axis=1))
+    # D^2 seeding covers (almost) every mixture component
+    owner = O.ivf_assign(O.VECTOR, O.L2_SQUARED, c, true_c)
+    assert len(set(owner)) >= 20
+
+
+def test_allreduce_hook_is_called_with_sums_counts_and_changes(pv):
+    import torch
+    rows, _ = _data(O.VECTOR, 2000, 8, 5, seed=3)
+    calls = []
+
+    def hook(ptr, count, dtype):
+        calls.append((count, dtype))     # single process: identity reduction
+
+    t = pv.Table(O.VECTOR, 8).append(rows)
+    c1, it1 = pv.kmeans(t, O.L2, rows[:5].copy(), max_iter=3, allreduce=hook)
+    c2, it2 = pv.kmeans(t, O.L2, rows[:5].copy(), max_iter=3)
+    assert np.array_equal(c1, c2) and it1 == it2
+    assert (5 * 8, 0) in calls and (5, 1) in calls and (1, 1) in calls
