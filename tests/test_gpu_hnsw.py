@@ -60,7 +60,19 @@ def test_recall_equals_reference_tie_mode(l2_graph):
     truth = [O.exact_topk(O.VECTOR, O.L2_SQUARED, q, rows, 10)[0] for q in queries]
     r_gpu, r_pg = recall_at_k(ids, truth), recall_at_k(pg_ids, truth)
     assert abs(r_gpu - r_pg) < 2e-3
-    assert r_gpu > 0.95      # test/t/012_hnsw_vector_build_recall.pl:94 asks >= 0.99 on 3-d data; 48-d mixture is harder
+    assert r_gpu > 0.5       # clustered 48-d data at ef=40; the reference's own floor (>= 0.99 on uniform 3-d, 012:94) is in test_uniform_3d_recall_floor
+
+
+def test_uniform_3d_recall_floor(pv):
+    """test/t/012_hnsw_vector_build_recall.pl:94: 10k x 3-d uniform, defaults, ef_search = 40 -> recall >= 0.99"""
+    rng = np.random.default_rng(12)
+    rows = rng.random((10000, 3)).astype(np.float32)
+    queries = rng.random((50, 3)).astype(np.float32)
+    og, gi, g = build_pair(pv, "vector_l2_ops", rows)
+    ids, _, _ = gi.search(queries, k=20, ef_search=40)
+    heap = g["elem_row"][ids]
+    truth = [O.exact_topk(O.VECTOR, O.L2_SQUARED, q, rows, 20)[0] for q in queries]
+    assert recall_at_k(heap, truth) >= 0.99
 
 
 @pytest.mark.parametrize("opclass,dim,n", [("vector_ip_ops", 32, 6000), ("vector_cosine_ops", 32, 6000), ("vector_l1_ops", 16, 5000),
