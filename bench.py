@@ -127,6 +127,8 @@ def build_index_arrays(args, rows, pv=None):
     slab = 65536
     for lo in range(0, n, slab):
         grouped[lo:lo + slab] = rows[order[lo:lo + slab]]
+    lens = counts.cpu().numpy()
+    how += f"; list sizes min/mean/max = {int(lens.min())}/{float(lens.mean()):.0f}/{int(lens.max())}"
     return centers.contiguous(), offsets.numpy(), grouped, order.contiguous(), how
 
 

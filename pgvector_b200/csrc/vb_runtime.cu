@@ -112,7 +112,7 @@ int table_append_host(Table& t, const void* rows, int64_t n) {
     uint8_t* dst = t.d + (size_t)t.n * t.stride;
     if (raw != t.stride) VB_CUDA(cudaMemsetAsync(dst, 0, (size_t)n * t.stride, c.stream));
     const size_t block_bytes = 32u << 20;
-    const int64_t rows_per_block = std::max<int64_t>(1, (int64_t)(block_bytes / raw));
+    const int64_t rows_per_block = std::min<int64_t>(1 << 20, std::max<int64_t>(1, (int64_t)(block_bytes / raw)));
     void *p0, *p1;
     VB_TRY(pinned_buffer((size_t)rows_per_block * raw, &p0));
     VB_TRY(pinned_buffer2((size_t)rows_per_block * raw, &p1));
@@ -142,8 +142,18 @@ int table_append_dev(Table& t, const void* rows_dev, int64_t n) {
     Context& c = ctx();
     const size_t raw = raw_row_bytes(t.elem, t.dim);
     uint8_t* dst = t.d + (size_t)t.n * t.stride;
-    if (raw != t.stride) VB_CUDA(cudaMemsetAsync(dst, 0, (size_t)n * t.stride, c.stream));
-    VB_CUDA(cudaMemcpy2DAsync(dst, t.stride, rows_dev, raw, raw, (size_t)n, cudaMemcpyDeviceToDevice, c.stream));
+    if (raw == t.stride) {
+        VB_CUDA(cudaMemcpyAsync(dst, rows_dev, (size_t)n * raw, cudaMemcpyDeviceToDevice, c.stream));
+    } else {
+        VB_CUDA(cudaMemsetAsync(dst, 0, (size_t)n * t.stride, c.stream));
+        // 2-D copies are issued in slabs: the height of one cudaMemcpy2D is kept well inside driver limits
+        const int64_t slab = 1 << 20;
+        for (int64_t r = 0; r < n; r += slab) {
+            int64_t m = std::min(slab, n - r);
+            VB_CUDA(cudaMemcpy2DAsync(dst + (size_t)r * t.stride, t.stride, (const uint8_t*)rows_dev + (size_t)r * raw, raw, raw, (size_t)m,
+                                      cudaMemcpyDeviceToDevice, c.stream));
+        }
+    }
     t.n += n;
     return VB_OK;
 }

@@ -87,7 +87,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
         const uint8_t* base = a.rows + (size_t)row_begin * a.stride;
         OUT* out = reinterpret_cast<OUT*>(a.out) + out_off;
 
-        for (int r0 = g; r0 < n_rows; r0 += G * RPI) {
+        // trip count is uniform over the CTA (groups of one warp must stay converged for the shuffles)
+        for (int rb = 0; rb < n_rows; rb += G * RPI) {
+            const int r0 = rb + g;
             Acc<ELEM, METRIC> acc[RPI];
             const uint4* rp[RPI];
 #pragma unroll
