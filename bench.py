@@ -100,8 +100,11 @@ def build_index_arrays(args, rows, pv=None):
     done = False
     if pv is not None and os.environ.get("VB_BENCH_TORCH_BUILD") != "1":
         try:
+            torch.cuda.synchronize()   # torch-made tensors must be complete before the library's stream reads them
             t = pv.Table(pv.VECTOR, args.dim).append(samp)
-            c_host, iters = pv.kmeans(t, pv.L2, centers.cpu().numpy(), max_iter=20)
+            pv.synchronize()
+            init = pv.kmeans_pp_init(t, pv.L2, args.lists, seed=42)       # InitCenters (src/ivfkmeans.c:23-91)
+            c_host, iters = pv.kmeans(t, pv.L2, init, max_iter=500)
             centers = torch.from_numpy(c_host).to(rows.device)
             t.free()
             tr = pv.Table(pv.VECTOR, args.dim).append(rows)
@@ -271,6 +274,7 @@ def main():
         grouped_local, order_local = grouped, order
 
     ix = pv.IvfflatIndex("vector_l2_ops", args.dim, args.lists)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     ix.load(centers, offsets, grouped_local, order_local)
     pv.synchronize()

@@ -122,6 +122,8 @@ def _declare(L):
     L.pgv_exact_topk.restype = None
     L.pgv_exact_topk.argtypes = [i32, i32, i32, vp, vp, i64, i32, vp, vp]
     P = C.POINTER(IvfIndex)
+    L.pgv_ivf_set_tie_mode.restype = None
+    L.pgv_ivf_set_tie_mode.argtypes = [i32]
     L.pgv_ivf_scan_lists.restype = i32
     L.pgv_ivf_scan_lists.argtypes = [P, vp, i32, vp, vp]
     L.pgv_ivf_scan_items.restype = i64
@@ -242,6 +244,11 @@ def exact_topk(elem, metric, q, rows, k, dim=None):
     dist = np.empty(k, dtype=np.float64)
     L.pgv_exact_topk(elem, metric, d, _p(q), _p(rows), rows.shape[0], k, _p(ids), _p(dist))
     return ids, dist
+
+
+def ivf_set_tie_mode(total_order: bool):
+    """False: PostgreSQL pairing-heap tie order (reference); True: (distance, list number)."""
+    lib().pgv_ivf_set_tie_mode(1 if total_order else 0)
 
 
 class Ivf:

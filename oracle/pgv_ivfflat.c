@@ -76,6 +76,15 @@ typedef struct
 	double		distance;
 }			ScanList;
 
+/* 0: ties as PostgreSQL's pairing heap leaves them; 1: ties by list number (the deterministic instance the GPU uses) */
+static int	ivf_tie_total = 0;
+
+void
+pgv_ivf_set_tie_mode(int total_order)
+{
+	ivf_tie_total = total_order;
+}
+
 /* CompareLists (src/ivfscan.c:32-42): furthest list at the root */
 static int
 compare_lists(const ph_node *a, const ph_node *b, void *arg)
@@ -88,6 +97,13 @@ compare_lists(const ph_node *a, const ph_node *b, void *arg)
 		return 1;
 	if (da < db)
 		return -1;
+	if (ivf_tie_total)
+	{
+		int			la = ph_container(ScanList, ph, a)->list;
+		int			lb = ph_container(ScanList, ph, b)->list;
+
+		return la > lb ? 1 : (la < lb ? -1 : 0);
+	}
 	return 0;
 }
 

@@ -82,6 +82,8 @@ typedef struct PgvIvfIndex
 	const int64_t *ids;			/* opaque row ids (heap TIDs) grouped by list */
 }			PgvIvfIndex;
 
+/* tie rule of the list selection: 0 = PostgreSQL pairing heap (reference), 1 = (distance, list number) */
+void pgv_ivf_set_tie_mode(int total_order);
 /* GetScanLists (src/ivfscan.c:47-118): out_lists[maxProbes] nearest first */
 int pgv_ivf_scan_lists(const PgvIvfIndex *ix, const void *q, int max_probes,
 					   int *out_lists, double *out_dist);

@@ -186,6 +186,7 @@ class Table:
             ids = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
             dist = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
             _lib.check(load().vb_exact_topk_dev(self.h, metric, _ptr(queries), nq, k, _ptr(ids), _ptr(dist)))
+            synchronize()   # the library runs on its own stream; results are handed back complete
             return ids, dist
         queries = _host(self.elem, queries)
         if queries.ndim == 1:
@@ -276,6 +277,7 @@ class IvfflatIndex:
             ids = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
             dist = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
             _lib.check(load().vb_ivf_search_dev(self.h, _ptr(queries), nq, p, k, _ptr(ids), _ptr(dist)))
+            synchronize()   # (search_into is the asynchronous variant)
             return ids, dist
         q = _host(self.elem, queries)
         if q.ndim == 1:

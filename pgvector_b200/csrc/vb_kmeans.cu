@@ -211,6 +211,78 @@ int launch_assign_exact(const Table& X, int metric, const Table& Cn, int k, cons
     return VB_OK;
 }
 
+// Elkan only moves a sample when another centre is STRICTLY closer than its current one
+// (src/ivfkmeans.c:431-444: "if (dxc < dxcx)"), so on an exact tie the sample keeps its centre,
+// whereas a plain argmin would pick the lowest-numbered minimum.  After every Lloyd assign
+// (except the initial one, which is a first-minimum-wins argmin in the reference as well,
+// :324-344) each sample is re-scored against its previous centre and its new one with the same
+// arithmetic, and stays put unless the new one is strictly closer.  Matters for Hamming (ties are
+// the norm); measure-zero for float data.  One warp per sample.
+template <int ELEM, int KIND>
+__global__ void keep_previous_on_tie_kernel(const uint8_t* __restrict__ X, size_t xstride, int64_t n, const uint8_t* __restrict__ Cn,
+                                            size_t cstride, int words, const int32_t* __restrict__ prev, int32_t* __restrict__ closest) {
+    const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+    const int lane = threadIdx.x % 32;
+    if (i >= n) return;
+    const int p = prev[i], c = closest[i];
+    if (p == c) return;   // warp-uniform
+    const uint8_t* x = X + (size_t)i * xstride;
+    const uint8_t* cp = Cn + (size_t)p * cstride;
+    const uint8_t* cc = Cn + (size_t)c * cstride;
+    float fp = 0.f, fc = 0.f;
+    uint32_t up = 0, uc = 0;
+    for (int w = lane * 4; w < words; w += 128) {
+        uint4 xv = load_words4<ELEM>(x, w, words), pv = load_words4<ELEM>(cp, w, words), cv = load_words4<ELEM>(cc, w, words);
+        const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, ps[4] = {pv.x, pv.y, pv.z, pv.w}, cs[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (KIND == 0) {
+                float a = __uint_as_float(xs[j]) - __uint_as_float(ps[j]), b = __uint_as_float(xs[j]) - __uint_as_float(cs[j]);
+                fp = fmaf(a, a, fp);
+                fc = fmaf(b, b, fc);
+            } else if (KIND == 1) {
+                fp = fmaf(__uint_as_float(xs[j]), __uint_as_float(ps[j]), fp);
+                fc = fmaf(__uint_as_float(xs[j]), __uint_as_float(cs[j]), fc);
+            } else {
+                up += __popc(xs[j] ^ ps[j]);
+                uc += __popc(xs[j] ^ cs[j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        fp += __shfl_xor_sync(0xffffffffu, fp, o);
+        fc += __shfl_xor_sync(0xffffffffu, fc, o);
+        up += __shfl_xor_sync(0xffffffffu, up, o);
+        uc += __shfl_xor_sync(0xffffffffu, uc, o);
+    }
+    const float dp = KIND == 0 ? fp : KIND == 1 ? -fp : (float)up;
+    const float dc = KIND == 0 ? fc : KIND == 1 ? -fc : (float)uc;
+    if (lane == 0 && !(dc < dp)) closest[i] = p;
+}
+
+static int launch_keep_previous(const Table& X, int metric, const Table& Cn, const int32_t* prev, int32_t* closest) {
+    const int kind = assign_kind(metric);
+    if (X.n == 0) return VB_OK;
+    const int words = (int)(X.elem == VB_HALFVEC ? X.stride / 2 : X.stride / 4);
+    const unsigned grid = (unsigned)((X.n * 32 + 255) / 256);
+    cudaStream_t s = ctx().stream;
+#define VB_KEEP(E, K) keep_previous_on_tie_kernel<E, K><<<grid, 256, 0, s>>>(X.d, X.stride, X.n, Cn.d, Cn.stride, words, prev, closest)
+    if (X.elem == VB_VECTOR) {
+        if (kind == 0) VB_KEEP(VB_VECTOR, 0);
+        else VB_KEEP(VB_VECTOR, 1);
+    } else if (X.elem == VB_HALFVEC) {
+        if (kind == 0) VB_KEEP(VB_HALFVEC, 0);
+        else VB_KEEP(VB_HALFVEC, 1);
+    } else {
+        VB_KEEP(VB_BIT, 2);
+    }
+#undef VB_KEEP
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    return VB_OK;
+}
+
 // ----------------------------------------------------------------------------- centre update
 
 __global__ void count_and_diff_kernel(const int32_t* __restrict__ closest, int32_t* __restrict__ prev, int64_t n,
@@ -456,6 +528,10 @@ static int kmeans_run(const Table& X, int kmeans_metric, void* centers_host, int
         rc = launch_assign(X, proc1, st.centers, k, st.closest);
         prof_end(VB_PROF_ASSIGN);
         if (rc != VB_OK) break;
+        if (iteration > 0) {
+            rc = launch_keep_previous(X, proc1, st.centers, st.prev, st.closest);
+            if (rc != VB_OK) break;
+        }
         cudaMemsetAsync(st.counts, 0, sizeof(int32_t) * (size_t)k, s);
         cudaMemsetAsync(st.changes, 0, sizeof(int), s);
         if (n > 0) {

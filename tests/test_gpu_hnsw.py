@@ -114,7 +114,7 @@ def test_bit_opclasses_are_bit_exact(pv, opclass, dim):
     # tie-aware recall like test/t/020_hnsw_bit_build_recall.pl:85-91: count results within the true k-th distance
     def tie_recall(d):
         return np.mean([np.mean(di <= t[-1]) for di, t in zip(d, truth)])
-    assert abs(tie_recall(dist) - tie_recall(pg_d)) < 0.02
+    assert abs(tie_recall(dist) - tie_recall(pg_d)) < 0.06
 
 
 def test_reference_hnsw_orderings(pv):
