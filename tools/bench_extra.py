@@ -1,0 +1,190 @@
+#!/usr/bin/env python3
+"""Secondary measurements (one JSON line each) for the rows of SURVEY section 8 that bench.py's headline
+does not cover: k-means assign on the tensor cores (config D shape, one GPU's share), HNSW search
+(configs C / E at reduced row counts: the graph is built by the CPU oracle, which bounds n), exact scan.
+
+    python tools/bench_extra.py assign   [--rows N --dim D --k K]
+    python tools/bench_extra.py hnsw     [--elem halfvec|bit --rows N --dim D --ef EF]
+    python tools/bench_extra.py exact    [--rows N --dim D]
+
+All timing with CUDA events on the library stream; inputs resident in HBM.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def timed(pv, torch, stream, fn, warmup=2, steps=5):
+    for _ in range(warmup):
+        fn()
+    pv.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    pv.synchronize()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def bench_assign(args):
+    import torch
+    import pgvector_b200 as pv
+    pv.init(0)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.ExternalStream(pv.stream_handle(), device=dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    comp = torch.randn((args.k, args.dim), generator=g, device=dev)
+    which = torch.randint(0, args.k, (args.rows,), generator=g, device=dev)
+    rows = comp[which] + 0.3 * torch.randn((args.rows, args.dim), generator=g, device=dev)
+    centers = (comp + 0.05 * torch.randn((args.k, args.dim), generator=g, device=dev)).contiguous()
+    torch.cuda.synchronize()
+    t = pv.Table(pv.VECTOR, args.dim).append(rows)
+    out = torch.empty(args.rows, dtype=torch.int32, device=dev)
+    res = {}
+    for name, tc in (("tcgen05_split_bf16", True), ("exact_fp32_cuda_cores", False)):
+        pv.set_tensor_cores(tc)
+        n_eff = args.rows if tc else min(args.rows, 131072)
+        tt = t if tc else pv.Table(pv.VECTOR, args.dim).append(rows[:n_eff].contiguous())
+        o = out[:n_eff]
+        ms = timed(pv, torch, stream, lambda: pv._lib.check(pv.load().vb_assign_dev(tt.h, pv.L2_SQUARED, pv._ptr(centers), args.k, pv._ptr(o))),
+                   warmup=1, steps=3)
+        flops = 2.0 * n_eff * args.k * args.dim
+        res[name] = {"ms": ms, "rows": n_eff, "useful_tflops": flops / ms / 1e9, "rechecked_rows": pv.last_assign_rechecked()}
+        if tc:
+            a_tc = out.clone()
+    pv.set_tensor_cores(True)
+    # agreement between the two paths on the exact sample
+    pv.set_tensor_cores(False)
+    n_eff = res["exact_fp32_cuda_cores"]["rows"]
+    ex = torch.empty(n_eff, dtype=torch.int32, device=dev)
+    tt = pv.Table(pv.VECTOR, args.dim).append(rows[:n_eff].contiguous())
+    pv._lib.check(pv.load().vb_assign_dev(tt.h, pv.L2_SQUARED, pv._ptr(centers), args.k, pv._ptr(ex)))
+    pv.set_tensor_cores(True)
+    agree = float((ex == a_tc[:n_eff]).float().mean().item())
+    hbm, bf16_burst, bf16_sus, src = peaks()
+    tc_ms = res["tcgen05_split_bf16"]["ms"]
+    issued = 3 * 2.0 * args.rows * args.k * args.dim / tc_ms / 1e9      # three bf16 MMAs per fp32-accurate product
+    print(json.dumps({"bench": "assign", "workload": f"assign {args.rows}x{args.dim} fp32 rows to {args.k} centres (L2)", "results": res,
+                      "tc_vs_exact_agreement": agree,
+                      "roofline": {"bound": "tensor", "achieved": issued, "peak": bf16_sus, "unit": "TFLOP/s", "frac": issued / bf16_sus,
+                                   "peak_source": src + " bf16_tflops_sustained", "note": "issued bf16 MMA flops (3 per useful fp32-accurate MAC pair)"}}))
+
+
+def bench_hnsw(args):
+    import torch
+    import oracle as O
+    import pgvector_b200 as pv
+    from tests.util import f32_to_half_bits, mixture
+    pv.init(0)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.ExternalStream(pv.stream_handle(), device=dev)
+    x, _ = mixture(args.rows, args.dim, 256, seed=6)
+    q, _ = mixture(args.queries, args.dim, 256, seed=7)
+    if args.elem == "halfvec":
+        elem, opclass, metric = O.HALFVEC, "halfvec_cosine_ops", O.NEG_IP
+        rows = O.l2_normalize(O.HALFVEC, f32_to_half_bits(x))
+        queries = O.l2_normalize(O.HALFVEC, f32_to_half_bits(q))
+        rb = args.dim * 2
+    else:
+        elem, opclass, metric = O.BIT, "bit_hamming_ops", O.HAMMING
+        rows, queries = O.binary_quantize(O.VECTOR, x), O.binary_quantize(O.VECTOR, q)
+        rb = (args.dim + 7) // 8
+    t0 = time.perf_counter()
+    og = O.Hnsw(elem, metric, rows, m=16, ef_construction=64, seed=1, dim=args.dim)
+    build_s = time.perf_counter() - t0
+    g = og.export()
+    gi = pv.HnswIndex(opclass, args.dim, m=16).load(rows[g["elem_row"]], g["levels"], g["nbr0"], g["upper_off"], g["upper"], g["entry"])
+    qd = torch.from_numpy(queries).to(dev)
+    k = 10
+    ids = torch.empty((args.queries, k), dtype=torch.int64, device=dev)
+    dist = torch.empty((args.queries, k), dtype=torch.float32, device=dev)
+    nd = torch.empty(args.queries, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    ms = timed(pv, torch, stream, lambda: gi.search_into(qd, k, args.ef, ids, dist, nd), warmup=2, steps=5)
+    ndist = float(nd.double().mean().item())
+    # parity + recall on a sample
+    ns = min(256, args.queries)
+    wi, wd, wnd = og.search_batch(queries[:ns], args.ef, k, ties=O.TIES_TOTAL, threads=os.cpu_count() or 1)
+    same = float(np.all(ids[:ns].cpu().numpy() == wi, axis=1).mean())
+    erows = rows[g["elem_row"]]
+    truth = [O.exact_topk(elem, metric, qq, erows, k, dim=args.dim)[0] for qq in queries[:64]]
+    rec = sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(ids[:64].cpu().numpy(), truth)) / (64 * k)
+    t0 = time.perf_counter()
+    og.search_batch(queries[:ns], args.ef, k, ties=O.TIES_PG, threads=os.cpu_count() or 1)
+    cpu_qps = ns / (time.perf_counter() - t0)
+    hbm, _, _, src = peaks()
+    qps = args.queries / (ms / 1000.0)
+    gbs = qps * (ndist * rb + (ndist / 16.0) * 32 * 4) / 1e9
+    print(json.dumps({"bench": "hnsw", "workload": f"HNSW {opclass} {args.rows}x{args.dim}, m=16, ef_search={args.ef}, k={k} "
+                                                   f"(graph built by the CPU oracle in {build_s:.0f}s)",
+                      "queries_per_s": qps, "ms_per_batch": ms, "batch": args.queries, "distance_evals_per_query": ndist,
+                      "recall_at_10": rec, "queries_identical_to_oracle": same,
+                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "peak_source": src,
+                                   "note": "latency-bound random gathers; bytes = n_dist*row + n_expand*lm*4"},
+                      "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port"}}))
+
+
+def bench_exact(args):
+    import torch
+    import pgvector_b200 as pv
+    pv.init(0)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.ExternalStream(pv.stream_handle(), device=dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    rows = torch.randn((args.rows, args.dim), generator=g, device=dev)
+    q = torch.randn((args.queries, args.dim), generator=g, device=dev)
+    torch.cuda.synchronize()
+    t = pv.Table(pv.VECTOR, args.dim).append(rows)
+    k = 10
+    ids = torch.empty((args.queries, k), dtype=torch.int64, device=dev)
+    dist = torch.empty((args.queries, k), dtype=torch.float32, device=dev)
+    ms = timed(pv, torch, stream, lambda: pv._lib.check(pv.load().vb_exact_topk_dev(t.h, pv.L2, pv._ptr(q), args.queries, k, pv._ptr(ids), pv._ptr(dist))))
+    hbm, _, _, src = peaks()
+    gbs = args.queries * args.rows * args.dim * 4 / (ms / 1000.0) / 1e9
+    print(json.dumps({"bench": "exact", "workload": f"exact L2 top-{k} over {args.rows}x{args.dim} fp32, {args.queries} queries per batch",
+                      "queries_per_s": args.queries / (ms / 1000.0), "ms_per_batch": ms,
+                      "roofline": {"bound": "hbm (L2-resident when the table fits in 126 MB)", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                                   "frac": gbs / hbm, "peak_source": src}}))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["assign", "hnsw", "exact"])
+    ap.add_argument("--rows", type=int, default=None)
+    ap.add_argument("--dim", type=int, default=None)
+    ap.add_argument("--k", type=int, default=4096)
+    ap.add_argument("--elem", default="halfvec")
+    ap.add_argument("--ef", type=int, default=100)
+    ap.add_argument("--queries", type=int, default=4096)
+    a = ap.parse_args()
+    if a.what == "assign":
+        a.rows = a.rows or 1_250_000          # one GPU's share of config D (10M rows / 8)
+        a.dim = a.dim or 1536
+        bench_assign(a)
+    elif a.what == "hnsw":
+        a.rows = a.rows or 100_000
+        a.dim = a.dim or (768 if a.elem == "halfvec" else 1024)
+        bench_hnsw(a)
+    else:
+        a.rows = a.rows or 10_000
+        a.dim = a.dim or 128
+        bench_exact(a)
