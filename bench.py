@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-recall", action="store_true")
+    ap.add_argument("--scan-impl", type=int, default=int(os.environ.get("VB_SCAN_IMPL", "0")),
+                    help="0 = LDG.128 streaming scan kernel, 1 = cp.async.bulk (TMA) staged scan kernel")
     return ap.parse_args()
 
 
@@ -249,6 +251,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     import pgvector_b200 as pv
     pv.init(local)
+    pv.set_option("scan_impl", args.scan_impl)
 
     # ---- setup (untimed): data, index, device image
     rows, queries = make_dataset(args, dev)
@@ -440,7 +443,8 @@ def main():
 def workload_config(args, how):
     return {"workload": f"IVFFlat L2 {args.rows}x{args.dim} fp32, lists={args.lists}, probes={args.probes}, k={args.k} "
                         f"(BASELINE.json configs[1])", "queries": args.queries, "batch": args.batch,
-            "index_build": how, "parallelism": "lists sharded l % N, one NCCL all-gather of k results per rank"}
+            "index_build": how, "scan_kernel": "cp.async.bulk+mbarrier staged" if args.scan_impl == 1 else "LDG.128 streaming",
+            "parallelism": "lists sharded l % N, one NCCL all-gather of k results per rank"}
 
 
 if __name__ == "__main__":

@@ -216,6 +216,11 @@ int			vb_assign_dev(vb_table *rows, int metric, const void *centers_dev, int k, 
  */
 int			vb_set_tensor_cores(int on);
 int64_t		vb_last_assign_rechecked(void);
+/*
+ * Tuning switches: "scan_impl" 0 = LDG.128 streaming kernel, 1 = cp.async.bulk (TMA) + mbarrier
+ * staged kernel for rows of at least 512 bytes; "tensor_cores" as vb_set_tensor_cores.
+ */
+int			vb_set_option(const char *name, int64_t value);
 
 /* -------------------------------------------------------------------- HNSW */
 

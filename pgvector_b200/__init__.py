@@ -422,3 +422,8 @@ def set_tensor_cores(on: bool):
 
 def last_assign_rechecked() -> int:
     return int(load().vb_last_assign_rechecked())
+
+
+def set_option(name: str, value: int):
+    """tuning switches of the library: "scan_impl" (0 = LDG kernel, 1 = bulk-copy/TMA kernel), "tensor_cores"."""
+    _lib.check(load().vb_set_option(name.encode(), int(value)))

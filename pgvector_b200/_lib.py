@@ -53,6 +53,7 @@ SIGNATURES = {
     "vb_assign_dev": (_i, [_vp, _i, _vp, _i, _vp]),
     "vb_set_tensor_cores": (_i, [_i]),
     "vb_last_assign_rechecked": (_i64, []),
+    "vb_set_option": (_i, [C.c_char_p, _i64]),
     "vb_hnsw_create": (_i, [_i, _i, _i, _i, C.POINTER(_vp)]),
     "vb_hnsw_load": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64]),
     "vb_hnsw_free": (_i, [_vp]),

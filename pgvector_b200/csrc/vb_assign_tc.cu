@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 namespace vb {
@@ -478,4 +479,17 @@ int vb_set_tensor_cores(int on) {
     return VB_OK;
 }
 int64_t vb_last_assign_rechecked(void) { return vb::ctx().last_assign_flagged; }
+int vb_set_option(const char* name, int64_t value) {
+    if (!name) return VB_EINVAL;
+    if (!strcmp(name, "scan_impl")) {
+        vb::ctx().scan_impl = (int)value;
+        return VB_OK;
+    }
+    if (!strcmp(name, "tensor_cores")) {
+        vb::set_tc_enabled(value != 0);
+        return VB_OK;
+    }
+    vb::set_error("unknown option %s", name);
+    return VB_EINVAL;
+}
 }

@@ -126,6 +126,30 @@ struct Acc {
 };
 
 
+// arguments of the scan kernels (vb_scan.cu: LDG variant, vb_scan_bulk.cu: bulk-copy/TMA variant)
+struct ScanArgs {
+    const uint8_t* rows;
+    size_t stride;        // padded row bytes
+    int vec_per_row;      // stride / 16
+    const uint8_t* queries;
+    size_t qstride;       // bytes of one query image
+    int qvec;             // qstride / 16
+    // chunk-list mode
+    const Chunk* chunks;
+    const int* n_chunks_dev;
+    // regular mode: every query x rows [0, n_rows) in chunks of rows_per_chunk
+    int64_t n_rows;
+    int64_t nq;
+    int rows_per_chunk;
+    int64_t chunks_per_q;
+    int64_t out_stride;
+    void* out;
+};
+
+// bulk-copy (TMA) variant; returns VB_EINVAL when the shape is not supported (caller falls back to the LDG variant)
+int launch_scan_bulk(int elem, int metric, const ScanArgs& a, bool out_f64, int max_chunks_hint);
+bool scan_bulk_supported(int elem, size_t stride, size_t qstride);
+
 // monotone map double -> uint64 (same conventions as orderable_key)
 __device__ __forceinline__ uint64_t orderable_key64(double d) {
     if (d != d) return ~0ull;

@@ -23,25 +23,6 @@
 
 namespace vb {
 
-struct ScanArgs {
-    const uint8_t* rows;
-    size_t stride;        // padded row bytes
-    int vec_per_row;      // stride / 16
-    const uint8_t* queries;
-    size_t qstride;       // bytes of one query image
-    int qvec;             // qstride / 16
-    // chunk-list mode
-    const Chunk* chunks;
-    const int* n_chunks_dev;
-    // regular mode: every query x rows [0, n_rows) in chunks of rows_per_chunk
-    int64_t n_rows;
-    int64_t nq;
-    int rows_per_chunk;
-    int64_t chunks_per_q;
-    int64_t out_stride;
-    void* out;
-};
-
 constexpr int SCAN_THREADS = 128;
 
 template <int ELEM, int METRIC, int LPR, int RPI, typename OUT>
@@ -202,6 +183,8 @@ static int scan_regular_impl(const Table& t, int metric, const void* q_dev, size
     a.out_stride = out_stride;
     a.out = out;
     int64_t total = nq * a.chunks_per_q;
+    if (ctx().scan_impl == 1 && scan_bulk_supported(t.elem, t.stride, qstride))
+        return launch_scan_bulk(t.elem, metric, a, sizeof(OUT) == 8, (int)std::min<int64_t>(total, 1 << 30));
     int grid = (int)std::min<int64_t>(total, scan_grid());
     return launch_scan_any<OUT>(t.elem, metric, a, grid, ctx().stream);
 }
@@ -228,6 +211,8 @@ int launch_scan_chunks(const Table& t, int metric, const void* q_dev, size_t qst
     a.chunks = chunks_dev;
     a.n_chunks_dev = n_chunks_dev;
     a.out = out;
+    if (ctx().scan_impl == 1 && scan_bulk_supported(t.elem, t.stride, qstride))
+        return launch_scan_bulk(t.elem, metric, a, false, max_chunks);
     int grid = std::min(max_chunks, scan_grid());
     return launch_scan_any<float>(t.elem, metric, a, grid, ctx().stream);
 }

@@ -21,8 +21,11 @@ RTOL = 1e-5   # north_star: L2/IP/cosine distances within 1e-5 relative
 
 @pytest.fixture(scope="module")
 def pv():
+    import os
     import pgvector_b200 as pv
     pv.init(0)
+    # VB_TEST_SCAN_IMPL=1 re-runs the suite on the bulk-copy (TMA) scan kernel
+    pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "0")))
     return pv
 
 
