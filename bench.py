@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--rows", type=int, default=1_000_000)
     ap.add_argument("--dim", type=int, default=1536)
     ap.add_argument("--lists", type=int, default=1000)
+    ap.add_argument("--components", type=int, default=0,
+                    help="Gaussian mixture components of the synthetic data (default 8 x lists, see DESIGN.md section 5)")
     ap.add_argument("--probes", type=int, default=10)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--queries", type=int, default=10_000)
@@ -52,9 +54,13 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-recall", action="store_true")
-    ap.add_argument("--scan-impl", type=int, default=int(os.environ.get("VB_SCAN_IMPL", "0")),
-                    help="0 = LDG.128 streaming scan kernel, 1 = cp.async.bulk (TMA) staged scan kernel")
-    return ap.parse_args()
+    ap.add_argument("--scan-impl", type=int, default=int(os.environ.get("VB_SCAN_IMPL", "2")),
+                    help="0 = LDG.128 streaming scan kernel, 1 = cp.async.bulk (TMA) staged scan kernel, "
+                         "2 = library default (bulk for tables larger than L2, LDG for L2-resident ones)")
+    args = ap.parse_args()
+    if args.components <= 0:
+        args.components = 8 * args.lists
+    return args
 
 
 # ----------------------------------------------------------------------------- synthetic data + index build (setup, untimed)
@@ -63,15 +69,15 @@ def make_dataset(args, device):
     """mixture of `lists` Gaussians; generated in slabs to bound temporary memory"""
     import torch
     g = torch.Generator(device=device).manual_seed(3)
-    comp = torch.randn((args.lists, args.dim), generator=g, device=device, dtype=torch.float32)
+    comp = torch.randn((args.components, args.dim), generator=g, device=device, dtype=torch.float32)
     rows = torch.empty((args.rows, args.dim), device=device, dtype=torch.float32)
     slab = 65536
     for lo in range(0, args.rows, slab):
         hi = min(args.rows, lo + slab)
-        which = torch.randint(0, args.lists, (hi - lo,), generator=g, device=device)
+        which = torch.randint(0, args.components, (hi - lo,), generator=g, device=device)
         rows[lo:hi] = comp[which] + 0.3 * torch.randn((hi - lo, args.dim), generator=g, device=device)
     g2 = torch.Generator(device=device).manual_seed(4)
-    which = torch.randint(0, args.lists, (args.queries,), generator=g2, device=device)
+    which = torch.randint(0, args.components, (args.queries,), generator=g2, device=device)
     queries = comp[which] + 0.3 * torch.randn((args.queries, args.dim), generator=g2, device=device)
     return rows, queries
 
@@ -398,7 +404,8 @@ def main():
     peak, peak_src = measured_peaks()
     scan_avg_ms = scan_ms / max(scan_n, 1)
     achieved = scan_bytes_per_launch / (scan_avg_ms / 1000.0) / 1e9 if scan_avg_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "scan_kernel<vector,L2^2> (GetScanItems list scan)", "achieved": achieved,
+    roofline = {"bound": "hbm", "kernel": ("scan_kernel" if args.scan_impl == 0 else "scan_bulk_kernel") + "<vector,L2^2> (GetScanItems list scan)",
+                "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "bytes_per_launch": scan_bytes_per_launch, "avg_launch_ms": scan_avg_ms,
                 "share_of_step": scan_ms / ms if ms > 0 else None,
@@ -442,8 +449,10 @@ def main():
 
 def workload_config(args, how):
     return {"workload": f"IVFFlat L2 {args.rows}x{args.dim} fp32, lists={args.lists}, probes={args.probes}, k={args.k} "
-                        f"(BASELINE.json configs[1])", "queries": args.queries, "batch": args.batch,
-            "index_build": how, "scan_kernel": "cp.async.bulk+mbarrier staged" if args.scan_impl == 1 else "LDG.128 streaming",
+                        f"(BASELINE.json configs[1])",
+            "data_law": f"mixture of {args.components} Gaussians (centres N(0,1), sigma 0.3), seeds 3/4", "queries": args.queries, "batch": args.batch,
+            "index_build": how, "scan_kernel": {0: "LDG.128 streaming (all scans)", 1: "cp.async.bulk+mbarrier staged (all scans)",
+                            2: "list scan: cp.async.bulk+mbarrier staged; centre scan: LDG.128 (L2-resident table)"}[args.scan_impl],
             "parallelism": "lists sharded l % N, one NCCL all-gather of k results per rank"}
 
 

@@ -166,11 +166,74 @@ vec_l1(int dim, const float *ax, const float *bx)
 /* ------------------------------------------------------------ fp16 loops */
 /* Halfvec*Default (src/halfutils.c:29-43, 81-92, 124-145, 197-209): widen, fp32 accumulate */
 
+#if defined(__F16C__) && defined(__AVX__) && defined(__FMA__)
+#include <immintrin.h>
+#define PGV_HAVE_F16C 1
+/*
+ * HalfvecL2SquaredDistanceF16c / HalfvecInnerProductF16c (src/halfutils.c:46-78, 94-121), the variants
+ * the reference dispatches to on x86-64 with F16C: 8 halves per step widened with vcvtph2ps, fp32 FMA
+ * into 8 lanes, lanes summed s[0]+...+s[7], scalar tail.
+ */
+static float
+half_l2sq_f16c(int dim, const uint16_t *ax, const uint16_t *bx)
+{
+	float		s[8];
+	float		distance;
+	int			i;
+	int			count = (dim / 8) * 8;
+	__m256		dist = _mm256_setzero_ps();
+
+	for (i = 0; i < count; i += 8)
+	{
+		__m256		a = _mm256_cvtph_ps(_mm_loadu_si128((const __m128i *) (ax + i)));
+		__m256		b = _mm256_cvtph_ps(_mm_loadu_si128((const __m128i *) (bx + i)));
+		__m256		diff = _mm256_sub_ps(a, b);
+
+		dist = _mm256_fmadd_ps(diff, diff, dist);
+	}
+	_mm256_storeu_ps(s, dist);
+	distance = s[0] + s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7];
+	for (; i < dim; i++)
+	{
+		float		diff = pgv_half_to_float(ax[i]) - pgv_half_to_float(bx[i]);
+
+		distance += diff * diff;
+	}
+	return distance;
+}
+
+static float
+half_ip_f16c(int dim, const uint16_t *ax, const uint16_t *bx)
+{
+	float		s[8];
+	float		distance;
+	int			i;
+	int			count = (dim / 8) * 8;
+	__m256		dist = _mm256_setzero_ps();
+
+	for (i = 0; i < count; i += 8)
+	{
+		__m256		a = _mm256_cvtph_ps(_mm_loadu_si128((const __m128i *) (ax + i)));
+		__m256		b = _mm256_cvtph_ps(_mm_loadu_si128((const __m128i *) (bx + i)));
+
+		dist = _mm256_fmadd_ps(a, b, dist);
+	}
+	_mm256_storeu_ps(s, dist);
+	distance = s[0] + s[1] + s[2] + s[3] + s[4] + s[5] + s[6] + s[7];
+	for (; i < dim; i++)
+		distance += pgv_half_to_float(ax[i]) * pgv_half_to_float(bx[i]);
+	return distance;
+}
+#endif
+
 static float
 half_l2sq(int dim, const uint16_t *ax, const uint16_t *bx)
 {
 	float		distance = 0.0f;
 
+#ifdef PGV_HAVE_F16C
+	return half_l2sq_f16c(dim, ax, bx);
+#endif
 	for (int i = 0; i < dim; i++)
 	{
 		float		diff = pgv_half_to_float(ax[i]) - pgv_half_to_float(bx[i]);
@@ -185,6 +248,9 @@ half_ip(int dim, const uint16_t *ax, const uint16_t *bx)
 {
 	float		distance = 0.0f;
 
+#ifdef PGV_HAVE_F16C
+	return half_ip_f16c(dim, ax, bx);
+#endif
 	for (int i = 0; i < dim; i++)
 		distance += pgv_half_to_float(ax[i]) * pgv_half_to_float(bx[i]);
 	return distance;

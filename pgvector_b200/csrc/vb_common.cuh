@@ -46,7 +46,7 @@ struct Context {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     int64_t launches = 0;
-    int scan_impl = 0;                 // 0 = LDG variant (vb_scan.cu), 1 = bulk-copy / TMA variant (vb_scan_bulk.cu)
+    int scan_impl = 2;                 // 0 = LDG variant (vb_scan.cu), 1 = bulk-copy / TMA variant (vb_scan_bulk.cu), 2 = by table size
     int64_t last_assign_flagged = -1;  // rows re-checked by the exact kernel in the last tensor-core assign (-1: exact path)
     // grow-only device workspace arenas (index = slot)
     void* ws[16] = {nullptr};

@@ -79,13 +79,27 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_kernel(ScanArgs a) {
                 // clamp so out-of-range lanes re-read a valid row (result discarded)
                 rp[i] = reinterpret_cast<const uint4*>(base + (size_t)min(r, n_rows - 1) * a.stride);
             }
+            // register double buffering: the loads of step v + LPR are issued before the FMAs of step v,
+            // so 2 * RPI independent 128-bit loads per thread stay in flight through the whole row set
+            uint4 cur[RPI];
+            if (l < V) {
+#pragma unroll
+                for (int i = 0; i < RPI; ++i) cur[i] = ldg_stream(rp[i] + l);
+            }
 #pragma unroll 2
             for (int v = l; v < V; v += LPR) {
-                uint4 x[RPI];
+                uint4 nxt[RPI];
+                const int vn = v + LPR;
+                if (vn < V) {
 #pragma unroll
-                for (int i = 0; i < RPI; ++i) x[i] = ldg_stream(rp[i] + v);
+                    for (int i = 0; i < RPI; ++i) nxt[i] = ldg_stream(rp[i] + vn);
+                }
 #pragma unroll
-                for (int i = 0; i < RPI; ++i) acc[i].add(x[i], sq, v);
+                for (int i = 0; i < RPI; ++i) acc[i].add(cur[i], sq, v);
+                if (vn < V) {
+#pragma unroll
+                    for (int i = 0; i < RPI; ++i) cur[i] = nxt[i];
+                }
             }
 #pragma unroll
             for (int i = 0; i < RPI; ++i) {
@@ -158,6 +172,17 @@ static int scan_rows_per_chunk(size_t stride) {
 
 int scan_chunk_rows(const Table& t) { return scan_rows_per_chunk(t.stride); }
 
+// Which scan kernel?  Measured on B200 (profiles/r1_listscan_*.md): the bulk-copy (TMA) kernel streams HBM at
+// ~6.7 TB/s (82 % DRAM utilisation at 14 % warp occupancy) but, with one CTA per SM, is slower than the
+// LDG kernel when the rows are L2-resident (centre table: 0.76 ms vs 1.39 ms for 2048 queries x 1000 centres).
+// scan_impl: 0 = always LDG, 1 = bulk whenever the shape allows, 2 (default) = bulk for tables larger than L2.
+static bool use_bulk_scan(const Table& t, int64_t n_rows, size_t qstride) {
+    const int impl = ctx().scan_impl;
+    if (impl == 0 || !scan_bulk_supported(t.elem, t.stride, qstride)) return false;
+    if (impl == 1) return true;
+    return (size_t)n_rows * t.stride > ((size_t)96 << 20);
+}
+
 static int scan_grid() {
     // persistent-style grid: a few CTAs per SM (multiple of the SM count)
     return ctx().sm_count * 8;
@@ -183,7 +208,7 @@ static int scan_regular_impl(const Table& t, int metric, const void* q_dev, size
     a.out_stride = out_stride;
     a.out = out;
     int64_t total = nq * a.chunks_per_q;
-    if (ctx().scan_impl == 1 && scan_bulk_supported(t.elem, t.stride, qstride))
+    if (use_bulk_scan(t, n_rows, qstride))
         return launch_scan_bulk(t.elem, metric, a, sizeof(OUT) == 8, (int)std::min<int64_t>(total, 1 << 30));
     int grid = (int)std::min<int64_t>(total, scan_grid());
     return launch_scan_any<OUT>(t.elem, metric, a, grid, ctx().stream);
@@ -211,7 +236,7 @@ int launch_scan_chunks(const Table& t, int metric, const void* q_dev, size_t qst
     a.chunks = chunks_dev;
     a.n_chunks_dev = n_chunks_dev;
     a.out = out;
-    if (ctx().scan_impl == 1 && scan_bulk_supported(t.elem, t.stride, qstride))
+    if (use_bulk_scan(t, t.n, qstride))
         return launch_scan_bulk(t.elem, metric, a, false, max_chunks);
     int grid = std::min(max_chunks, scan_grid());
     return launch_scan_any<float>(t.elem, metric, a, grid, ctx().stream);

@@ -25,7 +25,7 @@ def pv():
     import pgvector_b200 as pv
     pv.init(0)
     # VB_TEST_SCAN_IMPL=1 re-runs the suite on the bulk-copy (TMA) scan kernel
-    pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "0")))
+    pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
     return pv
 
 

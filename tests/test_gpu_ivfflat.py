@@ -14,7 +14,7 @@ def pv():
     import pgvector_b200 as pv
     pv.init(0)
     import os
-    pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "0")))
+    pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
     # equal centre distances are broken by list number on the GPU; put the oracle in the same
     # deterministic instance (the pairing-heap order is compared by recall, see test_tie_modes_agree_on_recall)
     O.ivf_set_tie_mode(True)
