@@ -82,6 +82,8 @@ def torch_allreduce_hook(device, group=None):
                                           "data": (int(ptr), False), "version": 2}
             t = torch.as_tensor(b, device=device)
             dist.all_reduce(t, group=group)
+            # the library resumes on its own stream as soon as the hook returns
+            torch.cuda.current_stream(device).synchronize()
         else:  # CPU tests: ptr is a host pointer
             buf = (ctypes.c_char * (int(count) * size)).from_address(int(ptr))
             t = torch.frombuffer(buf, dtype=tdtype)

@@ -68,7 +68,13 @@ def bench_assign(args):
         ms = timed(pv, torch, stream, lambda: pv._lib.check(pv.load().vb_assign_dev(tt.h, pv.L2_SQUARED, pv._ptr(centers), args.k, pv._ptr(o))),
                    warmup=1, steps=3)
         flops = 2.0 * n_eff * args.k * args.dim
-        res[name] = {"ms": ms, "rows": n_eff, "useful_tflops": flops / ms / 1e9, "rechecked_rows": pv.last_assign_rechecked()}
+        pv.prof_enable(True)
+        pv.prof_read(pv.PROF_ASSIGN)
+        pv._lib.check(pv.load().vb_assign_dev(tt.h, pv.L2_SQUARED, pv._ptr(centers), args.k, pv._ptr(o)))
+        dev_ms, _ = pv.prof_read(pv.PROF_ASSIGN)     # pack + GEMM + re-check on the device, without host-side allocation
+        pv.prof_enable(False)
+        res[name] = {"ms": ms, "device_ms": dev_ms, "rows": n_eff, "useful_tflops": flops / ms / 1e9,
+                     "useful_tflops_device": flops / dev_ms / 1e9, "rechecked_rows": pv.last_assign_rechecked()}
         if tc:
             a_tc = out.clone()
     pv.set_tensor_cores(True)
@@ -97,8 +103,11 @@ def bench_hnsw(args):
     pv.init(0)
     dev = torch.device("cuda", 0)
     stream = torch.cuda.ExternalStream(pv.stream_handle(), device=dev)
-    x, _ = mixture(args.rows, args.dim, 256, seed=6)
-    q, _ = mixture(args.queries, args.dim, 256, seed=7)
+    # low intrinsic dimension (like bench.py): a graph index on it has a meaningful recall
+    rng = np.random.default_rng(6)
+    frame = np.linalg.qr(rng.standard_normal((args.dim, 16)))[0].astype(np.float32)
+    x = (rng.standard_normal((args.rows, 16)).astype(np.float32) @ frame.T + 0.02 * rng.standard_normal((args.rows, args.dim)).astype(np.float32))
+    q = (rng.standard_normal((args.queries, 16)).astype(np.float32) @ frame.T + 0.02 * rng.standard_normal((args.queries, args.dim)).astype(np.float32))
     if args.elem == "halfvec":
         elem, opclass, metric = O.HALFVEC, "halfvec_cosine_ops", O.NEG_IP
         rows = O.l2_normalize(O.HALFVEC, f32_to_half_bits(x))
