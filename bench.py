@@ -216,6 +216,17 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+def ncu_traffic(args, world):
+    """dram__bytes_read + dram__bytes_write of the list-scan kernel from the committed `ncu --set full` capture
+    of this same command (profiles/listscan_traffic.json); only valid for the shape it was captured on."""
+    p = os.path.join(ROOT, "profiles", "listscan_traffic.json")
+    default_shape = (args.rows, args.dim, args.lists, args.probes, args.batch, args.components, args.latent_dim) == \
+                    (1_000_000, 1536, 1000, 10, 2048, 0, 16)
+    if world != 1 or args.scan_impl == 0 or not default_shape or not os.path.exists(p):
+        return None
+    return json.load(open(p))["traffic_bytes"]
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -436,7 +447,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": ("scan_kernel" if args.scan_impl == 0 else "scan_bulk_kernel") + "<vector,L2^2> (GetScanItems list scan)",
                 "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "bytes_per_launch": scan_bytes_per_launch, "avg_launch_ms": scan_avg_ms,
+                "traffic": ncu_traffic(args, world), "bytes_per_launch": scan_bytes_per_launch, "avg_launch_ms": scan_avg_ms,
                 "share_of_step": scan_ms / ms if ms > 0 else None,
                 "other_kernels_ms_per_step": {"centre_scan": lists_ms / max(lists_n, 1), "topk_select": topk_ms / max(topk_n, 1)},
                 "whole_step_algorithmic_gbs": (B * args.lists + cand_all) * args.dim * elem_bytes / (ms / args.steps / 1000.0) / 1e9}

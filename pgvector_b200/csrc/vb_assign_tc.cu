@@ -442,7 +442,10 @@ int launch_assign_tc(const Table& X, int metric, const Table& Cn, int k, int32_t
         a.k = k;
         a.is_l2 = is_l2;
         a.cmax = std::sqrt(cmax2);
-        a.tol = 1.0f / 4096.0f;   // 2^-12: 16x the 2^-16 truncation bound, covers fp32 accumulation in TMEM
+        // analytical bound of the split product: dropped lo.lo <= 2^-16 |x||c|, bf16 rounding of the lo planes
+        // <= 2 * 2^-18 |x||c| (together ~1.1e-5), plus the fp32 accumulation of 3 * dim terms in TMEM; 2^-13 = 1.2e-4
+        // leaves an order of magnitude of head-room
+        a.tol = 1.0f / 8192.0f;
         a.out_idx = out_idx;
         a.flagged = d_flagged;
         a.n_flagged = d_nflag;

@@ -49,8 +49,8 @@ struct Context {
     int scan_impl = 2;                 // 0 = LDG variant (vb_scan.cu), 1 = bulk-copy / TMA variant (vb_scan_bulk.cu), 2 = by table size
     int64_t last_assign_flagged = -1;  // rows re-checked by the exact kernel in the last tensor-core assign (-1: exact path)
     // grow-only device workspace arenas (index = slot)
-    void* ws[16] = {nullptr};
-    size_t ws_bytes[16] = {0};
+    void* ws[24] = {nullptr};
+    size_t ws_bytes[24] = {0};
     // pinned staging
     void* pinned = nullptr;
     size_t pinned_bytes = 0;

@@ -18,7 +18,7 @@
 
 namespace vb {
 
-enum { WSK_QIMG = 0, WSK_DIST = 1, WSK_A = 2, WSK_B = 3, WSK_C = 4, WSK_D = 5, WSK_E = 6, WSK_F = 7, WSK_G = 12, WSK_H = 13, WSK_I = 14, WSK_J = 15 };
+enum { WSK_QIMG = 0, WSK_DIST = 1, WSK_A = 2, WSK_B = 3, WSK_C = 4, WSK_D = 5, WSK_E = 6, WSK_F = 7, WSK_G = 12, WSK_H = 13, WSK_I = 14, WSK_J = 16 };
 
 // ----------------------------------------------------------------------------- exact assign
 
@@ -41,8 +41,13 @@ __device__ __forceinline__ uint4 load_words4(const uint8_t* row, int w, int word
 template <int ELEM, int KIND>
 __global__ void __launch_bounds__(AT_THREADS) assign_exact_kernel(const uint8_t* __restrict__ X, size_t xstride, int64_t n,
                                                                    const int32_t* __restrict__ row_sel, int64_t n_sel,
-                                                                   const uint8_t* __restrict__ Cn, size_t cstride, int k, int words,
-                                                                   int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+                                                                   const uint8_t* __restrict__ Cn, size_t cstride, int k_total, int words,
+                                                                   int32_t* __restrict__ out_idx, float* __restrict__ out_val,
+                                                                   int k_per_split, unsigned long long* __restrict__ packed) {
+    // blockIdx.y selects a slice of the centres (used when few rows are re-checked: keeps every SM busy);
+    // slices are merged with a 64-bit atomicMin on (orderable value, centre number) = first minimum wins
+    const int k_lo = blockIdx.y * k_per_split;
+    const int k = min(k_total, k_lo + k_per_split);
     __shared__ uint32_t Xs[AT_K][AT_M + 4];
     __shared__ uint32_t Cs[AT_K][AT_N + 4];
     const int tid = threadIdx.x;
@@ -69,7 +74,7 @@ __global__ void __launch_bounds__(AT_THREADS) assign_exact_kernel(const uint8_t*
         xrow[h] = X + (size_t)r * xstride;
     }
 
-    for (int n0 = 0; n0 < k; n0 += AT_N) {
+    for (int n0 = k_lo; n0 < k; n0 += AT_N) {
         const uint8_t* crow[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -163,13 +168,32 @@ __global__ void __launch_bounds__(AT_THREADS) assign_exact_kernel(const uint8_t*
         for (int i = 0; i < 8; ++i) {
             int64_t r = m0 + ty * 8 + i;
             if (r < total) {
-                int64_t dst = row_sel ? row_sel[r] : r;
-                // all-NaN / all-inf rows: closestCenter stays 0 like the reference (minDistance = DBL_MAX start)
-                out_idx[dst] = best_i[i] == 0x7fffffff ? 0 : best_i[i];
-                if (out_val) out_val[dst] = best_v[i];
+                if (packed) {
+                    // rows that never saw a finite value keep the initial all-ones key (-> centre 0 in the finalize step)
+                    if (best_i[i] != 0x7fffffff) {
+                        uint32_t u = __float_as_uint(best_v[i]);
+                        if (u == 0x80000000u) u = 0;
+                        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                        atomicMin(&packed[r], ((unsigned long long)u << 32) | (unsigned)best_i[i]);
+                    }
+                } else {
+                    int64_t dst = row_sel ? row_sel[r] : r;
+                    // all-NaN / all-inf rows: closestCenter stays 0 like the reference (minDistance = DBL_MAX start)
+                    out_idx[dst] = best_i[i] == 0x7fffffff ? 0 : best_i[i];
+                    if (out_val) out_val[dst] = best_v[i];
+                }
             }
         }
     }
+}
+
+__global__ void unpack_assign_kernel(const unsigned long long* __restrict__ packed, const int32_t* __restrict__ row_sel, int64_t total,
+                                     int32_t* __restrict__ out_idx) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= total) return;
+    unsigned long long key = packed[r];
+    int64_t dst = row_sel ? row_sel[r] : r;
+    out_idx[dst] = key == ~0ull ? 0 : (int32_t)(unsigned)key;
 }
 
 static int assign_kind(int metric) {
@@ -189,10 +213,25 @@ int launch_assign_exact(const Table& X, int metric, const Table& Cn, int k, cons
     const int64_t total = row_sel_dev ? n_sel : X.n;
     if (total <= 0 || k <= 0) return VB_OK;
     const int words = (int)(X.elem == VB_HALFVEC ? X.stride / 2 : X.stride / 4);
-    const unsigned grid = (unsigned)((total + AT_M - 1) / AT_M);
+    const unsigned gx = (unsigned)((total + AT_M - 1) / AT_M);
     cudaStream_t s = ctx().stream;
-#define VB_ASSIGN(E, K) \
-    assign_exact_kernel<E, K><<<grid, AT_THREADS, 0, s>>>(X.d, X.stride, X.n, row_sel_dev, n_sel, Cn.d, Cn.stride, k, words, out_idx, out_val)
+    // few row tiles (a re-check of flagged rows): slice the centres over blockIdx.y so the grid covers the GPU
+    int splits = 1;
+    const int ktiles = (k + AT_N - 1) / AT_N;
+    if (row_sel_dev && !out_val && (int)gx < ctx().sm_count) splits = std::min(ktiles, std::max(1, (2 * ctx().sm_count) / (int)gx));
+    const int k_per_split = ((ktiles + splits - 1) / splits) * AT_N;
+    splits = (k + k_per_split - 1) / k_per_split;
+    unsigned long long* packed = nullptr;
+    if (splits > 1) {
+        void* p;
+        VB_TRY(workspace(WSK_J, sizeof(unsigned long long) * (size_t)total, &p));
+        packed = (unsigned long long*)p;
+        VB_CUDA(cudaMemsetAsync(packed, 0xFF, sizeof(unsigned long long) * (size_t)total, s));
+    }
+    const dim3 grid(gx, (unsigned)splits);
+#define VB_ASSIGN(E, K)                                                                                                             \
+    assign_exact_kernel<E, K><<<grid, AT_THREADS, 0, s>>>(X.d, X.stride, X.n, row_sel_dev, n_sel, Cn.d, Cn.stride, k, words, out_idx, \
+                                                          out_val, k_per_split, packed)
     if (X.elem == VB_VECTOR) {
         if (kind == 0) VB_ASSIGN(VB_VECTOR, 0);
         else if (kind == 1) VB_ASSIGN(VB_VECTOR, 1);
@@ -208,6 +247,11 @@ int launch_assign_exact(const Table& X, int metric, const Table& Cn, int k, cons
 #undef VB_ASSIGN
     VB_CUDA(cudaGetLastError());
     count_launch();
+    if (packed) {
+        unpack_assign_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(packed, row_sel_dev, total, out_idx);
+        VB_CUDA(cudaGetLastError());
+        count_launch();
+    }
     return VB_OK;
 }
 
