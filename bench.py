@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
 """bench.py -- IVFFlat scan throughput (BASELINE.json metric) on B200.
 
-Workload (config B of BASELINE.json / SURVEY.md section 8d): 1,000,000 x 1536-d fp32 rows drawn from a
-1000-component Gaussian mixture (sigma 0.3, seed 3), ivfflat vector_l2_ops, lists = 1000,
-probes = 10, k = 10; 10,000 queries from the same mixture (seed 4).  A "step" is one batch
-of --batch queries through the hot path (probe selection + list scan + top-k).
+Workload (config B of BASELINE.json / SURVEY.md section 8d): 1,000,000 x 1536-d fp32 rows (seed 3; data law in
+make_dataset: 1536-d vectors of intrinsic dimension 16, see DESIGN.md section 5 for why not the isotropic
+mixture), ivfflat vector_l2_ops, lists = 1000 built by the library's own k-means++ / k-means / assign,
+probes = 10, k = 10; 10,000 queries from the same law (seed 4).  A "step" is one batch of --batch queries
+through the hot path (probe selection + list scan + top-k).
 
   value : queries/s with queries and outputs resident in HBM (device pointers, C ABI *_dev call)
   e2e   : queries/s through vb_ivf_search with HOST buffers (H2D of the queries and D2H of
@@ -187,7 +188,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -358,12 +359,18 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
-    for i in range(args.warmup):
-        step_dev(i)
-    barrier()
+    # the clock sampler starts before the warm-up (nvidia-smi needs ~0.3 s to print its first line) and is
+    # stopped right after the timed steps: every sample is taken with the scan running
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    # untimed extra load (same count on every rank: the steps contain collectives) while nvidia-smi spins up
+    for i in range(20):
+        step_dev(i)
+    barrier()
     pv.prof_enable(True)
     pv.prof_read(pv.PROF_SCAN_ITEMS)
     pv.prof_read(pv.PROF_SCAN_LISTS)
