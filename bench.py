@@ -295,6 +295,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     import pgvector_b200 as pv
     pv.init(local)
@@ -302,7 +303,11 @@ def main():
 
     # ---- setup (untimed): data, index, device image
     rows, queries = make_dataset(args, dev)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter()
     centers, offsets, grouped, order, how = build_index_arrays(args, rows, pv)
+    torch.cuda.synchronize()
+    how += f"; build {time.perf_counter() - t_build:.2f} s (k-means++ on {min(args.rows, max(args.lists * 50, 10000))} samples, k-means, assign of {args.rows} rows, grouping)"
     del rows
     torch.cuda.empty_cache()
     full_offsets = offsets

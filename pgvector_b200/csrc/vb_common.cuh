@@ -139,6 +139,8 @@ int scan_chunk_rows(const Table& t);
 int launch_assign_exact(const Table& X, int metric, const Table& Cn, int k, const int32_t* row_sel_dev, int64_t n_sel,
                         int32_t* out_idx, float* out_val);
 int launch_assign(const Table& X, int metric, const Table& Cn, int k, int32_t* out_idx);
+// all-pairs fp32 distances X x Cn -> out[x * ld + c] (register-tiled CUDA-core kernel, vb_kmeans.cu)
+int launch_distance_matrix(const Table& X, int metric, const Table& Cn, int k, float* out, int64_t ld);
 void set_tc_enabled(bool on);
 
 }  // namespace vb

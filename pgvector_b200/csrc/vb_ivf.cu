@@ -147,7 +147,22 @@ static int ivf_select_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t 
     void *d_cdist, *d_seg, *d_probe;
     VB_TRY(workspace(WS_CDIST, sizeof(float) * (size_t)nq * ix.lists, &d_cdist));
     prof_begin(VB_PROF_SCAN_LISTS);
-    VB_TRY(launch_scan_regular(ix.centers, key_metric(ix.metric), qimg, qstride, nq, ix.lists, (float*)d_cdist, ix.lists));
+    // many queries at once: the query image is itself a row table with the centres' stride (vector, bit), so the
+    // centre scan is computed tile-wise (both operands staged once per 128 x 128 tile).  Measured on B200 for 2048
+    // queries x 1000 centres x 1536-d: 1.31 ms as one-query-at-a-time scans (L2-resident, 12.6 GB of L2 reads).
+    const bool tiled = nq >= 64 && ix.elem != VB_HALFVEC && qstride == ix.centers.stride && ctx().scan_impl != 0 &&
+                       (key_metric(ix.metric) == VB_L2_SQUARED || key_metric(ix.metric) == VB_NEG_IP || key_metric(ix.metric) == VB_HAMMING);
+    if (tiled) {
+        Table Q;
+        Q.elem = ix.elem;
+        Q.dim = ix.dim;
+        Q.stride = qstride;
+        Q.n = nq;
+        Q.d = (uint8_t*)const_cast<void*>(qimg);
+        VB_TRY(launch_distance_matrix(Q, ix.metric, ix.centers, ix.lists, (float*)d_cdist, ix.lists));
+    } else {
+        VB_TRY(launch_scan_regular(ix.centers, key_metric(ix.metric), qimg, qstride, nq, ix.lists, (float*)d_cdist, ix.lists));
+    }
     prof_end(VB_PROF_SCAN_LISTS);
     VB_TRY(workspace(WS_SEG, (sizeof(int64_t) + sizeof(int32_t)) * (size_t)nq * 2 + 64, &d_seg));
     int64_t* seg_begin = (int64_t*)d_seg;

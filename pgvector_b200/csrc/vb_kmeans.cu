@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(AT_THREADS) assign_exact_kernel(const uint8_t*
                                                                    const int32_t* __restrict__ row_sel, int64_t n_sel,
                                                                    const uint8_t* __restrict__ Cn, size_t cstride, int k_total, int words,
                                                                    int32_t* __restrict__ out_idx, float* __restrict__ out_val,
-                                                                   int k_per_split, unsigned long long* __restrict__ packed) {
+                                                                   int k_per_split, unsigned long long* __restrict__ packed,
+                                                                   float* __restrict__ out_matrix, int64_t matrix_ld) {
     // blockIdx.y selects a slice of the centres (used when few rows are re-checked: keeps every SM busy);
     // slices are merged with a 64-bit atomicMin on (orderable value, centre number) = first minimum wins
     const int k_lo = blockIdx.y * k_per_split;
@@ -134,6 +135,21 @@ __global__ void __launch_bounds__(AT_THREADS) assign_exact_kernel(const uint8_t*
                     }
             }
         }
+        if (out_matrix) {
+            // distance-matrix mode (batched centre scan of GetScanLists): write the tile, no argmin
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t r = m0 + ty * 8 + i;
+                if (r >= total) continue;
+                float* orow = out_matrix + r * matrix_ld;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = n0 + tx * 8 + j;
+                    if (c < k) orow[c] = KIND == 0 ? acc[i][j] : KIND == 1 ? -acc[i][j] : (float)uacc[i][j];
+                }
+            }
+            continue;
+        }
         // fold this centre tile into the running argmin: strict <, first minimum wins (src/ivfbuild.c:183-192)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -163,6 +179,7 @@ __global__ void __launch_bounds__(AT_THREADS) assign_exact_kernel(const uint8_t*
             }
         }
     }
+    if (out_matrix) return;
     if (tx == 0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -231,7 +248,7 @@ int launch_assign_exact(const Table& X, int metric, const Table& Cn, int k, cons
     const dim3 grid(gx, (unsigned)splits);
 #define VB_ASSIGN(E, K)                                                                                                             \
     assign_exact_kernel<E, K><<<grid, AT_THREADS, 0, s>>>(X.d, X.stride, X.n, row_sel_dev, n_sel, Cn.d, Cn.stride, k, words, out_idx, \
-                                                          out_val, k_per_split, packed)
+                                                          out_val, k_per_split, packed, nullptr, 0)
     if (X.elem == VB_VECTOR) {
         if (kind == 0) VB_ASSIGN(VB_VECTOR, 0);
         else if (kind == 1) VB_ASSIGN(VB_VECTOR, 1);
@@ -252,6 +269,39 @@ int launch_assign_exact(const Table& X, int metric, const Table& Cn, int k, cons
         VB_CUDA(cudaGetLastError());
         count_launch();
     }
+    return VB_OK;
+}
+
+// Every row of X against every row of Cn -> out[x][c] (fp32 key metric), register-tiled: both operands are
+// staged through shared memory once per 128 x 128 tile instead of once per (query, row chunk).  Used for the
+// batched centre scan of GetScanLists (src/ivfscan.c:47-118) when many queries are searched at once.
+int launch_distance_matrix(const Table& X, int metric, const Table& Cn, int k, float* out, int64_t ld) {
+    const int kind = assign_kind(metric);
+    VB_REQUIRE(kind >= 0 && X.elem == Cn.elem && X.stride == Cn.stride, "distance matrix: unsupported operands");
+    if (X.n <= 0 || k <= 0) return VB_OK;
+    const int words = (int)(X.elem == VB_HALFVEC ? X.stride / 2 : X.stride / 4);
+    // one CTA per (128 queries, 128 centres) tile: outputs are disjoint, so centre slices need no merge
+    const dim3 grid((unsigned)((X.n + AT_M - 1) / AT_M), (unsigned)((k + AT_N - 1) / AT_N));
+    cudaStream_t s = ctx().stream;
+    const int kps = AT_N;
+#define VB_DM(E, K)                                                                                                                   \
+    assign_exact_kernel<E, K><<<grid, AT_THREADS, 0, s>>>(X.d, X.stride, X.n, nullptr, 0, Cn.d, Cn.stride, k, words, nullptr, nullptr, \
+                                                          kps, nullptr, out, ld)
+    if (X.elem == VB_VECTOR) {
+        if (kind == 0) VB_DM(VB_VECTOR, 0);
+        else if (kind == 1) VB_DM(VB_VECTOR, 1);
+        else VB_REQUIRE(false, "distance matrix: Hamming needs bit rows");
+    } else if (X.elem == VB_HALFVEC) {
+        if (kind == 0) VB_DM(VB_HALFVEC, 0);
+        else if (kind == 1) VB_DM(VB_HALFVEC, 1);
+        else VB_REQUIRE(false, "distance matrix: Hamming needs bit rows");
+    } else {
+        VB_REQUIRE(kind == 2, "distance matrix: bit rows need the Hamming metric");
+        VB_DM(VB_BIT, 2);
+    }
+#undef VB_DM
+    VB_CUDA(cudaGetLastError());
+    count_launch();
     return VB_OK;
 }
 
