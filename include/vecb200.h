@@ -104,6 +104,19 @@ int			vb_prof_read(int kernel, double *total_ms, int64_t *launches);
 int			vb_distance_batch(int elem, int metric, int dim, const void *q,
 							  const void *rows, int64_t n, double *out);
 
+/*
+ * Batched row transforms next to the distance path (host buffers in and out):
+ *   vb_norm_batch            vector_norm / l2_norm           (src/vector.c:767-780, src/halfvec.c:703-720)
+ *   vb_l2_normalize_batch    l2_normalize                    (src/vector.c:785-819, src/halfvec.c:725-759); what the cosine
+ *                            opclasses apply to every indexed row and to the query (src/ivfbuild.c:174-180, src/ivfscan.c:222-229);
+ *                            fails with "value out of range: overflow" like float_overflow_error()
+ *   vb_binary_quantize_batch binary_quantize                 (src/vector.c:952-978): out = (dim + 7) / 8 bytes per row, MSB first
+ * elem = VB_VECTOR or VB_HALFVEC; norms accumulate in fp64 as in the reference.
+ */
+int			vb_norm_batch(int elem, int dim, const void *rows, int64_t n, double *out);
+int			vb_l2_normalize_batch(int elem, int dim, const void *rows, int64_t n, void *out);
+int			vb_binary_quantize_batch(int elem, int dim, const void *rows, int64_t n, uint8_t *out);
+
 /* ------------------------------------------------------ resident row tables */
 
 typedef struct vb_table vb_table;	/* [n x dim] rows resident in HBM (exact scan, HNSW vectors, k-means samples) */

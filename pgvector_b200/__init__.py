@@ -427,3 +427,40 @@ def last_assign_rechecked() -> int:
 def set_option(name: str, value: int):
     """tuning switches of the library: "scan_impl" (0 = LDG kernel, 1 = bulk-copy/TMA kernel), "tensor_cores"."""
     _lib.check(load().vb_set_option(name.encode(), int(value)))
+
+
+# --------------------------------------------------------------------- row transforms
+
+def vector_norm(rows, elem=VECTOR):
+    """vector_norm / l2_norm of every row (src/vector.c:767-780, src/halfvec.c:703-720)."""
+    rows = _host(elem, rows)
+    single = rows.ndim == 1
+    r2 = rows.reshape(1, -1) if single else rows
+    out = np.empty(r2.shape[0], dtype=np.float64)
+    _lib.check(load().vb_norm_batch(elem, r2.shape[1], _ptr(r2), r2.shape[0], _ptr(out)))
+    return out[0] if single else out
+
+
+def l2_normalize(rows, elem=VECTOR):
+    """l2_normalize of every row (src/vector.c:785-819, src/halfvec.c:725-759); raises OverflowError like the reference."""
+    rows = _host(elem, rows)
+    single = rows.ndim == 1
+    r2 = np.ascontiguousarray(rows.reshape(1, -1) if single else rows)
+    out = np.empty_like(r2)
+    try:
+        _lib.check(load().vb_l2_normalize_batch(elem, r2.shape[1], _ptr(r2), r2.shape[0], _ptr(out)))
+    except VecB200Error as e:
+        if "overflow" in str(e):
+            raise OverflowError("value out of range: overflow") from None
+        raise
+    return out[0] if single else out
+
+
+def binary_quantize(rows, elem=VECTOR):
+    """binary_quantize of every row (src/vector.c:952-978): packed bits, MSB first."""
+    rows = _host(elem, rows)
+    single = rows.ndim == 1
+    r2 = np.ascontiguousarray(rows.reshape(1, -1) if single else rows)
+    out = np.empty((r2.shape[0], (r2.shape[1] + 7) // 8), dtype=np.uint8)
+    _lib.check(load().vb_binary_quantize_batch(elem, r2.shape[1], _ptr(r2), r2.shape[0], _ptr(out)))
+    return out[0] if single else out

@@ -29,6 +29,9 @@ SIGNATURES = {
     "vb_prof_enable": (_i, [_i]),
     "vb_prof_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "vb_distance_batch": (_i, [_i, _i, _i, _vp, _vp, _i64, _vp]),
+    "vb_norm_batch": (_i, [_i, _i, _vp, _i64, _vp]),
+    "vb_l2_normalize_batch": (_i, [_i, _i, _vp, _i64, _vp]),
+    "vb_binary_quantize_batch": (_i, [_i, _i, _vp, _i64, _vp]),
     "vb_table_create": (_i, [_i, _i, C.POINTER(_vp)]),
     "vb_table_append": (_i, [_vp, _vp, _i64]),
     "vb_table_append_dev": (_i, [_vp, _vp, _i64]),

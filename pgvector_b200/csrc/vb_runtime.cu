@@ -207,10 +207,24 @@ int upload_queries(int elem, int dim, const void* queries, int64_t nq, bool host
     uint8_t* d_raw = (uint8_t*)d_img + ((img * (size_t)nq + 15) & ~(size_t)15);
     const uint8_t* src_dev = (const uint8_t*)queries;
     if (host) {
-        void* pin;
-        VB_TRY(pinned_buffer(raw * (size_t)nq, &pin));
-        memcpy(pin, queries, raw * (size_t)nq);
-        VB_CUDA(cudaMemcpyAsync(d_raw, pin, raw * (size_t)nq, cudaMemcpyHostToDevice, c.stream));
+        // a caller buffer that is already page-locked (cudaHostAlloc / cudaHostRegister) is DMA'd in place;
+        // pageable memory goes through the library's pinned staging buffer
+        cudaPointerAttributes attr;
+        const void* src = queries;
+        if (cudaPointerGetAttributes(&attr, queries) != cudaSuccess || attr.type != cudaMemoryTypeHost) {
+            cudaGetLastError();   // clear the "not a registered pointer" status of older drivers
+            void* pin;
+            VB_TRY(pinned_buffer(raw * (size_t)nq, &pin));
+            memcpy(pin, queries, raw * (size_t)nq);
+            src = pin;
+        }
+        if (elem != VB_HALFVEC && raw == pad) {
+            // rows are already in image layout: DMA straight into the image, no repack kernel
+            VB_CUDA(cudaMemcpyAsync(d_img, src, raw * (size_t)nq, cudaMemcpyHostToDevice, c.stream));
+            *out_dev = d_img;
+            return VB_OK;
+        }
+        VB_CUDA(cudaMemcpyAsync(d_raw, src, raw * (size_t)nq, cudaMemcpyHostToDevice, c.stream));
         src_dev = d_raw;
     }
     query_image_kernel<<<(unsigned)nq, 128, 0, c.stream>>>(elem, dim, src_dev, raw, (uint8_t*)d_img, img, nq);
