@@ -152,6 +152,98 @@ def bench_hnsw(args):
                       "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": os.cpu_count(), "kind": "port"}}))
 
 
+def bench_ivf(args):
+    """IVFFlat scan throughput for halfvec / bit rows (bench.py covers vector)."""
+    import torch
+    import pgvector_b200 as pv
+    pv.init(0)
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.ExternalStream(pv.stream_handle(), device=dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    frame = torch.linalg.qr(torch.randn((args.dim, 16), generator=g, device=dev))[0]
+    x = torch.randn((args.rows, 16), generator=g, device=dev) @ frame.T + 0.02 * torch.randn((args.rows, args.dim), generator=g, device=dev)
+    q = torch.randn((args.queries, 16), generator=g, device=dev) @ frame.T + 0.02 * torch.randn((args.queries, args.dim), generator=g, device=dev)
+    if args.elem == "halfvec":
+        elem, opclass, kmetric, pmetric, rb = pv.HALFVEC, "halfvec_l2_ops", pv.L2, pv.L2_SQUARED, args.dim * 2
+        rows_t, q_t = x.half().contiguous(), q.half().contiguous()
+        rows_np = rows_t.cpu().numpy().view(np.uint16)
+    else:
+        elem, opclass, kmetric, pmetric, rb = pv.BIT, "bit_hamming_ops", pv.HAMMING, pv.HAMMING, args.dim // 8
+        def pack(t):
+            b = (t > 0).to(torch.uint8).reshape(t.shape[0], -1, 8)
+            w = torch.tensor([128, 64, 32, 16, 8, 4, 2, 1], dtype=torch.uint8, device=dev)
+            return (b * w).sum(-1).to(torch.uint8).contiguous()
+        rows_t, q_t = pack(x), pack(q)
+        rows_np = rows_t.cpu().numpy()
+    del x
+    torch.cuda.synchronize()
+    ns = min(args.rows, 50 * args.lists)
+    ts = pv.Table(elem, args.dim).append(rows_np[:ns])
+    init = pv.kmeans_pp_init(ts, kmetric, args.lists, seed=42)
+    centers, iters = pv.kmeans(ts, kmetric, init, max_iter=100)
+    ta = pv.Table(elem, args.dim).append(rows_t)
+    assign = pv.assign(ta, pmetric, centers)
+    ta.free()
+    a = torch.from_numpy(assign).to(dev).long()
+    order = torch.argsort(a, stable=True)
+    counts = torch.bincount(a, minlength=args.lists).cpu()
+    offsets = np.zeros(args.lists + 1, dtype=np.int64)
+    offsets[1:] = np.cumsum(counts.numpy())
+    grouped = rows_t[order].contiguous()
+    centers_t = torch.from_numpy(centers).to(dev)
+    torch.cuda.synchronize()
+    ix = pv.IvfflatIndex(opclass, args.dim, args.lists).load(centers_t, offsets, grouped, order.contiguous())
+    k, B = 10, args.queries
+    ids = torch.empty((B, k), dtype=torch.int64, device=dev)
+    dist = torch.empty((B, k), dtype=torch.float32, device=dev)
+    pv.prof_enable(True)
+    pv.prof_read(pv.PROF_SCAN_ITEMS)
+    ms = timed(pv, torch, stream, lambda: ix.search_into(q_t, k, args.probes, ids, dist), warmup=3, steps=10)
+    scan_ms, scan_n = pv.prof_read(pv.PROF_SCAN_ITEMS)
+    pv.prof_enable(False)
+    cand = ix.last_candidates()
+    hbm, _, _, src = peaks()
+    gbs = cand * rb / (scan_ms / scan_n / 1000.0) / 1e9
+    print(json.dumps({"bench": "ivf", "workload": f"IVFFlat {opclass} {args.rows}x{args.dim}, lists={args.lists}, probes={args.probes}, k={k}, {B} queries per batch "
+                                                  f"(k-means {iters} it; list sizes {int(counts.min())}/{int(counts.float().mean())}/{int(counts.max())})",
+                      "queries_per_s": B / (ms / 1000.0), "ms_per_batch": ms, "candidates_per_query": cand / B,
+                      "roofline": {"bound": "hbm", "kernel": "list scan", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                   "bytes_per_launch": cand * rb, "avg_launch_ms": scan_ms / scan_n, "share_of_step": scan_ms / scan_n / ms, "peak_source": src}}))
+
+
+def bench_kmeans(args):
+    """k-means of config D on one GPU: 50 * lists samples x dim, lists centres (k-means++ seeding + Lloyd iterations)."""
+    import torch
+    import pgvector_b200 as pv
+    pv.init(0)
+    dev = torch.device("cuda", 0)
+    n = 50 * args.k
+    g = torch.Generator(device=dev).manual_seed(5)
+    frame = torch.linalg.qr(torch.randn((args.dim, 16), generator=g, device=dev))[0]
+    rows = torch.randn((n, 16), generator=g, device=dev) @ frame.T + 0.02 * torch.randn((n, args.dim), generator=g, device=dev)
+    torch.cuda.synchronize()
+    t = pv.Table(pv.VECTOR, args.dim).append(rows)
+    pv.synchronize()
+    t0 = time.perf_counter()
+    init = pv.kmeans_pp_init(t, pv.L2, args.k, seed=42)
+    pp_s = time.perf_counter() - t0
+    pv.prof_enable(True)
+    pv.prof_read(pv.PROF_ASSIGN)
+    t0 = time.perf_counter()
+    centers, iters = pv.kmeans(t, pv.L2, init, max_iter=args.iters)
+    km_s = time.perf_counter() - t0
+    assign_ms, assign_n = pv.prof_read(pv.PROF_ASSIGN)
+    pv.prof_enable(False)
+    _, _, bf16_sus, src = peaks()
+    flops = 2.0 * n * args.k * args.dim
+    issued = 3 * flops / (assign_ms / assign_n) / 1e9
+    print(json.dumps({"bench": "kmeans", "workload": f"k-means {n}x{args.dim} fp32 samples, {args.k} centres (config D sample phase on one GPU)",
+                      "kmeanspp_s": pp_s, "kmeans_s": km_s, "iterations": iters, "s_per_iteration": km_s / max(iters, 1),
+                      "assign_ms_per_iteration": assign_ms / assign_n, "rechecked_rows_last": pv.last_assign_rechecked(),
+                      "roofline": {"bound": "tensor", "kernel": "assign step (pack + tcgen05 GEMM + re-check)", "achieved": issued, "peak": bf16_sus,
+                                   "unit": "TFLOP/s", "frac": issued / bf16_sus, "peak_source": src + " bf16_tflops_sustained"}}))
+
+
 def bench_exact(args):
     import torch
     import pgvector_b200 as pv
@@ -177,7 +269,10 @@ def bench_exact(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["assign", "hnsw", "exact"])
+    ap.add_argument("what", choices=["assign", "hnsw", "exact", "ivf", "kmeans"])
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--lists", type=int, default=1000)
+    ap.add_argument("--probes", type=int, default=10)
     ap.add_argument("--rows", type=int, default=None)
     ap.add_argument("--dim", type=int, default=None)
     ap.add_argument("--k", type=int, default=4096)
@@ -193,6 +288,13 @@ if __name__ == "__main__":
         a.rows = a.rows or 100_000
         a.dim = a.dim or (768 if a.elem == "halfvec" else 1024)
         bench_hnsw(a)
+    elif a.what == "kmeans":
+        a.dim = a.dim or 1536
+        bench_kmeans(a)
+    elif a.what == "ivf":
+        a.rows = a.rows or 1_000_000
+        a.dim = a.dim or (1536 if a.elem == "halfvec" else 1024)
+        bench_ivf(a)
     else:
         a.rows = a.rows or 10_000
         a.dim = a.dim or 128
