@@ -86,6 +86,22 @@ struct Acc {
             }
         }
     }
+    // halfvec row vector against 8 query elements kept as packed halves (the fp32 image of a halfvec query
+    // holds exact conversions of halves, so converting back and forth changes nothing)
+    __device__ __forceinline__ void add_h(uint4 r, uint4 qh) {
+        float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), q0 = __half22float2(*reinterpret_cast<const __half2*>(&qh.x));
+        float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&r.y)), q1 = __half22float2(*reinterpret_cast<const __half2*>(&qh.y));
+        float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&r.z)), q2 = __half22float2(*reinterpret_cast<const __half2*>(&qh.z));
+        float2 x3 = __half22float2(*reinterpret_cast<const __half2*>(&r.w)), q3 = __half22float2(*reinterpret_cast<const __half2*>(&qh.w));
+        add_f(x0.x, q0.x);
+        add_f(x0.y, q0.y);
+        add_f(x1.x, q1.x);
+        add_f(x1.y, q1.y);
+        add_f(x2.x, q2.x);
+        add_f(x2.y, q2.y);
+        add_f(x3.x, q3.x);
+        add_f(x3.y, q3.y);
+    }
     template <int LPR>
     __device__ __forceinline__ void reduce() {
 #pragma unroll

@@ -362,7 +362,23 @@ static int exact_topk_impl(vb_table* t, int metric, const void* queries, int64_t
         size_t qstride;
         VB_TRY(upload_queries(T.elem, T.dim, (const uint8_t*)queries + (size_t)q0 * rawq, m, host, WS_QIMG, &qimg, &qstride));
         VB_TRY(workspace(WS_DIST, sizeof(float) * (size_t)m * std::max<int64_t>(n, 1), &d_dist));
-        VB_TRY(launch_scan_regular(T, key_metric(metric), qimg, qstride, m, n, (float*)d_dist, n));
+        // A batch of queries against the whole table is a distance matrix: tile it (table rows read once per 128
+        // queries instead of once per query) when the query image has the table's row layout.  One query at a
+        // time, or a metric with a per-row epilogue, streams the table through the scan kernel instead.
+        const int km = key_metric(metric);
+        const bool tiled = m >= 64 && n >= 128 && n <= 65535LL * 128 && T.elem != VB_HALFVEC && qstride == T.stride && c.scan_impl != 0 &&
+                           (km == VB_L2_SQUARED || km == VB_NEG_IP || km == VB_HAMMING);
+        if (tiled) {
+            Table Q;
+            Q.elem = T.elem;
+            Q.dim = T.dim;
+            Q.stride = qstride;
+            Q.n = m;
+            Q.d = (uint8_t*)qimg;
+            VB_TRY(launch_distance_matrix(Q, km, T, (int)n, (float*)d_dist, n));
+        } else {
+            VB_TRY(launch_scan_regular(T, km, qimg, qstride, m, n, (float*)d_dist, n));
+        }
         VB_TRY(workspace(WS_SEG, (sizeof(int64_t) + sizeof(int32_t)) * (size_t)m + 64, &d_seg));
         int64_t* seg_begin = (int64_t*)d_seg;
         int32_t* seg_len = (int32_t*)(seg_begin + m);

@@ -693,10 +693,11 @@ __global__ void pp_weight_kernel(const float* __restrict__ key, int kmeans_metri
     wd[j] = (double)w;
 }
 
-// first j in [0, n-1) with choice - cumsum(w)[j] <= 0, else n-1 (src/ivfkmeans.c:77-83)
-__global__ void pp_pick_kernel(const double* __restrict__ cum, int64_t n, double u, int64_t* __restrict__ picked) {
+// first j in [0, n-1) with choice - cumsum(w)[j] <= 0, else n-1 (src/ivfkmeans.c:77-83).  The uniform draw and the
+// result stay on the device so a whole seeding run needs no host round trip per centre.
+__global__ void pp_pick_kernel(const double* __restrict__ cum, int64_t n, const double* __restrict__ u, int64_t* __restrict__ picked) {
     if (blockIdx.x || threadIdx.x) return;
-    double choice = cum[n - 1] * u;
+    double choice = cum[n - 1] * u[0];
     int64_t lo = 0, hi = n - 1;  // smallest j with cum[j] >= choice
     while (lo < hi) {
         int64_t mid = (lo + hi) >> 1;
@@ -704,6 +705,14 @@ __global__ void pp_pick_kernel(const double* __restrict__ cum, int64_t n, double
         else lo = mid + 1;
     }
     *picked = lo;
+}
+
+// out[i] = first `bytes` bytes of row picks[i]; one block per picked row
+__global__ void pp_gather_rows_kernel(const uint8_t* __restrict__ X, size_t stride, const int64_t* __restrict__ picks, size_t bytes,
+                                      size_t out_stride, uint8_t* __restrict__ out) {
+    const uint8_t* src = X + (size_t)picks[blockIdx.x] * stride;
+    uint8_t* dst = out + (size_t)blockIdx.x * out_stride;
+    for (size_t b = threadIdx.x; b < bytes; b += blockDim.x) dst[b] = src[b];
 }
 
 static double host_uniform(uint64_t* st) {
@@ -722,38 +731,45 @@ static int kmeans_pp(const Table& X, int kmeans_metric, void* centers_host, int 
     VB_REQUIRE(kmeans_metric == VB_L2 || kmeans_metric == VB_SPHERICAL || kmeans_metric == VB_HAMMING, "bad k-means metric");
     const int km = kmeans_metric == VB_L2 ? VB_L2_SQUARED : kmeans_metric == VB_SPHERICAL ? VB_NEG_IP : VB_HAMMING;
     const size_t raw = raw_row_bytes(X.elem, X.dim);
-    void *d_key, *d_w, *d_wd, *d_cum, *d_pick, *d_tmp, *d_q;
+    void *d_key, *d_w, *d_wd, *d_cum, *d_picks, *d_u, *d_tmp, *d_q, *d_qraw, *d_out;
     VB_TRY(workspace(WSK_DIST, sizeof(float) * (size_t)n, &d_key));
     VB_TRY(workspace(WSK_A, sizeof(float) * (size_t)n, &d_w));
     VB_TRY(workspace(WSK_B, sizeof(double) * (size_t)n, &d_wd));
     VB_TRY(workspace(WSK_C, sizeof(double) * (size_t)n, &d_cum));
-    VB_TRY(workspace(WSK_D, 64, &d_pick));
+    VB_TRY(workspace(WSK_G, sizeof(int64_t) * (size_t)k, &d_picks));
+    VB_TRY(workspace(WSK_F, sizeof(double) * (size_t)k, &d_u));
+    VB_TRY(workspace(WSK_H, X.stride, &d_qraw));
+    VB_TRY(workspace(WSK_I, raw * (size_t)k, &d_out));
     size_t tmp_bytes = 0;
     VB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, (double*)d_wd, (double*)d_cum, (int)n, s));
     VB_TRY(workspace(WSK_E, tmp_bytes, &d_tmp));
-    // FLT_MAX start (src/ivfkmeans.c:39-40)
+    // FLT_MAX start (src/ivfkmeans.c:39-40); every uniform draw is made up front, in the order the rounds consume them
     std::vector<float> w0((size_t)n, 3.402823466e+38f);
-    VB_CUDA(cudaMemcpyAsync(d_w, w0.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s));
-    VB_CUDA(cudaStreamSynchronize(s));
     uint64_t rs = seed ^ 0x5851f42d4c957f2dULL;
-    int64_t cur = (int64_t)(host_uniform(&rs) * (double)n);
-    if (cur >= n) cur = n - 1;
-    uint8_t* out = (uint8_t*)centers_host;
-    for (int i = 0; i < k; ++i) {
-        VB_CUDA(cudaMemcpyAsync(out + (size_t)i * raw, X.d + (size_t)cur * X.stride, raw, cudaMemcpyDeviceToHost, s));
-        if (i + 1 == k) break;
-        // distance of every sample to the new centre: the scan kernel with the centre as the query
+    int64_t first = (int64_t)(host_uniform(&rs) * (double)n);
+    if (first >= n) first = n - 1;
+    std::vector<double> u((size_t)k);
+    for (int i = 0; i + 1 < k; ++i) u[(size_t)i] = host_uniform(&rs);
+    VB_CUDA(cudaMemcpyAsync(d_w, w0.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s));
+    VB_CUDA(cudaMemcpyAsync(d_u, u.data(), sizeof(double) * (size_t)k, cudaMemcpyHostToDevice, s));
+    VB_CUDA(cudaMemcpyAsync(d_picks, &first, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    VB_CUDA(cudaStreamSynchronize(s));  // the host vectors above go out of use here
+    for (int i = 0; i + 1 < k; ++i) {
+        // distance of every sample to the newest centre: the scan kernel with that row as the query
+        pp_gather_rows_kernel<<<1, 256, 0, s>>>(X.d, X.stride, (const int64_t*)d_picks + i, X.stride, X.stride, (uint8_t*)d_qraw);
         size_t qstride;
-        VB_TRY(upload_queries(X.elem, X.dim, X.d + (size_t)cur * X.stride, 1, false, WSK_QIMG, &d_q, &qstride));
+        VB_TRY(upload_queries(X.elem, X.dim, d_qraw, 1, false, WSK_QIMG, &d_q, &qstride));
         VB_TRY(launch_scan_regular(X, km, d_q, qstride, 1, n, (float*)d_key, n));
         pp_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)d_key, kmeans_metric, n, (float*)d_w, (double*)d_wd);
         VB_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, (double*)d_wd, (double*)d_cum, (int)n, s));
-        pp_pick_kernel<<<1, 1, 0, s>>>((const double*)d_cum, n, host_uniform(&rs), (int64_t*)d_pick);
-        count_launch(3);
-        VB_CUDA(cudaMemcpyAsync(&cur, d_pick, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        VB_CUDA(cudaStreamSynchronize(s));
+        pp_pick_kernel<<<1, 1, 0, s>>>((const double*)d_cum, n, (const double*)d_u + i, (int64_t*)d_picks + i + 1);
+        count_launch(4);
     }
+    pp_gather_rows_kernel<<<(unsigned)k, 256, 0, s>>>(X.d, X.stride, (const int64_t*)d_picks, raw, raw, (uint8_t*)d_out);
+    count_launch(1);
+    VB_CUDA(cudaMemcpyAsync(centers_host, d_out, raw * (size_t)k, cudaMemcpyDeviceToHost, s));
     VB_CUDA(cudaStreamSynchronize(s));
+    VB_CUDA(cudaGetLastError());
     return VB_OK;
 }
 

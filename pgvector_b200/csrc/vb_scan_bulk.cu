@@ -140,7 +140,25 @@ __global__ void __launch_bounds__(SB_THREADS, 1) scan_bulk_kernel(ScanArgs a, Bu
             if (q != cur_q) {
                 sb_consumer_barrier();      // everyone is done with the previous query image
                 const uint4* gq = reinterpret_cast<const uint4*>(a.queries + (size_t)q * a.qstride);
-                for (int i = threadIdx.x; i < a.qvec; i += SB_CONSUMERS * 32) sq[i] = gq[i];
+                if (ELEM == VB_HALFVEC) {
+                    // fp32 image -> packed halves (exact: the image came from halves): halves the shared-memory
+                    // traffic of the query operand, which is what bounds the halfvec scan
+                    for (int i = threadIdx.x; i < V; i += SB_CONSUMERS * 32) {
+                        const uint4 lo = gq[2 * i], hi = gq[2 * i + 1];
+                        __half2 h0 = __floats2half2_rn(__uint_as_float(lo.x), __uint_as_float(lo.y));
+                        __half2 h1 = __floats2half2_rn(__uint_as_float(lo.z), __uint_as_float(lo.w));
+                        __half2 h2 = __floats2half2_rn(__uint_as_float(hi.x), __uint_as_float(hi.y));
+                        __half2 h3 = __floats2half2_rn(__uint_as_float(hi.z), __uint_as_float(hi.w));
+                        uint4 pk;
+                        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                        sq[i] = pk;
+                    }
+                } else {
+                    for (int i = threadIdx.x; i < a.qvec; i += SB_CONSUMERS * 32) sq[i] = gq[i];
+                }
                 sb_consumer_barrier();
                 cur_q = q;
             }
@@ -151,14 +169,42 @@ __global__ void __launch_bounds__(SB_THREADS, 1) scan_bulk_kernel(ScanArgs a, Bu
                 const int nr = min(sh.stage_rows, n_rows - r0);
                 sb_mbar_wait(&full_bar[s], ph);
                 const uint8_t* st = stage_base + (size_t)s * sh.stage_bytes;
-                // warp w owns rows w, w + 8, ... of the stage
-                for (int rr = warp; rr < nr; rr += SB_CONSUMERS) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(st + (size_t)rr * a.stride);
-                    Acc<ELEM, METRIC> acc;
+                // warp w owns rows w, w + 8, ... of the stage and takes them two at a time: the query vectors
+                // are read from shared memory once per pair and the two reductions overlap
+                for (int rr = warp; rr < nr; rr += 2 * SB_CONSUMERS) {
+                    const int rr1 = rr + SB_CONSUMERS;
+                    const uint4* rp0 = reinterpret_cast<const uint4*>(st + (size_t)rr * a.stride);
+                    if (rr1 < nr) {
+                        const uint4* rp1 = reinterpret_cast<const uint4*>(st + (size_t)rr1 * a.stride);
+                        Acc<ELEM, METRIC> a0, a1;
+#pragma unroll 2
+                        for (int v = lane; v < V; v += 32) {
+                            const uint4 x0 = rp0[v], x1 = rp1[v];
+                            if (ELEM == VB_HALFVEC) {
+                                const uint4 qh = sq[v];
+                                a0.add_h(x0, qh);
+                                a1.add_h(x1, qh);
+                            } else {
+                                a0.add(x0, sq, v);
+                                a1.add(x1, sq, v);
+                            }
+                        }
+                        a0.template reduce<32>();
+                        a1.template reduce<32>();
+                        if (lane == 0) {
+                            out[r0 + rr] = (OUT)a0.value();
+                            out[r0 + rr1] = (OUT)a1.value();
+                        }
+                    } else {
+                        Acc<ELEM, METRIC> acc;
 #pragma unroll 4
-                    for (int v = lane; v < V; v += 32) acc.add(rp[v], sq, v);
-                    acc.template reduce<32>();
-                    if (lane == 0) out[r0 + rr] = (OUT)acc.value();
+                        for (int v = lane; v < V; v += 32) {
+                            if (ELEM == VB_HALFVEC) acc.add_h(rp0[v], sq[v]);
+                            else acc.add(rp0[v], sq, v);
+                        }
+                        acc.template reduce<32>();
+                        if (lane == 0) out[r0 + rr] = (OUT)acc.value();
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) sb_mbar_arrive(&empty_bar[s]);
