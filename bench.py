@@ -63,7 +63,8 @@ def parse_args():
     ap.add_argument("--no-recall", action="store_true")
     ap.add_argument("--scan-impl", type=int, default=int(os.environ.get("VB_SCAN_IMPL", "2")),
                     help="0 = LDG.128 streaming scan kernel, 1 = cp.async.bulk (TMA) staged scan kernel, "
-                         "2 = library default (bulk for tables larger than L2, LDG for L2-resident ones)")
+                         "2 = library default (list-major batched scan for query batches; per-query: bulk for tables larger "
+                         "than L2, LDG for L2-resident ones), 3 = list-major wherever it applies")
     return ap.parse_args()
 
 
@@ -225,7 +226,7 @@ class ClockSampler:
 def ncu_traffic(args, world):
     """dram__bytes_read + dram__bytes_write of the list-scan kernel from the committed `ncu --set full` capture
     of this same command (profiles/listscan_traffic.json); only valid for the shape it was captured on."""
-    p = os.path.join(ROOT, "profiles", "listscan_traffic.json")
+    p = os.path.join(ROOT, "profiles", "listtile_traffic.json" if args.scan_impl >= 2 else "listscan_traffic.json")
     default_shape = (args.rows, args.dim, args.lists, args.probes, args.batch, args.components, args.latent_dim) == \
                     (1_000_000, 1536, 1000, 10, 2048, 0, 16)
     if world != 1 or args.scan_impl == 0 or not default_shape or not os.path.exists(p):
@@ -461,13 +462,24 @@ def main():
     peak, peak_src = measured_peaks()
     scan_avg_ms = scan_ms / max(scan_n, 1)
     achieved = scan_bytes_per_launch / (scan_avg_ms / 1000.0) / 1e9 if scan_avg_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": ("scan_kernel" if args.scan_impl == 0 else "scan_bulk_kernel") + "<vector,L2^2> (GetScanItems list scan)",
+    kernel_name = {0: "scan_kernel", 1: "scan_bulk_kernel"}.get(args.scan_impl, "list_tile_kernel")
+    roofline = {"bound": "hbm", "kernel": kernel_name + "<vector,L2^2> (GetScanItems list scan)",
                 "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args, world), "bytes_per_launch": scan_bytes_per_launch, "avg_launch_ms": scan_avg_ms,
                 "share_of_step": scan_ms / ms if ms > 0 else None,
                 "other_kernels_ms_per_step": {"centre_scan": lists_ms / max(lists_n, 1), "topk_select": topk_ms / max(topk_n, 1)},
                 "whole_step_algorithmic_gbs": (B * args.lists + cand_all) * args.dim * elem_bytes / (ms / args.steps / 1000.0) / 1e9}
+    if args.scan_impl >= 2:
+        # list-major: every probed list is read from HBM once per batch and reused by all queries that probe it, so
+        # the algorithmic bytes (one row read per distance) are served mostly from shared memory; the
+        # kernel is fp32-issue bound: one FADD2 + one FFMA2 per two (row, query, dimension) terms
+        terms = cand_per_step * args.dim
+        roofline["note"] = ("rows are reused across the queries of a batch: DRAM traffic per launch is at most the table "
+                            "(%.1f GB), so 'achieved' may exceed the HBM peak; the binding unit is the fp32 pipe" %
+                            (args.rows * args.dim * elem_bytes / 1e9 / world))
+        roofline["fp32_terms_per_s"] = terms / (scan_avg_ms / 1000.0) if scan_avg_ms > 0 else 0.0
+        roofline["table_bytes_per_launch_upper_bound"] = args.rows * args.dim * elem_bytes // world
 
     # ---- recall@10 vs exact brute force (GPU exact scan) and CPU baseline
     recall = None
@@ -493,7 +505,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args, how), index_upload_s=upload_s,
-                           l2_policy="inputs larger than L2: every step streams ~%d MB of list rows" % (cand_all * args.dim * 4 // 2**20)),
+                           l2_policy=("inputs larger than L2: every step streams ~%d MB of list rows" % (cand_all * args.dim * 4 // 2**20)) if args.scan_impl < 2 else
+                                     ("inputs larger than L2: every step reads the probed lists of a %d MB table once" % (args.rows * args.dim * 4 // world // 2**20))),
             "recall_at_10": recall, "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": B * args.dim * 4,
                     "d2h_bytes_per_step": B * k * 16, "ms_per_step": ms_h / args.steps},
@@ -511,7 +524,8 @@ def workload_config(args, how):
                          f"x = Q z + 0.02 eps, z ~ N(0, I_{args.latent_dim}), Q random {args.dim}x{args.latent_dim} orthonormal frame, seeds 3/4"),
             "queries": args.queries, "batch": args.batch,
             "index_build": how, "scan_kernel": {0: "LDG.128 streaming (all scans)", 1: "cp.async.bulk+mbarrier staged (all scans)",
-                            2: "list scan: cp.async.bulk+mbarrier staged; centre scan: LDG.128 (L2-resident table)"}[args.scan_impl],
+                            2: "list scan: list-major 256x32 fp32x2 register tiles (rows read once per batch); centre scan: 128x128 fp32 tiles",
+                            3: "list scan: list-major 256x32 fp32x2 register tiles; centre scan: 128x128 fp32 tiles"}[args.scan_impl],
             "parallelism": "lists sharded l % N, one NCCL all-gather of k results per rank"}
 
 

@@ -143,6 +143,19 @@ int launch_assign(const Table& X, int metric, const Table& Cn, int k, int32_t* o
 int launch_distance_matrix(const Table& X, int metric, const Table& Cn, int k, float* out, int64_t ld);
 void set_tc_enabled(bool on);
 
+// list-major batched list scan (vb_list_tile.cu): the (query, probe) pairs of a batch grouped by list, one CTA
+// per static row tile of the index against every query probing that list
+struct ListTile {
+    int64_t row_begin;   // first row of the tile in the list-ordered table
+    int32_t list;
+    int32_t n_rows;      // <= list_tile_rows()
+};
+int list_tile_rows();
+bool list_major_supported(int elem, int key_metric);
+int launch_list_major(const Table& rows, int key_metric, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists,
+                      int probes, const int32_t* cand_off, int64_t cap, const int64_t* d_list_off, int n_lists,
+                      const ListTile* d_tiles, int n_tiles, float* out);
+
 }  // namespace vb
 
 // opaque handle types of the C ABI

@@ -52,6 +52,8 @@ struct Ivf {
     std::vector<int64_t> sorted_len;  // list lengths, descending (bounds candidates per query)
     int64_t last_bytes = 0, last_cand = 0;
     int64_t* d_cand_sum = nullptr;    // device accumulator of candidates scanned
+    ListTile* d_tiles = nullptr;      // static row tiles of the lists (list-major batched scan)
+    int n_tiles = 0;
     bool loaded = false;
 };
 
@@ -215,7 +217,17 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
     count_launch();
     VB_TRY(workspace(WS_DIST, sizeof(float) * (size_t)nq * cap, &d_dist));
     prof_begin(VB_PROF_SCAN_ITEMS);
-    VB_TRY(launch_scan_chunks(ix.rows, key_metric(ix.metric), qimg, qstride, chunks, n_chunks, (int)max_chunks, (float*)d_dist));
+    // scan_impl: 0 = per-query LDG scan, 1 = per-query bulk-copy scan, 2 = automatic, 3 = list-major wherever it applies.
+    // Automatic: once a batch carries enough (query, probe) pairs to fill the GPU with row tiles, group them by list
+    // so each probed list is read once per batch instead of once per query.
+    const bool list_major = list_major_supported(ix.elem, key_metric(ix.metric)) && ix.n_tiles > 0 &&
+                            (c.scan_impl == 3 || (c.scan_impl == 2 && nq * probes >= 256));
+    if (list_major) {
+        VB_TRY(launch_list_major(ix.rows, key_metric(ix.metric), qimg, qstride, nq, d_lists, probes, cand_off, cap, ix.d_list_off,
+                                 ix.lists, ix.d_tiles, ix.n_tiles, (float*)d_dist));
+    } else {
+        VB_TRY(launch_scan_chunks(ix.rows, key_metric(ix.metric), qimg, qstride, chunks, n_chunks, (int)max_chunks, (float*)d_dist));
+    }
     prof_end(VB_PROF_SCAN_ITEMS);
     VB_TRY(workspace(WS_POS, (sizeof(int32_t) + sizeof(float)) * (size_t)nq * k, &d_pos));
     int32_t* pos = (int32_t*)d_pos;
@@ -461,6 +473,20 @@ static int ivf_set_offsets(Ivf& ix, const int64_t* list_offsets) {
     std::sort(ix.sorted_len.begin(), ix.sorted_len.end(), std::greater<int64_t>());
     if (!ix.d_list_off) VB_CUDA(cudaMalloc(&ix.d_list_off, sizeof(int64_t) * ((size_t)ix.lists + 1)));
     VB_CUDA(cudaMemcpy(ix.d_list_off, ix.h_list_off.data(), sizeof(int64_t) * ((size_t)ix.lists + 1), cudaMemcpyHostToDevice));
+    // row tiles of the list-major scan: fixed by the list boundaries, so built once per load
+    std::vector<ListTile> tiles;
+    const int tr = list_tile_rows();
+    for (int l = 0; l < ix.lists; ++l) {
+        const int64_t lo = ix.h_list_off[(size_t)l], hi = ix.h_list_off[(size_t)l + 1];
+        for (int64_t r = lo; r < hi; r += tr) tiles.push_back(ListTile{r, l, (int32_t)std::min<int64_t>(tr, hi - r)});
+    }
+    if (ix.d_tiles) cudaFree(ix.d_tiles);
+    ix.d_tiles = nullptr;
+    ix.n_tiles = (int)tiles.size();
+    if (ix.n_tiles) {
+        VB_CUDA(cudaMalloc(&ix.d_tiles, sizeof(ListTile) * tiles.size()));
+        VB_CUDA(cudaMemcpy(ix.d_tiles, tiles.data(), sizeof(ListTile) * tiles.size(), cudaMemcpyHostToDevice));
+    }
     return VB_OK;
 }
 
@@ -515,6 +541,7 @@ int vb_ivf_free(vb_ivf* h) {
     if (h->ix.d_ids) cudaFree(h->ix.d_ids);
     if (h->ix.d_list_off) cudaFree(h->ix.d_list_off);
     if (h->ix.d_cand_sum) cudaFree(h->ix.d_cand_sum);
+    if (h->ix.d_tiles) cudaFree(h->ix.d_tiles);
     delete h;
     return VB_OK;
 }

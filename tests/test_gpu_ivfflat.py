@@ -145,6 +145,41 @@ def test_other_opclasses(pv, opclass, dim):
         assert (ids == wi).mean() > 0.99
 
 
+@pytest.mark.parametrize("opclass,dim", [("vector_l2_ops", 3), ("vector_l2_ops", 96), ("vector_ip_ops", 40), ("vector_cosine_ops", 50),
+                                         ("halfvec_l2_ops", 72), ("halfvec_ip_ops", 130), ("halfvec_cosine_ops", 768)])
+def test_list_major_scan_equals_per_query_scan(pv, opclass, dim):
+    """The batched (list-major) scan writes the same candidate runs as the per-query scans: several row tiles per
+    list (one of them partial), query groups larger than one 32-query sub-tile, dimensions that end inside a
+    16-element staging step."""
+    elem, metric, normalize, _ = pv.OPCLASSES[opclass]
+    lists = 12
+    x, c = mixture(9000, dim, lists, seed=21)
+    q, _ = mixture(300, dim, lists, seed=22)
+    if elem == O.HALFVEC:
+        x, c, q = f32_to_half_bits(x), f32_to_half_bits(c), f32_to_half_bits(q)
+    if normalize or metric == O.NEG_IP:
+        x, c, q = O.l2_normalize(elem, x), O.l2_normalize(elem, c), O.l2_normalize(elem, q)
+    gix, oix = make_index(pv, opclass, x, c, dim=dim)
+    got = {}
+    try:
+        for impl in (0, 1, 3):
+            pv.set_option("scan_impl", impl)
+            got[impl] = gix.search(q, k=10, probes=5)
+            got[impl, 1] = gix.search(q[:3], k=7, probes=12)      # tiny batch, every list probed
+    finally:
+        import os
+        pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
+    wi, wd = oix.search_batch(q, 5, 10, threads=8)
+    for impl in (0, 1, 3):
+        ids, dist = got[impl]
+        assert np.allclose(dist, wd, rtol=RTOL, atol=1e-6), impl
+        assert (ids == wi).mean() > 0.99, impl
+    assert np.allclose(got[3][1], got[1][1], rtol=RTOL, atol=1e-6)
+    assert (got[3][0] == got[1][0]).mean() > 0.995
+    assert np.allclose(got[3, 1][1], got[0, 1][1], rtol=RTOL, atol=1e-6)
+    assert (got[3, 1][0] == got[0, 1][0]).mean() > 0.99
+
+
 def test_tie_modes_agree_on_recall(pv):
     """Hamming centre distances tie constantly: the reference's pairing-heap order and the GPU's
     (distance, list) order may probe different lists among equals, never worse ones"""
