@@ -11,12 +11,13 @@
 // per-query candidate run as the streaming scan writes them, so everything downstream (top-k by
 // (distance, position), heap-id lookup) is unchanged.
 //
-// Tile: 256 rows x 32 queries per CTA, 8 warps.  Warp w owns queries 4w..4w+3 (a warp whose
-// queries are all past the group's end skips the arithmetic), lane l owns rows 4l..4l+3 and
-// 128+4l..128+4l+3.  Operands are staged through shared memory in steps of 16 dimensions,
-// k-major, double buffered with register prefetch; the query operand is stored duplicated
-// ((q, q), negated for L2) so the inner loop is packed fp32x2: one FADD2 + one FFMA2 per two
-// (row, query) pairs.  fp32x2 results are IEEE-identical to the scalar instructions.
+// Tile: 256 rows x 32 queries per CTA, 8 warps.  Warp w owns rows 32w..32w+31 (one row per lane) against
+// all queries of the sub-tile; the query loop is compiled for every count of query quads 1..8, so a group
+// of 20 queries costs 20/32 of a full tile and every warp with rows stays busy.  Operands are staged
+// through shared memory in steps of 16 dimensions, k-major, double buffered with register prefetch; the
+// inner loop is packed fp32x2 over two queries: (x, x) + (-q0, -q1) with one FADD2, squared and accumulated
+// with one FFMA2.  fp32x2 results are IEEE-identical to the scalar instructions, and each (row, query)
+// distance is the plain sequential fmaf chain over the dimensions.
 //
 // Bound: fp32 issue (2 packed instructions per 2 pairs for L2, 1 for inner product); HBM traffic is
 // one pass over the probed lists per batch.
@@ -30,7 +31,7 @@ constexpr int LT_ROWS = 256;
 constexpr int LT_Q = 32;
 constexpr int LT_KS = 16;                 // dimensions per staging step
 constexpr int LT_THREADS = 256;
-constexpr int LT_XP = LT_ROWS + 4;        // padded line of one dimension across the row tile (words)
+constexpr int LT_XP = LT_ROWS + 2;        // line of one dimension across the row tile; +2 words makes the transposing stores conflict-free
 
 struct LtArgs {
     const uint8_t* rows;
@@ -83,6 +84,30 @@ __device__ __forceinline__ float4 lt_load4(const uint8_t* row, int e, int words)
     return v;
 }
 
+// one staging step (16 dimensions) of one row against the first 4 * NQ4 queries of the sub-tile
+template <int KIND, int NQ4>
+__device__ __forceinline__ void lt_step(const float (*__restrict__ xs)[LT_XP], const float (*__restrict__ qs)[LT_Q], int row,
+                                        unsigned long long (&acc)[LT_Q / 2]) {
+#pragma unroll
+    for (int kk = 0; kk < LT_KS; ++kk) {
+        const float x = xs[kk][row];
+        const unsigned long long xx = lt_pack(x, x);
+#pragma unroll
+        for (int jq = 0; jq < NQ4; ++jq) {
+            const ulonglong2 qv = *reinterpret_cast<const ulonglong2*>(&qs[kk][4 * jq]);
+            if (KIND == 0) {
+                const unsigned long long d0 = lt_add2(xx, qv.x);   // x + (-q)
+                const unsigned long long d1 = lt_add2(xx, qv.y);
+                acc[2 * jq] = lt_fma2(d0, d0, acc[2 * jq]);
+                acc[2 * jq + 1] = lt_fma2(d1, d1, acc[2 * jq + 1]);
+            } else {
+                acc[2 * jq] = lt_fma2(xx, qv.x, acc[2 * jq]);
+                acc[2 * jq + 1] = lt_fma2(xx, qv.y, acc[2 * jq + 1]);
+            }
+        }
+    }
+}
+
 // KIND 0: sum (x - q)^2      KIND 1: -sum x * q
 template <int ELEM, int KIND>
 __global__ void __launch_bounds__(LT_THREADS, 2) list_tile_kernel(LtArgs a) {
@@ -91,7 +116,7 @@ __global__ void __launch_bounds__(LT_THREADS, 2) list_tile_kernel(LtArgs a) {
     if (cnt == 0) return;   // list not probed by this batch
 
     __shared__ __align__(16) float Xs[2][LT_KS][LT_XP];
-    __shared__ __align__(16) float2 Qs[2][LT_KS][LT_Q];
+    __shared__ __align__(16) float Qs[2][LT_KS][LT_Q];   // negated for L2
     __shared__ int32_t s_q[LT_Q];
     __shared__ int64_t s_out[LT_Q];
 
@@ -100,6 +125,8 @@ __global__ void __launch_bounds__(LT_THREADS, 2) list_tile_kernel(LtArgs a) {
     const int64_t row_in_list0 = t.row_begin - a.list_off[t.list];
     const int words = a.words;
     const int nsteps = (words + LT_KS - 1) / LT_KS;
+    const int my_row = warp * 32 + lane;
+    const bool has_rows = warp * 32 < t.n_rows;   // warp-uniform
 
     // staging roles: 4 threads per row (one 4-element piece each), 64 rows per pass, 4 passes
     const int sp = tid % 4;
@@ -112,6 +139,7 @@ __global__ void __launch_bounds__(LT_THREADS, 2) list_tile_kernel(LtArgs a) {
 
     for (int q0 = 0; q0 < cnt; q0 += LT_Q) {
         const int nqt = min(LT_Q, cnt - q0);
+        const int nq4 = (nqt + 3) / 4;
         __syncthreads();   // the previous query sub-tile is done with s_q / s_out and both buffers
         if (tid < LT_Q) {
             const int s = gb + q0 + min(tid, nqt - 1);
@@ -119,14 +147,11 @@ __global__ void __launch_bounds__(LT_THREADS, 2) list_tile_kernel(LtArgs a) {
             s_out[tid] = a.pair_out[s];
         }
         __syncthreads();
-        const bool active = warp * 4 < nqt;
         const float* qrow = reinterpret_cast<const float*>(a.qimg + (size_t)s_q[(tid / 4) % LT_Q] * a.qstride);
 
-        unsigned long long acc[4][4];
+        unsigned long long acc[LT_Q / 2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+        for (int j = 0; j < LT_Q / 2; ++j) acc[j] = 0ull;
 
         float4 xr[4], qr;
         auto fetch = [&](int ks) {
@@ -148,10 +173,10 @@ __global__ void __launch_bounds__(LT_THREADS, 2) list_tile_kernel(LtArgs a) {
             if (tid < 4 * LT_Q) {
                 const int qi = tid / 4;
                 const float s = KIND == 0 ? -1.f : 1.f;
-                Qs[buf][4 * sp + 0][qi] = make_float2(s * qr.x, s * qr.x);
-                Qs[buf][4 * sp + 1][qi] = make_float2(s * qr.y, s * qr.y);
-                Qs[buf][4 * sp + 2][qi] = make_float2(s * qr.z, s * qr.z);
-                Qs[buf][4 * sp + 3][qi] = make_float2(s * qr.w, s * qr.w);
+                Qs[buf][4 * sp + 0][qi] = s * qr.x;
+                Qs[buf][4 * sp + 1][qi] = s * qr.y;
+                Qs[buf][4 * sp + 2][qi] = s * qr.z;
+                Qs[buf][4 * sp + 3][qi] = s * qr.w;
             }
         };
 
@@ -161,50 +186,35 @@ __global__ void __launch_bounds__(LT_THREADS, 2) list_tile_kernel(LtArgs a) {
         for (int ks = 0; ks < nsteps; ++ks) {
             const int buf = ks & 1;
             if (ks + 1 < nsteps) fetch(ks + 1);
-            if (active) {
-#pragma unroll
-                for (int kk = 0; kk < LT_KS; ++kk) {
-                    const ulonglong2 xa = *reinterpret_cast<const ulonglong2*>(&Xs[buf][kk][lane * 4]);
-                    const ulonglong2 xb = *reinterpret_cast<const ulonglong2*>(&Xs[buf][kk][128 + lane * 4]);
-                    const ulonglong2 qa = *reinterpret_cast<const ulonglong2*>(&Qs[buf][kk][warp * 4]);
-                    const ulonglong2 qb = *reinterpret_cast<const ulonglong2*>(&Qs[buf][kk][warp * 4 + 2]);
-                    const unsigned long long x[4] = {xa.x, xa.y, xb.x, xb.y};
-                    const unsigned long long q[4] = {qa.x, qa.y, qb.x, qb.y};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (KIND == 0) {
-                                const unsigned long long d = lt_add2(x[i], q[j]);   // x + (-q)
-                                acc[i][j] = lt_fma2(d, d, acc[i][j]);
-                            } else {
-                                acc[i][j] = lt_fma2(x[i], q[j], acc[i][j]);
-                            }
-                        }
+            if (has_rows) {
+                switch (nq4) {   // block-uniform
+                    case 1: lt_step<KIND, 1>(Xs[buf], Qs[buf], my_row, acc); break;
+                    case 2: lt_step<KIND, 2>(Xs[buf], Qs[buf], my_row, acc); break;
+                    case 3: lt_step<KIND, 3>(Xs[buf], Qs[buf], my_row, acc); break;
+                    case 4: lt_step<KIND, 4>(Xs[buf], Qs[buf], my_row, acc); break;
+                    case 5: lt_step<KIND, 5>(Xs[buf], Qs[buf], my_row, acc); break;
+                    case 6: lt_step<KIND, 6>(Xs[buf], Qs[buf], my_row, acc); break;
+                    case 7: lt_step<KIND, 7>(Xs[buf], Qs[buf], my_row, acc); break;
+                    default: lt_step<KIND, 8>(Xs[buf], Qs[buf], my_row, acc); break;
                 }
             }
             if (ks + 1 < nsteps) stage(buf ^ 1);
             __syncthreads();
         }
 
-        if (active) {
+        if (my_row < t.n_rows) {
+            // lanes = consecutive rows: one coalesced 128-byte store per (warp, query)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int qi = warp * 4 + j;
-                if (qi >= nqt) break;
-                float* o = a.out + s_out[qi] + row_in_list0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float lo, hi;
-                    lt_unpack(acc[i][j], lo, hi);
-                    if (KIND == 1) {
-                        lo = -lo;
-                        hi = -hi;
-                    }
-                    const int r = (i >> 1) * 128 + lane * 4 + (i & 1) * 2;
-                    if (r < t.n_rows) o[r] = lo;
-                    if (r + 1 < t.n_rows) o[r + 1] = hi;
+            for (int j = 0; j < LT_Q / 2; ++j) {
+                if (2 * j >= nqt) break;
+                float lo, hi;
+                lt_unpack(acc[j], lo, hi);
+                if (KIND == 1) {
+                    lo = -lo;
+                    hi = -hi;
                 }
+                a.out[s_out[2 * j] + row_in_list0 + my_row] = lo;
+                if (2 * j + 1 < nqt) a.out[s_out[2 * j + 1] + row_in_list0 + my_row] = hi;
             }
         }
     }

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 import oracle as O
-from tests.util import build_ivf_arrays, f32_to_half_bits, load_golden, mixture, parse_vector, recall_at_k
+from tests.util import assert_same_neighbours, build_ivf_arrays, f32_to_half_bits, load_golden, mixture, parse_vector, recall_at_k
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-5
@@ -87,7 +87,9 @@ def test_search_matches_oracle(l2_index, probes, k):
     finite = np.isfinite(wd)
     assert np.array_equal(np.isfinite(dist), finite)
     assert np.allclose(dist[finite], wd[finite], rtol=RTOL)
-    assert (ids == wi).mean() > 0.998
+    # ranks may swap only between candidates whose distances agree to rounding (k = 3000 of ~4700 candidates
+    # has neighbouring gaps of 1e-4 relative; fp32 summation order moves a distance by ~1e-6)
+    assert_same_neighbours(ids, dist, wi, wd, RTOL, min_positional=0.998 if k <= 100 else 0.99)
     assert np.array_equal(ids < 0, wi < 0)
     # recall is identical to the oracle's at the same probes (north_star)
     kk = min(k, 10)

@@ -60,3 +60,20 @@ def build_ivf_arrays(rows, assign, lists):
     offsets = np.zeros(lists + 1, dtype=np.int64)
     offsets[1:] = np.cumsum(counts)
     return np.ascontiguousarray(rows[order]), order.astype(np.int64), offsets
+
+
+def assert_same_neighbours(ids, dist, want_ids, want_dist, rtol, min_positional=0.99, boundary=2):
+    """Result lists agree up to floating-point near-ties: every id the two sides share carries the same distance
+    within `rtol`, ids found by one side only are confined to the cut at rank k (at most `boundary` per query),
+    and the positional agreement stays above `min_positional`."""
+    ids, want_ids = np.asarray(ids), np.asarray(want_ids)
+    dist, want_dist = np.asarray(dist, dtype=np.float64), np.asarray(want_dist, dtype=np.float64)
+    assert ids.shape == want_ids.shape
+    assert (ids == want_ids).mean() > min_positional, (ids == want_ids).mean()
+    for i in np.nonzero((ids != want_ids).any(axis=1))[0]:
+        a = {int(t): d for t, d in zip(ids[i], dist[i]) if t >= 0}
+        b = {int(t): d for t, d in zip(want_ids[i], want_dist[i]) if t >= 0}
+        only = set(a) ^ set(b)
+        assert len(only) <= 2 * boundary, (i, len(only))
+        for t in set(a) & set(b):
+            assert abs(a[t] - b[t]) <= rtol * max(abs(b[t]), 1e-30) + 1e-12, (i, t, a[t], b[t])

@@ -224,6 +224,10 @@ def bench_kmeans(args):
     torch.cuda.synchronize()
     t = pv.Table(pv.VECTOR, args.dim).append(rows)
     pv.synchronize()
+    # one untimed pass of each entry point first: workspace growth, pinned staging and lazy module loading are
+    # one-time costs of the process, not of a build
+    pv.kmeans(t, pv.L2, pv.kmeans_pp_init(t, pv.L2, min(args.k, 64), seed=1), max_iter=1)
+    pv.kmeans(t, pv.L2, rows[:args.k].cpu().numpy(), max_iter=1)
     t0 = time.perf_counter()
     init = pv.kmeans_pp_init(t, pv.L2, args.k, seed=42)
     pp_s = time.perf_counter() - t0
