@@ -64,7 +64,8 @@ def parse_args():
     ap.add_argument("--scan-impl", type=int, default=int(os.environ.get("VB_SCAN_IMPL", "2")),
                     help="0 = LDG.128 streaming scan kernel, 1 = cp.async.bulk (TMA) staged scan kernel, "
                          "2 = library default (list-major batched scan for query batches; per-query: bulk for tables larger "
-                         "than L2, LDG for L2-resident ones), 3 = list-major wherever it applies")
+                         "than L2, LDG for L2-resident ones), 3 = list-major wherever it applies, "
+                         "4 = tensor-core filter + exact re-score wherever it applies")
     return ap.parse_args()
 
 
@@ -226,7 +227,7 @@ class ClockSampler:
 def ncu_traffic(args, world):
     """dram__bytes_read + dram__bytes_write of the list-scan kernel from the committed `ncu --set full` capture
     of this same command (profiles/listscan_traffic.json); only valid for the shape it was captured on."""
-    p = os.path.join(ROOT, "profiles", "listtile_traffic.json" if args.scan_impl >= 2 else "listscan_traffic.json")
+    p = os.path.join(ROOT, "profiles", {0: "listscan_traffic.json", 1: "listscan_traffic.json", 4: "listtc_traffic.json"}.get(args.scan_impl, "listtile_traffic.json"))
     default_shape = (args.rows, args.dim, args.lists, args.probes, args.batch, args.components, args.latent_dim) == \
                     (1_000_000, 1536, 1000, 10, 2048, 0, 16)
     if world != 1 or args.scan_impl == 0 or not default_shape or not os.path.exists(p):
@@ -462,7 +463,7 @@ def main():
     peak, peak_src = measured_peaks()
     scan_avg_ms = scan_ms / max(scan_n, 1)
     achieved = scan_bytes_per_launch / (scan_avg_ms / 1000.0) / 1e9 if scan_avg_ms > 0 else 0.0
-    kernel_name = {0: "scan_kernel", 1: "scan_bulk_kernel"}.get(args.scan_impl, "list_tile_kernel")
+    kernel_name = {0: "scan_kernel", 1: "scan_bulk_kernel", 4: "list_tc_kernel"}.get(args.scan_impl, "list_tile_kernel")
     roofline = {"bound": "hbm", "kernel": kernel_name + "<vector,L2^2> (GetScanItems list scan)",
                 "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
@@ -470,6 +471,8 @@ def main():
                 "share_of_step": scan_ms / ms if ms > 0 else None,
                 "other_kernels_ms_per_step": {"centre_scan": lists_ms / max(lists_n, 1), "topk_select": topk_ms / max(topk_n, 1)},
                 "whole_step_algorithmic_gbs": (B * args.lists + cand_all) * args.dim * elem_bytes / (ms / args.steps / 1000.0) / 1e9}
+    if args.scan_impl == 4:
+        roofline["certificate_fallback_queries"] = ix.tc_fallbacks()
     if args.scan_impl >= 2:
         # list-major: every probed list is read from HBM once per batch and reused by all queries that probe it, so
         # the algorithmic bytes (one row read per distance) are served mostly from shared memory; the
@@ -525,7 +528,9 @@ def workload_config(args, how):
             "queries": args.queries, "batch": args.batch,
             "index_build": how, "scan_kernel": {0: "LDG.128 streaming (all scans)", 1: "cp.async.bulk+mbarrier staged (all scans)",
                             2: "list scan: list-major 256x32 fp32x2 register tiles (rows read once per batch); centre scan: 128x128 fp32 tiles",
-                            3: "list scan: list-major 256x32 fp32x2 register tiles; centre scan: 128x128 fp32 tiles"}[args.scan_impl],
+                            3: "list scan: list-major 256x32 fp32x2 register tiles; centre scan: 128x128 fp32 tiles",
+                            4: "list scan: tcgen05 split-bf16 filter (128x64 UMMA tiles, rows read once per batch as packed planes) + exact fp32 "
+                               "re-score of k'=32 candidates + certificate; centre scan: 128x128 fp32 tiles"}[args.scan_impl],
             "parallelism": "lists sharded l % N, one NCCL all-gather of k results per rank"}
 
 

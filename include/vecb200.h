@@ -189,6 +189,9 @@ int			vb_ivf_search_dev(vb_ivf *ix, const void *queries_dev, int64_t nq, int pro
 /* algorithmic bytes of the last vb_ivf_search*: sum over queries of (lists + candidates) * dim * elem size */
 int64_t		vb_ivf_last_scan_bytes(const vb_ivf *ix);
 int64_t		vb_ivf_last_candidates(const vb_ivf *ix);
+/* Queries (cumulative) whose tensor-core filter result could not be certified against the error bound and were
+ * re-run on the exact fp32 kernel (option "scan_impl" = 4); 0 when that path is not in use. */
+int64_t		vb_ivf_tc_fallbacks(const vb_ivf *ix);
 
 /* ------------------------------------------------------- IVFFlat build path */
 
@@ -230,8 +233,12 @@ int			vb_assign_dev(vb_table *rows, int metric, const void *centers_dev, int k, 
 int			vb_set_tensor_cores(int on);
 int64_t		vb_last_assign_rechecked(void);
 /*
- * Tuning switches: "scan_impl" 0 = LDG.128 streaming kernel, 1 = cp.async.bulk (TMA) + mbarrier
- * staged kernel for rows of at least 512 bytes; "tensor_cores" as vb_set_tensor_cores.
+ * Tuning switches.  "scan_impl" selects the list / table scan: 0 = per-query LDG.128 streaming kernel,
+ * 1 = per-query cp.async.bulk (TMA) + mbarrier staged kernel for rows of at least 512 bytes, 2 (default) =
+ * automatic (query batches are scanned list-major: each probed list read once per batch, fp32x2 register
+ * tiles; single queries stream), 3 = list-major wherever it applies, 4 = tensor-core filter (split-bf16
+ * tcgen05 distances, exact fp32 re-score of k' candidates, certificate, exact fallback) wherever it applies.
+ * Every setting returns the same neighbours.  "tensor_cores" as vb_set_tensor_cores.
  */
 int			vb_set_option(const char *name, int64_t value);
 

@@ -302,6 +302,10 @@ class IvfflatIndex:
     def last_candidates(self):
         return int(load().vb_ivf_last_candidates(self.h))
 
+    def tc_fallbacks(self):
+        """queries re-run exactly because the tensor-core filter could not certify them (scan_impl = 4)"""
+        return int(load().vb_ivf_tc_fallbacks(self.h))
+
     def free(self):
         if self.h:
             load().vb_ivf_free(self.h)

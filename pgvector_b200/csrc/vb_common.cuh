@@ -150,6 +150,44 @@ struct ListTile {
     int32_t list;
     int32_t n_rows;      // <= list_tile_rows()
 };
+// (query, probe) pairs of a batch grouped by list: slots [begin[l], begin[l] + cnt[l]) belong to list l
+struct QueryGroups {
+    int32_t* cnt;        // [lists]
+    int32_t* begin;      // [lists]
+    int32_t* gt_begin;   // [lists] first query tile of each list (only when built with gt_rows > 0)
+    int32_t* pair_q;     // [pairs] query number
+    int32_t* pair_list;  // [pairs] list number
+    int64_t* pair_out;   // [pairs] offset of the pair's candidate run in the distance buffer
+    int64_t n_pairs;
+};
+int build_query_groups(const int32_t* d_lists, int64_t nq, int probes, const int32_t* cand_off, int64_t cap, int n_lists, int gt_rows,
+                       QueryGroups* g);
+// tensor-core filter of the batched list scan (vb_list_tc.cu)
+struct ListUnit {
+    int32_t list;
+    int32_t tile;        // 128-row tile of the list-ordered table that intersects the list
+};
+struct ListTcImage {
+    uint8_t* planes = nullptr;   // bf16 hi/lo planes of the whole table, swizzled smem image per (tile, 64-dim block)
+    float* xn = nullptr;         // |row|^2
+    ListUnit* units = nullptr;
+    int n_units = 0;
+    int n_kblocks = 0;
+    int64_t n_tiles = 0;
+    float xmax = 0.f;            // max |row|
+    bool finite = true;          // false when a row norm is Inf / NaN (no error bound -> exact path only)
+};
+bool list_tc_supported(int elem, int key_metric, int k);
+int list_tc_kp(int k);
+int list_tc_prepare(const Table& rows, ListTcImage* im);
+void list_tc_release(ListTcImage* im);
+int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
+                   const int32_t* d_lists, int probes, const int32_t* cand_off, int64_t cap, const int64_t* d_list_off, int n_lists,
+                   float* out, const float** qn_out);
+int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
+                          int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
+                          const int32_t* seg_len, const float* qn, const int32_t* pos_kp, const float* approx_kp, int32_t* out_pos,
+                          float* out_key, int* n_failed_host);
 int list_tile_rows();
 bool list_major_supported(int elem, int key_metric);
 int launch_list_major(const Table& rows, int key_metric, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists,

@@ -54,6 +54,8 @@ struct Ivf {
     int64_t* d_cand_sum = nullptr;    // device accumulator of candidates scanned
     ListTile* d_tiles = nullptr;      // static row tiles of the lists (list-major batched scan)
     int n_tiles = 0;
+    ListTcImage tc;                   // packed bf16 planes + norms + (list, tile) units, built on first tensor-core scan
+    int64_t last_tc_failed = 0, total_tc_failed = 0;
     bool loaded = false;
 };
 
@@ -189,6 +191,25 @@ static int ivf_select_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t 
     return VB_OK;
 }
 
+// packed planes, row norms and the (list, table tile) work units of the tensor-core scan; built lazily because the
+// planes double the index footprint and only batched searches use them
+static int ivf_ensure_tc_image(Ivf& ix) {
+    if (ix.tc.planes) return VB_OK;
+    VB_TRY(list_tc_prepare(ix.rows, &ix.tc));
+    std::vector<ListUnit> units;
+    for (int l = 0; l < ix.lists; ++l) {
+        const int64_t lo = ix.h_list_off[(size_t)l], hi = ix.h_list_off[(size_t)l + 1];
+        if (hi <= lo) continue;
+        for (int64_t t = lo / 128; t <= (hi - 1) / 128; ++t) units.push_back(ListUnit{l, (int32_t)t});
+    }
+    ix.tc.n_units = (int)units.size();
+    if (!units.empty()) {
+        VB_CUDA(cudaMalloc(&ix.tc.units, sizeof(ListUnit) * units.size()));
+        VB_CUDA(cudaMemcpy(ix.tc.units, units.data(), sizeof(ListUnit) * units.size(), cudaMemcpyHostToDevice));
+    }
+    return VB_OK;
+}
+
 // scan the given probe lists for a batch of queries and keep the k nearest per query
 static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists, int probes, int k,
                          int64_t* out_ids_dev, float* out_f_dev, double* out_d_dev, int32_t** cand_total_dev) {
@@ -217,16 +238,54 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
     count_launch();
     VB_TRY(workspace(WS_DIST, sizeof(float) * (size_t)nq * cap, &d_dist));
     prof_begin(VB_PROF_SCAN_ITEMS);
-    // scan_impl: 0 = per-query LDG scan, 1 = per-query bulk-copy scan, 2 = automatic, 3 = list-major wherever it applies.
+    // scan_impl: 0 = per-query LDG scan, 1 = per-query bulk-copy scan, 2 = automatic, 3 = list-major fp32 wherever it
+    // applies, 4 = tensor-core filter + exact re-score wherever it applies.
     // Automatic: once a batch carries enough (query, probe) pairs to fill the GPU with row tiles, group them by list
     // so each probed list is read once per batch instead of once per query.
-    const bool list_major = list_major_supported(ix.elem, key_metric(ix.metric)) && ix.n_tiles > 0 &&
-                            (c.scan_impl == 3 || (c.scan_impl == 2 && nq * probes >= 256));
+    const int km = key_metric(ix.metric);
+    const bool batched = nq * probes >= 256;
+    bool tc = c.scan_impl == 4 && batched && list_tc_supported(ix.elem, km, k) && ix.rows.n > 0;
+    if (tc) {
+        VB_TRY(ivf_ensure_tc_image(ix));
+        tc = ix.tc.finite;   // rows with Inf / NaN norms have no error bound: exact path
+    }
+    if (tc) {
+        const int kp = list_tc_kp(k);
+        const float* qn = nullptr;
+        VB_TRY(launch_list_tc(ix.rows, ix.tc, km, qimg, qstride, nq, d_lists, probes, cand_off, cap, ix.d_list_off, ix.lists,
+                              (float*)d_dist, &qn));
+        prof_end(VB_PROF_SCAN_ITEMS);
+        VB_TRY(workspace(WS_POS, (sizeof(int32_t) + sizeof(float)) * (size_t)nq * (k + kp), &d_pos));
+        int32_t* pos = (int32_t*)d_pos;
+        float* key = (float*)(pos + (size_t)nq * k);
+        int32_t* pos_kp = (int32_t*)(key + (size_t)nq * k);
+        float* key_kp = (float*)(pos_kp + (size_t)nq * kp);
+        prof_begin(VB_PROF_TOPK);
+        VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, nullptr, nullptr, nq, kp, pos_kp, key_kp));
+        int n_failed = 0;
+        VB_TRY(launch_list_tc_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off, seg_len, qn,
+                                     pos_kp, key_kp, pos, key, &n_failed));
+        prof_end(VB_PROF_TOPK);
+        ix.last_tc_failed = n_failed;
+        ix.total_tc_failed += n_failed;
+        if (n_failed == 0) {
+            ivf_finish_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, c.stream>>>(ix.metric, nq, k, probes, pos, key, d_lists, cand_off,
+                                                                                      ix.d_list_off, ix.d_ids, out_ids_dev, out_f_dev,
+                                                                                      out_d_dev);
+            VB_CUDA(cudaGetLastError());
+            count_launch();
+            if (cand_total_dev) *cand_total_dev = seg_len;
+            return VB_OK;
+        }
+        // some certificate failed: the whole batch goes through the exact kernel below (rare by construction)
+        prof_begin(VB_PROF_SCAN_ITEMS);
+    }
+    const bool list_major = list_major_supported(ix.elem, km) && ix.n_tiles > 0 && (c.scan_impl >= 3 || (c.scan_impl == 2 && batched));
     if (list_major) {
-        VB_TRY(launch_list_major(ix.rows, key_metric(ix.metric), qimg, qstride, nq, d_lists, probes, cand_off, cap, ix.d_list_off,
-                                 ix.lists, ix.d_tiles, ix.n_tiles, (float*)d_dist));
+        VB_TRY(launch_list_major(ix.rows, km, qimg, qstride, nq, d_lists, probes, cand_off, cap, ix.d_list_off, ix.lists, ix.d_tiles,
+                                 ix.n_tiles, (float*)d_dist));
     } else {
-        VB_TRY(launch_scan_chunks(ix.rows, key_metric(ix.metric), qimg, qstride, chunks, n_chunks, (int)max_chunks, (float*)d_dist));
+        VB_TRY(launch_scan_chunks(ix.rows, km, qimg, qstride, chunks, n_chunks, (int)max_chunks, (float*)d_dist));
     }
     prof_end(VB_PROF_SCAN_ITEMS);
     VB_TRY(workspace(WS_POS, (sizeof(int32_t) + sizeof(float)) * (size_t)nq * k, &d_pos));
@@ -482,6 +541,7 @@ static int ivf_set_offsets(Ivf& ix, const int64_t* list_offsets) {
     }
     if (ix.d_tiles) cudaFree(ix.d_tiles);
     ix.d_tiles = nullptr;
+    list_tc_release(&ix.tc);   // rows are about to change: planes are rebuilt on the next tensor-core scan
     ix.n_tiles = (int)tiles.size();
     if (ix.n_tiles) {
         VB_CUDA(cudaMalloc(&ix.d_tiles, sizeof(ListTile) * tiles.size()));
@@ -542,6 +602,7 @@ int vb_ivf_free(vb_ivf* h) {
     if (h->ix.d_list_off) cudaFree(h->ix.d_list_off);
     if (h->ix.d_cand_sum) cudaFree(h->ix.d_cand_sum);
     if (h->ix.d_tiles) cudaFree(h->ix.d_tiles);
+    list_tc_release(&h->ix.tc);
     delete h;
     return VB_OK;
 }
@@ -682,6 +743,8 @@ int vb_ivf_search(vb_ivf* h, const void* queries, int64_t nq, int probes, int k,
 int vb_ivf_search_dev(vb_ivf* h, const void* queries_dev, int64_t nq, int probes, int k, int64_t* out_ids_dev, float* out_dist_dev) {
     return ivf_search_impl(h, queries_dev, nq, probes, k, false, out_ids_dev, out_dist_dev, nullptr);
 }
+
+int64_t vb_ivf_tc_fallbacks(const vb_ivf* h) { return h ? h->ix.total_tc_failed : 0; }
 
 int64_t vb_ivf_last_candidates(const vb_ivf* h) {
     if (!h || !h->ix.d_cand_sum) return 0;

@@ -1,0 +1,474 @@
+// vb_list_tc.cu -- the batched IVFFlat list scan on the tensor cores, as a FILTER in front of the exact
+// fp32 arithmetic.
+//
+// GetScanItems (src/ivfscan.c:124-180) needs, per query, the k nearest of ~probes * rows/lists candidates.
+// The list-major formulation (vb_list_tile.cu) already reads every probed list once per batch; what is left
+// is 2 fp32 instructions per (row, query, dimension).  Here that arithmetic moves to tcgen05:
+//
+//   1. approximate pass:  d~ = |x|^2 + |q|^2 - 2 x.q   (or -x.q), x.q from three bf16 MMAs on the hi/lo split of
+//      both operands (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM) -- |d~ - d| <= eps(q), a rigorous bound;
+//   2. the k' = k + slack smallest d~ of every query are selected (segment_topk_kernel);
+//   3. those k' candidates are re-scored with the exact scan arithmetic (Acc<>, same as scan_kernel);
+//   4. the k nearest by (exact distance, position) are emitted, and the query is CERTIFIED: every candidate that
+//      was not re-scored has d >= d~ - eps >= (k'-th d~) - eps, so if that is > the k-th exact distance the
+//      result equals the full exact scan.  Queries that fail the certificate are re-run on the exact kernel.
+//
+// Layout.  The index rows are packed once per load into bf16 hi/lo planes in the 128-byte-swizzled shared-memory
+// image, one 32 KB block per (128-row table tile, 64-dimension block); a unit of work is a (list, table tile)
+// pair (tiles straddling a list boundary are visited by both lists, rows outside the list masked).  The queries
+// of each list's group are gathered and packed per batch into 64-query B tiles (16 KB per dimension block).
+// CTA = persistent, one per SM: warp 0 = bulk-copy producer (A 32 KB + B 16 KB per stage, 4 stages), warp 1 =
+// MMA issuer (UMMA 128x64x16, 12 per stage), warp 2 = TMEM allocator, warps 4-7 = epilogue (thread = row;
+// two 64-column accumulator stages so the epilogue of one tile overlaps the MMAs of the next).
+//
+// Roofline: HBM -- one pass over the packed planes of the probed lists per batch (4 bytes per row element).
+#include "vb_tc.cuh"
+#include "vb_distance.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace vb {
+
+constexpr int LC_M = 128;
+constexpr int LC_N = 64;
+constexpr int LC_STAGES = 4;
+constexpr int LC_THREADS = 256;
+constexpr uint32_t LC_A_PLANE = LC_M * TC_K * 2;        // 16 KB
+constexpr uint32_t LC_B_PLANE = LC_N * TC_K * 2;        // 8 KB
+constexpr uint32_t LC_A_STAGE = 2 * LC_A_PLANE;
+constexpr uint32_t LC_B_STAGE = 2 * LC_B_PLANE;
+constexpr uint32_t LC_STAGE = LC_A_STAGE + LC_B_STAGE;  // 48 KB
+constexpr size_t LC_SMEM = (size_t)LC_STAGES * LC_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int LC_MAX_KP = 64;                            // candidates re-scored per query, at most
+
+struct LcArgs {
+    const uint8_t* A;          // table planes [tile][kb][2][128 x 64]
+    const uint8_t* B;          // query-group planes [gtile][kb][2][64 x 64]
+    const ListUnit* units;
+    int n_units;
+    const int64_t* list_off;
+    const int32_t* grp_begin;
+    const int32_t* grp_cnt;
+    const int32_t* gt_begin;
+    const int32_t* pair_q;
+    const int64_t* pair_out;
+    const float* xn;           // |x|^2 per table row
+    const float* qn;           // |q|^2 per query of the batch
+    float* out;
+    int n_kblocks;
+    int is_l2;
+};
+
+__global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
+    extern __shared__ uint8_t lc_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)LC_STAGES * LC_STAGE);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + LC_STAGES;
+    uint64_t* tfull_bar = bars + 2 * LC_STAGES;
+    uint64_t* tempty_bar = bars + 2 * LC_STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * LC_STAGES + 4);
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < LC_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 2 * LC_N);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== producer =====
+        uint32_t it = 0;
+        for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+            const ListUnit un = a.units[u];
+            const int cnt = a.grp_cnt[un.list];
+            if (cnt == 0) continue;
+            const int nqt = (cnt + LC_N - 1) / LC_N;
+            const int gt0 = a.gt_begin[un.list];
+            for (int qt = 0; qt < nqt; ++qt)
+                for (int kb = 0; kb < a.n_kblocks; ++kb, ++it) {
+                    const int s = it % LC_STAGES;
+                    const uint32_t ph = (it / LC_STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = smem + (size_t)s * LC_STAGE;
+                    uint8_t* sb = sa + LC_A_STAGE;
+                    mbar_arrive_expect_tx(&full_bar[s], LC_STAGE);
+                    bulk_g2s(sa, a.A + ((size_t)un.tile * a.n_kblocks + kb) * LC_A_STAGE, LC_A_STAGE, &full_bar[s]);
+                    bulk_g2s(sb, a.B + ((size_t)(gt0 + qt) * a.n_kblocks + kb) * LC_B_STAGE, LC_B_STAGE, &full_bar[s]);
+                }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc_bf16(LC_M, LC_N);
+        uint32_t it = 0, tile = 0;
+        for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+            const ListUnit un = a.units[u];
+            const int cnt = a.grp_cnt[un.list];
+            if (cnt == 0) continue;
+            const int nqt = (cnt + LC_N - 1) / LC_N;
+            for (int qt = 0; qt < nqt; ++qt, ++tile) {
+                const int as = tile & 1;
+                const uint32_t aph = (tile >> 1) & 1;
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)as * LC_N;
+                for (int kb = 0; kb < a.n_kblocks; ++kb, ++it) {
+                    const int s = it % LC_STAGES;
+                    const uint32_t ph = (it / LC_STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)s * LC_STAGE);
+                    const uint32_t sb = sa + LC_A_STAGE;
+                    const uint64_t da_hi = make_sw128_desc(sa), da_lo = make_sw128_desc(sa + LC_A_PLANE);
+                    const uint64_t db_hi = make_sw128_desc(sb), db_lo = make_sw128_desc(sb + LC_B_PLANE);
+#pragma unroll
+                    for (int k = 0; k < TC_K / 16; ++k) {
+                        const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+                        umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kb | k) != 0);
+                        umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+                        umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tfull_bar[as]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: thread = one table row of the tile; columns = queries of the group =====
+        const int qr = warp - 4;
+        uint32_t tile = 0;
+        for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+            const ListUnit un = a.units[u];
+            const int cnt = a.grp_cnt[un.list];
+            if (cnt == 0) continue;
+            const int nqt = (cnt + LC_N - 1) / LC_N;
+            const int64_t lo = a.list_off[un.list], hi = a.list_off[un.list + 1];
+            const int64_t r_table = (int64_t)un.tile * LC_M + qr * 32 + lane;
+            const bool valid_row = r_table >= lo && r_table < hi;
+            const float xnr = valid_row && a.is_l2 ? a.xn[r_table] : 0.f;
+            const int gb = a.grp_begin[un.list];
+            for (int qt = 0; qt < nqt; ++qt, ++tile) {
+                const int as = tile & 1;
+                const uint32_t aph = (tile >> 1) & 1;
+                mbar_wait(&tfull_bar[as], aph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(qr * 32) << 16) + (uint32_t)as * LC_N;
+#pragma unroll
+                for (int c0 = 0; c0 < LC_N; c0 += 32) {
+                    const int col0 = qt * LC_N + c0;
+                    if (col0 >= cnt) break;   // warp-uniform
+                    uint32_t acc[32];
+                    tmem_ld32(taddr + c0, acc);
+                    // lane j fetches the bookkeeping of column j once; broadcast in the loop
+                    const int myc = col0 + lane;
+                    int64_t my_out = 0;
+                    float my_qn = 0.f;
+                    if (myc < cnt) {
+                        my_out = a.pair_out[gb + myc];
+                        if (a.is_l2) my_qn = a.qn[a.pair_q[gb + myc]];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int64_t po = __shfl_sync(0xffffffffu, my_out, j);
+                        const float qn = __shfl_sync(0xffffffffu, my_qn, j);
+                        if (col0 + j < cnt && valid_row) {
+                            const float dot = __uint_as_float(acc[j]);
+                            a.out[po + (r_table - lo)] = a.is_l2 ? fmaf(-2.f, dot, xnr + qn) : -dot;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 2 * LC_N);
+}
+
+// gather + split the queries of every (query, list) pair into the B tiles of its list's group:
+// thread = one 16-byte chunk (8 dimensions) of one pair
+__global__ void pack_groups_kernel(const float* __restrict__ qimg, size_t qstride, int dim, int n_kblocks, int64_t n_pairs,
+                                   const int32_t* __restrict__ pair_q, const int32_t* __restrict__ pair_list,
+                                   const int32_t* __restrict__ grp_begin, const int32_t* __restrict__ gt_begin,
+                                   uint8_t* __restrict__ out) {
+    const int64_t chunk = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int chunks_per_row = n_kblocks * 8;
+    const int64_t slot = chunk / chunks_per_row;
+    if (slot >= n_pairs) return;
+    const int cr = (int)(chunk % chunks_per_row);
+    const int kb = cr / 8, c = cr % 8;
+    const int l = pair_list[slot];
+    const int j = (int)(slot - grp_begin[l]);
+    const int64_t gtile = gt_begin[l] + j / LC_N;
+    const int r = j % LC_N;
+    const float* src = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(qimg) + (size_t)pair_q[slot] * qstride);
+    const int e0 = kb * TC_K + c * 8;
+    float v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = e0 + t < dim ? src[e0 + t] : 0.f;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * t]), h1 = __float2bfloat16_rn(v[2 * t + 1]);
+        __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * t] - __bfloat162float(h0));
+        __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * t + 1] - __bfloat162float(h1));
+        hi[t] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lo[t] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    uint8_t* base = out + ((size_t)(gtile * n_kblocks + kb) * 2) * LC_B_PLANE;
+    const size_t off = (size_t)r * 128 + (size_t)((c ^ (r & 7)) * 16);
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + LC_B_PLANE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// exact distance of the selected candidates: one warp per (query, candidate), the arithmetic of the scan kernels
+template <int ELEM, int METRIC>
+__global__ void rescore_kernel(const uint8_t* __restrict__ rows, size_t stride, int V, const uint8_t* __restrict__ qimg,
+                               size_t qstride, int64_t nq, int kp, int probes, const int32_t* __restrict__ pos,
+                               const int32_t* __restrict__ probe_lists, const int32_t* __restrict__ cand_off,
+                               const int64_t* __restrict__ list_off, float* __restrict__ exact) {
+    const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+    const int lane = threadIdx.x % 32;
+    if (w >= nq * kp) return;
+    const int64_t q = w / kp;
+    const int32_t ps = pos[w];
+    if (ps < 0) {
+        if (lane == 0) exact[w] = __int_as_float(0x7F800000);
+        return;
+    }
+    const int32_t* co = cand_off + q * (probes + 1);
+    int lo = 0, hi = probes;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (co[mid] <= ps) lo = mid;
+        else hi = mid;
+    }
+    while (lo + 1 < probes && co[lo + 1] <= ps) ++lo;   // empty lists share an offset
+    const int l = probe_lists[q * probes + lo];
+    const int64_t row = list_off[l] + (ps - co[lo]);
+    const uint4* rp = reinterpret_cast<const uint4*>(rows + (size_t)row * stride);
+    const uint4* sq = reinterpret_cast<const uint4*>(qimg + (size_t)q * qstride);
+    Acc<ELEM, METRIC> acc;
+#pragma unroll 4
+    for (int v = lane; v < V; v += 32) acc.add(__ldg(rp + v), sq, v);
+    acc.template reduce<32>();
+    if (lane == 0) exact[w] = (float)acc.value();
+}
+
+// one warp per query: order the re-scored candidates by (exact distance, position), emit the first k, and check
+// the certificate  (k'-th approximate distance) - eps > (k-th exact distance)
+__global__ void certify_kernel(int64_t nq, int k, int kp, int is_l2, float c_dot, float c_sum, float xmax,
+                               const float* __restrict__ qn, const int32_t* __restrict__ seg_len,
+                               const int32_t* __restrict__ pos_kp, const float* __restrict__ approx_kp,
+                               const float* __restrict__ exact_kp, int32_t* __restrict__ out_pos, float* __restrict__ out_key,
+                               int* __restrict__ n_failed, uint8_t* __restrict__ failed) {
+    const int64_t q = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+    const int lane = threadIdx.x % 32;
+    if (q >= nq) return;
+    __shared__ uint64_t s_key[8][LC_MAX_KP];
+    uint64_t* keys = s_key[(threadIdx.x / 32) % 8];
+    for (int i = lane; i < LC_MAX_KP; i += 32) {
+        uint64_t key = 0xFFFFFFFF00000000ull | (uint32_t)i;   // absent entries sort last, distinct
+        if (i < kp) {
+            const int32_t p = pos_kp[q * kp + i];
+            if (p >= 0) key = ((uint64_t)orderable_key(exact_kp[q * kp + i]) << 32) | (uint32_t)p;
+        }
+        keys[i] = key;
+    }
+    __syncwarp();
+    float kth = __int_as_float(0x7F800000);
+    for (int i = lane; i < kp; i += 32) {
+        const uint64_t mine = keys[i];
+        int rank = 0;
+        for (int j = 0; j < kp; ++j) rank += keys[j] < mine;
+        if (rank < k) {
+            const bool present = pos_kp[q * kp + i] >= 0;
+            out_pos[q * k + rank] = present ? (int32_t)(uint32_t)mine : -1;
+            out_key[q * k + rank] = present ? key_to_float((uint32_t)(mine >> 32)) : __int_as_float(0x7F800000);
+        }
+        if (rank == k - 1) kth = key_to_float((uint32_t)(mine >> 32));
+    }
+    // the lane that held rank k-1 has the k-th exact distance; everyone else +inf
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kth = fminf(kth, __shfl_xor_sync(0xffffffffu, kth, o));
+    if (lane == 0) {
+        bool ok = true;
+        if (seg_len[q] > kp) {   // some candidates were not re-scored
+            const float qnorm = sqrtf(qn[q]);
+            const float eps = c_dot * qnorm * xmax + (is_l2 ? c_sum * (xmax * xmax + qn[q]) : 0.f);
+            const float last = approx_kp[q * kp + kp - 1];
+            ok = (last - eps) > kth;   // false for NaN
+        }
+        failed[q] = ok ? 0 : 1;
+        if (!ok) atomicAdd(n_failed, 1);
+    }
+}
+
+// ----------------------------------------------------------------------------- host side
+
+enum { WSC_B = 21, WSC_N = 22, WSC_K = 23 };
+
+bool list_tc_supported(int elem, int key_metric, int k) {
+    return (elem == VB_VECTOR || elem == VB_HALFVEC) && (key_metric == VB_L2_SQUARED || key_metric == VB_NEG_IP) && k >= 1 &&
+           list_tc_kp(k) <= LC_MAX_KP;
+}
+
+int list_tc_kp(int k) {
+    // slack of the filter: the certificate needs the k'-th approximate distance to clear the k-th exact one by eps
+    return k <= 10 ? 32 : k <= 24 ? 48 : k <= 40 ? 64 : 1 << 20;
+}
+
+// packed planes + norms of the whole table (once per index load)
+int list_tc_prepare(const Table& rows, ListTcImage* im) {
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    const int64_t n = rows.n;
+    const int n_kblocks = (rows.dim + TC_K - 1) / TC_K;
+    const int64_t n_tiles = (n + LC_M - 1) / LC_M;
+    const size_t bytes = (size_t)n_tiles * n_kblocks * LC_A_STAGE;
+    VB_CUDA(cudaMalloc(&im->planes, std::max<size_t>(bytes, 16)));
+    VB_CUDA(cudaMalloc(&im->xn, sizeof(float) * (size_t)std::max<int64_t>(n_tiles * LC_M, 1)));
+    im->n_kblocks = n_kblocks;
+    im->n_tiles = n_tiles;
+    if (n == 0) {
+        im->xmax = 0.f;
+        return VB_OK;
+    }
+    const int64_t chunks = n_tiles * LC_M * n_kblocks * 8;
+    const unsigned grid = (unsigned)((chunks + 255) / 256);
+    const unsigned g2 = (unsigned)((n_tiles * LC_M * 32 + 255) / 256);
+    if (rows.elem == VB_VECTOR) {
+        pack_planes_kernel<VB_VECTOR><<<grid, 256, 0, s>>>(rows.d, rows.stride, 0, n, rows.dim, LC_M, n_kblocks, im->planes, nullptr);
+        row_sqnorm_kernel<VB_VECTOR><<<g2, 256, 0, s>>>(rows.d, rows.stride, n, rows.dim, im->xn, n_tiles * LC_M, 0.f);
+    } else {
+        pack_planes_kernel<VB_HALFVEC><<<grid, 256, 0, s>>>(rows.d, rows.stride, 0, n, rows.dim, LC_M, n_kblocks, im->planes, nullptr);
+        row_sqnorm_kernel<VB_HALFVEC><<<g2, 256, 0, s>>>(rows.d, rows.stride, n, rows.dim, im->xn, n_tiles * LC_M, 0.f);
+    }
+    VB_CUDA(cudaGetLastError());
+    count_launch(2);
+    std::vector<float> h((size_t)n);
+    VB_CUDA(cudaMemcpyAsync(h.data(), im->xn, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    VB_CUDA(cudaStreamSynchronize(s));
+    float m2 = 0.f;
+    bool finite = true;
+    for (float v : h) {
+        if (!(v == v) || v > 3.0e38f) finite = false;
+        else m2 = std::max(m2, v);
+    }
+    im->xmax = std::sqrt(m2);
+    im->finite = finite;
+    return VB_OK;
+}
+
+void list_tc_release(ListTcImage* im) {
+    if (im->planes) cudaFree(im->planes);
+    if (im->xn) cudaFree(im->xn);
+    if (im->units) cudaFree(im->units);
+    *im = ListTcImage{};
+}
+
+// approximate pass: fills `out` (the per-query candidate runs) with d~
+int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
+                   const int32_t* d_lists, int probes, const int32_t* cand_off, int64_t cap, const int64_t* d_list_off, int n_lists,
+                   float* out, const float** qn_out) {
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    QueryGroups g{};
+    VB_TRY(build_query_groups(d_lists, nq, probes, cand_off, cap, n_lists, LC_N, &g));
+    const int64_t max_gtiles = g.n_pairs / LC_N + n_lists + 1;
+    void *d_B, *d_qn;
+    VB_TRY(workspace(WSC_B, (size_t)max_gtiles * im.n_kblocks * LC_B_STAGE, &d_B));
+    VB_TRY(workspace(WSC_N, sizeof(float) * (size_t)nq + 64, &d_qn));
+    // the query image is fp32 with the rows' padded dimension count for both element types
+    const int qdim = (int)(qstride / 4);
+    row_sqnorm_kernel<VB_VECTOR><<<(unsigned)((nq * 32 + 255) / 256), 256, 0, s>>>((const uint8_t*)qimg, qstride, nq, qdim, (float*)d_qn,
+                                                                                  nq, 0.f);
+    const int64_t chunks = g.n_pairs * im.n_kblocks * 8;
+    pack_groups_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>((const float*)qimg, qstride, qdim, im.n_kblocks, g.n_pairs,
+                                                                        g.pair_q, g.pair_list, g.begin, g.gt_begin, (uint8_t*)d_B);
+    VB_CUDA(cudaGetLastError());
+    count_launch(2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        VB_CUDA(cudaFuncSetAttribute(list_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC_SMEM));
+        attr_set = true;
+    }
+    LcArgs a{};
+    a.A = im.planes;
+    a.B = (const uint8_t*)d_B;
+    a.units = im.units;
+    a.n_units = im.n_units;
+    a.list_off = d_list_off;
+    a.grp_begin = g.begin;
+    a.grp_cnt = g.cnt;
+    a.gt_begin = g.gt_begin;
+    a.pair_q = g.pair_q;
+    a.pair_out = g.pair_out;
+    a.xn = im.xn;
+    a.qn = (const float*)d_qn;
+    a.out = out;
+    a.n_kblocks = im.n_kblocks;
+    a.is_l2 = key_metric == VB_L2_SQUARED;
+    const int grid = std::max(1, std::min(im.n_units, c.sm_count));
+    list_tc_kernel<<<grid, LC_THREADS, LC_SMEM, s>>>(a);
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    (void)rows;
+    *qn_out = (const float*)d_qn;
+    return VB_OK;
+}
+
+// steps 3 + 4: exact re-score of the k' selected candidates, final order, certificate.  n_failed_host receives the
+// number of queries whose certificate failed (the caller re-runs those exactly).
+int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
+                          int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
+                          const int32_t* seg_len, const float* qn, const int32_t* pos_kp, const float* approx_kp, int32_t* out_pos,
+                          float* out_key, int* n_failed_host) {
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    void* d_ws;
+    VB_TRY(workspace(WSC_K, sizeof(float) * (size_t)nq * kp + (size_t)nq + 64, &d_ws));
+    int* n_failed = (int*)d_ws;
+    float* exact = (float*)d_ws + 16;
+    uint8_t* failed = (uint8_t*)(exact + (size_t)nq * kp);
+    VB_CUDA(cudaMemsetAsync(n_failed, 0, sizeof(int), s));
+    const int V = (int)(rows.stride / 16);
+    const unsigned grid = (unsigned)((nq * kp * 32 + 255) / 256);
+#define VB_RS(E, M) rescore_kernel<E, M><<<grid, 256, 0, s>>>(rows.d, rows.stride, V, (const uint8_t*)qimg, qstride, nq, kp, probes, pos_kp, d_lists, cand_off, d_list_off, exact)
+    if (rows.elem == VB_VECTOR) {
+        if (key_metric == VB_L2_SQUARED) VB_RS(VB_VECTOR, VB_L2_SQUARED);
+        else VB_RS(VB_VECTOR, VB_NEG_IP);
+    } else {
+        if (key_metric == VB_L2_SQUARED) VB_RS(VB_HALFVEC, VB_L2_SQUARED);
+        else VB_RS(VB_HALFVEC, VB_NEG_IP);
+    }
+#undef VB_RS
+    // |d~ - d| <= eps: split product 2^-13 |x||q| (x2 in the L2 form), fp32 norms and the final sum 2^-17 (|x|^2 + |q|^2)
+    const int is_l2 = key_metric == VB_L2_SQUARED;
+    const float c_dot = is_l2 ? 1.0f / 4096.0f : 1.0f / 8192.0f;
+    const float c_sum = 1.0f / 131072.0f;
+    certify_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, s>>>(nq, k, kp, is_l2, c_dot, c_sum, im.xmax, qn, seg_len, pos_kp, approx_kp,
+                                                                    exact, out_pos, out_key, n_failed, failed);
+    VB_CUDA(cudaGetLastError());
+    count_launch(2);
+    VB_CUDA(cudaMemcpyAsync(n_failed_host, n_failed, sizeof(int), cudaMemcpyDeviceToHost, s));
+    VB_CUDA(cudaStreamSynchronize(s));
+    return VB_OK;
+}
+
+}  // namespace vb

@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(1024) lt_scan_kernel(const int32_t* __restrict
 
 __global__ void lt_scatter_kernel(const int32_t* __restrict__ probe_lists, int64_t n_pairs, int probes,
                                   const int32_t* __restrict__ cand_off, int64_t cap, const int32_t* __restrict__ begin,
-                                  int32_t* __restrict__ cursor, int32_t* __restrict__ pair_q, int64_t* __restrict__ pair_out) {
+                                  int32_t* __restrict__ cursor, int32_t* __restrict__ pair_q, int64_t* __restrict__ pair_out,
+                                  int32_t* __restrict__ pair_list) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     const int l = probe_lists[i];
@@ -277,6 +278,13 @@ __global__ void lt_scatter_kernel(const int32_t* __restrict__ probe_lists, int64
     const int slot = begin[l] + atomicAdd(&cursor[l], 1);
     pair_q[slot] = (int32_t)q;
     pair_out[slot] = q * cap + cand_off[q * (probes + 1) + p];
+    pair_list[slot] = l;
+}
+
+// tiles[l] = ceil(cnt[l] / rows_per_tile): the number of query tiles of each list (input of a second prefix sum)
+__global__ void lt_tiles_kernel(const int32_t* __restrict__ cnt, int n, int rows_per_tile, int32_t* __restrict__ tiles) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tiles[i] = (cnt[i] + rows_per_tile - 1) / rows_per_tile;
 }
 
 bool list_major_supported(int elem, int key_metric) {
@@ -285,30 +293,53 @@ bool list_major_supported(int elem, int key_metric) {
 
 enum { WSL_GROUPS = 20 };
 
-int launch_list_major(const Table& rows, int key_metric, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists,
-                      int probes, const int32_t* cand_off, int64_t cap, const int64_t* d_list_off, int n_lists,
-                      const ListTile* d_tiles, int n_tiles, float* out) {
-    VB_REQUIRE(list_major_supported(rows.elem, key_metric), "list-major scan: unsupported element type / metric");
-    if (nq <= 0 || n_tiles <= 0) return VB_OK;
+// Group the (query, probe) pairs of a batch by list.  gt_rows > 0 additionally numbers the query tiles of
+// gt_rows queries over all lists (tensor-core path: one packed B tile per query tile).
+int build_query_groups(const int32_t* d_lists, int64_t nq, int probes, const int32_t* cand_off, int64_t cap, int n_lists, int gt_rows,
+                       QueryGroups* g) {
     Context& c = ctx();
     cudaStream_t s = c.stream;
     const int64_t n_pairs = nq * probes;
     VB_REQUIRE(n_pairs < (int64_t)INT32_MAX, "too many (query, probe) pairs");
     void* d_ws;
-    const size_t ints = (size_t)n_lists * 3 + (size_t)n_pairs;
+    const size_t ints = (size_t)n_lists * 5 + (size_t)n_pairs * 2;
     VB_TRY(workspace(WSL_GROUPS, sizeof(int64_t) * (size_t)n_pairs + sizeof(int32_t) * ints + 64, &d_ws));
-    int64_t* pair_out = (int64_t*)d_ws;
-    int32_t* pair_q = (int32_t*)(pair_out + n_pairs);
-    int32_t* cnt = pair_q + n_pairs;
-    int32_t* cursor = cnt + n_lists;
-    int32_t* begin = cursor + n_lists;
-    VB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)n_lists * 2, s));
+    g->pair_out = (int64_t*)d_ws;
+    g->pair_q = (int32_t*)(g->pair_out + n_pairs);
+    g->pair_list = g->pair_q + n_pairs;
+    g->cnt = g->pair_list + n_pairs;
+    int32_t* cursor = g->cnt + n_lists;
+    g->begin = cursor + n_lists;
+    int32_t* tiles = g->begin + n_lists;
+    g->gt_begin = tiles + n_lists;
+    g->n_pairs = n_pairs;
+    VB_CUDA(cudaMemsetAsync(g->cnt, 0, sizeof(int32_t) * (size_t)n_lists * 2, s));
     const unsigned gp = (unsigned)((n_pairs + 255) / 256);
-    lt_count_kernel<<<gp, 256, 0, s>>>(d_lists, n_pairs, cnt);
-    lt_scan_kernel<<<1, 1024, 0, s>>>(cnt, n_lists, begin);
-    lt_scatter_kernel<<<gp, 256, 0, s>>>(d_lists, n_pairs, probes, cand_off, cap, begin, cursor, pair_q, pair_out);
-    VB_CUDA(cudaGetLastError());
+    lt_count_kernel<<<gp, 256, 0, s>>>(d_lists, n_pairs, g->cnt);
+    lt_scan_kernel<<<1, 1024, 0, s>>>(g->cnt, n_lists, g->begin);
+    lt_scatter_kernel<<<gp, 256, 0, s>>>(d_lists, n_pairs, probes, cand_off, cap, g->begin, cursor, g->pair_q, g->pair_out, g->pair_list);
     count_launch(3);
+    if (gt_rows > 0) {
+        lt_tiles_kernel<<<(unsigned)((n_lists + 255) / 256), 256, 0, s>>>(g->cnt, n_lists, gt_rows, tiles);
+        lt_scan_kernel<<<1, 1024, 0, s>>>(tiles, n_lists, g->gt_begin);
+        count_launch(2);
+    }
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
+int launch_list_major(const Table& rows, int key_metric, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists,
+                      int probes, const int32_t* cand_off, int64_t cap, const int64_t* d_list_off, int n_lists,
+                      const ListTile* d_tiles, int n_tiles, float* out) {
+    VB_REQUIRE(list_major_supported(rows.elem, key_metric), "list-major scan: unsupported element type / metric");
+    if (nq <= 0 || n_tiles <= 0) return VB_OK;
+    cudaStream_t s = ctx().stream;
+    QueryGroups g{};
+    VB_TRY(build_query_groups(d_lists, nq, probes, cand_off, cap, n_lists, 0, &g));
+    int32_t* begin = g.begin;
+    int32_t* cnt = g.cnt;
+    int32_t* pair_q = g.pair_q;
+    int64_t* pair_out = g.pair_out;
 
     LtArgs a{};
     a.rows = rows.d;

@@ -164,7 +164,7 @@ def test_list_major_scan_equals_per_query_scan(pv, opclass, dim):
     gix, oix = make_index(pv, opclass, x, c, dim=dim)
     got = {}
     try:
-        for impl in (0, 1, 3):
+        for impl in (0, 1, 3, 4):
             pv.set_option("scan_impl", impl)
             got[impl] = gix.search(q, k=10, probes=5)
             got[impl, 1] = gix.search(q[:3], k=7, probes=12)      # tiny batch, every list probed
@@ -172,14 +172,43 @@ def test_list_major_scan_equals_per_query_scan(pv, opclass, dim):
         import os
         pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
     wi, wd = oix.search_batch(q, 5, 10, threads=8)
-    for impl in (0, 1, 3):
+    for impl in (0, 1, 3, 4):
         ids, dist = got[impl]
         assert np.allclose(dist, wd, rtol=RTOL, atol=1e-6), impl
         assert (ids == wi).mean() > 0.99, impl
+    # the tensor-core filter re-scores with the per-query scan arithmetic: same values as the streaming kernels
+    assert np.allclose(got[4][1], got[1][1], rtol=RTOL, atol=1e-6)
+    assert (got[4][0] == got[1][0]).mean() > 0.995
     assert np.allclose(got[3][1], got[1][1], rtol=RTOL, atol=1e-6)
     assert (got[3][0] == got[1][0]).mean() > 0.995
     assert np.allclose(got[3, 1][1], got[0, 1][1], rtol=RTOL, atol=1e-6)
     assert (got[3, 1][0] == got[0, 1][0]).mean() > 0.99
+
+
+def test_tensor_core_filter_falls_back_when_it_cannot_certify(pv):
+    """Duplicated rows put the k-th and the k'-th candidate at the same distance, so the certificate
+    (k'-th approximate distance - eps > k-th exact distance) cannot hold: those batches must come back from the
+    exact kernel, identical to the other scan settings, and be counted."""
+    import os
+    rng = np.random.default_rng(5)
+    base = rng.standard_normal((40, 64)).astype(np.float32)
+    rows = np.repeat(base, 100, axis=0)                      # 4000 rows, every vector 100 times
+    centers = base[:8].copy()
+    q = (base[rng.integers(0, 40, 300)] + 0.01 * rng.standard_normal((300, 64))).astype(np.float32)
+    gix, oix = make_index(pv, "vector_l2_ops", rows, centers)
+    try:
+        pv.set_option("scan_impl", 3)
+        ids3, d3 = gix.search(q, k=10, probes=8)
+        before = gix.tc_fallbacks()
+        pv.set_option("scan_impl", 4)
+        ids4, d4 = gix.search(q, k=10, probes=8)
+        assert gix.tc_fallbacks() > before
+    finally:
+        pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
+    assert np.array_equal(ids3, ids4)
+    assert np.array_equal(d3, d4)
+    wi, wd = oix.search_batch(q, 8, 10, threads=8)
+    assert np.allclose(d4, wd, rtol=RTOL, atol=1e-6)
 
 
 def test_tie_modes_agree_on_recall(pv):
