@@ -194,7 +194,17 @@ static int ivf_select_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t 
 // packed planes, row norms and the (list, table tile) work units of the tensor-core scan; built lazily because the
 // planes double the index footprint and only batched searches use them
 static int ivf_ensure_tc_image(Ivf& ix) {
-    if (ix.tc.planes) return VB_OK;
+    if (ix.tc.planes || !ix.tc.finite) return VB_OK;
+    {
+        // the planes are as large as an fp32 table: keep the exact kernels when they do not fit beside the index
+        const size_t need = (size_t)((ix.rows.n + 127) / 128) * 128 * ((size_t)(ix.rows.dim + 63) / 64) * 64 * 4;
+        size_t free_b = 0, total_b = 0;
+        VB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (free_b < need + ((size_t)4 << 30)) {
+            ix.tc.finite = false;
+            return VB_OK;
+        }
+    }
     VB_TRY(list_tc_prepare(ix.rows, &ix.tc));
     std::vector<ListUnit> units;
     for (int l = 0; l < ix.lists; ++l) {
@@ -241,10 +251,11 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
     // scan_impl: 0 = per-query LDG scan, 1 = per-query bulk-copy scan, 2 = automatic, 3 = list-major fp32 wherever it
     // applies, 4 = tensor-core filter + exact re-score wherever it applies.
     // Automatic: once a batch carries enough (query, probe) pairs to fill the GPU with row tiles, group them by list
-    // so each probed list is read once per batch instead of once per query.
+    // so each probed list is read once per batch instead of once per query; small k goes through the tensor-core
+    // filter (HBM-bound), larger k through the fp32 list-major kernel (FMA-pipe bound).
     const int km = key_metric(ix.metric);
     const bool batched = nq * probes >= 256;
-    bool tc = c.scan_impl == 4 && batched && list_tc_supported(ix.elem, km, k) && ix.rows.n > 0;
+    bool tc = (c.scan_impl == 4 || c.scan_impl == 2) && batched && list_tc_supported(ix.elem, km, k) && ix.rows.n > 0;
     if (tc) {
         VB_TRY(ivf_ensure_tc_image(ix));
         tc = ix.tc.finite;   // rows with Inf / NaN norms have no error bound: exact path
