@@ -45,7 +45,7 @@ except Exception:
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000)
@@ -381,7 +381,9 @@ def main():
         step_dev(i)
     barrier()
     # untimed extra load (same count on every rank: the steps contain collectives) while nvidia-smi spins up
-    for i in range(20):
+    # (a step is ~1.6 ms with the batched kernels: a few hundred steps give the 20 ms sampler ~30 lines before the
+    # timed region starts; it keeps running through the timed device steps and the end-to-end steps)
+    for i in range(300 if args.scan_impl >= 2 else 30):
         step_dev(i)
     barrier()
     pv.prof_enable(True)
@@ -402,7 +404,6 @@ def main():
     lists_ms, lists_n = pv.prof_read(pv.PROF_SCAN_LISTS)
     topk_ms, topk_n = pv.prof_read(pv.PROF_TOPK)
     pv.prof_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
     # candidates of the last step (same batch size every step; lists differ slightly per batch)
     cand_last = ix.last_candidates()
     if world > 1:
@@ -446,6 +447,7 @@ def main():
     h1.record(stream)
     barrier()
     ms_h = h0.elapsed_time(h1)
+    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms_h], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -319,7 +319,8 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswDev g, c
 
 template <int ELEM, int METRIC>
 static int hnsw_launch_t(const HnswDev& g, const void* qimg, size_t qstride, int64_t nq, int ef, int k, uint32_t* vis, uint32_t vis_cap,
-                         uint32_t vis_upper, int grid, int64_t* out_ids, float* out_f, double* out_d, int64_t* out_nd, int* overflow) {
+                         uint32_t vis_upper, int grid, int64_t* out_ids, float* out_f, double* out_d, int64_t* out_nd, int* overflow,
+                         int* occ_out) {
     const int qvec = (int)(qstride / 16);
     size_t per_warp = (size_t)qvec * 16 + (size_t)ef * 2 * 8 + (size_t)ef * 2 * 4 + 32 * 8 + 32 * 4;
     per_warp = (per_warp + 15) & ~(size_t)15;
@@ -330,6 +331,11 @@ static int hnsw_launch_t(const HnswDev& g, const void* qimg, size_t qstride, int
     do {                                                                                                                  \
         auto kern = hnsw_search_kernel<ELEM, METRIC, LPR>;                                                                \
         if (smem > 48 * 1024) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        if (occ_out) {                                                                                                    \
+            /* sizing pass: how many CTAs of this instantiation are resident per SM (the grid is exactly one wave) */     \
+            VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, HN_WARPS * 32, smem));                   \
+            return VB_OK;                                                                                                 \
+        }                                                                                                                 \
         kern<<<grid, HN_WARPS * 32, smem, s>>>(g, (const uint8_t*)qimg, qstride, nq, ef, k, vis, vis_cap, vis_upper, out_ids, out_f, out_d, \
                                                out_nd, overflow);                                                        \
     } while (0)
@@ -346,8 +352,9 @@ static int hnsw_launch_t(const HnswDev& g, const void* qimg, size_t qstride, int
 }
 
 static int hnsw_launch(const Hnsw& h, const HnswDev& g, const void* qimg, size_t qstride, int64_t nq, int ef, int k, uint32_t* vis,
-                       uint32_t vis_cap, uint32_t vis_upper, int grid, int64_t* out_ids, float* out_f, double* out_d, int64_t* out_nd, int* overflow) {
-#define VB_HC(E, M) return hnsw_launch_t<E, M>(g, qimg, qstride, nq, ef, k, vis, vis_cap, vis_upper, grid, out_ids, out_f, out_d, out_nd, overflow)
+                       uint32_t vis_cap, uint32_t vis_upper, int grid, int64_t* out_ids, float* out_f, double* out_d, int64_t* out_nd, int* overflow,
+                       int* occ_out = nullptr) {
+#define VB_HC(E, M) return hnsw_launch_t<E, M>(g, qimg, qstride, nq, ef, k, vis, vis_cap, vis_upper, grid, out_ids, out_f, out_d, out_nd, overflow, occ_out)
     if (h.elem == VB_VECTOR) {
         switch (h.metric) {
             case VB_L2_SQUARED: VB_HC(VB_VECTOR, VB_L2_SQUARED);
@@ -425,7 +432,9 @@ static int hnsw_search_impl(Hnsw& h, const void* queries, int64_t nq, int ef, in
 
     // resident warps: a few CTAs per SM; every warp owns one visited table
     const int64_t want_ctas = (nq + HN_WARPS - 1) / HN_WARPS;
-    const int grid = (int)std::min<int64_t>(want_ctas, (int64_t)c.sm_count * 6);
+    int resident = 0;
+    VB_TRY(hnsw_launch(h, g, qimg, qstride, nq, ef, k, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, &resident));
+    const int grid = (int)std::min<int64_t>(want_ctas, (int64_t)c.sm_count * std::max(1, resident));
     // layer-0 table: generous for ef * 2m insertions per expansion wave; grows on overflow
     uint32_t cap = 1u << 14;
     while (cap < (uint32_t)(ef * h.m * 16) && cap < (1u << 22)) cap <<= 1;

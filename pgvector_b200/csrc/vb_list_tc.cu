@@ -458,10 +458,12 @@ int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metr
         else VB_RS(VB_HALFVEC, VB_NEG_IP);
     }
 #undef VB_RS
-    // |d~ - d| <= eps: split product 2^-13 |x||q| (x2 in the L2 form), fp32 norms and the final sum 2^-17 (|x|^2 + |q|^2)
+    // |d~ - d_fp32| <= eps.  Split product: representation 2^-18 + 2^-17, TMEM accumulation over 3 * dim / 16 steps
+    // -> 2^-13 |x||q| with ~2.5x head-room (x2 in the L2 form).  The fp32 norms, the final sum and the rounding of
+    // the exact fp32 distance it is compared with: 2^-16 (|x|^2 + |q|^2) for L2, 2^-17 |x||q| for the inner product.
     const int is_l2 = key_metric == VB_L2_SQUARED;
-    const float c_dot = is_l2 ? 1.0f / 4096.0f : 1.0f / 8192.0f;
-    const float c_sum = 1.0f / 131072.0f;
+    const float c_dot = is_l2 ? 1.0f / 4096.0f : 1.0f / 8192.0f + 1.0f / 131072.0f;
+    const float c_sum = 1.0f / 65536.0f;
     certify_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, s>>>(nq, k, kp, is_l2, c_dot, c_sum, im.xmax, qn, seg_len, pos_kp, approx_kp,
                                                                     exact, out_pos, out_key, n_failed, failed);
     VB_CUDA(cudaGetLastError());
