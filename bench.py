@@ -303,7 +303,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        # rank 0 prints exactly one JSON line on stdout: NCCL's version banner / debug output (printed whenever
+        # NCCL_DEBUG is set, even to WARN) goes to stderr instead
+        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=dev)
     import pgvector_b200 as pv
     pv.init(local)

@@ -55,6 +55,8 @@ struct Ivf {
     ListTile* d_tiles = nullptr;      // static row tiles of the lists (list-major batched scan)
     int n_tiles = 0;
     ListTcImage tc;                   // packed bf16 planes + norms + (list, tile) units, built on first tensor-core scan
+    ListTcImage ctc;                  // the same for the centre table (one pseudo list probed by every query)
+    int64_t* d_centre_off = nullptr;  // {0, lists}
     int64_t last_tc_failed = 0, total_tc_failed = 0;
     bool loaded = false;
 };
@@ -144,12 +146,78 @@ static int64_t ivf_cap(const Ivf& ix, int probes) {
     return std::max<int64_t>(cap, 1);
 }
 
+// every query "probes" pseudo list 0 = the whole centre table: probe_lists[q] = 0, cand_off[q] = {0, lists}
+__global__ void centre_pairs_kernel(int64_t nq, int32_t lists, int32_t* __restrict__ probe_lists, int32_t* __restrict__ cand_off) {
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    probe_lists[q] = 0;
+    cand_off[2 * q] = 0;
+    cand_off[2 * q + 1] = lists;
+}
+
+static int ivf_ensure_centre_tc(Ivf& ix) {
+    if (ix.ctc.planes || !ix.ctc.finite) return VB_OK;
+    VB_TRY(list_tc_prepare(ix.centers, &ix.ctc));
+    std::vector<ListUnit> units;
+    for (int64_t t = 0; t * 128 < ix.lists; ++t) units.push_back(ListUnit{0, (int32_t)t});
+    ix.ctc.n_units = (int)units.size();
+    VB_CUDA(cudaMalloc(&ix.ctc.units, sizeof(ListUnit) * units.size()));
+    VB_CUDA(cudaMemcpy(ix.ctc.units, units.data(), sizeof(ListUnit) * units.size(), cudaMemcpyHostToDevice));
+    if (!ix.d_centre_off) VB_CUDA(cudaMalloc(&ix.d_centre_off, 2 * sizeof(int64_t)));
+    const int64_t off[2] = {0, ix.lists};
+    VB_CUDA(cudaMemcpy(ix.d_centre_off, off, sizeof(off), cudaMemcpyHostToDevice));
+    return VB_OK;
+}
+
 // probe selection for a batch of query images: d_probe_lists [nq x probes] ascending by (distance, list)
 static int ivf_select_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, int probes, int32_t** d_lists,
                              float** d_ldist) {
     Context& c = ctx();
     void *d_cdist, *d_seg, *d_probe;
     VB_TRY(workspace(WS_CDIST, sizeof(float) * (size_t)nq * ix.lists, &d_cdist));
+    // Query batches: the same tensor-core filter as the list scan, with the centre table as ONE list probed by every
+    // query -- approximate distances to all centres, the k' nearest re-scored exactly, order (distance, list number)
+    // certified; any uncertified query sends the batch through the exact tiles below.
+    const int km = key_metric(ix.metric);
+    bool tc = (c.scan_impl == 2 || c.scan_impl == 4) && nq >= 256 && ix.lists >= 128 && list_tc_supported(ix.elem, km, probes);
+    if (tc) {
+        VB_TRY(ivf_ensure_centre_tc(ix));
+        tc = ix.ctc.finite && ix.ctc.planes != nullptr;
+    }
+    if (tc) {
+        const int kp = list_tc_kp(probes);
+        void *d_pairs, *d_seg2, *d_probe2;
+        VB_TRY(workspace(WS_MISC, sizeof(int32_t) * (size_t)nq * 3 + 64, &d_pairs));
+        int32_t* zero_lists = (int32_t*)d_pairs;
+        int32_t* pair_off = zero_lists + nq;
+        VB_TRY(workspace(WS_SEG, (sizeof(int64_t) + sizeof(int32_t)) * (size_t)nq * 2 + 64, &d_seg2));
+        int64_t* sb = (int64_t*)d_seg2;
+        int32_t* sl = (int32_t*)(sb + nq);
+        VB_TRY(workspace(WS_PROBES, (sizeof(int32_t) + sizeof(float)) * (size_t)nq * (probes + kp), &d_probe2));
+        int32_t* lists = (int32_t*)d_probe2;
+        float* ldist = (float*)(lists + (size_t)nq * probes);
+        int32_t* pos_kp = (int32_t*)(ldist + (size_t)nq * probes);
+        float* key_kp = (float*)(pos_kp + (size_t)nq * kp);
+        prof_begin(VB_PROF_SCAN_LISTS);
+        centre_pairs_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c.stream>>>(nq, ix.lists, zero_lists, pair_off);
+        regular_segments_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, c.stream>>>(nq, ix.lists, ix.lists, sb, sl);
+        VB_CUDA(cudaGetLastError());
+        count_launch(2);
+        const float* qn = nullptr;
+        VB_TRY(launch_list_tc(ix.centers, ix.ctc, km, qimg, qstride, nq, zero_lists, 1, pair_off, ix.lists, ix.d_centre_off, 1,
+                              (float*)d_cdist, &qn, true));
+        VB_TRY(launch_segment_topk_v((const float*)d_cdist, sb, sl, nullptr, nullptr, nq, kp, pos_kp, key_kp));
+        int n_failed = 0;
+        VB_TRY(launch_list_tc_refine(ix.centers, ix.ctc, km, qimg, qstride, nq, probes, kp, 1, zero_lists, pair_off, ix.d_centre_off, sl,
+                                     qn, pos_kp, key_kp, lists, ldist, &n_failed));
+        prof_end(VB_PROF_SCAN_LISTS);
+        ix.total_tc_failed += n_failed;
+        if (n_failed == 0) {
+            *d_lists = lists;
+            *d_ldist = ldist;
+            return VB_OK;
+        }
+    }
     prof_begin(VB_PROF_SCAN_LISTS);
     // many queries at once: the query image is itself a row table with the centres' stride (vector, bit), so the
     // centre scan is computed tile-wise (both operands staged once per 128 x 128 tile).  Measured on B200 for 2048
@@ -553,6 +621,7 @@ static int ivf_set_offsets(Ivf& ix, const int64_t* list_offsets) {
     if (ix.d_tiles) cudaFree(ix.d_tiles);
     ix.d_tiles = nullptr;
     list_tc_release(&ix.tc);   // rows are about to change: planes are rebuilt on the next tensor-core scan
+    list_tc_release(&ix.ctc);
     ix.n_tiles = (int)tiles.size();
     if (ix.n_tiles) {
         VB_CUDA(cudaMalloc(&ix.d_tiles, sizeof(ListTile) * tiles.size()));
@@ -614,6 +683,8 @@ int vb_ivf_free(vb_ivf* h) {
     if (h->ix.d_cand_sum) cudaFree(h->ix.d_cand_sum);
     if (h->ix.d_tiles) cudaFree(h->ix.d_tiles);
     list_tc_release(&h->ix.tc);
+    list_tc_release(&h->ix.ctc);
+    if (h->ix.d_centre_off) cudaFree(h->ix.d_centre_off);
     delete h;
     return VB_OK;
 }

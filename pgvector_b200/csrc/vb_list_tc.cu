@@ -59,7 +59,25 @@ struct LcArgs {
     float* out;
     int n_kblocks;
     int is_l2;
+    int uniform_nqt;           // > 0: every unit has this many query tiles and a job is one (unit, query tile) pair --
+                               // the centre scan, where ONE "list" (the centre table) is probed by every query
+    int n_jobs;
 };
+
+struct LcJob {
+    ListUnit un;
+    int cnt, q_lo, q_hi;
+};
+// job j of the static round-robin: a (list, table tile) unit with all its query tiles, or one query tile of it
+__device__ __forceinline__ bool lc_job(const LcArgs& a, int j, LcJob& jb) {
+    jb.un = a.units[a.uniform_nqt ? j / a.uniform_nqt : j];
+    jb.cnt = a.grp_cnt[jb.un.list];
+    if (jb.cnt == 0) return false;
+    const int nqt = (jb.cnt + LC_N - 1) / LC_N;
+    jb.q_lo = a.uniform_nqt ? j % a.uniform_nqt : 0;
+    jb.q_hi = a.uniform_nqt ? min(jb.q_lo + 1, nqt) : nqt;
+    return jb.q_lo < jb.q_hi;
+}
 
 __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
     extern __shared__ uint8_t lc_smem_raw[];
@@ -92,13 +110,12 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
     if (warp == 0 && lane == 0) {
         // ===== producer =====
         uint32_t it = 0;
-        for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
-            const ListUnit un = a.units[u];
-            const int cnt = a.grp_cnt[un.list];
-            if (cnt == 0) continue;
-            const int nqt = (cnt + LC_N - 1) / LC_N;
+        for (int j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
+            LcJob jb;
+            if (!lc_job(a, j, jb)) continue;
+            const ListUnit un = jb.un;
             const int gt0 = a.gt_begin[un.list];
-            for (int qt = 0; qt < nqt; ++qt)
+            for (int qt = jb.q_lo; qt < jb.q_hi; ++qt)
                 for (int kb = 0; kb < a.n_kblocks; ++kb, ++it) {
                     const int s = it % LC_STAGES;
                     const uint32_t ph = (it / LC_STAGES) & 1;
@@ -114,12 +131,10 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = make_idesc_bf16(LC_M, LC_N);
         uint32_t it = 0, tile = 0;
-        for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
-            const ListUnit un = a.units[u];
-            const int cnt = a.grp_cnt[un.list];
-            if (cnt == 0) continue;
-            const int nqt = (cnt + LC_N - 1) / LC_N;
-            for (int qt = 0; qt < nqt; ++qt, ++tile) {
+        for (int j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
+            LcJob jb;
+            if (!lc_job(a, j, jb)) continue;
+            for (int qt = jb.q_lo; qt < jb.q_hi; ++qt, ++tile) {
                 const int as = tile & 1;
                 const uint32_t aph = (tile >> 1) & 1;
                 mbar_wait(&tempty_bar[as], aph ^ 1);
@@ -150,17 +165,17 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
         // ===== epilogue: thread = one table row of the tile; columns = queries of the group =====
         const int qr = warp - 4;
         uint32_t tile = 0;
-        for (int u = blockIdx.x; u < a.n_units; u += gridDim.x) {
-            const ListUnit un = a.units[u];
-            const int cnt = a.grp_cnt[un.list];
-            if (cnt == 0) continue;
-            const int nqt = (cnt + LC_N - 1) / LC_N;
+        for (int j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
+            LcJob jb;
+            if (!lc_job(a, j, jb)) continue;
+            const ListUnit un = jb.un;
+            const int cnt = jb.cnt;
             const int64_t lo = a.list_off[un.list], hi = a.list_off[un.list + 1];
             const int64_t r_table = (int64_t)un.tile * LC_M + qr * 32 + lane;
             const bool valid_row = r_table >= lo && r_table < hi;
             const float xnr = valid_row && a.is_l2 ? a.xn[r_table] : 0.f;
             const int gb = a.grp_begin[un.list];
-            for (int qt = 0; qt < nqt; ++qt, ++tile) {
+            for (int qt = jb.q_lo; qt < jb.q_hi; ++qt, ++tile) {
                 const int as = tile & 1;
                 const uint32_t aph = (tile >> 1) & 1;
                 mbar_wait(&tfull_bar[as], aph);
@@ -385,7 +400,7 @@ void list_tc_release(ListTcImage* im) {
 // approximate pass: fills `out` (the per-query candidate runs) with d~
 int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
                    const int32_t* d_lists, int probes, const int32_t* cand_off, int64_t cap, const int64_t* d_list_off, int n_lists,
-                   float* out, const float** qn_out) {
+                   float* out, const float** qn_out, bool one_list_all_queries) {
     Context& c = ctx();
     cudaStream_t s = c.stream;
     QueryGroups g{};
@@ -424,7 +439,9 @@ int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, con
     a.out = out;
     a.n_kblocks = im.n_kblocks;
     a.is_l2 = key_metric == VB_L2_SQUARED;
-    const int grid = std::max(1, std::min(im.n_units, c.sm_count));
+    a.uniform_nqt = one_list_all_queries ? (int)((nq * probes + LC_N - 1) / LC_N) : 0;
+    a.n_jobs = a.uniform_nqt ? im.n_units * a.uniform_nqt : im.n_units;
+    const int grid = std::max(1, std::min(a.n_jobs, c.sm_count));
     list_tc_kernel<<<grid, LC_THREADS, LC_SMEM, s>>>(a);
     VB_CUDA(cudaGetLastError());
     count_launch();

@@ -185,6 +185,39 @@ def test_list_major_scan_equals_per_query_scan(pv, opclass, dim):
     assert (got[3, 1][0] == got[0, 1][0]).mean() > 0.99
 
 
+@pytest.mark.parametrize("opclass", ["vector_l2_ops", "vector_cosine_ops", "halfvec_l2_ops"])
+def test_probe_selection_through_the_tensor_core_filter(pv, opclass):
+    """GetScanLists for a query batch over >= 128 centres runs the filter + exact re-score + certificate: the probed
+    lists and their order equal the exact kernels' and the oracle's."""
+    import os
+    elem, metric, normalize, _ = pv.OPCLASSES[opclass]
+    lists, dim = 160, 48
+    x, c = mixture(16000, dim, lists, seed=31)
+    q, _ = mixture(320, dim, lists, seed=32)
+    if elem == O.HALFVEC:
+        x, c, q = f32_to_half_bits(x), f32_to_half_bits(c), f32_to_half_bits(q)
+    if normalize:
+        x, c, q = O.l2_normalize(elem, x), O.l2_normalize(elem, c), O.l2_normalize(elem, q)
+    gix, oix = make_index(pv, opclass, x, c, dim=dim)
+    try:
+        pv.set_option("scan_impl", 3)
+        l3, d3 = gix.scan_lists(q, 7)
+        i3, s3 = gix.search(q, k=10, probes=7)
+        pv.set_option("scan_impl", 4)
+        l4, d4 = gix.scan_lists(q, 7)
+        i4, s4 = gix.search(q, k=10, probes=7)
+    finally:
+        pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
+    assert np.array_equal(l3, l4)
+    assert np.allclose(d3, d4, rtol=RTOL, atol=1e-6)
+    for i in range(0, 320, 16):
+        wl, wd = oix.scan_lists(q[i], 7)
+        assert np.array_equal(l4[i][:len(wl)], wl), i
+        assert np.allclose(d4[i][:len(wl)], wd, rtol=RTOL, atol=1e-6)
+    assert np.allclose(s3, s4, rtol=RTOL, atol=1e-6)
+    assert (i3 == i4).mean() > 0.995
+
+
 def test_tensor_core_filter_falls_back_when_it_cannot_certify(pv):
     """Duplicated rows put the k-th and the k'-th candidate at the same distance, so the certificate
     (k'-th approximate distance - eps > k-th exact distance) cannot hold: those batches must come back from the
