@@ -57,6 +57,9 @@ struct Ivf {
     ListTcImage tc;                   // packed bf16 planes + norms + (list, tile) units, built on first tensor-core scan
     ListTcImage ctc;                  // the same for the centre table (one pseudo list probed by every query)
     int64_t* d_centre_off = nullptr;  // {0, lists}
+    int* d_tc_fail = nullptr;         // device counters of uncertified queries: [0] probe selection, [1] list scan
+    bool defer_tc_check = false;      // batched search: counters are read once, with the results
+    bool force_exact = false;         // re-run of a batch whose certificate failed
     int64_t last_tc_failed = 0, total_tc_failed = 0;
     bool loaded = false;
 };
@@ -179,10 +182,15 @@ static int ivf_select_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t 
     // query -- approximate distances to all centres, the k' nearest re-scored exactly, order (distance, list number)
     // certified; any uncertified query sends the batch through the exact tiles below.
     const int km = key_metric(ix.metric);
-    bool tc = (c.scan_impl == 2 || c.scan_impl == 4) && nq >= 256 && ix.lists >= 128 && list_tc_supported(ix.elem, km, probes);
+    bool tc = (c.scan_impl == 2 || c.scan_impl == 4) && !ix.force_exact && nq >= 256 && ix.lists >= 128 &&
+              list_tc_supported(ix.elem, km, probes);
     if (tc) {
         VB_TRY(ivf_ensure_centre_tc(ix));
         tc = ix.ctc.finite && ix.ctc.planes != nullptr;
+    }
+    if (tc && !ix.d_tc_fail) {
+        VB_CUDA(cudaMalloc(&ix.d_tc_fail, 2 * sizeof(int)));
+        VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, 2 * sizeof(int), c.stream));
     }
     if (tc) {
         const int kp = list_tc_kp(probes);
@@ -208,11 +216,12 @@ static int ivf_select_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t 
                               (float*)d_cdist, &qn, true));
         VB_TRY(launch_segment_topk_v((const float*)d_cdist, sb, sl, nullptr, nullptr, nq, kp, pos_kp, key_kp));
         int n_failed = 0;
+        if (!ix.defer_tc_check) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, sizeof(int), c.stream));
         VB_TRY(launch_list_tc_refine(ix.centers, ix.ctc, km, qimg, qstride, nq, probes, kp, 1, zero_lists, pair_off, ix.d_centre_off, sl,
-                                     qn, pos_kp, key_kp, lists, ldist, &n_failed));
+                                     qn, pos_kp, key_kp, lists, ldist, ix.d_tc_fail, ix.defer_tc_check ? nullptr : &n_failed));
         prof_end(VB_PROF_SCAN_LISTS);
         ix.total_tc_failed += n_failed;
-        if (n_failed == 0) {
+        if (n_failed == 0) {   // (deferred: optimistic, the caller checks the counter with its own synchronisation)
             *d_lists = lists;
             *d_ldist = ldist;
             return VB_OK;
@@ -323,7 +332,7 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
     // filter (HBM-bound), larger k through the fp32 list-major kernel (FMA-pipe bound).
     const int km = key_metric(ix.metric);
     const bool batched = nq * probes >= 256;
-    bool tc = (c.scan_impl == 4 || c.scan_impl == 2) && batched && list_tc_supported(ix.elem, km, k) && ix.rows.n > 0;
+    bool tc = (c.scan_impl == 4 || c.scan_impl == 2) && !ix.force_exact && batched && list_tc_supported(ix.elem, km, k) && ix.rows.n > 0;
     if (tc) {
         VB_TRY(ivf_ensure_tc_image(ix));
         tc = ix.tc.finite;   // rows with Inf / NaN norms have no error bound: exact path
@@ -342,8 +351,13 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
         prof_begin(VB_PROF_TOPK);
         VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, nullptr, nullptr, nq, kp, pos_kp, key_kp));
         int n_failed = 0;
+        if (!ix.d_tc_fail) {
+            VB_CUDA(cudaMalloc(&ix.d_tc_fail, 2 * sizeof(int)));
+            VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, 2 * sizeof(int), c.stream));
+        }
+        if (!ix.defer_tc_check) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail + 1, 0, sizeof(int), c.stream));
         VB_TRY(launch_list_tc_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off, seg_len, qn,
-                                     pos_kp, key_kp, pos, key, &n_failed));
+                                     pos_kp, key_kp, pos, key, ix.d_tc_fail + 1, ix.defer_tc_check ? nullptr : &n_failed));
         prof_end(VB_PROF_TOPK);
         ix.last_tc_failed = n_failed;
         ix.total_tc_failed += n_failed;
@@ -685,6 +699,7 @@ int vb_ivf_free(vb_ivf* h) {
     list_tc_release(&h->ix.tc);
     list_tc_release(&h->ix.ctc);
     if (h->ix.d_centre_off) cudaFree(h->ix.d_centre_off);
+    if (h->ix.d_tc_fail) cudaFree(h->ix.d_tc_fail);
     delete h;
     return VB_OK;
 }
@@ -793,8 +808,13 @@ static int ivf_search_impl(vb_ivf* h, const void* queries, int64_t nq, int probe
     const int64_t bq = ivf_batch_limit(ix, probes);
     if (!ix.d_cand_sum) VB_CUDA(cudaMalloc(&ix.d_cand_sum, sizeof(int64_t)));
     VB_CUDA(cudaMemsetAsync(ix.d_cand_sum, 0, sizeof(int64_t), c.stream));
-    for (int64_t q0 = 0; q0 < nq; q0 += bq) {
-        int64_t m = std::min(bq, nq - q0);
+    // One pass of a sub-batch.  The tensor-core filter runs optimistically: its certificate counters are read back
+    // together with the results (one synchronisation per sub-batch); a sub-batch with an uncertified query is run
+    // again on the exact kernels.
+    auto run = [&](int64_t q0, int64_t m, bool exact, int* fails) -> int {
+        ix.force_exact = exact;
+        ix.defer_tc_check = !exact;
+        if (ix.d_tc_fail) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, 2 * sizeof(int), c.stream));
         void* qimg;
         size_t qstride;
         VB_TRY(upload_queries(ix.elem, ix.dim, (const uint8_t*)queries + (size_t)q0 * rawq, m, host, WS_QIMG, &qimg, &qstride));
@@ -809,11 +829,28 @@ static int ivf_search_impl(vb_ivf* h, const void* queries, int64_t nq, int probe
             VB_TRY(ivf_scan_topk(ix, qimg, qstride, m, d_lists, probes, k, o_ids, nullptr, o_d, nullptr));
             VB_CUDA(cudaMemcpyAsync(out_ids + q0 * k, o_ids, sizeof(int64_t) * (size_t)m * k, cudaMemcpyDeviceToHost, c.stream));
             VB_CUDA(cudaMemcpyAsync(out_d + q0 * k, o_d, sizeof(double) * (size_t)m * k, cudaMemcpyDeviceToHost, c.stream));
-            VB_CUDA(cudaStreamSynchronize(c.stream));
         } else {
             VB_TRY(ivf_scan_topk(ix, qimg, qstride, m, d_lists, probes, k, out_ids + q0 * k, out_f + q0 * k, nullptr, nullptr));
         }
+        fails[0] = fails[1] = 0;
+        const bool check = !exact && ix.d_tc_fail != nullptr;
+        if (check) VB_CUDA(cudaMemcpyAsync(fails, ix.d_tc_fail, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        if (host || check) VB_CUDA(cudaStreamSynchronize(c.stream));
+        return VB_OK;
+    };
+    int rc = VB_OK;
+    for (int64_t q0 = 0; q0 < nq && rc == VB_OK; q0 += bq) {
+        const int64_t m = std::min(bq, nq - q0);
+        int fails[2];
+        rc = run(q0, m, false, fails);
+        if (rc == VB_OK && fails[0] + fails[1] > 0) {
+            ix.total_tc_failed += fails[0] + fails[1];
+            rc = run(q0, m, true, fails);
+        }
     }
+    ix.force_exact = false;
+    ix.defer_tc_check = false;
+    VB_TRY(rc);
     ix.last_cand = -1;  // fetched lazily
     ix.last_bytes = nq;
     return VB_OK;

@@ -8,10 +8,11 @@
 //   1. approximate pass:  d~ = |x|^2 + |q|^2 - 2 x.q   (or -x.q), x.q from three bf16 MMAs on the hi/lo split of
 //      both operands (hi.hi + hi.lo + lo.hi, fp32 accumulation in TMEM) -- |d~ - d| <= eps(q), a rigorous bound;
 //   2. the k' = k + slack smallest d~ of every query are selected (segment_topk_kernel);
-//   3. those k' candidates are re-scored with the exact scan arithmetic (Acc<>, same as scan_kernel);
-//   4. the k nearest by (exact distance, position) are emitted, and the query is CERTIFIED: every candidate that
-//      was not re-scored has d >= d~ - eps >= (k'-th d~) - eps, so if that is > the k-th exact distance the
-//      result equals the full exact scan.  Queries that fail the certificate are re-run on the exact kernel.
+//   3. of those, the candidates with d~ <= (k-th d~) + 2 eps are re-scored with the exact scan arithmetic (Acc<>,
+//      same as scan_kernel) -- nothing above that threshold can be among the k nearest;
+//   4. the k nearest by (exact distance, position) are emitted, and the query is CERTIFIED when the k'-th d~ is
+//      itself above the threshold (then so is every candidate that was not selected), i.e. the result equals the
+//      full exact scan.  A batch with an uncertified query is re-run on the exact kernel.
 //
 // Layout.  The index rows are packed once per load into bf16 hi/lo planes in the 128-byte-swizzled shared-memory
 // image, one 32 KB block per (128-row table tile, 64-dimension block); a unit of work is a (list, table tile)
@@ -251,10 +252,26 @@ __global__ void pack_groups_kernel(const float* __restrict__ qimg, size_t qstrid
     *reinterpret_cast<uint4*>(base + LC_B_PLANE + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// exact distance of the selected candidates: one warp per (query, candidate), the arithmetic of the scan kernels
+// |d~ - d_fp32| <= eps(q) for every candidate of query q
+struct LcBound {
+    int is_l2;
+    float c_dot, c_sum, xmax;
+};
+__device__ __forceinline__ float lc_eps(const LcBound& b, float qn) {
+    return b.c_dot * sqrtf(qn) * b.xmax + (b.is_l2 ? b.c_sum * (b.xmax * b.xmax + qn) : 0.f);
+}
+// Only candidates with d~ <= (k-th smallest d~) + 2 eps can belong to the k nearest: the k candidates with the
+// smallest d~ all have d <= (k-th d~) + eps, and anything above the threshold has d > (k-th d~) + eps.
+__device__ __forceinline__ float lc_threshold(const LcBound& b, float qn, const float* approx_q, int k, int kp) {
+    return approx_q[min(k, kp) - 1] + 2.f * lc_eps(b, qn);
+}
+
+// exact distance of the candidates under the threshold: one warp per (query, candidate), the arithmetic of the
+// scan kernels; the others get +inf (they sort behind every re-scored one)
 template <int ELEM, int METRIC>
 __global__ void rescore_kernel(const uint8_t* __restrict__ rows, size_t stride, int V, const uint8_t* __restrict__ qimg,
-                               size_t qstride, int64_t nq, int kp, int probes, const int32_t* __restrict__ pos,
+                               size_t qstride, int64_t nq, int k, int kp, int probes, LcBound bound, const float* __restrict__ qn,
+                               const int32_t* __restrict__ pos, const float* __restrict__ approx,
                                const int32_t* __restrict__ probe_lists, const int32_t* __restrict__ cand_off,
                                const int64_t* __restrict__ list_off, float* __restrict__ exact) {
     const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
@@ -262,7 +279,7 @@ __global__ void rescore_kernel(const uint8_t* __restrict__ rows, size_t stride, 
     if (w >= nq * kp) return;
     const int64_t q = w / kp;
     const int32_t ps = pos[w];
-    if (ps < 0) {
+    if (ps < 0 || approx[w] > lc_threshold(bound, qn[q], approx + q * kp, k, kp)) {   // NaN compares false: re-scored
         if (lane == 0) exact[w] = __int_as_float(0x7F800000);
         return;
     }
@@ -286,8 +303,9 @@ __global__ void rescore_kernel(const uint8_t* __restrict__ rows, size_t stride, 
 }
 
 // one warp per query: order the re-scored candidates by (exact distance, position), emit the first k, and check
-// the certificate  (k'-th approximate distance) - eps > (k-th exact distance)
-__global__ void certify_kernel(int64_t nq, int k, int kp, int is_l2, float c_dot, float c_sum, float xmax,
+// the certificate: the k'-th approximate distance lies above the threshold, so no candidate outside the k' can
+// be under it either (or every candidate of the query was among the k')
+__global__ void certify_kernel(int64_t nq, int k, int kp, LcBound bound,
                                const float* __restrict__ qn, const int32_t* __restrict__ seg_len,
                                const int32_t* __restrict__ pos_kp, const float* __restrict__ approx_kp,
                                const float* __restrict__ exact_kp, int32_t* __restrict__ out_pos, float* __restrict__ out_key,
@@ -306,7 +324,6 @@ __global__ void certify_kernel(int64_t nq, int k, int kp, int is_l2, float c_dot
         keys[i] = key;
     }
     __syncwarp();
-    float kth = __int_as_float(0x7F800000);
     for (int i = lane; i < kp; i += 32) {
         const uint64_t mine = keys[i];
         int rank = 0;
@@ -316,19 +333,11 @@ __global__ void certify_kernel(int64_t nq, int k, int kp, int is_l2, float c_dot
             out_pos[q * k + rank] = present ? (int32_t)(uint32_t)mine : -1;
             out_key[q * k + rank] = present ? key_to_float((uint32_t)(mine >> 32)) : __int_as_float(0x7F800000);
         }
-        if (rank == k - 1) kth = key_to_float((uint32_t)(mine >> 32));
     }
-    // the lane that held rank k-1 has the k-th exact distance; everyone else +inf
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) kth = fminf(kth, __shfl_xor_sync(0xffffffffu, kth, o));
     if (lane == 0) {
         bool ok = true;
-        if (seg_len[q] > kp) {   // some candidates were not re-scored
-            const float qnorm = sqrtf(qn[q]);
-            const float eps = c_dot * qnorm * xmax + (is_l2 ? c_sum * (xmax * xmax + qn[q]) : 0.f);
-            const float last = approx_kp[q * kp + kp - 1];
-            ok = (last - eps) > kth;   // false for NaN
-        }
+        if (seg_len[q] > kp)   // candidates beyond the k' exist: the last of the k' must already be above the threshold
+            ok = approx_kp[q * kp + kp - 1] > lc_threshold(bound, qn[q], approx_kp + q * kp, k, kp);   // false for NaN
         failed[q] = ok ? 0 : 1;
         if (!ok) atomicAdd(n_failed, 1);
     }
@@ -450,23 +459,31 @@ int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, con
     return VB_OK;
 }
 
-// steps 3 + 4: exact re-score of the k' selected candidates, final order, certificate.  n_failed_host receives the
-// number of queries whose certificate failed (the caller re-runs those exactly).
+// steps 3 + 4: exact re-score of the selected candidates, final order, certificate.  The number of queries whose
+// certificate failed is ADDED to *fail_dev (a device counter the caller zeroes); with n_failed_host the counter is
+// also read back (one stream synchronisation), otherwise the caller checks it when it synchronises anyway.
 int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
                           int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
                           const int32_t* seg_len, const float* qn, const int32_t* pos_kp, const float* approx_kp, int32_t* out_pos,
-                          float* out_key, int* n_failed_host) {
+                          float* out_key, int* fail_dev, int* n_failed_host) {
     Context& c = ctx();
     cudaStream_t s = c.stream;
     void* d_ws;
     VB_TRY(workspace(WSC_K, sizeof(float) * (size_t)nq * kp + (size_t)nq + 64, &d_ws));
-    int* n_failed = (int*)d_ws;
+    int* n_failed = fail_dev;
     float* exact = (float*)d_ws + 16;
     uint8_t* failed = (uint8_t*)(exact + (size_t)nq * kp);
-    VB_CUDA(cudaMemsetAsync(n_failed, 0, sizeof(int), s));
     const int V = (int)(rows.stride / 16);
     const unsigned grid = (unsigned)((nq * kp * 32 + 255) / 256);
-#define VB_RS(E, M) rescore_kernel<E, M><<<grid, 256, 0, s>>>(rows.d, rows.stride, V, (const uint8_t*)qimg, qstride, nq, kp, probes, pos_kp, d_lists, cand_off, d_list_off, exact)
+    // |d~ - d_fp32| <= eps.  Split product: representation 2^-18 + 2^-17, TMEM accumulation over 3 * dim / 16 steps
+    // -> 2^-13 |x||q| with ~2.5x head-room (x2 in the L2 form).  The fp32 norms, the final sum and the rounding of
+    // the exact fp32 distance it is compared with: 2^-16 (|x|^2 + |q|^2) for L2, 2^-17 |x||q| for the inner product.
+    LcBound bound;
+    bound.is_l2 = key_metric == VB_L2_SQUARED;
+    bound.c_dot = bound.is_l2 ? 1.0f / 4096.0f : 1.0f / 8192.0f + 1.0f / 131072.0f;
+    bound.c_sum = 1.0f / 65536.0f;
+    bound.xmax = im.xmax;
+#define VB_RS(E, M) rescore_kernel<E, M><<<grid, 256, 0, s>>>(rows.d, rows.stride, V, (const uint8_t*)qimg, qstride, nq, k, kp, probes, bound, qn, pos_kp, approx_kp, d_lists, cand_off, d_list_off, exact)
     if (rows.elem == VB_VECTOR) {
         if (key_metric == VB_L2_SQUARED) VB_RS(VB_VECTOR, VB_L2_SQUARED);
         else VB_RS(VB_VECTOR, VB_NEG_IP);
@@ -475,18 +492,14 @@ int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metr
         else VB_RS(VB_HALFVEC, VB_NEG_IP);
     }
 #undef VB_RS
-    // |d~ - d_fp32| <= eps.  Split product: representation 2^-18 + 2^-17, TMEM accumulation over 3 * dim / 16 steps
-    // -> 2^-13 |x||q| with ~2.5x head-room (x2 in the L2 form).  The fp32 norms, the final sum and the rounding of
-    // the exact fp32 distance it is compared with: 2^-16 (|x|^2 + |q|^2) for L2, 2^-17 |x||q| for the inner product.
-    const int is_l2 = key_metric == VB_L2_SQUARED;
-    const float c_dot = is_l2 ? 1.0f / 4096.0f : 1.0f / 8192.0f + 1.0f / 131072.0f;
-    const float c_sum = 1.0f / 65536.0f;
-    certify_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, s>>>(nq, k, kp, is_l2, c_dot, c_sum, im.xmax, qn, seg_len, pos_kp, approx_kp,
-                                                                    exact, out_pos, out_key, n_failed, failed);
+    certify_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, s>>>(nq, k, kp, bound, qn, seg_len, pos_kp, approx_kp, exact, out_pos, out_key,
+                                                                    n_failed, failed);
     VB_CUDA(cudaGetLastError());
     count_launch(2);
-    VB_CUDA(cudaMemcpyAsync(n_failed_host, n_failed, sizeof(int), cudaMemcpyDeviceToHost, s));
-    VB_CUDA(cudaStreamSynchronize(s));
+    if (n_failed_host) {
+        VB_CUDA(cudaMemcpyAsync(n_failed_host, n_failed, sizeof(int), cudaMemcpyDeviceToHost, s));
+        VB_CUDA(cudaStreamSynchronize(s));
+    }
     return VB_OK;
 }
 
