@@ -494,6 +494,7 @@ def main():
             roofline["fp32_terms_per_s"] = cand_per_step * args.dim / (scan_avg_ms / 1000.0) if scan_avg_ms > 0 else 0.0
         else:
             roofline["certificate_fallback_queries"] = ix.tc_fallbacks()
+            roofline["level1_fallback_queries"] = ix.tc_level1_fallbacks()
             roofline["bf16_mma_tflops_issued"] = 3 * 2.0 * cand_per_step * args.dim / (scan_avg_ms / 1000.0) / 1e12 if scan_avg_ms > 0 else 0.0
 
     # ---- recall@10 vs exact brute force (GPU exact scan) and CPU baseline

@@ -192,6 +192,9 @@ int64_t		vb_ivf_last_candidates(const vb_ivf *ix);
 /* Queries (cumulative) whose tensor-core filter result could not be certified against the error bound and were
  * re-run on the exact fp32 kernel (option "scan_impl" = 4); 0 when that path is not in use. */
 int64_t		vb_ivf_tc_fallbacks(const vb_ivf *ix);
+/* Queries (cumulative) the first filter level (hi plane of the rows only, option "tc_level1") could not certify; their
+ * batches were repeated with both planes.  After such a batch the level rests for 64 batches. */
+int64_t		vb_ivf_tc_level1_fallbacks(const vb_ivf *ix);
 
 /* ------------------------------------------------------- IVFFlat build path */
 
@@ -238,7 +241,9 @@ int64_t		vb_last_assign_rechecked(void);
  * automatic (query batches are scanned list-major: each probed list read once per batch, fp32x2 register
  * tiles; single queries stream), 3 = list-major wherever it applies, 4 = tensor-core filter (split-bf16
  * tcgen05 distances, exact fp32 re-score of k' candidates, certificate, exact fallback) wherever it applies.
- * Every setting returns the same neighbours.  "tensor_cores" as vb_set_tensor_cores.
+ * Every setting returns the same neighbours.  "tc_level1" (default 1): the tensor-core filter first reads only the
+ * hi plane of the rows (half the HBM traffic, 2^-7 relative error bound) and repeats a batch with both planes when a
+ * certificate fails.  "tensor_cores" as vb_set_tensor_cores.
  */
 int			vb_set_option(const char *name, int64_t value);
 

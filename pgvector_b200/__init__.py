@@ -302,6 +302,10 @@ class IvfflatIndex:
     def last_candidates(self):
         return int(load().vb_ivf_last_candidates(self.h))
 
+    def tc_level1_fallbacks(self):
+        """queries the hi-plane-only filter level could not certify (their batches were repeated with both planes)"""
+        return int(load().vb_ivf_tc_level1_fallbacks(self.h))
+
     def tc_fallbacks(self):
         """queries re-run exactly because the tensor-core filter could not certify them (scan_impl = 4)"""
         return int(load().vb_ivf_tc_fallbacks(self.h))

@@ -51,6 +51,7 @@ SIGNATURES = {
     "vb_ivf_last_scan_bytes": (_i64, [_vp]),
     "vb_ivf_last_candidates": (_i64, [_vp]),
     "vb_ivf_tc_fallbacks": (_i64, [_vp]),
+    "vb_ivf_tc_level1_fallbacks": (_i64, [_vp]),
     "vb_kmeans": (_i, [_vp, _i, _vp, _i, _i, _u64, _vp, _vp, _vp]),
     "vb_kmeans_pp_init": (_i, [_vp, _i, _vp, _i, _u64]),
     "vb_assign": (_i, [_vp, _i, _vp, _i, _vp]),

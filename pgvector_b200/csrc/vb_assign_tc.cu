@@ -324,6 +324,10 @@ int vb_set_option(const char* name, int64_t value) {
         vb::ctx().scan_impl = (int)value;
         return VB_OK;
     }
+    if (!strcmp(name, "tc_level1")) {
+        vb::ctx().tc_level1 = value != 0;
+        return VB_OK;
+    }
     if (!strcmp(name, "tensor_cores")) {
         vb::set_tc_enabled(value != 0);
         return VB_OK;

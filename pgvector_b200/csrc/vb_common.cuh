@@ -46,6 +46,7 @@ struct Context {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     int64_t launches = 0;
+    int tc_level1 = 1;                 // batched list scan: try the hi-plane-only filter first (vb_set_option "tc_level1")
     int scan_impl = 2;                 // 0 = LDG variant (vb_scan.cu), 1 = bulk-copy / TMA variant (vb_scan_bulk.cu), 2 = by table size
     int64_t last_assign_flagged = -1;  // rows re-checked by the exact kernel in the last tensor-core assign (-1: exact path)
     // grow-only device workspace arenas (index = slot)
@@ -178,16 +179,16 @@ struct ListTcImage {
     bool finite = true;          // false when a row norm is Inf / NaN (no error bound -> exact path only)
 };
 bool list_tc_supported(int elem, int key_metric, int k);
-int list_tc_kp(int k);
+int list_tc_kp(int k, int level = 2);
 int list_tc_prepare(const Table& rows, ListTcImage* im);
 void list_tc_release(ListTcImage* im);
 int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
                    const int32_t* d_lists, int probes, const int32_t* cand_off, int64_t cap, const int64_t* d_list_off, int n_lists,
-                   float* out, const float** qn_out, bool one_list_all_queries = false);
+                   float* out, const float** qn_out, bool one_list_all_queries = false, int level = 2);
 int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
                           int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
                           const int32_t* seg_len, const float* qn, const int32_t* pos_kp, const float* approx_kp, int32_t* out_pos,
-                          float* out_key, int* fail_dev, int* n_failed_host);
+                          float* out_key, int* fail_dev, int* n_failed_host, int level = 2);
 int list_tile_rows();
 bool list_major_supported(int elem, int key_metric);
 int launch_list_major(const Table& rows, int key_metric, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists,

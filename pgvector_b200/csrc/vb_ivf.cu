@@ -60,7 +60,10 @@ struct Ivf {
     int* d_tc_fail = nullptr;         // device counters of uncertified queries: [0] probe selection, [1] list scan
     bool defer_tc_check = false;      // batched search: counters are read once, with the results
     bool force_exact = false;         // re-run of a batch whose certificate failed
-    int64_t last_tc_failed = 0, total_tc_failed = 0;
+    bool force_level2 = false;        // re-run of a batch whose level-1 (hi plane only) certificate failed
+    int last_list_level = 0;          // filter level the last batched list scan ran at (0 = exact kernels)
+    int l1_cooldown = 0;              // batches left before level 1 is tried again after it failed
+    int64_t last_tc_failed = 0, total_tc_failed = 0, total_l1_failed = 0;
     bool loaded = false;
 };
 
@@ -337,11 +340,18 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
         VB_TRY(ivf_ensure_tc_image(ix));
         tc = ix.tc.finite;   // rows with Inf / NaN norms have no error bound: exact path
     }
+    ix.last_list_level = 0;
     if (tc) {
-        const int kp = list_tc_kp(k);
+        // level 1 reads only the hi plane of the rows (half the HBM traffic, error bound 2^-7 |x||q|): it certifies
+        // whenever the neighbours are separated by more than that, otherwise the batch is repeated at level 2 (both
+        // planes, 2^-12) and level 1 rests for a while
+        const int level = (c.tc_level1 && !ix.force_level2 && ix.l1_cooldown == 0 && list_tc_kp(k, 1) <= 128) ? 1 : 2;
+        if (ix.l1_cooldown > 0 && !ix.force_level2) --ix.l1_cooldown;
+        ix.last_list_level = level;
+        const int kp = list_tc_kp(k, level);
         const float* qn = nullptr;
         VB_TRY(launch_list_tc(ix.rows, ix.tc, km, qimg, qstride, nq, d_lists, probes, cand_off, cap, ix.d_list_off, ix.lists,
-                              (float*)d_dist, &qn));
+                              (float*)d_dist, &qn, false, level));
         prof_end(VB_PROF_SCAN_ITEMS);
         VB_TRY(workspace(WS_POS, (sizeof(int32_t) + sizeof(float)) * (size_t)nq * (k + kp), &d_pos));
         int32_t* pos = (int32_t*)d_pos;
@@ -357,7 +367,7 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
         }
         if (!ix.defer_tc_check) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail + 1, 0, sizeof(int), c.stream));
         VB_TRY(launch_list_tc_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off, seg_len, qn,
-                                     pos_kp, key_kp, pos, key, ix.d_tc_fail + 1, ix.defer_tc_check ? nullptr : &n_failed));
+                                     pos_kp, key_kp, pos, key, ix.d_tc_fail + 1, ix.defer_tc_check ? nullptr : &n_failed, level));
         prof_end(VB_PROF_TOPK);
         ix.last_tc_failed = n_failed;
         ix.total_tc_failed += n_failed;
@@ -811,8 +821,10 @@ static int ivf_search_impl(vb_ivf* h, const void* queries, int64_t nq, int probe
     // One pass of a sub-batch.  The tensor-core filter runs optimistically: its certificate counters are read back
     // together with the results (one synchronisation per sub-batch); a sub-batch with an uncertified query is run
     // again on the exact kernels.
-    auto run = [&](int64_t q0, int64_t m, bool exact, int* fails) -> int {
+    auto run = [&](int64_t q0, int64_t m, int mode, int* fails) -> int {   // mode 0: automatic, 1: filter level 2, 2: exact
+        const bool exact = mode == 2;
         ix.force_exact = exact;
+        ix.force_level2 = mode == 1;
         ix.defer_tc_check = !exact;
         if (ix.d_tc_fail) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, 2 * sizeof(int), c.stream));
         void* qimg;
@@ -842,13 +854,21 @@ static int ivf_search_impl(vb_ivf* h, const void* queries, int64_t nq, int probe
     for (int64_t q0 = 0; q0 < nq && rc == VB_OK; q0 += bq) {
         const int64_t m = std::min(bq, nq - q0);
         int fails[2];
-        rc = run(q0, m, false, fails);
+        rc = run(q0, m, 0, fails);
+        if (rc == VB_OK && fails[0] == 0 && fails[1] > 0 && ix.last_list_level == 1) {
+            // the hi-plane filter could not separate the neighbours of some query: both planes, and leave level 1 alone
+            // for the next batches (the data decides this, not the batch)
+            ix.total_l1_failed += fails[1];
+            ix.l1_cooldown = 64;
+            rc = run(q0, m, 1, fails);
+        }
         if (rc == VB_OK && fails[0] + fails[1] > 0) {
             ix.total_tc_failed += fails[0] + fails[1];
-            rc = run(q0, m, true, fails);
+            rc = run(q0, m, 2, fails);
         }
     }
     ix.force_exact = false;
+    ix.force_level2 = false;
     ix.defer_tc_check = false;
     VB_TRY(rc);
     ix.last_cand = -1;  // fetched lazily
@@ -864,6 +884,7 @@ int vb_ivf_search_dev(vb_ivf* h, const void* queries_dev, int64_t nq, int probes
 }
 
 int64_t vb_ivf_tc_fallbacks(const vb_ivf* h) { return h ? h->ix.total_tc_failed : 0; }
+int64_t vb_ivf_tc_level1_fallbacks(const vb_ivf* h) { return h ? h->ix.total_l1_failed : 0; }
 
 int64_t vb_ivf_last_candidates(const vb_ivf* h) {
     if (!h || !h->ix.d_cand_sum) return 0;

@@ -42,7 +42,7 @@ constexpr uint32_t LC_A_STAGE = 2 * LC_A_PLANE;
 constexpr uint32_t LC_B_STAGE = 2 * LC_B_PLANE;
 constexpr uint32_t LC_STAGE = LC_A_STAGE + LC_B_STAGE;  // 48 KB
 constexpr size_t LC_SMEM = (size_t)LC_STAGES * LC_STAGE + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int LC_MAX_KP = 64;                            // candidates re-scored per query, at most
+constexpr int LC_MAX_KP = 128;                           // candidates selected per query, at most
 
 struct LcArgs {
     const uint8_t* A;          // table planes [tile][kb][2][128 x 64]
@@ -60,6 +60,7 @@ struct LcArgs {
     float* out;
     int n_kblocks;
     int is_l2;
+    int hi_only;               // level 1: only the hi plane of the rows is read and multiplied (x_hi . (q_hi + q_lo))
     int uniform_nqt;           // > 0: every unit has this many query tiles and a job is one (unit, query tile) pair --
                                // the centre scan, where ONE "list" (the centre table) is probed by every query
     int n_jobs;
@@ -123,8 +124,9 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + (size_t)s * LC_STAGE;
                     uint8_t* sb = sa + LC_A_STAGE;
-                    mbar_arrive_expect_tx(&full_bar[s], LC_STAGE);
-                    bulk_g2s(sa, a.A + ((size_t)un.tile * a.n_kblocks + kb) * LC_A_STAGE, LC_A_STAGE, &full_bar[s]);
+                    const uint32_t a_bytes = a.hi_only ? LC_A_PLANE : LC_A_STAGE;   // the hi plane leads each 32 KB block
+                    mbar_arrive_expect_tx(&full_bar[s], a_bytes + LC_B_STAGE);
+                    bulk_g2s(sa, a.A + ((size_t)un.tile * a.n_kblocks + kb) * LC_A_STAGE, a_bytes, &full_bar[s]);
                     bulk_g2s(sb, a.B + ((size_t)(gt0 + qt) * a.n_kblocks + kb) * LC_B_STAGE, LC_B_STAGE, &full_bar[s]);
                 }
         }
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
                         const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
                         umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kb | k) != 0);
                         umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
-                        umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
+                        if (!a.hi_only) umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
                     }
                     umma_commit(&empty_bar[s]);
                 }
@@ -349,11 +351,13 @@ enum { WSC_B = 21, WSC_N = 22, WSC_K = 23 };
 
 bool list_tc_supported(int elem, int key_metric, int k) {
     return (elem == VB_VECTOR || elem == VB_HALFVEC) && (key_metric == VB_L2_SQUARED || key_metric == VB_NEG_IP) && k >= 1 &&
-           list_tc_kp(k) <= LC_MAX_KP;
+           list_tc_kp(k, 2) <= LC_MAX_KP;
 }
 
-int list_tc_kp(int k) {
-    // slack of the filter: the certificate needs the k'-th approximate distance to clear the k-th exact one by eps
+int list_tc_kp(int k, int level) {
+    // candidates kept per query.  Only those under the threshold are re-scored, so a generous k' costs a slightly
+    // larger selection, not more exact distances; the certificate fails only when ALL k' are under the threshold.
+    if (level == 1) return k <= 40 ? 128 : 1 << 20;
     return k <= 10 ? 32 : k <= 24 ? 48 : k <= 40 ? 64 : 1 << 20;
 }
 
@@ -409,7 +413,7 @@ void list_tc_release(ListTcImage* im) {
 // approximate pass: fills `out` (the per-query candidate runs) with d~
 int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
                    const int32_t* d_lists, int probes, const int32_t* cand_off, int64_t cap, const int64_t* d_list_off, int n_lists,
-                   float* out, const float** qn_out, bool one_list_all_queries) {
+                   float* out, const float** qn_out, bool one_list_all_queries, int level) {
     Context& c = ctx();
     cudaStream_t s = c.stream;
     QueryGroups g{};
@@ -448,6 +452,7 @@ int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, con
     a.out = out;
     a.n_kblocks = im.n_kblocks;
     a.is_l2 = key_metric == VB_L2_SQUARED;
+    a.hi_only = level == 1;
     a.uniform_nqt = one_list_all_queries ? (int)((nq * probes + LC_N - 1) / LC_N) : 0;
     a.n_jobs = a.uniform_nqt ? im.n_units * a.uniform_nqt : im.n_units;
     const int grid = std::max(1, std::min(a.n_jobs, c.sm_count));
@@ -465,7 +470,7 @@ int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, con
 int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
                           int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
                           const int32_t* seg_len, const float* qn, const int32_t* pos_kp, const float* approx_kp, int32_t* out_pos,
-                          float* out_key, int* fail_dev, int* n_failed_host) {
+                          float* out_key, int* fail_dev, int* n_failed_host, int level) {
     Context& c = ctx();
     cudaStream_t s = c.stream;
     void* d_ws;
@@ -482,6 +487,11 @@ int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metr
     bound.is_l2 = key_metric == VB_L2_SQUARED;
     bound.c_dot = bound.is_l2 ? 1.0f / 4096.0f : 1.0f / 8192.0f + 1.0f / 131072.0f;
     bound.c_sum = 1.0f / 65536.0f;
+    if (level == 1) {
+        // rows reduced to their hi plane: |x - x_hi| <= 2^-8 |x| (bf16 unit roundoff), so the product is off by at most
+        // 2^-8 |x||q| on top of the level-2 terms (query split, accumulation)
+        bound.c_dot = bound.is_l2 ? 1.0f / 128.0f + 1.0f / 4096.0f : 1.0f / 256.0f + 1.0f / 8192.0f + 1.0f / 131072.0f;
+    }
     bound.xmax = im.xmax;
 #define VB_RS(E, M) rescore_kernel<E, M><<<grid, 256, 0, s>>>(rows.d, rows.stride, V, (const uint8_t*)qimg, qstride, nq, k, kp, probes, bound, qn, pos_kp, approx_kp, d_lists, cand_off, d_list_off, exact)
     if (rows.elem == VB_VECTOR) {

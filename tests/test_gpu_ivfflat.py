@@ -218,6 +218,43 @@ def test_probe_selection_through_the_tensor_core_filter(pv, opclass):
     assert (i3 == i4).mean() > 0.995
 
 
+@pytest.mark.parametrize("latent", [0, 8])
+def test_filter_levels_return_identical_results(pv, latent):
+    """Level 1 (hi plane of the rows only) and level 2 (both planes) of the tensor-core filter end in the same exact
+    re-score, so whatever level certifies a batch the output is bit-identical.  Isotropic data (latent = 0) has
+    neighbour gaps below the level-1 bound -> escalation to level 2; low intrinsic dimension certifies at level 1."""
+    import os
+    rng = np.random.default_rng(41)
+    if latent:
+        frame = np.linalg.qr(rng.standard_normal((64, latent)))[0].astype(np.float32)
+        x = (rng.standard_normal((20000, latent)).astype(np.float32) @ frame.T + 0.01 * rng.standard_normal((20000, 64))).astype(np.float32)
+        q = (rng.standard_normal((400, latent)).astype(np.float32) @ frame.T + 0.01 * rng.standard_normal((400, 64))).astype(np.float32)
+        c = x[rng.choice(20000, 40, replace=False)].copy()
+    else:
+        x, c = mixture(20000, 64, 40, seed=42)
+        q, _ = mixture(400, 64, 40, seed=43)
+    gix, oix = make_index(pv, "vector_l2_ops", x, c)
+    try:
+        pv.set_option("scan_impl", 4)
+        pv.set_option("tc_level1", 0)
+        i2, d2 = gix.search(q, k=10, probes=6)
+        before = gix.tc_level1_fallbacks()
+        pv.set_option("tc_level1", 1)
+        i1, d1 = gix.search(q, k=10, probes=6)
+        l1_failed = gix.tc_level1_fallbacks() - before
+        i1b, d1b = gix.search(q, k=10, probes=6)          # while level 1 rests after a failure
+    finally:
+        pv.set_option("tc_level1", 1)
+        pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    assert np.array_equal(i1b, i2) and np.array_equal(d1b, d2)
+    if latent:
+        assert l1_failed == 0          # well separated neighbours: the cheap level is enough
+    wi, wd = oix.search_batch(q, 6, 10, threads=8)
+    assert np.allclose(d1, wd, rtol=RTOL, atol=1e-6)
+    assert (i1 == wi).mean() > 0.99
+
+
 def test_tensor_core_filter_falls_back_when_it_cannot_certify(pv):
     """Duplicated rows put the k-th and the k'-th candidate at the same distance, so the certificate
     (k'-th approximate distance - eps > k-th exact distance) cannot hold: those batches must come back from the
