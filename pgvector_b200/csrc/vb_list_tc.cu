@@ -34,14 +34,17 @@ namespace vb {
 
 constexpr int LC_M = 128;
 constexpr int LC_N = 64;
-constexpr int LC_STAGES = 4;
+constexpr int LC_STAGES = 4;                             // level 2: 4 x 48 KB in flight per SM
+constexpr int LC_STAGES_L1 = 7;                          // level 1: 7 x 32 KB (A hi plane + B)
+constexpr int LC_MAX_STAGES = 8;
 constexpr int LC_THREADS = 256;
 constexpr uint32_t LC_A_PLANE = LC_M * TC_K * 2;        // 16 KB
 constexpr uint32_t LC_B_PLANE = LC_N * TC_K * 2;        // 8 KB
 constexpr uint32_t LC_A_STAGE = 2 * LC_A_PLANE;
 constexpr uint32_t LC_B_STAGE = 2 * LC_B_PLANE;
 constexpr uint32_t LC_STAGE = LC_A_STAGE + LC_B_STAGE;  // 48 KB
-constexpr size_t LC_SMEM = (size_t)LC_STAGES * LC_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t LC_STAGE_L1 = LC_A_PLANE + LC_B_STAGE;  // 32 KB
+constexpr size_t LC_SMEM = std::max((size_t)LC_STAGES * LC_STAGE, (size_t)LC_STAGES_L1 * LC_STAGE_L1) + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int LC_MAX_KP = 128;                           // candidates selected per query, at most
 
 struct LcArgs {
@@ -84,16 +87,21 @@ __device__ __forceinline__ bool lc_job(const LcArgs& a, int j, LcJob& jb) {
 __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
     extern __shared__ uint8_t lc_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(lc_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)LC_STAGES * LC_STAGE);
+    // stage ring: level 2 = 4 stages of (A hi+lo 32 KB | B 16 KB), level 1 = 7 stages of (A hi 16 KB | B 16 KB) --
+    // the bytes in flight per SM are what keeps HBM busy
+    const int n_stages = a.hi_only ? LC_STAGES_L1 : LC_STAGES;
+    const uint32_t stage_bytes = a.hi_only ? LC_STAGE_L1 : LC_STAGE;
+    const uint32_t a_bytes = a.hi_only ? LC_A_PLANE : LC_A_STAGE;   // the hi plane leads each 32 KB block of the image
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)n_stages * stage_bytes);
     uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + LC_STAGES;
-    uint64_t* tfull_bar = bars + 2 * LC_STAGES;
-    uint64_t* tempty_bar = bars + 2 * LC_STAGES + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * LC_STAGES + 4);
+    uint64_t* empty_bar = bars + LC_MAX_STAGES;
+    uint64_t* tfull_bar = bars + 2 * LC_MAX_STAGES;
+    uint64_t* tempty_bar = bars + 2 * LC_MAX_STAGES + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * LC_MAX_STAGES + 4);
 
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < LC_STAGES; ++s) {
+        for (int s = 0; s < n_stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
         }
@@ -118,21 +126,31 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
             const ListUnit un = jb.un;
             const int gt0 = a.gt_begin[un.list];
             for (int qt = jb.q_lo; qt < jb.q_hi; ++qt)
+            {
+                // a query tile with at most 32 queries is multiplied as N = 32: only the first half of each B plane moves
+                const bool n32 = jb.cnt - qt * LC_N <= 32;
                 for (int kb = 0; kb < a.n_kblocks; ++kb, ++it) {
-                    const int s = it % LC_STAGES;
-                    const uint32_t ph = (it / LC_STAGES) & 1;
+                    const int s = it % n_stages;
+                    const uint32_t ph = (it / n_stages) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* sa = smem + (size_t)s * LC_STAGE;
-                    uint8_t* sb = sa + LC_A_STAGE;
-                    const uint32_t a_bytes = a.hi_only ? LC_A_PLANE : LC_A_STAGE;   // the hi plane leads each 32 KB block
-                    mbar_arrive_expect_tx(&full_bar[s], a_bytes + LC_B_STAGE);
+                    uint8_t* sa = smem + (size_t)s * stage_bytes;
+                    uint8_t* sb = sa + a_bytes;
+                    const uint8_t* gb = a.B + ((size_t)(gt0 + qt) * a.n_kblocks + kb) * LC_B_STAGE;
+                    mbar_arrive_expect_tx(&full_bar[s], a_bytes + (n32 ? LC_B_STAGE / 2 : LC_B_STAGE));
                     bulk_g2s(sa, a.A + ((size_t)un.tile * a.n_kblocks + kb) * LC_A_STAGE, a_bytes, &full_bar[s]);
-                    bulk_g2s(sb, a.B + ((size_t)(gt0 + qt) * a.n_kblocks + kb) * LC_B_STAGE, LC_B_STAGE, &full_bar[s]);
+                    if (n32) {
+                        bulk_g2s(sb, gb, LC_B_PLANE / 2, &full_bar[s]);
+                        bulk_g2s(sb + LC_B_PLANE, gb + LC_B_PLANE, LC_B_PLANE / 2, &full_bar[s]);
+                    } else {
+                        bulk_g2s(sb, gb, LC_B_STAGE, &full_bar[s]);
+                    }
                 }
+            }
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = make_idesc_bf16(LC_M, LC_N);
+        constexpr uint32_t idesc64 = make_idesc_bf16(LC_M, LC_N);
+        constexpr uint32_t idesc32 = make_idesc_bf16(LC_M, 32);
         uint32_t it = 0, tile = 0;
         for (int j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
             LcJob jb;
@@ -143,13 +161,14 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
                 mbar_wait(&tempty_bar[as], aph ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)as * LC_N;
+                const uint32_t idesc = jb.cnt - qt * LC_N <= 32 ? idesc32 : idesc64;
                 for (int kb = 0; kb < a.n_kblocks; ++kb, ++it) {
-                    const int s = it % LC_STAGES;
-                    const uint32_t ph = (it / LC_STAGES) & 1;
+                    const int s = it % n_stages;
+                    const uint32_t ph = (it / n_stages) & 1;
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)s * LC_STAGE);
-                    const uint32_t sb = sa + LC_A_STAGE;
+                    const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+                    const uint32_t sb = sa + a_bytes;
                     const uint64_t da_hi = make_sw128_desc(sa), da_lo = make_sw128_desc(sa + LC_A_PLANE);
                     const uint64_t db_hi = make_sw128_desc(sb), db_lo = make_sw128_desc(sb + LC_B_PLANE);
 #pragma unroll

@@ -256,13 +256,13 @@ def test_filter_levels_return_identical_results(pv, latent):
 
 
 def test_tensor_core_filter_falls_back_when_it_cannot_certify(pv):
-    """Duplicated rows put the k-th and the k'-th candidate at the same distance, so the certificate
-    (k'-th approximate distance - eps > k-th exact distance) cannot hold: those batches must come back from the
-    exact kernel, identical to the other scan settings, and be counted."""
+    """More duplicates of the nearest row than candidates kept per query put the k-th and the k'-th candidate at
+    the same approximate distance, so no filter level can certify: those batches must come back from the exact
+    kernel, identical to the other scan settings, and be counted."""
     import os
     rng = np.random.default_rng(5)
     base = rng.standard_normal((40, 64)).astype(np.float32)
-    rows = np.repeat(base, 100, axis=0)                      # 4000 rows, every vector 100 times
+    rows = np.repeat(base, 200, axis=0)                      # 8000 rows, every vector 200 times (> the 128 candidates kept)
     centers = base[:8].copy()
     q = (base[rng.integers(0, 40, 300)] + 0.01 * rng.standard_normal((300, 64))).astype(np.float32)
     gix, oix = make_index(pv, "vector_l2_ops", rows, centers)
