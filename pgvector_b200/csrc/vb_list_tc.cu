@@ -45,7 +45,6 @@ constexpr uint32_t LC_B_STAGE = 2 * LC_B_PLANE;
 constexpr uint32_t LC_STAGE = LC_A_STAGE + LC_B_STAGE;  // 48 KB
 constexpr uint32_t LC_STAGE_L1 = LC_A_PLANE + LC_B_STAGE;  // 32 KB
 constexpr size_t LC_SMEM = std::max((size_t)LC_STAGES * LC_STAGE, (size_t)LC_STAGES_L1 * LC_STAGE_L1) + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int LC_CHAINS = 4;                             // independent accumulation chains per tile (TMEM column groups)
 constexpr int LC_MAX_KP = 128;                           // candidates selected per query, at most
 
 struct LcArgs {
@@ -112,7 +111,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 2 * LC_CHAINS * LC_N);   // 512 columns = the whole TMEM (one CTA per SM)
+    if (warp == 2) tmem_alloc(tmem_slot, 2 * LC_N);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -161,11 +160,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
                 const uint32_t aph = (tile >> 1) & 1;
                 mbar_wait(&tempty_bar[as], aph ^ 1);
                 tc_fence_after();
-                // With N = 32 / 64 one UMMA is only 8-16 cycles of tensor work and back-to-back MMAs into the SAME accumulator
-                // serialise on it (measured ~120 cycles each).  The products of a tile are therefore dealt round-robin
-                // onto LC_CHAINS accumulators in separate TMEM column groups; the epilogue adds the partial sums.
-                const uint32_t tmem_t = tmem_base + (uint32_t)as * (LC_CHAINS * LC_N);
-                uint32_t m = 0;
+                const uint32_t tmem_d = tmem_base + (uint32_t)as * LC_N;
                 const uint32_t idesc = jb.cnt - qt * LC_N <= 32 ? idesc32 : idesc64;
                 for (int kb = 0; kb < a.n_kblocks; ++kb, ++it) {
                     const int s = it % n_stages;
@@ -179,14 +174,9 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
 #pragma unroll
                     for (int k = 0; k < TC_K / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
-                        umma_bf16(tmem_t + (m % LC_CHAINS) * LC_N, da_hi + adv, db_hi + adv, idesc, m >= LC_CHAINS);
-                        ++m;
-                        umma_bf16(tmem_t + (m % LC_CHAINS) * LC_N, da_hi + adv, db_lo + adv, idesc, m >= LC_CHAINS);
-                        ++m;
-                        if (!a.hi_only) {
-                            umma_bf16(tmem_t + (m % LC_CHAINS) * LC_N, da_lo + adv, db_hi + adv, idesc, m >= LC_CHAINS);
-                            ++m;
-                        }
+                        umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kb | k) != 0);
+                        umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+                        if (!a.hi_only) umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
                     }
                     umma_commit(&empty_bar[s]);
                 }
@@ -212,20 +202,13 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
                 const uint32_t aph = (tile >> 1) & 1;
                 mbar_wait(&tfull_bar[as], aph);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(qr * 32) << 16) + (uint32_t)as * (LC_CHAINS * LC_N);
+                const uint32_t taddr = tmem_base + ((uint32_t)(qr * 32) << 16) + (uint32_t)as * LC_N;
 #pragma unroll
                 for (int c0 = 0; c0 < LC_N; c0 += 32) {
                     const int col0 = qt * LC_N + c0;
                     if (col0 >= cnt) break;   // warp-uniform
                     uint32_t acc[32];
                     tmem_ld32(taddr + c0, acc);
-#pragma unroll
-                    for (int ch = 1; ch < LC_CHAINS; ++ch) {   // add the partial sums of the other chains
-                        uint32_t part[32];
-                        tmem_ld32(taddr + ch * LC_N + c0, part);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(part[j]));
-                    }
                     // lane j fetches the bookkeeping of column j once; broadcast in the loop
                     const int myc = col0 + lane;
                     int64_t my_out = 0;
@@ -251,7 +234,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
         }
     }
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 2 * LC_CHAINS * LC_N);
+    if (warp == 2) tmem_dealloc(tmem_base, 2 * LC_N);
 }
 
 // gather + split the queries of every (query, list) pair into the B tiles of its list's group:
