@@ -45,6 +45,7 @@ constexpr uint32_t LC_B_STAGE = 2 * LC_B_PLANE;
 constexpr uint32_t LC_STAGE = LC_A_STAGE + LC_B_STAGE;  // 48 KB
 constexpr uint32_t LC_STAGE_L1 = LC_A_PLANE + LC_B_STAGE;  // 32 KB
 constexpr size_t LC_SMEM = std::max((size_t)LC_STAGES * LC_STAGE, (size_t)LC_STAGES_L1 * LC_STAGE_L1) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int LC_ACC = 2 * LC_N;                         // TMEM columns of one accumulator stage: [x.q_hi | x.q_lo]
 constexpr int LC_MAX_KP = 128;                           // candidates selected per query, at most
 
 struct LcArgs {
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 2 * LC_N);
+    if (warp == 2) tmem_alloc(tmem_slot, 2 * LC_ACC);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -138,9 +139,9 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
                     const uint8_t* gb = a.B + ((size_t)(gt0 + qt) * a.n_kblocks + kb) * LC_B_STAGE;
                     mbar_arrive_expect_tx(&full_bar[s], a_bytes + (n32 ? LC_B_STAGE / 2 : LC_B_STAGE));
                     bulk_g2s(sa, a.A + ((size_t)un.tile * a.n_kblocks + kb) * LC_A_STAGE, a_bytes, &full_bar[s]);
-                    if (n32) {
+                    if (n32) {   // [q_hi rows 0..31 | q_lo rows 0..31] back to back = one 64-row operand
                         bulk_g2s(sb, gb, LC_B_PLANE / 2, &full_bar[s]);
-                        bulk_g2s(sb + LC_B_PLANE, gb + LC_B_PLANE, LC_B_PLANE / 2, &full_bar[s]);
+                        bulk_g2s(sb + LC_B_PLANE / 2, gb + LC_B_PLANE, LC_B_PLANE / 2, &full_bar[s]);
                     } else {
                         bulk_g2s(sb, gb, LC_B_STAGE, &full_bar[s]);
                     }
@@ -149,7 +150,12 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc64 = make_idesc_bf16(LC_M, LC_N);
+        // One UMMA costs ~130 cycles here whatever its N (it re-reads the 128 x 16 A tile from shared memory), so the
+        // products are merged along N: B = [q_hi ; q_lo] is ONE operand of 2n rows, and x_hi . [q_hi ; q_lo] lands in the
+        // column groups [0, n) and [n, 2n) of the accumulator with a single instruction per K step; level 2 adds
+        // x_lo . q_hi into [0, n).  The epilogue sums the two groups.
+        constexpr uint32_t idesc128 = make_idesc_bf16(LC_M, 128);
+        constexpr uint32_t idesc64 = make_idesc_bf16(LC_M, 64);
         constexpr uint32_t idesc32 = make_idesc_bf16(LC_M, 32);
         uint32_t it = 0, tile = 0;
         for (int j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
@@ -160,8 +166,10 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
                 const uint32_t aph = (tile >> 1) & 1;
                 mbar_wait(&tempty_bar[as], aph ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + (uint32_t)as * LC_N;
-                const uint32_t idesc = jb.cnt - qt * LC_N <= 32 ? idesc32 : idesc64;
+                const uint32_t tmem_d = tmem_base + (uint32_t)as * LC_ACC;
+                const bool n32 = jb.cnt - qt * LC_N <= 32;
+                const uint32_t idesc_both = n32 ? idesc64 : idesc128;   // N = 2n
+                const uint32_t idesc_one = n32 ? idesc32 : idesc64;     // N = n
                 for (int kb = 0; kb < a.n_kblocks; ++kb, ++it) {
                     const int s = it % n_stages;
                     const uint32_t ph = (it / n_stages) & 1;
@@ -170,13 +178,12 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
                     const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
                     const uint32_t sb = sa + a_bytes;
                     const uint64_t da_hi = make_sw128_desc(sa), da_lo = make_sw128_desc(sa + LC_A_PLANE);
-                    const uint64_t db_hi = make_sw128_desc(sb), db_lo = make_sw128_desc(sb + LC_B_PLANE);
+                    const uint64_t db = make_sw128_desc(sb);
 #pragma unroll
                     for (int k = 0; k < TC_K / 16; ++k) {
                         const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
-                        umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kb | k) != 0);
-                        umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
-                        if (!a.hi_only) umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
+                        umma_bf16(tmem_d, da_hi + adv, db + adv, idesc_both, (kb | k) != 0);
+                        if (!a.hi_only) umma_bf16(tmem_d, da_lo + adv, db + adv, idesc_one, 1);
                     }
                     umma_commit(&empty_bar[s]);
                 }
@@ -202,13 +209,17 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
                 const uint32_t aph = (tile >> 1) & 1;
                 mbar_wait(&tfull_bar[as], aph);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(qr * 32) << 16) + (uint32_t)as * LC_N;
+                const uint32_t taddr = tmem_base + ((uint32_t)(qr * 32) << 16) + (uint32_t)as * LC_ACC;
+                const int n = cnt - qt * LC_N <= 32 ? 32 : LC_N;   // queries per column group of this tile
 #pragma unroll
                 for (int c0 = 0; c0 < LC_N; c0 += 32) {
                     const int col0 = qt * LC_N + c0;
                     if (col0 >= cnt) break;   // warp-uniform
-                    uint32_t acc[32];
-                    tmem_ld32(taddr + c0, acc);
+                    uint32_t acc[32], part[32];
+                    tmem_ld32(taddr + c0, acc);          // x_hi . q_hi (+ x_lo . q_hi)
+                    tmem_ld32(taddr + n + c0, part);     // x_hi . q_lo
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(__uint_as_float(acc[j]) + __uint_as_float(part[j]));
                     // lane j fetches the bookkeeping of column j once; broadcast in the loop
                     const int myc = col0 + lane;
                     int64_t my_out = 0;
@@ -234,7 +245,7 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
         }
     }
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 2 * LC_N);
+    if (warp == 2) tmem_dealloc(tmem_base, 2 * LC_ACC);
 }
 
 // gather + split the queries of every (query, list) pair into the B tiles of its list's group:
