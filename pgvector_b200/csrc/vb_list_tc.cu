@@ -118,8 +118,9 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
-        // ===== producer =====
+    if (warp == 0) {
+        // ===== producer (whole warp converged, one elected lane issues the copies) =====
+        const bool leader = elect_one();
         uint32_t it = 0;
         for (int j = blockIdx.x; j < a.n_jobs; j += gridDim.x) {
             LcJob jb;
@@ -137,19 +138,25 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
                     uint8_t* sa = smem + (size_t)s * stage_bytes;
                     uint8_t* sb = sa + a_bytes;
                     const uint8_t* gb = a.B + ((size_t)(gt0 + qt) * a.n_kblocks + kb) * LC_B_STAGE;
-                    mbar_arrive_expect_tx(&full_bar[s], a_bytes + (n32 ? LC_B_STAGE / 2 : LC_B_STAGE));
-                    bulk_g2s(sa, a.A + ((size_t)un.tile * a.n_kblocks + kb) * LC_A_STAGE, a_bytes, &full_bar[s]);
-                    if (n32) {   // [q_hi rows 0..31 | q_lo rows 0..31] back to back = one 64-row operand
-                        bulk_g2s(sb, gb, LC_B_PLANE / 2, &full_bar[s]);
-                        bulk_g2s(sb + LC_B_PLANE / 2, gb + LC_B_PLANE, LC_B_PLANE / 2, &full_bar[s]);
-                    } else {
-                        bulk_g2s(sb, gb, LC_B_STAGE, &full_bar[s]);
+                    if (leader) {
+                        mbar_arrive_expect_tx(&full_bar[s], a_bytes + (n32 ? LC_B_STAGE / 2 : LC_B_STAGE));
+                        bulk_g2s(sa, a.A + ((size_t)un.tile * a.n_kblocks + kb) * LC_A_STAGE, a_bytes, &full_bar[s]);
+                        if (n32) {   // [q_hi rows 0..31 | q_lo rows 0..31] back to back = one 64-row operand
+                            bulk_g2s(sb, gb, LC_B_PLANE / 2, &full_bar[s]);
+                            bulk_g2s(sb + LC_B_PLANE / 2, gb + LC_B_PLANE, LC_B_PLANE / 2, &full_bar[s]);
+                        } else {
+                            bulk_g2s(sb, gb, LC_B_STAGE, &full_bar[s]);
+                        }
                     }
+                    __syncwarp();
                 }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
+    } else if (warp == 1) {
+        // ===== MMA issuer: the whole warp walks the loop (warp-uniform control flow and operands), one elected lane
+        // issues.  Under "lane == 0" the compiler wraps every tcgen05 instruction in an ELECT / BRA.U.ANY loop and the
+        // lone thread's scalar code (~160 instructions per K block) becomes the bottleneck of the kernel. =====
+        const bool leader = elect_one();
         // One UMMA costs ~130 cycles here whatever its N (it re-reads the 128 x 16 A tile from shared memory), so the
         // products are merged along N: B = [q_hi ; q_lo] is ONE operand of 2n rows, and x_hi . [q_hi ; q_lo] lands in the
         // column groups [0, n) and [n, 2n) of the accumulator with a single instruction per K step; level 2 adds
@@ -179,15 +186,19 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
                     const uint32_t sb = sa + a_bytes;
                     const uint64_t da_hi = make_sw128_desc(sa), da_lo = make_sw128_desc(sa + LC_A_PLANE);
                     const uint64_t db = make_sw128_desc(sb);
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < TC_K / 16; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
-                        umma_bf16(tmem_d, da_hi + adv, db + adv, idesc_both, (kb | k) != 0);
-                        if (!a.hi_only) umma_bf16(tmem_d, da_lo + adv, db + adv, idesc_one, 1);
+                        for (int k = 0; k < TC_K / 16; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);
+                            umma_bf16(tmem_d, da_hi + adv, db + adv, idesc_both, (kb | k) != 0);
+                            if (!a.hi_only) umma_bf16(tmem_d, da_lo + adv, db + adv, idesc_one, 1);
+                        }
+                        umma_commit(&empty_bar[s]);
                     }
-                    umma_commit(&empty_bar[s]);
+                    __syncwarp();
                 }
-                umma_commit(&tfull_bar[as]);
+                if (leader) umma_commit(&tfull_bar[as]);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
