@@ -94,8 +94,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(TcArgs a) {
     const size_t a_tile_bytes = (size_t)a.n_kblocks * A_STAGE_BYTES;   // per m tile
     const size_t b_tile_bytes = (size_t)a.n_kblocks * B_STAGE_BYTES;   // per n tile
 
-    if (warp == 0 && lane == 0) {
+    // The producer and the MMA warp run CONVERGED and one lane elected with elect.sync issues the uniform-datapath
+    // instructions: under "lane == 0" the compiler wraps each of them in an ELECT / BRA.U.ANY loop, and the lone
+    // thread's scalar code becomes a bottleneck of its own (measured on list_tc_kernel, profiles/r1_listtc_ncu.md).
+    if (warp == 0) {
         // ===== producer: two bulk copies per stage =====
+        const bool leader = elect_one();
         uint32_t it = 0;
         for (int mt = blockIdx.x; mt < a.n_mtiles; mt += gridDim.x)
             for (int nt = 0; nt < a.n_ntiles; ++nt)
@@ -105,12 +109,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(TcArgs a) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + (size_t)s * STAGE_BYTES;
                     uint8_t* sb = sa + A_STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
-                    bulk_g2s(sa, a.A + (size_t)mt * a_tile_bytes + (size_t)kb * A_STAGE_BYTES, A_STAGE_BYTES, &full_bar[s]);
-                    bulk_g2s(sb, a.B + (size_t)nt * b_tile_bytes + (size_t)kb * B_STAGE_BYTES, B_STAGE_BYTES, &full_bar[s]);
+                    if (leader) {
+                        mbar_arrive_expect_tx(&full_bar[s], STAGE_BYTES);
+                        bulk_g2s(sa, a.A + (size_t)mt * a_tile_bytes + (size_t)kb * A_STAGE_BYTES, A_STAGE_BYTES, &full_bar[s]);
+                        bulk_g2s(sb, a.B + (size_t)nt * b_tile_bytes + (size_t)kb * B_STAGE_BYTES, B_STAGE_BYTES, &full_bar[s]);
+                    }
+                    __syncwarp();
                 }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===== MMA issuer =====
+        const bool leader = elect_one();
         constexpr uint32_t idesc = make_idesc_bf16(TC_M, TC_N);
         uint32_t it = 0, tile = 0;
         for (int mt = blockIdx.x; mt < a.n_mtiles; mt += gridDim.x)
@@ -129,16 +137,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(TcArgs a) {
                     const uint32_t sb = sa + A_STAGE_BYTES;
                     const uint64_t da_hi = make_sw128_desc(sa), da_lo = make_sw128_desc(sa + A_PLANE_BYTES);
                     const uint64_t db_hi = make_sw128_desc(sb), db_lo = make_sw128_desc(sb + B_PLANE_BYTES);
+                    if (leader) {
 #pragma unroll
-                    for (int k = 0; k < TC_K / 16; ++k) {
-                        const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per UMMA_K step inside the atom
-                        umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kb | k) != 0);
-                        umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
-                        umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
+                        for (int k = 0; k < TC_K / 16; ++k) {
+                            const uint64_t adv = (uint64_t)((k * 16 * 2) >> 4);   // 32 bytes per UMMA_K step inside the atom
+                            umma_bf16(tmem_d, da_hi + adv, db_hi + adv, idesc, (kb | k) != 0);
+                            umma_bf16(tmem_d, da_hi + adv, db_lo + adv, idesc, 1);
+                            umma_bf16(tmem_d, da_lo + adv, db_hi + adv, idesc, 1);
+                        }
+                        umma_commit(&empty_bar[s]);           // smem stage reusable once these MMAs retire
                     }
-                    umma_commit(&empty_bar[s]);           // smem stage reusable once these MMAs retire
+                    __syncwarp();
                 }
-                umma_commit(&tfull_bar[as]);              // accumulator complete -> epilogue
+                if (leader) umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+                __syncwarp();
             }
     } else if (warp >= 4) {
         // ===== epilogue: thread = one row; running best / second best over all centres =====

@@ -398,7 +398,7 @@ bool list_tc_supported(int elem, int key_metric, int k) {
 int list_tc_kp(int k, int level) {
     // candidates kept per query.  Only those under the threshold are re-scored, so a generous k' costs a slightly
     // larger selection, not more exact distances; the certificate fails only when ALL k' are under the threshold.
-    if (level == 1) return k <= 40 ? 128 : 1 << 20;
+    if (level == 1) return k <= 10 ? 64 : k <= 40 ? 128 : 1 << 20;
     return k <= 10 ? 32 : k <= 24 ? 48 : k <= 40 ? 64 : 1 << 20;
 }
 
