@@ -495,7 +495,13 @@ def main():
         else:
             roofline["certificate_fallback_queries"] = ix.tc_fallbacks()
             roofline["level1_fallback_queries"] = ix.tc_level1_fallbacks()
-            roofline["bf16_mma_tflops_issued"] = 3 * 2.0 * cand_per_step * args.dim / (scan_avg_ms / 1000.0) / 1e12 if scan_avg_ms > 0 else 0.0
+            # filter level 1 (hi plane of the rows) issues 2 bf16 products per fp32 term, level 2 (both planes) 3
+            level = 1 if roofline["level1_fallback_queries"] == 0 else 2
+            roofline["filter_level"] = level
+            roofline["bf16_mma_tflops_issued"] = (level + 1) * 2.0 * cand_per_step * args.dim / (scan_avg_ms / 1000.0) / 1e12 if scan_avg_ms > 0 else 0.0
+            if level == 2:
+                roofline.pop("dram", None)     # the committed DRAM-traffic capture is of the level-1 kernel
+                roofline["traffic"] = None
 
     # ---- recall@10 vs exact brute force (GPU exact scan) and CPU baseline
     recall = None

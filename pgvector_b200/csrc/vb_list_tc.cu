@@ -18,11 +18,19 @@
 // image, one 32 KB block per (128-row table tile, 64-dimension block); a unit of work is a (list, table tile)
 // pair (tiles straddling a list boundary are visited by both lists, rows outside the list masked).  The queries
 // of each list's group are gathered and packed per batch into 64-query B tiles (16 KB per dimension block).
-// CTA = persistent, one per SM: warp 0 = bulk-copy producer (A 32 KB + B 16 KB per stage, 4 stages), warp 1 =
-// MMA issuer (UMMA 128x64x16, 12 per stage), warp 2 = TMEM allocator, warps 4-7 = epilogue (thread = row;
-// two 64-column accumulator stages so the epilogue of one tile overlaps the MMAs of the next).
+// CTA = persistent, one per SM: warp 0 = bulk-copy producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (thread = row; two 128-column accumulator stages so the epilogue of one tile overlaps the
+// MMAs of the next).  The query operand of a tile is ONE shared-memory tile [q_hi ; q_lo] of 2n rows (n = 32 or 64):
+// x_hi . [q_hi ; q_lo] is a single UMMA 128 x 2n x 16 per K step whose two column groups the epilogue adds;
+// level 2 adds x_lo . q_hi (128 x n x 16).
 //
-// Roofline: HBM -- one pass over the packed planes of the probed lists per batch (4 bytes per row element).
+// Two filter levels.  Level 1 streams only the hi plane of the rows (16 KB + B per stage, 7 stages in flight): half
+// the HBM traffic, error bound 2^-7 |x||q|.  A batch with an uncertified query is repeated at level 2 (both planes,
+// 4 x 48 KB stages, bound 2^-12 |x||q|), and only then on the exact kernel; after a level-1 failure the level rests
+// for 64 batches (whether it certifies is a property of the data, not of the batch).
+//
+// Roofline: HBM -- one pass over the packed hi planes (level 1: 2 bytes per row element) or both planes (level 2:
+// 4 bytes) of the probed lists per batch.
 #include "vb_tc.cuh"
 #include "vb_distance.cuh"
 
