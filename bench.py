@@ -547,8 +547,9 @@ def workload_config(args, how):
             "queries": args.queries, "batch": args.batch,
             "index_build": how, "scan_kernel": {0: "LDG.128 streaming (all scans)", 1: "cp.async.bulk+mbarrier staged (all scans)",
                             3: "list scan: list-major 256x32 fp32x2 register tiles (rows read once per batch); centre scan: 128x128 fp32 tiles",
-                            }.get(args.scan_impl, "list scan: tcgen05 split-bf16 filter (128x64 UMMA tiles over packed hi/lo planes, rows read once per "
-                                                  "batch) + exact fp32 re-score of k'=32 candidates + certificate; centre scan: 128x128 fp32 tiles"),
+                            }.get(args.scan_impl, "list scan and probe selection: tcgen05 split-bf16 filter over packed row planes (each probed list read once per "
+                                                  "batch; level 1 = hi plane only, level 2 = both planes on certificate failure) + exact fp32 re-score of the "
+                                                  "candidates under the certificate threshold; exact list-major kernel as the last resort"),
             "parallelism": "lists sharded l % N, one NCCL all-gather of k results per rank"}
 
 
