@@ -303,10 +303,21 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        # rank 0 prints exactly one JSON line on stdout: NCCL's version banner / debug output (printed whenever
-        # NCCL_DEBUG is set, even to WARN) goes to stderr instead
-        os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
-        dist.init_process_group("nccl", device_id=dev)
+        # rank 0 prints exactly one JSON line on stdout.  NCCL writes its version banner to the process's stdout when
+        # the communicator is created (whatever NCCL_DEBUG_FILE says): create it, and run the first collective, with
+        # file descriptor 1 pointing at stderr, then put stdout back.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     import pgvector_b200 as pv
     pv.init(local)
     pv.set_option("scan_impl", args.scan_impl)
