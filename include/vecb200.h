@@ -186,6 +186,15 @@ int			vb_ivf_search(vb_ivf *ix, const void *queries, int64_t nq, int probes, int
 /* Same with device-resident queries and outputs (float distances), asynchronous on vb_stream(). */
 int			vb_ivf_search_dev(vb_ivf *ix, const void *queries_dev, int64_t nq, int probes, int k,
 							  int64_t *out_ids_dev, float *out_dist_dev);
+/*
+ * Pipelined host path.  vb_ivf_prefetch_queries starts the host->device copy of the NEXT batch of queries on a second
+ * stream (slot 0 or 1; `queries` should be page-locked and must stay valid until the matching search returns) and
+ * returns at once; vb_ivf_search_prefetched runs the search of a slot filled earlier (same results as vb_ivf_search)
+ * and returns when its results are in `out_ids` / `out_dist`.  Alternating the two slots overlaps every copy with the
+ * previous batch's compute.  vector queries with dim % 4 == 0 only; VB_EINVAL otherwise.
+ */
+int			vb_ivf_prefetch_queries(vb_ivf *ix, const void *queries, int64_t nq, int slot);
+int			vb_ivf_search_prefetched(vb_ivf *ix, int slot, int probes, int k, int64_t *out_ids, double *out_dist);
 /* algorithmic bytes of the last vb_ivf_search*: sum over queries of (lists + candidates) * dim * elem size */
 int64_t		vb_ivf_last_scan_bytes(const vb_ivf *ix);
 int64_t		vb_ivf_last_candidates(const vb_ivf *ix);

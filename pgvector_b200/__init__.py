@@ -296,6 +296,14 @@ class IvfflatIndex:
     def search_host_into(self, queries, k, probes, ids, dist):
         _lib.check(load().vb_ivf_search(self.h, _ptr(queries), queries.shape[0], int(probes), int(k), _ptr(ids), _ptr(dist)))
 
+    def prefetch_queries(self, queries, slot):
+        """start the H2D copy of the next batch (pinned host array) into slot 0 / 1; returns at once"""
+        _lib.check(load().vb_ivf_prefetch_queries(self.h, _ptr(queries), queries.shape[0], int(slot)))
+
+    def search_prefetched_into(self, slot, k, probes, ids, dist):
+        """search the batch prefetched into `slot`; host outputs (int64 ids, float64 distances)"""
+        _lib.check(load().vb_ivf_search_prefetched(self.h, int(slot), int(probes), int(k), _ptr(ids), _ptr(dist)))
+
     def last_scan_bytes(self):
         return int(load().vb_ivf_last_scan_bytes(self.h))
 

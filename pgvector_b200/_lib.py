@@ -48,6 +48,8 @@ SIGNATURES = {
     "vb_ivf_scan_items": (_i, [_vp, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
     "vb_ivf_search": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
     "vb_ivf_search_dev": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
+    "vb_ivf_prefetch_queries": (_i, [_vp, _vp, _i64, _i]),
+    "vb_ivf_search_prefetched": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "vb_ivf_last_scan_bytes": (_i64, [_vp]),
     "vb_ivf_last_candidates": (_i64, [_vp]),
     "vb_ivf_tc_fallbacks": (_i64, [_vp]),

@@ -57,6 +57,11 @@ struct Ivf {
     ListTcImage tc;                   // packed bf16 planes + norms + (list, tile) units, built on first tensor-core scan
     ListTcImage ctc;                  // the same for the centre table (one pseudo list probed by every query)
     int64_t* d_centre_off = nullptr;  // {0, lists}
+    cudaStream_t q_stream = nullptr;  // copy stream of the pipelined host path (vb_ivf_prefetch_queries)
+    cudaEvent_t q_ready[2] = {nullptr, nullptr};
+    void* q_buf[2] = {nullptr, nullptr};
+    size_t q_bytes[2] = {0, 0};
+    int64_t q_nq[2] = {0, 0};
     int* d_tc_fail = nullptr;         // device counters of uncertified queries: [0] probe selection, [1] list scan
     bool defer_tc_check = false;      // batched search: counters are read once, with the results
     bool force_exact = false;         // re-run of a batch whose certificate failed
@@ -710,6 +715,11 @@ int vb_ivf_free(vb_ivf* h) {
     list_tc_release(&h->ix.ctc);
     if (h->ix.d_centre_off) cudaFree(h->ix.d_centre_off);
     if (h->ix.d_tc_fail) cudaFree(h->ix.d_tc_fail);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ix.q_buf[i]) cudaFree(h->ix.q_buf[i]);
+        if (h->ix.q_ready[i]) cudaEventDestroy(h->ix.q_ready[i]);
+    }
+    if (h->ix.q_stream) cudaStreamDestroy(h->ix.q_stream);
     delete h;
     return VB_OK;
 }
@@ -805,8 +815,9 @@ int vb_ivf_scan_items(vb_ivf* h, const void* q, const int32_t* lists, int nlists
     return VB_OK;
 }
 
-static int ivf_search_impl(vb_ivf* h, const void* queries, int64_t nq, int probes, int k, bool host, int64_t* out_ids, float* out_f,
-                           double* out_d) {
+// host: results go to host memory (int64 ids + float8 distances); q_host: the queries are host memory
+static int ivf_search_impl(vb_ivf* h, const void* queries, int64_t nq, int probes, int k, bool host, bool q_host, int64_t* out_ids,
+                           float* out_f, double* out_d) {
     VB_TRY(require_init());
     VB_REQUIRE(h && h->ix.loaded, "index not loaded");
     VB_REQUIRE(queries && probes >= 1 && k >= 1, "bad search arguments");
@@ -829,7 +840,7 @@ static int ivf_search_impl(vb_ivf* h, const void* queries, int64_t nq, int probe
         if (ix.d_tc_fail) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, 2 * sizeof(int), c.stream));
         void* qimg;
         size_t qstride;
-        VB_TRY(upload_queries(ix.elem, ix.dim, (const uint8_t*)queries + (size_t)q0 * rawq, m, host, WS_QIMG, &qimg, &qstride));
+        VB_TRY(upload_queries(ix.elem, ix.dim, (const uint8_t*)queries + (size_t)q0 * rawq, m, q_host, WS_QIMG, &qimg, &qstride));
         int32_t* d_lists;
         float* d_ldist;
         VB_TRY(ivf_select_probes(ix, qimg, qstride, m, probes, &d_lists, &d_ldist));
@@ -877,10 +888,51 @@ static int ivf_search_impl(vb_ivf* h, const void* queries, int64_t nq, int probe
 }
 
 int vb_ivf_search(vb_ivf* h, const void* queries, int64_t nq, int probes, int k, int64_t* out_ids, double* out_dist) {
-    return ivf_search_impl(h, queries, nq, probes, k, true, out_ids, nullptr, out_dist);
+    return ivf_search_impl(h, queries, nq, probes, k, true, true, out_ids, nullptr, out_dist);
 }
 int vb_ivf_search_dev(vb_ivf* h, const void* queries_dev, int64_t nq, int probes, int k, int64_t* out_ids_dev, float* out_dist_dev) {
-    return ivf_search_impl(h, queries_dev, nq, probes, k, false, out_ids_dev, out_dist_dev, nullptr);
+    return ivf_search_impl(h, queries_dev, nq, probes, k, false, false, out_ids_dev, out_dist_dev, nullptr);
+}
+
+// Pipelined host path: the queries of the NEXT call are copied to the device on a second stream while the current
+// call computes.  Two slots; a slot is reusable once the search that read it has been synchronised (it has, when
+// vb_ivf_search_prefetched returns).
+int vb_ivf_prefetch_queries(vb_ivf* h, const void* queries, int64_t nq, int slot) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && h->ix.loaded && queries && nq > 0 && (slot == 0 || slot == 1), "bad prefetch arguments");
+    Ivf& ix = h->ix;
+    const size_t raw = raw_row_bytes(ix.elem, ix.dim);
+    VB_REQUIRE(ix.elem == VB_VECTOR && raw == padded_row_bytes(ix.elem, ix.dim),
+               "query prefetch needs vector queries whose dimension is a multiple of 4 (use vb_ivf_search otherwise)");
+    if (!ix.q_stream) {
+        VB_CUDA(cudaStreamCreateWithFlags(&ix.q_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) VB_CUDA(cudaEventCreateWithFlags(&ix.q_ready[i], cudaEventDisableTiming));
+    }
+    const size_t bytes = raw * (size_t)nq;
+    if (ix.q_bytes[slot] < bytes) {
+        if (ix.q_buf[slot]) {
+            VB_CUDA(cudaStreamSynchronize(ctx().stream));
+            VB_CUDA(cudaFree(ix.q_buf[slot]));
+            ix.q_buf[slot] = nullptr;
+            ix.q_bytes[slot] = 0;
+        }
+        VB_CUDA(cudaMalloc(&ix.q_buf[slot], bytes));
+        ix.q_bytes[slot] = bytes;
+    }
+    VB_CUDA(cudaMemcpyAsync(ix.q_buf[slot], queries, bytes, cudaMemcpyHostToDevice, ix.q_stream));
+    VB_CUDA(cudaEventRecord(ix.q_ready[slot], ix.q_stream));
+    ix.q_nq[slot] = nq;
+    return VB_OK;
+}
+
+int vb_ivf_search_prefetched(vb_ivf* h, int slot, int probes, int k, int64_t* out_ids, double* out_dist) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && h->ix.loaded && (slot == 0 || slot == 1) && h->ix.q_nq[slot] > 0, "no prefetched queries in this slot");
+    Ivf& ix = h->ix;
+    VB_CUDA(cudaStreamWaitEvent(ctx().stream, ix.q_ready[slot], 0));
+    const int64_t nq = ix.q_nq[slot];
+    ix.q_nq[slot] = 0;   // consumed: the slot may be refilled as soon as this call returns (it synchronises)
+    return ivf_search_impl(h, ix.q_buf[slot], nq, probes, k, true, false, out_ids, nullptr, out_dist);
 }
 
 int64_t vb_ivf_tc_fallbacks(const vb_ivf* h) { return h ? h->ix.total_tc_failed : 0; }

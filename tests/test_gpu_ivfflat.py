@@ -255,6 +255,30 @@ def test_filter_levels_return_identical_results(pv, latent):
     assert (i1 == wi).mean() > 0.99
 
 
+def test_prefetched_search_equals_search(pv, l2_index):
+    """The pipelined host path (copy of batch i + 1 on a second stream while batch i computes) returns exactly what
+    vb_ivf_search returns; dimensions that are not a multiple of 4 are refused."""
+    import torch
+    gix, oix, rows, queries = l2_index
+    batches = [torch.from_numpy(np.ascontiguousarray(queries[i * 50:(i + 1) * 50])).pin_memory().numpy() for i in range(4)]
+    want = [gix.search(b, k=10, probes=8) for b in batches]
+    ids = np.empty((50, 10), dtype=np.int64)
+    dist = np.empty((50, 10), dtype=np.float64)
+    gix.prefetch_queries(batches[0], 0)
+    for i in range(4):
+        if i + 1 < 4:
+            gix.prefetch_queries(batches[i + 1], (i + 1) % 2)
+        gix.search_prefetched_into(i % 2, 10, 8, ids, dist)
+        assert np.array_equal(ids, want[i][0]), i
+        assert np.array_equal(dist, want[i][1]), i
+    with pytest.raises(pv.VecB200Error):
+        gix.search_prefetched_into(0, 10, 8, ids, dist)      # slot already consumed
+    x, c = mixture(500, 6, 4, seed=51)
+    odd, _ = make_index(pv, "vector_l2_ops", x, c)
+    with pytest.raises(pv.VecB200Error):
+        odd.prefetch_queries(x[:8], 0)                       # dim % 4 != 0
+
+
 def test_tensor_core_filter_falls_back_when_it_cannot_certify(pv):
     """More duplicates of the nearest row than candidates kept per query put the k-th and the k'-th candidate at
     the same approximate distance, so no filter level can certify: those batches must come back from the exact
