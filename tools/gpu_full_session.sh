@@ -1,5 +1,5 @@
 #!/bin/bash
-# Thirteenth-pass GPU session: final state of the round -- full suite, headline, reference arm, assign / k-means with
+# gpurun session, ~12 GPU-minutes: full GPU suite, smoke, headline, reference arm, assign / k-means with
 # the converged-leader tensor-core kernels, ncu capture + launch list of the headline command.
 TAG=${1:-r1t}
 mkdir -p gpurun_out

@@ -1,5 +1,5 @@
 #!/bin/bash
-# quick check of a list_tc_kernel change: IVFFlat parity + headline + level-2 workload
+# gpurun session, ~1.5 GPU-minutes: IVFFlat parity, the headline bench, and a workload that needs filter level 2
 TAG=${1:-r1q}
 mkdir -p gpurun_out
 python __graft_entry__.py > gpurun_out/build_$TAG.log 2>&1 || { tail -20 gpurun_out/build_$TAG.log; exit 1; }
