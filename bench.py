@@ -8,11 +8,16 @@ probes = 10, k = 10; 10,000 queries from the same law (seed 4).  A "step" is one
 through the hot path (probe selection + list scan + top-k).
 
   value : queries/s with queries and outputs resident in HBM (device pointers, C ABI *_dev call)
-  e2e   : queries/s through vb_ivf_search with HOST buffers (H2D of the queries and D2H of
-          ids + distances inside the timed region); the index image stays resident in HBM
-          (it is uploaded once per index version, like shared_buffers; upload time reported
+  e2e   : queries/s through the host-buffer C ABI (vb_ivf_prefetch_queries for the next batch +
+          vb_ivf_search_prefetched for the current one: every step has its H2D copy of 2048 queries from
+          pinned memory and its D2H of ids + distances inside the timed region, the copy overlapping the
+          previous batch's device work; the last step is compared with plain vb_ivf_search); the index
+          image stays resident in HBM (uploaded once per index version, like shared_buffers; upload time
           in config.index_upload_s)
-  roofline : algorithmic bytes of the list-scan kernel / its CUDA-event time, vs MEASURED_PEAKS.json
+  roofline : SURVEY 8(d)'s algorithmic bytes of the list scan (one row read per distance, not amortised
+          over the batch) / the kernel's CUDA-event time vs MEASURED_PEAKS.json, plus `dram`: the ncu
+          DRAM bytes of the same launch / the same time (the batched kernels read each probed list once
+          per batch, so `frac` > 1 is the reuse factor and `dram.frac` the physical roofline)
   cpu_baseline : the oracle port of the same scan on the host cores (bounded sample)
 
 `--impl reference` times only the CPU arm (oracle port of src/ivfscan.c; PostgreSQL itself is
