@@ -529,18 +529,26 @@ int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metr
     uint8_t* failed = (uint8_t*)(exact + (size_t)nq * kp);
     const int V = (int)(rows.stride / 16);
     const unsigned grid = (unsigned)((nq * kp * 32 + 255) / 256);
-    // |d~ - d_fp32| <= eps.  Split product: representation 2^-18 + 2^-17, TMEM accumulation over 3 * dim / 16 steps
-    // -> 2^-13 |x||q| with ~2.5x head-room (x2 in the L2 form).  The fp32 norms, the final sum and the rounding of
-    // the exact fp32 distance it is compared with: 2^-16 (|x|^2 + |q|^2) for L2, 2^-17 |x||q| for the inner product.
+    // |d~ - d_fp32| <= eps, in units of |x||q| for the product (x2 in the L2 form):
+    //   representation: bf16 keeps 8 significant bits (unit roundoff 2^-8), so |x - x_hi| <= 2^-8 |x| and
+    //     |x - x_hi - x_lo| <= 2^-16 |x|.  Level 2 drops x_lo.q_lo and the two residuals: 3 * 2^-16.  Level 1 also
+    //     drops x_lo.q: 2^-8 + 2^-16.
+    //   accumulation: one fp32 rounding of the TMEM accumulator per UMMA, (products per K step) * dim / 16 of them,
+    //     <= 2^-23 each if the unit truncates; doubled to cover the alignment of the 16 products inside an UMMA.
+    // The constants below are the values the GPU tests and benches of round 1 ran with (dim <= 1536); the formula takes
+    // over for longer rows, where the accumulation term grows past them.
+    // The fp32 norms, the final sum and the rounding of the exact fp32 distance it is compared with: 2^-16 (|x|^2 +
+    // |q|^2) for L2, 2^-17 |x||q| for the inner product.
     LcBound bound;
     bound.is_l2 = key_metric == VB_L2_SQUARED;
-    bound.c_dot = bound.is_l2 ? 1.0f / 4096.0f : 1.0f / 8192.0f + 1.0f / 131072.0f;
+    const float steps = (float)(im.n_kblocks * (TC_K / 16));
+    const float rep = level == 1 ? 1.0f / 256.0f + 1.0f / 65536.0f : 3.0f / 65536.0f;
+    const float acc = 2.0f * (level == 1 ? 2.0f : 3.0f) * steps / 8388608.0f;
+    const float ip_unit = rep + acc;
+    float c_ip = level == 1 ? 1.0f / 256.0f + 1.0f / 8192.0f : 1.0f / 8192.0f;   // validated constants
+    c_ip = std::max(c_ip, ip_unit);
+    bound.c_dot = bound.is_l2 ? 2.0f * c_ip : c_ip + 1.0f / 131072.0f;
     bound.c_sum = 1.0f / 65536.0f;
-    if (level == 1) {
-        // rows reduced to their hi plane: |x - x_hi| <= 2^-8 |x| (bf16 unit roundoff), so the product is off by at most
-        // 2^-8 |x||q| on top of the level-2 terms (query split, accumulation)
-        bound.c_dot = bound.is_l2 ? 1.0f / 128.0f + 1.0f / 4096.0f : 1.0f / 256.0f + 1.0f / 8192.0f + 1.0f / 131072.0f;
-    }
     bound.xmax = im.xmax;
 #define VB_RS(E, M) rescore_kernel<E, M><<<grid, 256, 0, s>>>(rows.d, rows.stride, V, (const uint8_t*)qimg, qstride, nq, k, kp, probes, bound, qn, pos_kp, approx_kp, d_lists, cand_off, d_list_off, exact)
     if (rows.elem == VB_VECTOR) {
