@@ -76,6 +76,11 @@ void	   *vb_stream(void);
 /* Kernels launched by this library since vb_init (a claim for bench.py's gpu_launches). */
 int64_t		vb_launch_count(void);
 int			vb_synchronize(void);
+/*
+ * Order the library stream after work the caller enqueued on another stream: `cuda_event` is a cudaEvent_t recorded
+ * there.  Needed before a _dev call whose inputs were produced on a different stream (vb_stream() is non-blocking).
+ */
+int			vb_stream_wait_event(void *cuda_event);
 
 /*
  * Optional per-kernel timing with CUDA events on vb_stream(), used by bench.py for the
@@ -229,6 +234,13 @@ int			vb_kmeans(vb_table *samples, int kmeans_metric, void *centers, int k, int 
 					  uint64_t seed, vb_allreduce_fn allreduce, void *allreduce_ctx, int *iters_out);
 /* InitCenters (src/ivfkmeans.c:23-91): k-means++ seeding on the device, centres out (host). */
 int			vb_kmeans_pp_init(vb_table *samples, int kmeans_metric, void *centers, int k, uint64_t seed);
+/*
+ * Same with the caller's random draws (the extension passes pg_prng's, the parity tests the oracle's): the first
+ * centre is sample first_row (RandomInt() % numSamples, src/ivfkmeans.c:36); u[i], i < k - 1, is the RandomDouble()
+ * of round i (src/ivfkmeans.c:78).  picked_out (may be NULL): the k chosen sample rows.
+ */
+int			vb_kmeans_pp_init_draws(vb_table *samples, int kmeans_metric, void *centers, int k, int64_t first_row,
+									const double *u, int64_t *picked_out);
 /*
  * AddTupleToSort's argmin (src/ivfbuild.c:161-219): out_list[i] = first centre
  * minimising the proc-1 distance (strict <).  metric = VB_L2_SQUARED / VB_NEG_IP / VB_HAMMING.

@@ -139,6 +139,8 @@ def _declare(L):
         f.argtypes = [i32, i32, i32, vp, i64, vp, i32, i32, C.c_uint64, vp]
     L.pgv_kmeans_pp_init.restype = None
     L.pgv_kmeans_pp_init.argtypes = [i32, i32, i32, vp, i64, vp, i32, C.c_uint64]
+    L.pgv_kmeans_pp_init_draws.restype = None
+    L.pgv_kmeans_pp_init_draws.argtypes = [i32, i32, i32, vp, i64, vp, i32, i64, vp, vp]
     L.pgv_hnsw_create.restype = vp
     L.pgv_hnsw_create.argtypes = [i32, i32, i32, i32, i32, C.c_uint64]
     L.pgv_hnsw_free.restype = None
@@ -318,6 +320,17 @@ def kmeans_pp_init(elem, kmeans_metric, samples, k, seed=42, dim=None):
     centers = np.empty((k,) + samples.shape[1:], dtype=samples.dtype)
     lib().pgv_kmeans_pp_init(elem, kmeans_metric, d, _p(samples), samples.shape[0], _p(centers), k, seed)
     return centers
+
+
+def kmeans_pp_init_draws(elem, kmeans_metric, samples, k, first, u, dim=None):
+    """InitCenters with caller-supplied draws; returns (centres, picked sample rows)."""
+    samples = _rows(elem, samples)
+    d = dim if dim is not None else samples.shape[-1]
+    centers = np.empty((k,) + samples.shape[1:], dtype=samples.dtype)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    picked = np.empty(k, dtype=np.int64)
+    lib().pgv_kmeans_pp_init_draws(elem, kmeans_metric, d, _p(samples), samples.shape[0], _p(centers), k, int(first), _p(u), _p(picked))
+    return centers, picked
 
 
 class Hnsw:

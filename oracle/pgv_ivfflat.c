@@ -457,6 +457,52 @@ init_centers(int elem, int metric, int dim, const void *samples, int64_t n, void
 	free(weight);
 }
 
+/*
+ * InitCenters (src/ivfkmeans.c:23-91) with the draws supplied by the caller: first = RandomInt() % numSamples
+ * (:36), u[i] = RandomDouble() of round i (:78).  picked (optional) = chosen sample rows.  Same loop as init_centers.
+ */
+void
+pgv_kmeans_pp_init_draws(int elem, int metric, int dim, const void *samples, int64_t n, void *centers, int k,
+						 int64_t first, const double *u, int64_t *picked)
+{
+	size_t		rb = pgv_row_bytes(elem, dim);
+	float	   *weight = malloc(sizeof(float) * (size_t) n);
+
+	memcpy(centers, (const char *) samples + (size_t) first * rb, rb);
+	if (picked)
+		picked[0] = first;
+	for (int64_t j = 0; j < n; j++)
+		weight[j] = FLT_MAX;
+	for (int i = 0; i + 1 < k; i++)
+	{
+		int64_t		j;
+		double		sum = 0.0,
+					choice;
+
+		for (j = 0; j < n; j++)
+		{
+			double		distance = pgv_distance(elem, metric, dim, (const char *) samples + (size_t) j * rb,
+												(const char *) centers + (size_t) i * rb);
+
+			distance *= distance;
+			if (distance < weight[j])
+				weight[j] = (float) distance;
+			sum += weight[j];
+		}
+		choice = sum * u[i];
+		for (j = 0; j < n - 1; j++)
+		{
+			choice -= weight[j];
+			if (choice <= 0)
+				break;
+		}
+		memcpy((char *) centers + (size_t) (i + 1) * rb, (const char *) samples + (size_t) j * rb, rb);
+		if (picked)
+			picked[i + 1] = j;
+	}
+	free(weight);
+}
+
 void
 pgv_kmeans_pp_init(int elem, int kmeans_metric, int dim, const void *samples, int64_t n, void *centers, int k, uint64_t seed)
 {

@@ -121,6 +121,10 @@ int pgv_kmeans_lloyd(int elem, int kmeans_metric, int dim, const void *samples, 
 void pgv_kmeans_pp_init(int elem, int kmeans_metric, int dim, const void *samples, int64_t n,
 						void *centers, int k, uint64_t seed);
 
+/* same with caller-supplied draws: first row, u[k-1] uniforms; picked[k] optional */
+void pgv_kmeans_pp_init_draws(int elem, int kmeans_metric, int dim, const void *samples, int64_t n,
+							  void *centers, int k, int64_t first, const double *u, int64_t *picked);
+
 /* ---- pgv_hnsw.c -------------------------------------------------------- */
 typedef struct PgvHnsw PgvHnsw;
 

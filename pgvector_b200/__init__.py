@@ -75,7 +75,29 @@ def synchronize():
     _lib.check(load().vb_synchronize())
 
 
+def _after_torch(*tensors):
+    """The library launches on its own non-blocking stream: before a call that reads torch CUDA tensors, make that
+    stream wait for whatever torch's current stream has enqueued so far (the tensors' producers)."""
+    if any(_is_torch(t) and t.is_cuda for t in tensors):
+        import torch
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        _lib.check(load().vb_stream_wait_event(C.c_void_p(ev.cuda_event)))
+
+
 def _host(elem, a):
+    """host array in the payload layout of the type.  halfvec rows are IEEE binary16 BIT PATTERNS (uint16): float16
+    arrays are reinterpreted, float32/64 arrays are rounded to half (RNE, like the vector -> halfvec cast,
+    src/halfvec.c:540-555, without its overflow check) -- never value-cast to integers."""
+    a = np.asarray(a)
+    if elem == HALFVEC and a.dtype != np.uint16:
+        if a.dtype == np.float16:
+            a = a.view(np.uint16)
+        elif a.dtype in (np.float32, np.float64):
+            with np.errstate(over="ignore"):
+                a = a.astype(np.float16).view(np.uint16)
+        else:
+            raise TypeError(f"halfvec rows must be uint16 bit patterns or a float array, not {a.dtype}")
     return np.ascontiguousarray(a, dtype=_NP[elem])
 
 
@@ -169,6 +191,7 @@ class Table:
 
     def append(self, rows):
         if _is_torch(rows):
+            _after_torch(rows)
             _lib.check(load().vb_table_append_dev(self.h, _ptr(rows), rows.shape[0]))
         else:
             rows = _host(self.elem, rows)
@@ -185,6 +208,7 @@ class Table:
             nq = queries.shape[0]
             ids = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
             dist = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+            _after_torch(queries)
             _lib.check(load().vb_exact_topk_dev(self.h, metric, _ptr(queries), nq, k, _ptr(ids), _ptr(dist)))
             synchronize()   # the library runs on its own stream; results are handed back complete
             return ids, dist
@@ -214,7 +238,10 @@ class Table:
 class IvfflatIndex:
     """Device image of an ivfflat index and its scan (src/ivfscan.c).
 
-    ``probes`` mirrors the ivfflat.probes GUC (src/ivfflat.c:45-47)."""
+    ``probes`` mirrors the ivfflat.probes GUC (src/ivfflat.c:45-47).  For the cosine opclasses (``self.normalize``)
+    the reference stores l2_normalize'd rows (src/ivfbuild.c:174-180) and normalises the query once per scan
+    (src/ivfscan.c:222-229); this image takes rows and centres as stored, and ``prepare_query`` applies the
+    query-side normalisation."""
 
     def __init__(self, opclass, dim, lists):
         self.opclass = opclass
@@ -233,6 +260,7 @@ class IvfflatIndex:
         self._off = off
         if _is_torch(rows):
             self._keep = (centers, rows, ids)
+            _after_torch(centers, rows, ids)
             _lib.check(load().vb_ivf_load_dev(self.h, _ptr(centers), _ptr(off), _ptr(rows), _ptr(ids)))
         else:
             centers = _host(self.elem, centers)
@@ -240,6 +268,11 @@ class IvfflatIndex:
             ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
             _lib.check(load().vb_ivf_load(self.h, _ptr(centers), _ptr(off), _ptr(rows), _ptr(ids)))
         return self
+
+    def prepare_query(self, q):
+        """what ivfflatgettuple does to the ORDER BY value before the scan (src/ivfscan.c:213-231): l2_normalize for
+        the cosine opclasses, identity otherwise."""
+        return l2_normalize(q, self.elem) if self.normalize else q
 
     def scan_lists(self, queries, max_probes=None):
         """GetScanLists: nearest lists per query, ascending."""
@@ -276,6 +309,7 @@ class IvfflatIndex:
             nq = queries.shape[0]
             ids = torch.empty((nq, k), dtype=torch.int64, device=queries.device)
             dist = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+            _after_torch(queries)
             _lib.check(load().vb_ivf_search_dev(self.h, _ptr(queries), nq, p, k, _ptr(ids), _ptr(dist)))
             synchronize()   # (search_into is the asynchronous variant)
             return ids, dist
@@ -289,7 +323,9 @@ class IvfflatIndex:
         return ids, dist
 
     def search_into(self, queries_dev, k, probes, ids_dev, dist_dev):
-        """asynchronous device-resident search into preallocated torch tensors (bench inner loop)."""
+        """asynchronous device-resident search into preallocated torch tensors (bench inner loop): enqueued on the
+        library stream after torch's current stream; the caller synchronises (pv.synchronize()) before reading."""
+        _after_torch(queries_dev)
         _lib.check(load().vb_ivf_search_dev(self.h, _ptr(queries_dev), queries_dev.shape[0], int(probes), int(k),
                                             _ptr(ids_dev), _ptr(dist_dev)))
 
@@ -361,11 +397,22 @@ def kmeans_pp_init(samples: Table, kmeans_metric, k, seed=42):
     return centers
 
 
+def kmeans_pp_init_draws(samples: Table, kmeans_metric, k, first_row, u):
+    """InitCenters (src/ivfkmeans.c:23-91) with the caller's draws; returns (centres, picked sample rows)."""
+    raw = (samples.dim + 7) // 8 if samples.elem == BIT else samples.dim
+    centers = np.empty((k, raw), dtype=_NP[samples.elem])
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    picked = np.empty(k, dtype=np.int64)
+    _lib.check(load().vb_kmeans_pp_init_draws(samples.h, kmeans_metric, _ptr(centers), k, int(first_row), _ptr(u), _ptr(picked)))
+    return centers, picked
+
+
 def assign(rows: Table, metric, centers):
     """AddTupleToSort's nearest-centre pass (src/ivfbuild.c:161-219)."""
     if _is_torch(centers):
         import torch
         out = torch.empty(len(rows), dtype=torch.int32, device=centers.device)
+        _after_torch(centers)
         _lib.check(load().vb_assign_dev(rows.h, metric, _ptr(centers), centers.shape[0], _ptr(out)))
         return out
     centers = _host(rows.elem, centers)
@@ -416,6 +463,7 @@ class HnswIndex:
         return ids, dist, nd
 
     def search_into(self, queries_dev, k, ef, ids_dev, dist_dev, nd_dev=None):
+        _after_torch(queries_dev)
         _lib.check(load().vb_hnsw_search_dev(self.h, _ptr(queries_dev), queries_dev.shape[0], int(ef), int(k),
                                              _ptr(ids_dev), _ptr(dist_dev), _ptr(nd_dev)))
 

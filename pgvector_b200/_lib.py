@@ -26,6 +26,7 @@ SIGNATURES = {
     "vb_stream": (_vp, []),
     "vb_launch_count": (_i64, []),
     "vb_synchronize": (_i, []),
+    "vb_stream_wait_event": (_i, [_vp]),
     "vb_prof_enable": (_i, [_i]),
     "vb_prof_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "vb_distance_batch": (_i, [_i, _i, _i, _vp, _vp, _i64, _vp]),
@@ -56,6 +57,7 @@ SIGNATURES = {
     "vb_ivf_tc_level1_fallbacks": (_i64, [_vp]),
     "vb_kmeans": (_i, [_vp, _i, _vp, _i, _i, _u64, _vp, _vp, _vp]),
     "vb_kmeans_pp_init": (_i, [_vp, _i, _vp, _i, _u64]),
+    "vb_kmeans_pp_init_draws": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
     "vb_assign": (_i, [_vp, _i, _vp, _i, _vp]),
     "vb_assign_dev": (_i, [_vp, _i, _vp, _i, _vp]),
     "vb_set_tensor_cores": (_i, [_i]),

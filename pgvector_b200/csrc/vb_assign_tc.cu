@@ -56,6 +56,7 @@ struct TcArgs {
     int is_l2;              // 1: value = cn - 2 dot ; 0: value = -dot
     float cmax;             // max |c| over real centres
     float tol;              // relative error bound of the split-bf16 product
+    float sum_tol;          // relative error bound of the fp32 norms / final sum (L2 form)
     int32_t* out_idx;       // [n] global
     int32_t* flagged;       // list of global row numbers needing the exact kernel
     int* n_flagged;
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) assign_tc_kernel(TcArgs a) {
                 a.out_idx[row] = best_i == 0x7fffffff ? 0 : best_i;
                 // error bound of the split product: |err(x.c)| <= tol |x| |c|  (both compared values carry it)
                 const float xnorm = sqrtf(a.xn[r_slab]);
-                const float eps = (a.is_l2 ? 4.f : 2.f) * a.tol * xnorm * a.cmax + (a.is_l2 ? 1e-6f * a.cmax * a.cmax : 0.f);
+                const float eps = (a.is_l2 ? 4.f : 2.f) * a.tol * xnorm * a.cmax + (a.is_l2 ? a.sum_tol * (a.cmax * a.cmax + xnorm * xnorm) : 0.f);
                 if (!(second - best > eps)) {      // also catches NaN / Inf rows
                     int p = atomicAdd(a.n_flagged, 1);
                     a.flagged[p] = (int32_t)row;
@@ -290,10 +291,18 @@ int launch_assign_tc(const Table& X, int metric, const Table& Cn, int k, int32_t
         a.k = k;
         a.is_l2 = is_l2;
         a.cmax = std::sqrt(cmax2);
-        // analytical bound of the split product: dropped lo.lo <= 2^-16 |x||c|, bf16 rounding of the lo planes
-        // <= 2 * 2^-18 |x||c| (together ~1.1e-5), plus the fp32 accumulation of 3 * dim terms in TMEM; 2^-13 = 1.2e-4
-        // leaves an order of magnitude of head-room
-        a.tol = 1.0f / 8192.0f;
+        // |err(x.c)| <= tol |x||c| for the split product (same derivation as launch_list_tc_refine, vb_list_tc.cu):
+        //   representation: hi.hi + hi.lo + lo.hi drops lo.lo and the two bf16 residuals: 3 * 2^-16;
+        //   accumulation: one fp32 rounding of the TMEM accumulator per UMMA, 3 UMMAs per 16-element K step, 2^-23 each
+        //     (truncation), doubled for the alignment of the 16 products inside an UMMA -> 6 * (dim / 16) * 2^-23.
+        // 2^-13 covers both up to ~1650 dimensions (the shapes validated in round 1); longer rows (ivfflat allows 2000
+        // for vector, 4000 for halfvec) take the formula.  The fp32 norms |x|^2, |c|^2 are sums of dim / 32 terms per
+        // lane plus a 5-step shuffle tree: (dim / 32 + 8) * 2^-23 relative, at least 1e-6.
+        {
+            const float steps = (float)(n_kblocks * (TC_K / 16));
+            a.tol = std::max(1.0f / 8192.0f, 3.0f / 65536.0f + 6.0f * steps / 8388608.0f);
+            a.sum_tol = std::max(1e-6f, ((float)dim / 32.0f + 8.0f) / 8388608.0f);
+        }
         a.out_idx = out_idx;
         a.flagged = d_flagged;
         a.n_flagged = d_nflag;

@@ -723,7 +723,10 @@ static double host_uniform(uint64_t* st) {
     return (double)(z >> 11) * (1.0 / 9007199254740992.0);
 }
 
-static int kmeans_pp(const Table& X, int kmeans_metric, void* centers_host, int k, uint64_t seed) {
+// first_row / u: the draws of InitCenters (src/ivfkmeans.c:36, 78) when the caller supplies them (parity tests feed the
+// oracle the same ones); otherwise they come from the seed.  picked_out (optional, host): the chosen sample rows.
+static int kmeans_pp(const Table& X, int kmeans_metric, void* centers_host, int k, uint64_t seed, int64_t first_row = -1,
+                     const double* u_in = nullptr, int64_t* picked_out = nullptr) {
     Context& c = ctx();
     cudaStream_t s = c.stream;
     const int64_t n = X.n;
@@ -750,6 +753,9 @@ static int kmeans_pp(const Table& X, int kmeans_metric, void* centers_host, int 
     if (first >= n) first = n - 1;
     std::vector<double> u((size_t)k);
     for (int i = 0; i + 1 < k; ++i) u[(size_t)i] = host_uniform(&rs);
+    if (first_row >= 0) first = std::min<int64_t>(first_row, n - 1);
+    if (u_in)
+        for (int i = 0; i + 1 < k; ++i) u[(size_t)i] = u_in[i];
     VB_CUDA(cudaMemcpyAsync(d_w, w0.data(), sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, s));
     VB_CUDA(cudaMemcpyAsync(d_u, u.data(), sizeof(double) * (size_t)k, cudaMemcpyHostToDevice, s));
     VB_CUDA(cudaMemcpyAsync(d_picks, &first, sizeof(int64_t), cudaMemcpyHostToDevice, s));
@@ -768,6 +774,7 @@ static int kmeans_pp(const Table& X, int kmeans_metric, void* centers_host, int 
     pp_gather_rows_kernel<<<(unsigned)k, 256, 0, s>>>(X.d, X.stride, (const int64_t*)d_picks, raw, raw, (uint8_t*)d_out);
     count_launch(1);
     VB_CUDA(cudaMemcpyAsync(centers_host, d_out, raw * (size_t)k, cudaMemcpyDeviceToHost, s));
+    if (picked_out) VB_CUDA(cudaMemcpyAsync(picked_out, d_picks, sizeof(int64_t) * (size_t)k, cudaMemcpyDeviceToHost, s));
     VB_CUDA(cudaStreamSynchronize(s));
     VB_CUDA(cudaGetLastError());
     return VB_OK;
@@ -790,6 +797,13 @@ int vb_kmeans_pp_init(vb_table* samples, int kmeans_metric, void* centers, int k
     VB_TRY(require_init());
     VB_REQUIRE(samples && centers && k >= 1, "bad k-means++ arguments");
     return kmeans_pp(samples->t, kmeans_metric, centers, k, seed);
+}
+
+int vb_kmeans_pp_init_draws(vb_table* samples, int kmeans_metric, void* centers, int k, int64_t first_row, const double* u,
+                            int64_t* picked_out) {
+    VB_TRY(require_init());
+    VB_REQUIRE(samples && centers && k >= 1 && first_row >= 0 && (u || k == 1), "bad k-means++ arguments");
+    return kmeans_pp(samples->t, kmeans_metric, centers, k, 0, first_row, u, picked_out);
 }
 
 static int assign_impl(vb_table* rows, int metric, const void* centers, int k, bool host, int32_t* out) {

@@ -548,7 +548,9 @@ int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metr
     float c_ip = level == 1 ? 1.0f / 256.0f + 1.0f / 8192.0f : 1.0f / 8192.0f;   // validated constants
     c_ip = std::max(c_ip, ip_unit);
     bound.c_dot = bound.is_l2 ? 2.0f * c_ip : c_ip + 1.0f / 131072.0f;
-    bound.c_sum = 1.0f / 65536.0f;
+    // norms and the exact fp32 distance each sum dim / 32 terms per lane plus a shuffle tree: 3 * (dim / 32 + 8) * 2^-24 of
+    // (|x|^2 + |q|^2) covers the two norms and the distance (<= 2 (|x|^2 + |q|^2)); 2^-16 up to ~2700 dimensions
+    bound.c_sum = std::max(1.0f / 65536.0f, 3.0f * ((float)rows.dim / 32.0f + 8.0f) / 16777216.0f);
     bound.xmax = im.xmax;
 #define VB_RS(E, M) rescore_kernel<E, M><<<grid, 256, 0, s>>>(rows.d, rows.stride, V, (const uint8_t*)qimg, qstride, nq, k, kp, probes, bound, qn, pos_kp, approx_kp, d_lists, cand_off, d_list_off, exact)
     if (rows.elem == VB_VECTOR) {

@@ -360,6 +360,13 @@ int vb_shutdown(void) {
 
 void* vb_stream(void) { return (void*)vb::ctx().stream; }
 
+int vb_stream_wait_event(void* cuda_event) {
+    VB_TRY(vb::require_init());
+    VB_REQUIRE(cuda_event, "null event");
+    VB_CUDA(cudaStreamWaitEvent(vb::ctx().stream, (cudaEvent_t)cuda_event, 0));
+    return VB_OK;
+}
+
 int vb_prof_enable(int on) {
     vb::prof_set(on != 0);
     return VB_OK;

@@ -145,3 +145,57 @@ def test_allreduce_hook_is_called_with_sums_counts_and_changes(pv):
     c2, it2 = pv.kmeans(t, O.L2, rows[:5].copy(), max_iter=3)
     assert np.array_equal(c1, c2) and it1 == it2
     assert (5 * 8, 0) in calls and (5, 1) in calls and (1, 1) in calls
+
+
+@pytest.mark.parametrize("elem,km,n,dim,k,unit", [(O.VECTOR, O.L2, 6000, 64, 60, False), (O.VECTOR, O.L2, 3000, 3, 100, False),
+                                                  (O.HALFVEC, O.L2, 4000, 200, 40, False), (O.VECTOR, O.SPHERICAL, 4000, 48, 30, True),
+                                                  (O.BIT, O.HAMMING, 4000, 256, 25, False)])
+def test_kmeans_pp_picks_the_oracles_rows_from_shared_draws(pv, elem, km, n, dim, k, unit):
+    """InitCenters (src/ivfkmeans.c:23-91): fed the same first row and the same RandomDouble() draws, the GPU seeding
+    (distance scan + weight update + prefix sum + pick per round) chooses the same sample rows as the oracle's
+    sequential loop.  A pick may differ only when the draw lands within rounding of a boundary of the cumulative
+    weights (the GPU adds the doubles in scan order, the reference subtracts them one by one); every later pick then
+    differs too, so the comparison is the common prefix."""
+    if dim == 3:
+        rows = np.random.default_rng(3).random((n, 3)).astype(np.float32)
+    else:
+        rows, _ = _data(elem, n, dim, k, seed=n + dim, unit=unit)
+    rng = np.random.default_rng(k)
+    first = int(rng.integers(0, n))
+    u = rng.random(k - 1)
+    want_c, want_p = O.kmeans_pp_init_draws(elem, km, rows, k, first, u, dim=dim)
+    t = pv.Table(elem, dim).append(rows)
+    got_c, got_p = pv.kmeans_pp_init_draws(t, km, k, first, u)
+    same = got_p == want_p
+    prefix = k if same.all() else int(np.argmin(same))
+    assert prefix >= (k if elem != O.BIT else 1), (prefix, got_p[:prefix + 2], want_p[:prefix + 2])
+    assert np.array_equal(got_c[:prefix], want_c[:prefix])
+    if elem == O.BIT and prefix < k:
+        # Hamming weights are small integers: equal cumulative sums are ordinary, and a draw exactly on a boundary is
+        # resolved the same way by both ("choice <= 0" = first j with cum >= choice) -- a mismatch needs explaining
+        j, a, b = prefix, int(got_p[prefix]), int(want_p[prefix])
+        assert abs(a - b) <= 1, (j, a, b)
+
+
+def test_assign_tolerance_grows_with_the_row_length(pv):
+    """halfvec rows of 4000 dimensions (HNSW_MAX_DIM * 2, the ivfflat limit for halfvec, src/ivfflat.h:37-38 via
+    halfvec.h): the split-bf16 product's accumulation error exceeds the 2^-13 constant of shorter rows, so the margin
+    test must use the dimension-dependent bound -- tensor-core assign == exact fp32 assign == oracle."""
+    n, dim, k = 4096, 4000, 64
+    rng = np.random.default_rng(4000)
+    c = rng.standard_normal((k, dim)).astype(np.float32)
+    # rows sit between pairs of centres so best / second-best margins are small
+    a, b = rng.integers(0, k, n), rng.integers(0, k, n)
+    w = rng.random((n, 1)).astype(np.float32) * 0.02 + 0.49
+    x = (w * c[a] + (1 - w) * c[b] + 0.05 * rng.standard_normal((n, dim))).astype(np.float32)
+    rows, centers = f32_to_half_bits(x), f32_to_half_bits(c)
+    t = pv.Table(O.HALFVEC, dim).append(rows)
+    pv.set_tensor_cores(False)
+    try:
+        exact = pv.assign(t, O.L2_SQUARED, centers)
+    finally:
+        pv.set_tensor_cores(True)
+    got = pv.assign(t, O.L2_SQUARED, centers)
+    assert pv.last_assign_rechecked() >= 0
+    assert np.array_equal(got, exact)
+    assert _assign_agreement(O.HALFVEC, O.L2_SQUARED, rows, centers, got, dim=dim) >= 0.999
