@@ -286,6 +286,26 @@ int			vb_hnsw_load(vb_hnsw *h, const void *rows, int64_t n, const int32_t *level
 						 int64_t upper_slots, int64_t entry);
 int			vb_hnsw_free(vb_hnsw *h);
 /*
+ * CREATE INDEX ... USING hnsw on the device: the in-memory build of src/hnswbuild.c:437-480 --
+ * HnswFindElementNeighbors (src/hnswutils.c:1280-1357) with ef_construction, the SelectNeighbors heuristic
+ * (:1065-1165), duplicate folding (src/hnswbuild.c:343-364) and HnswUpdateConnection (:1184-1231) -- for rows
+ * inserted in batches the way the reference's parallel workers insert concurrently.  Row i becomes element i.
+ * levels: the per-row level draws of HnswInitElement (src/hnswutils.c:248-254) when the caller owns the PRNG
+ * (the extension passes pg_prng's), NULL = drawn from `seed`.  The index is searchable afterwards (vb_hnsw_search)
+ * and vb_hnsw_export returns the graph in the layout vb_hnsw_load takes, for the page writer
+ * (HnswSetNeighborTuple, src/hnswutils.c:455-486): levels [n], nbr0 [n x 2m], upper_off [n], upper
+ * [vb_hnsw_upper_slots() x m], entry point, and dup_of [n] = the element a duplicate row was folded into (its heap
+ * TID joins that element's, HNSW_HEAPTIDS = 10 at most, src/hnsw.h:69) or -1.  Any output may be NULL.
+ */
+int			vb_hnsw_build(vb_hnsw *h, const void *rows, int64_t n, int ef_construction, uint64_t seed,
+						  const int32_t *levels);
+int			vb_hnsw_build_dev(vb_hnsw *h, const void *rows_dev, int64_t n, int ef_construction, uint64_t seed,
+							  const int32_t *levels);
+int64_t		vb_hnsw_rows(const vb_hnsw *h);
+int64_t		vb_hnsw_upper_slots(const vb_hnsw *h);
+int			vb_hnsw_export(vb_hnsw *h, int32_t *levels, int32_t *nbr0, int64_t *upper_off, int32_t *upper,
+						   int64_t *entry, int32_t *dup_of);
+/*
  * GetScanItems (src/hnswscan.c:25-56): greedy descent with ef = 1 through the
  * upper layers, then HnswSearchLayer (src/hnswutils.c:824-987) with ef at layer 0;
  * results nearest first (src/hnswscan.c:293-326), k <= ef of them per query,

@@ -449,6 +449,34 @@ class HnswIndex:
                                        _ptr(upper) if slots else None, slots, int(entry)))
         return self
 
+    def build(self, rows, ef_construction=64, seed=42, levels=None):
+        """CREATE INDEX on the device (src/hnswbuild.c:437-480 in batches): row i becomes element i."""
+        lv = None if levels is None else np.ascontiguousarray(levels, dtype=np.int32)
+        if _is_torch(rows):
+            _after_torch(rows)
+            self.n = rows.shape[0]
+            _lib.check(load().vb_hnsw_build_dev(self.h, _ptr(rows), self.n, int(ef_construction), int(seed), _ptr(lv)))
+        else:
+            rows = _host(self.elem, rows)
+            self.n = rows.shape[0]
+            _lib.check(load().vb_hnsw_build(self.h, _ptr(rows), self.n, int(ef_construction), int(seed), _ptr(lv)))
+        return self
+
+    def export(self):
+        """the graph as arrays (the layout load() takes, plus dup_of): what the page writer consumes"""
+        n, m = int(load().vb_hnsw_rows(self.h)), self.m
+        slots = int(load().vb_hnsw_upper_slots(self.h))
+        levels = np.empty(n, dtype=np.int32)
+        nbr0 = np.empty((n, 2 * m), dtype=np.int32)
+        upper_off = np.empty(n, dtype=np.int64)
+        upper = np.full((max(slots, 1), m), -1, dtype=np.int32)
+        dup_of = np.empty(n, dtype=np.int32)
+        entry = C.c_int64(-1)
+        _lib.check(load().vb_hnsw_export(self.h, _ptr(levels), _ptr(nbr0), _ptr(upper_off), _ptr(upper), C.byref(entry), _ptr(dup_of)))
+        e = int(entry.value)
+        return dict(levels=levels, nbr0=nbr0, upper_off=upper_off, upper=upper[:slots], entry=e,
+                    entry_level=int(levels[e]) if e >= 0 else -1, m=m, dup_of=dup_of)
+
     def search(self, queries, k=None, ef_search=None):
         ef = int(ef_search or self.ef_search)
         k = int(k or ef)

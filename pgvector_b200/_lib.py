@@ -66,6 +66,11 @@ SIGNATURES = {
     "vb_hnsw_create": (_i, [_i, _i, _i, _i, C.POINTER(_vp)]),
     "vb_hnsw_load": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64]),
     "vb_hnsw_free": (_i, [_vp]),
+    "vb_hnsw_build": (_i, [_vp, _vp, _i64, _i, _u64, _vp]),
+    "vb_hnsw_build_dev": (_i, [_vp, _vp, _i64, _i, _u64, _vp]),
+    "vb_hnsw_rows": (_i64, [_vp]),
+    "vb_hnsw_upper_slots": (_i64, [_vp]),
+    "vb_hnsw_export": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
     "vb_hnsw_search": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "vb_hnsw_search_dev": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
 }

@@ -16,69 +16,12 @@
 //
 // Roofline: HBM (latency-bound random row gathers).  Algorithmic bytes per query =
 // n_dist * dim * element size + n_expand * lm * 4; n_dist is returned per query.
-#include "vb_common.cuh"
-#include "vb_distance.cuh"
+#include "vb_hnsw.cuh"
 
 #include <algorithm>
 #include <vector>
 
 namespace vb {
-
-struct HnswDev {
-    const uint8_t* rows;
-    size_t stride;
-    int V;                    // 16-byte vectors per row
-    const int32_t* levels;    // [n]
-    const int32_t* nbr0;      // [n][2m]
-    const int32_t* upper_off; // [n] slot index or -1
-    const int32_t* upper;     // [slots][m]
-    int m;
-    int64_t n;
-    int entry;
-    int entry_level;
-};
-
-struct Hnsw {
-    int elem, metric, dim, m;
-    Table rows;
-    int32_t *levels = nullptr, *nbr0 = nullptr, *upper_off = nullptr, *upper = nullptr;
-    int64_t n = 0, entry = -1;
-    int entry_level = -1;
-    bool loaded = false;
-    uint32_t* vis = nullptr;  // visited hash tables, one per resident warp
-    size_t vis_bytes = 0;
-};
-
-constexpr int HN_WARPS = 4;             // queries per CTA
-constexpr uint32_t VIS_EMPTY = 0xFFFFFFFFu;
-
-__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
-    x ^= x >> 16;
-    x *= 0x7feb352du;
-    x ^= x >> 15;
-    x *= 0x846ca68bu;
-    x ^= x >> 16;
-    return x;
-}
-
-// returns true when id was NOT in the set (and inserts it)
-__device__ __forceinline__ bool vis_insert(uint32_t* tab, uint32_t mask, uint32_t id) {
-    uint32_t h = hash_u32(id) & mask;
-    for (;;) {
-        uint32_t old = atomicCAS(&tab[h], VIS_EMPTY, id);
-        if (old == VIS_EMPTY) return true;
-        if (old == id) return false;
-        h = (h + 1) & mask;
-    }
-}
-
-struct Ent {
-    uint64_t key;   // orderable64(distance)
-    uint32_t id;    // element number, bit 31 = expanded
-};
-__device__ __forceinline__ bool ent_less(uint64_t ka, uint32_t ia, uint64_t kb, uint32_t ib) {
-    return ka < kb || (ka == kb && (ia & 0x7fffffffu) < (ib & 0x7fffffffu));
-}
 
 // One warp = one query at a time.
 template <int ELEM, int METRIC, int LPR>
@@ -90,7 +33,7 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswDev g, c
     extern __shared__ uint4 smem[];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int qvec = (int)(qstride / 16);
-    // per-warp carve-up: query image | keys A | keys B | ids A | ids B | batch keys | batch ids
+    // per-warp carve-up: query image | keys A | keys B | batch keys | ids A | ids B | batch ids
     const size_t per_warp = (size_t)qvec * 16 + (size_t)ef * 2 * 8 + (size_t)ef * 2 * 4 + 32 * 8 + 32 * 4;
     const size_t per_warp_al = (per_warp + 15) & ~(size_t)15;
     uint8_t* base = reinterpret_cast<uint8_t*>(smem) + (size_t)warp * per_warp_al;
@@ -105,19 +48,20 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswDev g, c
     const int gwarp = blockIdx.x * HN_WARPS + warp;
     const int nwarps = gridDim.x * HN_WARPS;
     uint32_t* vis = vis_all + (size_t)gwarp * vis_cap;
-    constexpr int GROUPS = 32 / LPR;       // rows scored at once
-    const int grp = lane / LPR, gl = lane % LPR;
 
     for (int64_t q = gwarp; q < nq; q += nwarps) {
         const uint4* gq = reinterpret_cast<const uint4*>(queries + (size_t)q * qstride);
         for (int i = lane; i < qvec; i += 32) sq[i] = gq[i];
         __syncwarp();
 
-        uint64_t* rk = keyA;
-        uint32_t* ri = idA;
-        uint64_t* nk = keyB;
-        uint32_t* ni = idB;
-        int len = 0;
+        HnswWarpState S;
+        S.rk = keyA;
+        S.ri = idA;
+        S.nk = keyB;
+        S.ni = idB;
+        S.bkey = bkey;
+        S.bid = bid;
+        S.len = 0;
         int64_t ndist = 0;
         bool failed = false;
 
@@ -128,186 +72,26 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswDev g, c
             for (int v = lane; v < g.V; v += 32) acc.add(ldg_stream(rp + v), sq, v);
             acc.template reduce<32>();
             if (lane == 0) {
-                rk[0] = orderable_key64(acc.value());
-                ri[0] = (uint32_t)g.entry;
+                S.rk[0] = orderable_key64(acc.value());
+                S.ri[0] = (uint32_t)g.entry;
             }
-            len = 1;
+            S.len = 1;
             __syncwarp();
         }
 
         for (int lc = g.entry_level; lc >= 0 && !failed; --lc) {
-            const int efl = lc == 0 ? ef : 1;
-            const int lm = lc == 0 ? 2 * g.m : g.m;
-            // visited set of this layer (InitVisited, src/hnswutils.c:671-680)
-            // (the ef = 1 layers use a small region of their own so only it is cleared per layer)
+            // (the ef = 1 layers use a small visited region of their own so only it is cleared per layer)
             uint32_t* tab = lc == 0 ? vis + vis_upper : vis;
             const uint32_t cap = lc == 0 ? vis_cap - vis_upper : vis_upper;
-            const uint32_t mask = cap - 1;
-            for (uint32_t i = lane; i < cap; i += 32) tab[i] = VIS_EMPTY;
-            __syncwarp();
-            uint32_t inserted = 0;
-            // entry points: visited, unexpanded; they count towards `tuples` at layer 0 (src/hnswutils.c:866-873)
-            for (int i = lane; i < len; i += 32) {
-                ri[i] &= 0x7fffffffu;
-                vis_insert(tab, mask, ri[i]);
-            }
-            inserted += (uint32_t)len;
-            if (lc == 0) ndist += len;
-            if (len > efl) len = efl;   // cannot happen (len <= previous efl = 1), kept for safety
-            __syncwarp();
-
-            for (;;) {
-                // nearest unexpanded element of R
-                int first = 0x7fffffff;
-                for (int i = lane; i < len; i += 32)
-                    if (!(ri[i] & 0x80000000u)) {
-                        first = i;
-                        break;
-                    }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-                if (first == 0x7fffffff) break;
-                const uint32_t c = ri[first] & 0x7fffffffu;
-                __syncwarp();
-                if (lane == 0) ri[first] = c | 0x80000000u;
-                __syncwarp();
-
-                // neighbour list of c at layer lc, in on-disk order (HnswLoadNeighborTids, src/hnswutils.c:761-791)
-                const int32_t* nb = nullptr;
-                if (lc == 0) nb = g.nbr0 + (size_t)c * lm;
-                else if (g.levels[c] >= lc) nb = g.upper + ((size_t)g.upper_off[c] + (lc - 1)) * (size_t)lm;
-                if (nb == nullptr) continue;
-
-                for (int off = 0; off < lm; off += 32) {
-                    int nid = (off + lane < lm) ? nb[off + lane] : -1;
-                    bool valid = nid >= 0;
-                    // an invalid TID terminates the list (src/hnswutils.c:809-810)
-                    unsigned vmask = __ballot_sync(0xffffffffu, valid);
-                    unsigned inval = ~vmask;
-                    int first_inval = inval ? __ffs(inval) - 1 : 32;
-                    valid = valid && lane < first_inval;
-                    bool fresh = valid && vis_insert(tab, mask, (uint32_t)nid);
-                    inserted += (uint32_t)__popc(__ballot_sync(0xffffffffu, fresh));
-                    // elements below this layer are skipped (src/hnswutils.c:949-950)
-                    if (fresh && lc > 0 && g.levels[nid] < lc) fresh = false;
-                    unsigned fm = __ballot_sync(0xffffffffu, fresh);
-                    const int cnt = __popc(fm);
-                    if (cnt == 0) {
-                        if (first_inval < 32) break;
-                        continue;
-                    }
-                    if (lc == 0) ndist += cnt;
-                    const int pos = __popc(fm & ((1u << lane) - 1u));
-                    if (fresh) bid[pos] = (uint32_t)nid;
-                    __syncwarp();
-
-                    // score the batch: GROUPS rows per pass, RPI passes in flight
-                    constexpr int RPI = (LPR == 32) ? 4 : 2;   // (8 in flight measured the same: 821 k vs 816 k queries/s, at 128 registers)
-                    for (int b0 = 0; b0 < cnt; b0 += GROUPS * RPI) {
-                        Acc<ELEM, METRIC> acc[RPI];
-                        const uint4* rp[RPI];
-#pragma unroll
-                        for (int i = 0; i < RPI; ++i) {
-                            int bi = b0 + i * GROUPS + grp;
-                            uint32_t e = bid[min(bi, cnt - 1)];
-                            rp[i] = reinterpret_cast<const uint4*>(g.rows + (size_t)e * g.stride);
-                        }
-                        for (int v = gl; v < g.V; v += LPR) {
-                            uint4 x[RPI];
-#pragma unroll
-                            for (int i = 0; i < RPI; ++i) x[i] = ldg_stream(rp[i] + v);
-#pragma unroll
-                            for (int i = 0; i < RPI; ++i) acc[i].add(x[i], sq, v);
-                        }
-#pragma unroll
-                        for (int i = 0; i < RPI; ++i) {
-                            acc[i].template reduce<LPR>();
-                            int bi = b0 + i * GROUPS + grp;
-                            if (gl == 0 && bi < cnt) bkey[bi] = orderable_key64(acc[i].value());
-                        }
-                    }
-                    __syncwarp();
-
-                    // sort the batch by (key, id): bitonic over 32 lanes, empty lanes = +inf
-                    uint64_t mk = lane < cnt ? bkey[lane] : ~0ull;
-                    uint32_t mi = lane < cnt ? bid[lane] : 0x7fffffffu;
-#pragma unroll
-                    for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-                        for (int st = size >> 1; st > 0; st >>= 1) {
-                            uint64_t ok = __shfl_xor_sync(0xffffffffu, mk, st);
-                            uint32_t oi = __shfl_xor_sync(0xffffffffu, mi, st);
-                            bool up = (lane & size) == 0;
-                            bool lower = (lane & st) == 0;
-                            bool other_less = ent_less(ok, oi, mk, mi);
-                            // keep min in the lower lane of an ascending pair, max otherwise
-                            bool take = (lower == up) ? other_less : !other_less;
-                            if (take) {
-                                mk = ok;
-                                mi = oi;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane < cnt) {
-                        bkey[lane] = mk;
-                        bid[lane] = mi;
-                    }
-                    __syncwarp();
-
-                    // merge R (len, sorted) with the batch (cnt, sorted) into the other buffer, keep efl
-                    for (int j = lane; j < len; j += 32) {
-                        uint64_t kj = rk[j];
-                        uint32_t ij = ri[j];
-                        int lo = 0, hi = cnt;   // number of batch elements < R[j]
-                        while (lo < hi) {
-                            int mid = (lo + hi) >> 1;
-                            if (ent_less(bkey[mid], bid[mid], kj, ij)) lo = mid + 1;
-                            else hi = mid;
-                        }
-                        int np = j + lo;
-                        if (np < efl) {
-                            nk[np] = kj;
-                            ni[np] = ij;
-                        }
-                    }
-                    if (lane < cnt) {
-                        int lo = 0, hi = len;   // number of R elements < batch[lane]
-                        while (lo < hi) {
-                            int mid = (lo + hi) >> 1;
-                            if (ent_less(rk[mid], ri[mid], mk, mi)) lo = mid + 1;
-                            else hi = mid;
-                        }
-                        int np = lane + lo;
-                        if (np < efl) {
-                            nk[np] = mk;
-                            ni[np] = mi;     // unexpanded
-                        }
-                    }
-                    __syncwarp();
-                    len = min(efl, len + cnt);
-                    uint64_t* tk = rk;
-                    rk = nk;
-                    nk = tk;
-                    uint32_t* ti = ri;
-                    ri = ni;
-                    ni = ti;
-                    if (first_inval < 32) break;
-                }
-                // keep the table at most half full; otherwise report and let the host retry with a larger one
-                if (inserted > cap / 2) {
-                    failed = true;
-                    break;
-                }
-            }
+            failed = !hnsw_search_layer<ELEM, METRIC, LPR>(g, sq, lc, lc == 0 ? ef : 1, lane, S, tab, cap, lc == 0 ? &ndist : nullptr);
         }
 
         if (failed && lane == 0) atomicExch(overflow, 1);
         // results nearest first (src/hnswscan.c:293-326)
         for (int i = lane; i < k; i += 32) {
-            bool have = i < len && !failed;
-            int64_t id = have ? (int64_t)(ri[i] & 0x7fffffffu) : -1;
-            double d = have ? key64_to_double(rk[i]) : (double)INFINITY;
+            bool have = i < S.len && !failed;
+            int64_t id = have ? (int64_t)(S.ri[i] & 0x7fffffffu) : -1;
+            double d = have ? key64_to_double(S.rk[i]) : (double)INFINITY;
             out_ids[q * k + i] = id;
             if (out_f) out_f[q * k + i] = (float)d;
             if (out_d) out_d[q * k + i] = d;
@@ -478,13 +262,29 @@ static int hnsw_search_impl(Hnsw& h, const void* queries, int64_t nq, int ef, in
     return VB_OK;
 }
 
+void hnsw_release(Hnsw& h) {
+    table_free(h.rows);
+    cudaFree(h.levels);
+    cudaFree(h.nbr0);
+    cudaFree(h.upper_off);
+    cudaFree(h.upper);
+    cudaFree(h.vis);
+    cudaFree(h.nd0);
+    cudaFree(h.upper_d);
+    cudaFree(h.dup_of);
+    cudaFree(h.n_heaptids);
+    h.levels = h.nbr0 = h.upper_off = h.upper = nullptr;
+    h.nd0 = h.upper_d = nullptr;
+    h.dup_of = h.n_heaptids = nullptr;
+    h.vis = nullptr;
+    h.vis_bytes = 0;
+    h.upper_slots = 0;
+    h.loaded = false;
+}
+
 }  // namespace vb
 
 using namespace vb;
-
-struct vb_hnsw {
-    Hnsw h;
-};
 
 extern "C" {
 
@@ -505,19 +305,6 @@ int vb_hnsw_create(int elem, int metric, int dim, int m, vb_hnsw** out) {
     p->h.rows.stride = padded_row_bytes(elem, dim);
     *out = p;
     return VB_OK;
-}
-
-static void hnsw_release(Hnsw& h) {
-    table_free(h.rows);
-    cudaFree(h.levels);
-    cudaFree(h.nbr0);
-    cudaFree(h.upper_off);
-    cudaFree(h.upper);
-    cudaFree(h.vis);
-    h.levels = h.nbr0 = h.upper_off = h.upper = nullptr;
-    h.vis = nullptr;
-    h.vis_bytes = 0;
-    h.loaded = false;
 }
 
 int vb_hnsw_load(vb_hnsw* p, const void* rows, int64_t n, const int32_t* levels, const int32_t* nbr0, const int64_t* upper_off,

@@ -1,0 +1,291 @@
+// vb_hnsw.cuh -- device pieces shared by the HNSW scan (vb_hnsw.cu) and the HNSW build (vb_hnsw_build.cu):
+// the graph image, the per-warp visited hash, batched row scoring and HnswSearchLayer
+// (src/hnswutils.c:824-987) in its sorted-array formulation.
+//
+// Formulation.  Every distance comparison of the reference is taken on the total order
+// (distance, element number).  Under a total order the two pairing heaps collapse into ONE
+// sorted array R of the best <= ef elements seen so far, each with an "expanded" flag:
+//   W (results)    = R;   f = R[len-1]
+//   C (candidates) = unexpanded elements of R  (anything evicted from W is > f for ever,
+//                    so the reference would break on it before expanding it)
+//   pop nearest(C) = first unexpanded element of R;  "c > f -> break" = no unexpanded left
+//   admit e        = e lands inside the first ef entries of merge(R, {e})
+// which is order independent, so the <= lm neighbours of one expansion are scored
+// together: one neighbour-list read, lm independent row gathers in flight,
+// a warp bitonic sort of the batch and a parallel merge into R.
+#pragma once
+
+#include "vb_common.cuh"
+#include "vb_distance.cuh"
+
+namespace vb {
+
+struct HnswDev {
+    const uint8_t* rows;
+    size_t stride;
+    int V;                    // 16-byte vectors per row
+    const int32_t* levels;    // [n]
+    const int32_t* nbr0;      // [n][2m]
+    const int32_t* upper_off; // [n] slot index or -1
+    const int32_t* upper;     // [slots][m]
+    int m;
+    int64_t n;
+    int entry;
+    int entry_level;
+};
+
+struct Hnsw {
+    int elem, metric, dim, m;
+    Table rows;
+    int32_t *levels = nullptr, *nbr0 = nullptr, *upper_off = nullptr, *upper = nullptr;
+    int64_t n = 0, entry = -1;
+    int entry_level = -1;
+    bool loaded = false;
+    uint32_t* vis = nullptr;  // visited hash tables, one per resident warp
+    size_t vis_bytes = 0;
+    // build-side state (vb_hnsw_build.cu); nd0 / upper_d hold the distance stored with every neighbour
+    // (HnswCandidate.distance, src/hnsw.h:143-148), dup_of the element a duplicate row was folded into
+    float *nd0 = nullptr, *upper_d = nullptr;
+    int32_t *dup_of = nullptr, *n_heaptids = nullptr;
+    int64_t upper_slots = 0;
+};
+
+void hnsw_release(Hnsw& h);
+
+constexpr int HN_WARPS = 4;             // queries (or inserted elements) per CTA
+constexpr uint32_t VIS_EMPTY = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x7feb352du;
+    x ^= x >> 15;
+    x *= 0x846ca68bu;
+    x ^= x >> 16;
+    return x;
+}
+
+// returns true when id was NOT in the set (and inserts it)
+__device__ __forceinline__ bool vis_insert(uint32_t* tab, uint32_t mask, uint32_t id) {
+    uint32_t h = hash_u32(id) & mask;
+    for (;;) {
+        uint32_t old = atomicCAS(&tab[h], VIS_EMPTY, id);
+        if (old == VIS_EMPTY) return true;
+        if (old == id) return false;
+        h = (h + 1) & mask;
+    }
+}
+
+__device__ __forceinline__ bool ent_less(uint64_t ka, uint32_t ia, uint64_t kb, uint32_t ib) {
+    return ka < kb || (ka == kb && (ia & 0x7fffffffu) < (ib & 0x7fffffffu));
+}
+
+// a table row as the "query image" the Acc<> arithmetic reads from shared memory: vector and bit rows as they
+// are, halfvec rows widened to fp32 (exact, HalfToFloat4)
+template <int ELEM>
+__device__ __forceinline__ void load_row_image(const uint8_t* row, int V, uint4* img, int lane) {
+    const uint4* rp = reinterpret_cast<const uint4*>(row);
+    for (int v = lane; v < V; v += 32) {
+        const uint4 r = __ldg(rp + v);
+        if (ELEM == VB_HALFVEC) {
+            const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+            const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+            const float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&r.z));
+            const float2 x3 = __half22float2(*reinterpret_cast<const __half2*>(&r.w));
+            img[2 * v] = make_uint4(__float_as_uint(x0.x), __float_as_uint(x0.y), __float_as_uint(x1.x), __float_as_uint(x1.y));
+            img[2 * v + 1] = make_uint4(__float_as_uint(x2.x), __float_as_uint(x2.y), __float_as_uint(x3.x), __float_as_uint(x3.y));
+        } else {
+            img[v] = r;
+        }
+    }
+}
+
+// distances of the image `sq` to the rows bid[0..cnt): GROUPS rows per pass (LPR lanes per row), RPI passes in flight.
+// bkey[i] = orderable key of the float8 the opclass's proc 1 returns.
+template <int ELEM, int METRIC, int LPR>
+__device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* sq, const uint32_t* bid, int cnt, uint64_t* bkey,
+                                                 int lane) {
+    constexpr int GROUPS = 32 / LPR;
+    constexpr int RPI = (LPR == 32) ? 4 : 2;   // (8 in flight measured the same: 821 k vs 816 k queries/s, at 128 registers)
+    const int grp = lane / LPR, gl = lane % LPR;
+    for (int b0 = 0; b0 < cnt; b0 += GROUPS * RPI) {
+        Acc<ELEM, METRIC> acc[RPI];
+        const uint4* rp[RPI];
+#pragma unroll
+        for (int i = 0; i < RPI; ++i) {
+            int bi = b0 + i * GROUPS + grp;
+            uint32_t e = bid[min(bi, cnt - 1)] & 0x7fffffffu;
+            rp[i] = reinterpret_cast<const uint4*>(g.rows + (size_t)e * g.stride);
+        }
+        for (int v = gl; v < g.V; v += LPR) {
+            uint4 x[RPI];
+#pragma unroll
+            for (int i = 0; i < RPI; ++i) x[i] = ldg_stream(rp[i] + v);
+#pragma unroll
+            for (int i = 0; i < RPI; ++i) acc[i].add(x[i], sq, v);
+        }
+#pragma unroll
+        for (int i = 0; i < RPI; ++i) {
+            acc[i].template reduce<LPR>();
+            int bi = b0 + i * GROUPS + grp;
+            if (gl == 0 && bi < cnt) bkey[bi] = orderable_key64(acc[i].value());
+        }
+    }
+}
+
+// the two buffers of the sorted result array R and the expansion batch of one warp (shared memory)
+struct HnswWarpState {
+    uint64_t *rk, *nk;    // keys of R (current / next)
+    uint32_t *ri, *ni;    // ids of R, bit 31 = expanded
+    uint64_t* bkey;       // [32]
+    uint32_t* bid;        // [32]
+    int len;
+};
+
+// HnswSearchLayer (src/hnswutils.c:824-987) at layer lc with ef = efl from the entry points already in R
+// (S.len of them, sorted).  tab / cap: this layer's visited table (cleared here, InitVisited :671-680).
+// ndist (may be null) accumulates the reference's `tuples` counter (:866-873, 905-906).  Returns false when the
+// visited table filled beyond half (the caller retries with a larger one).
+template <int ELEM, int METRIC, int LPR>
+__device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4* sq, int lc, int efl, int lane, HnswWarpState& S,
+                                                  uint32_t* tab, uint32_t cap, int64_t* ndist) {
+    const int lm = lc == 0 ? 2 * g.m : g.m;
+    const uint32_t mask = cap - 1;
+    for (uint32_t i = lane; i < cap; i += 32) tab[i] = VIS_EMPTY;
+    __syncwarp();
+    uint32_t inserted = 0;
+    // entry points: visited, unexpanded; they count towards `tuples` (src/hnswutils.c:866-873)
+    if (S.len > efl) S.len = efl;   // ef shrinks only between an ef_construction layer and ... never; kept for safety
+    for (int i = lane; i < S.len; i += 32) {
+        S.ri[i] &= 0x7fffffffu;
+        vis_insert(tab, mask, S.ri[i]);
+    }
+    inserted += (uint32_t)S.len;
+    if (ndist) *ndist += S.len;
+    __syncwarp();
+
+    for (;;) {
+        // nearest unexpanded element of R
+        int first = 0x7fffffff;
+        for (int i = lane; i < S.len; i += 32)
+            if (!(S.ri[i] & 0x80000000u)) {
+                first = i;
+                break;
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        if (first == 0x7fffffff) break;
+        const uint32_t c = S.ri[first] & 0x7fffffffu;
+        __syncwarp();
+        if (lane == 0) S.ri[first] = c | 0x80000000u;
+        __syncwarp();
+
+        // neighbour list of c at layer lc, in on-disk order (HnswLoadNeighborTids, src/hnswutils.c:761-791)
+        const int32_t* nb = nullptr;
+        if (lc == 0) nb = g.nbr0 + (size_t)c * lm;
+        else if (g.levels[c] >= lc) nb = g.upper + ((size_t)g.upper_off[c] + (lc - 1)) * (size_t)lm;
+        if (nb == nullptr) continue;
+
+        for (int off = 0; off < lm; off += 32) {
+            int nid = (off + lane < lm) ? nb[off + lane] : -1;
+            bool valid = nid >= 0;
+            // an invalid TID terminates the list (src/hnswutils.c:809-810)
+            unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            unsigned inval = ~vmask;
+            int first_inval = inval ? __ffs(inval) - 1 : 32;
+            valid = valid && lane < first_inval;
+            bool fresh = valid && vis_insert(tab, mask, (uint32_t)nid);
+            inserted += (uint32_t)__popc(__ballot_sync(0xffffffffu, fresh));
+            // elements below this layer are skipped (src/hnswutils.c:949-950)
+            if (fresh && lc > 0 && g.levels[nid] < lc) fresh = false;
+            unsigned fm = __ballot_sync(0xffffffffu, fresh);
+            const int cnt = __popc(fm);
+            if (cnt == 0) {
+                if (first_inval < 32) break;
+                continue;
+            }
+            if (ndist) *ndist += cnt;
+            const int pos = __popc(fm & ((1u << lane) - 1u));
+            if (fresh) S.bid[pos] = (uint32_t)nid;
+            __syncwarp();
+
+            hnsw_score_batch<ELEM, METRIC, LPR>(g, sq, S.bid, cnt, S.bkey, lane);
+            __syncwarp();
+
+            // sort the batch by (key, id): bitonic over 32 lanes, empty lanes = +inf
+            uint64_t mk = lane < cnt ? S.bkey[lane] : ~0ull;
+            uint32_t mi = lane < cnt ? S.bid[lane] : 0x7fffffffu;
+#pragma unroll
+            for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+                for (int st = size >> 1; st > 0; st >>= 1) {
+                    uint64_t ok = __shfl_xor_sync(0xffffffffu, mk, st);
+                    uint32_t oi = __shfl_xor_sync(0xffffffffu, mi, st);
+                    bool up = (lane & size) == 0;
+                    bool lower = (lane & st) == 0;
+                    bool other_less = ent_less(ok, oi, mk, mi);
+                    // keep min in the lower lane of an ascending pair, max otherwise
+                    bool take = (lower == up) ? other_less : !other_less;
+                    if (take) {
+                        mk = ok;
+                        mi = oi;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane < cnt) {
+                S.bkey[lane] = mk;
+                S.bid[lane] = mi;
+            }
+            __syncwarp();
+
+            // merge R (len, sorted) with the batch (cnt, sorted) into the other buffer, keep efl
+            const int len = S.len;
+            for (int j = lane; j < len; j += 32) {
+                uint64_t kj = S.rk[j];
+                uint32_t ij = S.ri[j];
+                int lo = 0, hi = cnt;   // number of batch elements < R[j]
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (ent_less(S.bkey[mid], S.bid[mid], kj, ij)) lo = mid + 1;
+                    else hi = mid;
+                }
+                int np = j + lo;
+                if (np < efl) {
+                    S.nk[np] = kj;
+                    S.ni[np] = ij;
+                }
+            }
+            if (lane < cnt) {
+                int lo = 0, hi = len;   // number of R elements < batch[lane]
+                while (lo < hi) {
+                    int mid = (lo + hi) >> 1;
+                    if (ent_less(S.rk[mid], S.ri[mid], mk, mi)) lo = mid + 1;
+                    else hi = mid;
+                }
+                int np = lane + lo;
+                if (np < efl) {
+                    S.nk[np] = mk;
+                    S.ni[np] = mi;     // unexpanded
+                }
+            }
+            __syncwarp();
+            S.len = min(efl, len + cnt);
+            uint64_t* tk = S.rk;
+            S.rk = S.nk;
+            S.nk = tk;
+            uint32_t* ti = S.ri;
+            S.ri = S.ni;
+            S.ni = ti;
+            if (first_inval < 32) break;
+        }
+        // keep the table at most half full; otherwise report and let the host retry with a larger one
+        if (inserted > cap / 2) return false;
+    }
+    return true;
+}
+
+}  // namespace vb
+
+struct vb_hnsw {
+    vb::Hnsw h;
+};
