@@ -349,6 +349,14 @@ int vb_set_option(const char* name, int64_t value) {
         vb::ctx().tc_level1 = value != 0;
         return VB_OK;
     }
+    if (!strcmp(name, "hnsw_build_fraction")) {
+        vb::ctx().hnsw_build_fraction = (int)std::max<int64_t>(1, value);
+        return VB_OK;
+    }
+    if (!strcmp(name, "hnsw_build_batch")) {
+        vb::ctx().hnsw_build_batch = (int)std::max<int64_t>(1, std::min<int64_t>(value, 1 << 20));
+        return VB_OK;
+    }
     if (!strcmp(name, "tensor_cores")) {
         vb::set_tc_enabled(value != 0);
         return VB_OK;

@@ -14,7 +14,7 @@
 //                            and in insertion order;
 //   K2  hnsw_update_kernel   one warp per (target, layer): HnswUpdateConnection for each incoming element in turn
 //                            (append while there is room, otherwise the heuristic decides which connection goes).
-// Batches grow with the graph (at most 1/8 of the elements already inserted, capped) and end at an element that
+// Batches grow with the graph (at most 1/64 of the elements already inserted, capped) and end at an element that
 // becomes the new entry point, so the entry point every search starts from is the reference's.
 //
 // SelectNeighbors is evaluated EAGERLY: candidates are visited nearest first; an accepted candidate r marks every
@@ -564,12 +564,16 @@ static int hnsw_build_impl(Hnsw& h, const void* rows, bool rows_on_host, int64_t
     uint32_t cap = 1u << 14;
     while (cap < (uint32_t)(efc * m * 16) && cap < (1u << 22)) cap <<= 1;
 
-    const int64_t b_max = std::min<int64_t>(1 << 20, std::max<int64_t>(4096, std::min<int64_t>(65536, n / 64)));
+    // Elements of one batch do not see each other (like concurrent workers), so a batch stays a small fraction of the
+    // graph it is inserted into: 1/64 by default (measured on B200, 20 000 x 48-d mixture, ef_search 80: recall@10 0.65
+    // at 1/8 vs 0.73 for the serial build).  Options "hnsw_build_fraction" / "hnsw_build_batch".
+    const int64_t frac = std::max<int64_t>(1, c.hnsw_build_fraction);
+    const int64_t b_max = std::min<int64_t>(1 << 20, std::max<int64_t>(1, c.hnsw_build_batch));
     int64_t done = 1;   // element 0 is the first entry point: no neighbours (src/hnswutils.c:1300-1302)
     h.entry = 0;
     h.entry_level = levels[0];
     while (done < n) {
-        int64_t B = std::min<int64_t>(std::min<int64_t>(b_max, std::max<int64_t>(1, done / 8)), n - done);
+        int64_t B = std::min<int64_t>(std::min<int64_t>(b_max, std::max<int64_t>(1, done / frac)), n - done);
         // a batch ends at the first element that rises above the entry point: it becomes the entry point of the next batch
         int64_t promote = -1;
         int64_t max_edges = 0;
