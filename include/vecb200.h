@@ -210,6 +210,43 @@ int64_t		vb_ivf_tc_fallbacks(const vb_ivf *ix);
  * batches were repeated with both planes.  After such a batch the level rests for 64 batches. */
 int64_t		vb_ivf_tc_level1_fallbacks(const vb_ivf *ix);
 
+/*
+ * Traffic accounting of the tensor-core filter kernel (profiling, off by default): with on != 0 every launch also
+ * sums, from the job list the kernel walks, the bytes its bulk copies request and the distinct bytes among them.
+ * out8 (may be NULL): read and reset the counters -- list scan [0] bytes requested, [1] distinct row-plane bytes,
+ * [2] distinct query-tile bytes, [3] launches; [4..7] the same for the centre scan (probe selection).
+ */
+int			vb_ivf_tc_traffic(int on, int64_t *out8);
+
+/*
+ * List-sharded search over the library's communicator (vb_comm_init): this rank's image holds its own lists under
+ * the GLOBAL list numbering (every other list empty) and all centres.  Probe selection runs on this rank's slice of
+ * the queries, the probe lists are all-gathered, every rank scans its lists for all queries, the per-rank k nearest
+ * are all-gathered and merged by (distance, id).  All ranks call it with the same queries and get the full result.
+ * Device pointers; asynchronous on vb_stream() apart from one read of the filter's certificate counters.
+ */
+int			vb_ivf_search_sharded_dev(vb_ivf *ix, const void *queries_dev, int64_t nq, int probes, int k,
+									  int64_t *out_ids_dev, float *out_dist_dev);
+
+/* --------------------------------------------------------------- communicator */
+
+/*
+ * One process per GPU.  vb_comm_unique_id (on one rank) fills the 128-byte NCCL id the host passes to the others
+ * (the extension: through its DSM segment, like the reference's parallel-build state, src/ivfbuild.c:830-966);
+ * vb_comm_init (every rank, collectively) creates the communicator on the library's device.  While it exists,
+ * vb_kmeans / vb_kmeans_pp_init treat `samples` as this rank's slice of a row-sharded sample set (centre sums,
+ * counts, the change counter, k-means++ weight sums and chosen rows are exchanged with ncclAllReduce /
+ * ncclAllGather on vb_stream()), and vb_ivf_search_sharded_dev is available.  dtype: 0 fp32, 1 int32, 2 int64,
+ * 3 fp64, 4 uint32.
+ */
+int			vb_comm_unique_id(void *out, size_t cap);
+int			vb_comm_init(const void *id_bytes, int rank, int world);
+int			vb_comm_free(void);
+int			vb_comm_world(void);
+int			vb_comm_rank(void);
+int			vb_comm_allreduce(void *buf_dev, int64_t count, int dtype);
+int			vb_comm_allgather(const void *send_dev, void *recv_dev, int64_t bytes_per_rank);
+
 /* ------------------------------------------------------- IVFFlat build path */
 
 /*

@@ -329,6 +329,12 @@ class IvfflatIndex:
         _lib.check(load().vb_ivf_search_dev(self.h, _ptr(queries_dev), queries_dev.shape[0], int(probes), int(k),
                                             _ptr(ids_dev), _ptr(dist_dev)))
 
+    def search_sharded_into(self, queries_dev, k, probes, ids_dev, dist_dev):
+        """list-sharded search over the library's communicator (collective; every rank gets the full result)"""
+        _after_torch(queries_dev)
+        _lib.check(load().vb_ivf_search_sharded_dev(self.h, _ptr(queries_dev), queries_dev.shape[0], int(probes), int(k),
+                                                    _ptr(ids_dev), _ptr(dist_dev)))
+
     def search_host_into(self, queries, k, probes, ids, dist):
         _lib.check(load().vb_ivf_search(self.h, _ptr(queries), queries.shape[0], int(probes), int(k), _ptr(ids), _ptr(dist)))
 
@@ -505,6 +511,35 @@ class HnswIndex:
             self.free()
         except Exception:
             pass
+
+
+# --------------------------------------------------------------------- communicator (one process per GPU)
+
+def comm_unique_id() -> bytes:
+    """the 128-byte NCCL id one rank creates and the host hands to the others"""
+    buf = C.create_string_buffer(128)
+    _lib.check(load().vb_comm_unique_id(buf, 128))
+    return buf.raw
+
+
+def comm_init(id_bytes: bytes, rank: int, world: int):
+    """collective: create the library's own NCCL communicator on its device"""
+    _lib.check(load().vb_comm_init(C.c_char_p(id_bytes), int(rank), int(world)))
+
+
+def comm_free():
+    _lib.check(load().vb_comm_free())
+
+
+def comm_world() -> int:
+    return int(load().vb_comm_world())
+
+
+def tc_traffic(on=True, read=False):
+    """traffic accounting of the tensor-core filter launches; read=True returns and resets the 8 counters"""
+    out = np.zeros(8, dtype=np.int64) if read else None
+    _lib.check(load().vb_ivf_tc_traffic(1 if on else 0, _ptr(out)))
+    return out
 
 
 def set_tensor_cores(on: bool):

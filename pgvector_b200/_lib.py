@@ -54,6 +54,15 @@ SIGNATURES = {
     "vb_ivf_last_scan_bytes": (_i64, [_vp]),
     "vb_ivf_last_candidates": (_i64, [_vp]),
     "vb_ivf_tc_fallbacks": (_i64, [_vp]),
+    "vb_ivf_tc_traffic": (_i, [_i, _vp]),
+    "vb_ivf_search_sharded_dev": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
+    "vb_comm_unique_id": (_i, [_vp, C.c_size_t]),
+    "vb_comm_init": (_i, [_vp, _i, _i]),
+    "vb_comm_free": (_i, []),
+    "vb_comm_world": (_i, []),
+    "vb_comm_rank": (_i, []),
+    "vb_comm_allreduce": (_i, [_vp, _i64, _i]),
+    "vb_comm_allgather": (_i, [_vp, _vp, _i64]),
     "vb_ivf_tc_level1_fallbacks": (_i64, [_vp]),
     "vb_kmeans": (_i, [_vp, _i, _vp, _i, _i, _u64, _vp, _vp, _vp]),
     "vb_kmeans_pp_init": (_i, [_vp, _i, _vp, _i, _u64]),

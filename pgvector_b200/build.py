@@ -54,7 +54,7 @@ def build_library(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -73,6 +73,15 @@ inline void count_launch(int n = 1) { ctx().launches += n; }
 void prof_begin(int which);
 void prof_end(int which);
 
+// ---------------------------------------------------------------- communicator (vb_comm.cu)
+// world size / rank of the library's NCCL communicator (1 / 0 when none was created)
+int comm_world();
+int comm_rank();
+// in-place sum over the ranks on the library stream; dtype 0 = fp32, 1 = int32, 2 = int64, 3 = fp64, 4 = uint32
+int comm_allreduce(void* buf_dev, int64_t count, int dtype);
+// recv[r * bytes .. ) = rank r's send buffer, on the library stream (a plain copy when there is one rank)
+int comm_allgather(const void* send_dev, void* recv_dev, int64_t bytes_per_rank);
+
 // ---------------------------------------------------------------- layout
 inline size_t raw_row_bytes(int elem, int dim) {
     return elem == VB_VECTOR ? (size_t)dim * 4 : elem == VB_HALFVEC ? (size_t)dim * 2 : ((size_t)dim + 7) / 8;
@@ -191,6 +200,8 @@ int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metr
                           int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
                           const int32_t* seg_len, const float* qn, const int32_t* pos_kp, const float* approx_kp, int32_t* out_pos,
                           float* out_key, int* fail_dev, int* n_failed_host, int level = 2);
+// traffic accounting of list_tc_kernel launches (profiling): enable / read-and-reset 8 counters (lists: 0-3, centres: 4-7)
+int list_tc_traffic(int on, int64_t* out8);
 int list_tile_rows();
 bool list_major_supported(int elem, int key_metric);
 int launch_list_major(const Table& rows, int key_metric, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists,

@@ -1,6 +1,7 @@
 // vb_ivf.cu -- C ABI for the batched distance operator, resident tables, exact
 // top-k and the IVFFlat scan path (GetScanLists + GetScanItems, src/ivfscan.c:47-187).
 #include "vb_common.cuh"
+#include "vb_distance.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -420,6 +421,62 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
     count_launch();
     if (cand_total_dev) *cand_total_dev = seg_len;
     return VB_OK;
+}
+
+// k-way merge of the per-rank results of the list-sharded scan: gathered [world][nq][k] (ids, distances) -> the k
+// nearest per query by (distance, id).  One CTA per query, bitonic sort of the world * k entries in shared memory.
+__global__ void __launch_bounds__(128) merge_ranks_kernel(const int64_t* __restrict__ g_ids, const float* __restrict__ g_dist, int world,
+                                                          int64_t nq, int k, int P, int64_t* __restrict__ out_ids,
+                                                          float* __restrict__ out_dist) {
+    extern __shared__ uint64_t mk[];            // P keys: orderable(distance) << 32 | slot
+    const int64_t q = blockIdx.x;
+    const int total = world * k;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        uint64_t key = ~0ull;
+        if (i < total) {
+            const int r = i / k, j = i % k;
+            const size_t at = ((size_t)r * nq + q) * k + j;
+            if (g_ids[at] >= 0) key = ((uint64_t)orderable_key(g_dist[at]) << 32) | (uint32_t)i;
+        }
+        mk[i] = key;
+    }
+    __syncthreads();
+    // equal distances: the smaller id first (slots are rank-major, so compare ids explicitly on ties)
+    for (int size = 2; size <= P; size <<= 1)
+        for (int st = size >> 1; st > 0; st >>= 1) {
+            for (int a = threadIdx.x; a < P; a += blockDim.x) {
+                const int c = a ^ st;
+                if (c > a) {
+                    const uint64_t x = mk[a], y = mk[c];
+                    bool gt = x > y;
+                    if ((x >> 32) == (y >> 32) && x != ~0ull && y != ~0ull) {
+                        const int sx = (int)(uint32_t)x, sy = (int)(uint32_t)y;
+                        const int64_t ix = g_ids[((size_t)(sx / k) * nq + q) * k + sx % k];
+                        const int64_t iy = g_ids[((size_t)(sy / k) * nq + q) * k + sy % k];
+                        gt = ix > iy;
+                    }
+                    const bool up = (a & size) == 0;
+                    if (gt == up) {
+                        mk[a] = y;
+                        mk[c] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const uint64_t key = mk[i];
+        int64_t id = -1;
+        float d = __int_as_float(0x7F800000);
+        if (key != ~0ull) {
+            const int sl = (int)(uint32_t)key;
+            const size_t at = ((size_t)(sl / k) * nq + q) * k + sl % k;
+            id = g_ids[at];
+            d = g_dist[at];
+        }
+        out_ids[q * k + i] = id;
+        out_dist[q * k + i] = d;
+    }
 }
 
 static int64_t ivf_batch_limit(const Ivf& ix, int probes) {
@@ -933,6 +990,101 @@ int vb_ivf_search_prefetched(vb_ivf* h, int slot, int probes, int k, int64_t* ou
     const int64_t nq = ix.q_nq[slot];
     ix.q_nq[slot] = 0;   // consumed: the slot may be refilled as soon as this call returns (it synchronises)
     return ivf_search_impl(h, ix.q_buf[slot], nq, probes, k, true, false, out_ids, nullptr, out_dist);
+}
+
+// List-sharded search: this rank's image holds its own lists under the GLOBAL list numbering (the other
+// lists are empty) and all centres.  Per batch: probe selection for this rank's slice of the queries -> all-gather of
+// the probe lists -> local list scan + top-k for ALL queries -> all-gather of k (distance, id) pairs per rank ->
+// k-way merge.  Every rank returns the full result.  Collectives are NCCL calls on the library stream; the
+// certificate counters of the tensor-core filter are summed over the ranks before they are read, so all ranks
+// repeat a batch together.
+int vb_ivf_search_sharded_dev(vb_ivf* h, const void* queries_dev, int64_t nq, int probes, int k, int64_t* out_ids_dev,
+                              float* out_dist_dev) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && h->ix.loaded, "index not loaded");
+    VB_REQUIRE(queries_dev && probes >= 1 && k >= 1 && out_ids_dev && out_dist_dev, "bad search arguments");
+    Ivf& ix = h->ix;
+    Context& c = ctx();
+    const int world = comm_world(), rank = comm_rank();
+    probes = std::min(probes, ix.lists);
+    if (nq <= 0) return VB_OK;
+    VB_REQUIRE(nq <= ivf_batch_limit(ix, probes), "sharded search: at most %lld queries per call for this index", (long long)ivf_batch_limit(ix, probes));
+    int P = 2;
+    while (P < world * k) P <<= 1;
+    VB_REQUIRE(P <= 4096, "sharded search: world * k must not exceed 4096");
+    const int64_t chunk = (nq + world - 1) / world;
+    const int64_t q0 = std::min<int64_t>(nq, (int64_t)rank * chunk), m = std::min<int64_t>(chunk, nq - q0);
+    enum { WS_SH_LISTS = 19, WS_SH_RES = 20 };
+    void *d_sh, *d_res;
+    VB_TRY(workspace(WS_SH_LISTS, sizeof(int32_t) * (size_t)chunk * probes * (world + 1) + 64, &d_sh));
+    int32_t* my_lists = (int32_t*)d_sh;                          // [chunk x probes]
+    int32_t* all_lists = my_lists + (size_t)chunk * probes;      // [world x chunk x probes] = [nq' x probes]
+    const size_t res_ids = sizeof(int64_t) * (size_t)nq * k, res_dist = sizeof(float) * (size_t)nq * k;
+    VB_TRY(workspace(WS_SH_RES, (res_ids + res_dist) * (size_t)(world + 1) + 256, &d_res));
+    int64_t* my_ids = (int64_t*)d_res;
+    float* my_dist = (float*)((uint8_t*)d_res + res_ids);
+    int64_t* all_ids = (int64_t*)((uint8_t*)d_res + res_ids + res_dist);
+    float* all_dist = (float*)((uint8_t*)all_ids + res_ids * (size_t)world);
+    if (!ix.d_cand_sum) VB_CUDA(cudaMalloc(&ix.d_cand_sum, sizeof(int64_t)));
+    VB_CUDA(cudaMemsetAsync(ix.d_cand_sum, 0, sizeof(int64_t), c.stream));
+    if (!ix.d_tc_fail) VB_CUDA(cudaMalloc(&ix.d_tc_fail, 2 * sizeof(int)));
+
+    auto run = [&](int mode, int* fails) -> int {   // mode 0: automatic, 1: filter level 2, 2: exact
+        const bool exact = mode == 2;
+        ix.force_exact = exact;
+        ix.force_level2 = mode == 1;
+        ix.defer_tc_check = !exact;
+        VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, 2 * sizeof(int), c.stream));
+        void* qimg;
+        size_t qstride;
+        VB_TRY(upload_queries(ix.elem, ix.dim, queries_dev, nq, false, WS_QIMG, &qimg, &qstride));
+        VB_CUDA(cudaMemsetAsync(my_lists, 0xFF, sizeof(int32_t) * (size_t)chunk * probes, c.stream));
+        if (m > 0) {
+            int32_t* d_lists;
+            float* d_ldist;
+            VB_TRY(ivf_select_probes(ix, (const uint8_t*)qimg + (size_t)q0 * qstride, qstride, m, probes, &d_lists, &d_ldist));
+            VB_CUDA(cudaMemcpyAsync(my_lists, d_lists, sizeof(int32_t) * (size_t)m * probes, cudaMemcpyDeviceToDevice, c.stream));
+        }
+        VB_TRY(comm_allgather(my_lists, all_lists, (int64_t)sizeof(int32_t) * chunk * probes));
+        // (ranks hold `chunk` queries each, the last one possibly fewer: the gathered array is query-major for q < nq)
+        VB_TRY(ivf_scan_topk(ix, qimg, qstride, nq, all_lists, probes, k, my_ids, my_dist, nullptr, nullptr));
+        // one buffer per rank: [ids | distances]; gathered rank-major, so view it as two strided arrays
+        VB_TRY(comm_allgather(my_ids, all_ids, (int64_t)res_ids));
+        VB_TRY(comm_allgather(my_dist, all_dist, (int64_t)res_dist));
+        merge_ranks_kernel<<<(unsigned)nq, 128, (size_t)P * 8, c.stream>>>(all_ids, all_dist, world, nq, k, P, out_ids_dev, out_dist_dev);
+        VB_CUDA(cudaGetLastError());
+        count_launch();
+        fails[0] = fails[1] = 0;
+        if (!exact) {
+            VB_TRY(comm_allreduce(ix.d_tc_fail, 2, 1));
+            VB_CUDA(cudaMemcpyAsync(fails, ix.d_tc_fail, 2 * sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+            VB_CUDA(cudaStreamSynchronize(c.stream));
+        }
+        return VB_OK;
+    };
+    int fails[2];
+    int rc = run(0, fails);
+    if (rc == VB_OK && fails[0] == 0 && fails[1] > 0 && ix.last_list_level == 1) {
+        ix.total_l1_failed += fails[1];
+        ix.l1_cooldown = 64;
+        rc = run(1, fails);
+    }
+    if (rc == VB_OK && fails[0] + fails[1] > 0) {
+        ix.total_tc_failed += fails[0] + fails[1];
+        rc = run(2, fails);
+    }
+    ix.force_exact = false;
+    ix.force_level2 = false;
+    ix.defer_tc_check = false;
+    VB_TRY(rc);
+    ix.last_cand = -1;
+    ix.last_bytes = nq;
+    return VB_OK;
+}
+
+int vb_ivf_tc_traffic(int on, int64_t* out8) {
+    VB_TRY(require_init());
+    return list_tc_traffic(on, out8);
 }
 
 int64_t vb_ivf_tc_fallbacks(const vb_ivf* h) { return h ? h->ix.total_tc_failed : 0; }

@@ -549,6 +549,10 @@ static int kmeans_update_centers(const Table& X, KmeansState& st, int k, bool sp
             set_error("allreduce hook failed");
             return VB_ESTATE;
         }
+    } else if (comm_world() > 1) {
+        // the library's own communicator: ncclAllReduce on the library stream, no host round trip
+        VB_TRY(comm_allreduce(st.agg, (int64_t)k * dim, 0));
+        VB_TRY(comm_allreduce(st.counts, k, 1));
     }
     finish_centers_kernel<<<(unsigned)(((int64_t)k * dim + 255) / 256), 256, 0, s>>>(st.agg, st.counts, k, dim, seed, iteration);
     VB_CUDA(cudaGetLastError());
@@ -635,6 +639,11 @@ static int kmeans_run(const Table& X, int kmeans_metric, void* centers_host, int
         rc = kmeans_update_centers(X, st, k, spherical, seed, iteration, allreduce, actx);
         if (rc != VB_OK) break;
         int changes = 0;
+        if (!allreduce && comm_world() > 1) {
+            // every rank must take the same branch: sum the change counters on the device, before the read
+            rc = comm_allreduce(st.changes, 1, 1);
+            if (rc != VB_OK) break;
+        }
         if (cudaMemcpyAsync(&changes, st.changes, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
             cudaStreamSynchronize(s) != cudaSuccess) {
             set_error("k-means: reading the change counter failed");
@@ -780,6 +789,154 @@ static int kmeans_pp(const Table& X, int kmeans_metric, void* centers_host, int 
     return VB_OK;
 }
 
+// ----------------------------------------------------------------------------- k-means++ over row-sharded samples
+//
+// Every rank holds a slice of the samples (global sample order = rank order, then local order).  Per new centre:
+// local distance pass + weight update + local prefix sums as in kmeans_pp; ncclAllGather of the local weight sums;
+// every rank locates the owner of choice = u * total (the first rank whose running sum reaches it) on the device;
+// the owner's pick kernel selects its local row, the others contribute zeros, and ncclAllReduce (uint32 sum of the
+// row's bit pattern) hands the new centre to everybody -- no host round trip per centre.
+
+__global__ void pp_pick_sharded_kernel(const double* __restrict__ cum, int64_t n_local, const double* __restrict__ sums, int world,
+                                       int rank, const double* __restrict__ u, int64_t* __restrict__ picked_local,
+                                       int64_t* __restrict__ picked_global, const int64_t* __restrict__ row_base) {
+    if (blockIdx.x || threadIdx.x) return;
+    double total = 0;
+    for (int r = 0; r < world; ++r) total += sums[r];
+    double choice = total * u[0];
+    // owner: first rank whose running sum reaches the draw (the last rank takes what rounding leaves over)
+    int owner = world - 1;
+    double before = 0;
+    for (int r = 0; r < world; ++r) {
+        if (before + sums[r] >= choice && (sums[r] > 0 || r == world - 1)) {
+            owner = r;
+            break;
+        }
+        before += sums[r];
+    }
+    int64_t j = -1;
+    if (owner == rank && n_local > 0) {
+        const double local = choice - before;
+        int64_t lo = 0, hi = n_local - 1;   // smallest j with cum[j] >= local, else the last row
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (cum[mid] >= local) hi = mid;
+            else lo = mid + 1;
+        }
+        j = lo;
+    }
+    *picked_local = j;
+    if (picked_global) *picked_global = j >= 0 ? row_base[rank] + j : 0;   // summed over the ranks afterwards
+}
+
+// the picked row's bytes (owner) or zeros (everybody else), as uint32 words for the sum-allreduce
+__global__ void pp_contribute_row_kernel(const uint8_t* __restrict__ X, size_t stride, const int64_t* __restrict__ picked_local,
+                                         uint32_t* __restrict__ out, int words) {
+    const int64_t j = *picked_local;
+    const uint32_t* src = j >= 0 ? reinterpret_cast<const uint32_t*>(X + (size_t)j * stride) : nullptr;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < words; w += gridDim.x * blockDim.x) out[w] = src ? src[w] : 0u;
+}
+
+__global__ void pp_local_sum_kernel(const double* __restrict__ cum, int64_t n_local, double* __restrict__ out) {
+    if (blockIdx.x || threadIdx.x) return;
+    *out = n_local > 0 ? cum[n_local - 1] : 0.0;
+}
+
+__global__ void pp_store_centre_kernel(const uint8_t* __restrict__ row, size_t raw, uint8_t* __restrict__ out) {
+    for (size_t b = threadIdx.x; b < raw; b += blockDim.x) out[b] = row[b];
+}
+
+static int kmeans_pp_sharded(const Table& X, int kmeans_metric, void* centers_host, int k, uint64_t seed, int64_t* picked_out) {
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    const int world = comm_world(), rank = comm_rank();
+    const int64_t n = X.n;
+    VB_REQUIRE(k > 0, "k-means++ needs k > 0");
+    VB_REQUIRE(kmeans_metric == VB_L2 || kmeans_metric == VB_SPHERICAL || kmeans_metric == VB_HAMMING, "bad k-means metric");
+    const int km = kmeans_metric == VB_L2 ? VB_L2_SQUARED : kmeans_metric == VB_SPHERICAL ? VB_NEG_IP : VB_HAMMING;
+    const size_t raw = raw_row_bytes(X.elem, X.dim);
+    const int words = (int)(X.stride / 4);
+    void *d_key, *d_w, *d_wd, *d_cum, *d_u, *d_tmp = nullptr, *d_q, *d_row, *d_out, *d_misc;
+    VB_TRY(workspace(WSK_DIST, sizeof(float) * (size_t)std::max<int64_t>(n, 1), &d_key));
+    VB_TRY(workspace(WSK_A, sizeof(float) * (size_t)std::max<int64_t>(n, 1), &d_w));
+    VB_TRY(workspace(WSK_B, sizeof(double) * (size_t)std::max<int64_t>(n, 1), &d_wd));
+    VB_TRY(workspace(WSK_C, sizeof(double) * (size_t)std::max<int64_t>(n, 1), &d_cum));
+    VB_TRY(workspace(WSK_F, sizeof(double) * (size_t)k, &d_u));
+    VB_TRY(workspace(WSK_H, X.stride, &d_row));
+    VB_TRY(workspace(WSK_I, raw * (size_t)k, &d_out));
+    // misc: sums[world] doubles | local sum | row_base[world] | picked_local | picked_global[k]
+    VB_TRY(workspace(WSK_G, sizeof(double) * (size_t)(world + 1) + sizeof(int64_t) * (size_t)(world + 1 + k) + 64, &d_misc));
+    double* d_sums = (double*)d_misc;
+    double* d_lsum = d_sums + world;
+    int64_t* d_base = (int64_t*)(d_lsum + 1);
+    int64_t* d_pick = d_base + world;
+    int64_t* d_gpick = d_pick + 1;
+    size_t tmp_bytes = 0;
+    if (n > 0) {
+        VB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, (double*)d_wd, (double*)d_cum, (int)n, s));
+        VB_TRY(workspace(WSK_E, tmp_bytes, &d_tmp));
+    }
+    // global row numbering: every rank learns every slice length (one exchange at the start)
+    std::vector<int64_t> lens((size_t)world, 0), base((size_t)world, 0);
+    {
+        int64_t* d_len = d_gpick;   // borrowed before the rounds start
+        VB_REQUIRE(k >= world, "k-means++ over %d ranks needs at least as many centres", world);
+        VB_CUDA(cudaMemcpyAsync(d_len + rank, &n, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        VB_TRY(comm_allgather(d_len + rank, d_len, sizeof(int64_t)));
+        VB_CUDA(cudaMemcpyAsync(lens.data(), d_len, sizeof(int64_t) * (size_t)world, cudaMemcpyDeviceToHost, s));
+        VB_CUDA(cudaStreamSynchronize(s));
+    }
+    int64_t n_total = 0;
+    for (int r = 0; r < world; ++r) {
+        base[(size_t)r] = n_total;
+        n_total += lens[(size_t)r];
+    }
+    VB_REQUIRE(n_total > 0, "k-means++ needs samples");
+    std::vector<float> w0((size_t)std::max<int64_t>(n, 1), 3.402823466e+38f);
+    uint64_t rs = seed ^ 0x5851f42d4c957f2dULL;
+    int64_t first = (int64_t)(host_uniform(&rs) * (double)n_total);
+    if (first >= n_total) first = n_total - 1;
+    std::vector<double> u((size_t)k);
+    for (int i = 0; i + 1 < k; ++i) u[(size_t)i] = host_uniform(&rs);
+    int64_t first_local = (first >= base[(size_t)rank] && first < base[(size_t)rank] + n) ? first - base[(size_t)rank] : -1;
+    VB_CUDA(cudaMemcpyAsync(d_w, w0.data(), sizeof(float) * (size_t)std::max<int64_t>(n, 1), cudaMemcpyHostToDevice, s));
+    VB_CUDA(cudaMemcpyAsync(d_u, u.data(), sizeof(double) * (size_t)k, cudaMemcpyHostToDevice, s));
+    VB_CUDA(cudaMemcpyAsync(d_base, base.data(), sizeof(int64_t) * (size_t)world, cudaMemcpyHostToDevice, s));
+    VB_CUDA(cudaMemcpyAsync(d_pick, &first_local, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    int64_t first_contrib = first_local >= 0 ? first : 0;
+    VB_CUDA(cudaMemcpyAsync(d_gpick, &first_contrib, sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    VB_CUDA(cudaStreamSynchronize(s));   // the host vectors above go out of use here
+    for (int i = 0; i < k; ++i) {
+        // centre i: the owner's row reaches every rank
+        pp_contribute_row_kernel<<<4, 256, 0, s>>>(X.d, X.stride, d_pick, (uint32_t*)d_row, words);
+        count_launch();
+        VB_TRY(comm_allreduce(d_row, words, 4));
+        pp_store_centre_kernel<<<1, 256, 0, s>>>((const uint8_t*)d_row, raw, (uint8_t*)d_out + (size_t)i * raw);
+        count_launch();
+        if (i + 1 == k) break;
+        if (n > 0) {
+            size_t qstride;
+            VB_TRY(upload_queries(X.elem, X.dim, d_row, 1, false, WSK_QIMG, &d_q, &qstride));
+            VB_TRY(launch_scan_regular(X, km, d_q, qstride, 1, n, (float*)d_key, n));
+            pp_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)d_key, kmeans_metric, n, (float*)d_w, (double*)d_wd);
+            VB_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, (double*)d_wd, (double*)d_cum, (int)n, s));
+            count_launch(2);
+        }
+        pp_local_sum_kernel<<<1, 1, 0, s>>>((const double*)d_cum, n, d_lsum);
+        VB_TRY(comm_allgather(d_lsum, d_sums, sizeof(double)));
+        pp_pick_sharded_kernel<<<1, 1, 0, s>>>((const double*)d_cum, n, d_sums, world, rank, (const double*)d_u + i, d_pick,
+                                               d_gpick + i + 1, d_base);
+        count_launch(2);
+    }
+    // global row numbers of the picks (each is non-zero on its owner only)
+    VB_TRY(comm_allreduce(d_gpick, k, 2));
+    VB_CUDA(cudaMemcpyAsync(centers_host, d_out, raw * (size_t)k, cudaMemcpyDeviceToHost, s));
+    if (picked_out) VB_CUDA(cudaMemcpyAsync(picked_out, d_gpick, sizeof(int64_t) * (size_t)k, cudaMemcpyDeviceToHost, s));
+    VB_CUDA(cudaStreamSynchronize(s));
+    VB_CUDA(cudaGetLastError());
+    return VB_OK;
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -796,6 +953,8 @@ int vb_kmeans(vb_table* samples, int kmeans_metric, void* centers, int k, int ma
 int vb_kmeans_pp_init(vb_table* samples, int kmeans_metric, void* centers, int k, uint64_t seed) {
     VB_TRY(require_init());
     VB_REQUIRE(samples && centers && k >= 1, "bad k-means++ arguments");
+    // with a communicator the samples are this rank's slice of a row-sharded sample set: every rank gets the same centres
+    if (comm_world() > 1) return kmeans_pp_sharded(samples->t, kmeans_metric, centers, k, seed, nullptr);
     return kmeans_pp(samples->t, kmeans_metric, centers, k, seed);
 }
 

@@ -394,9 +394,36 @@ __global__ void certify_kernel(int64_t nq, int k, int kp, LcBound bound,
     }
 }
 
+// Bytes one launch of list_tc_kernel moves, from the same job list the kernel walks (profiling only):
+//   [0] bytes requested by the bulk copies (every (unit, query tile, K block) stage: A tile + B tile),
+//   [1] distinct A bytes (each active (list, table tile) unit's planes once: re-reads by further query tiles of the
+//       same unit come from L2),   [2] distinct B bytes (each list's query tiles once: shared by the list's units),
+//   [3] launches accounted.
+__global__ void lc_traffic_kernel(LcArgs a, uint32_t a_bytes, unsigned long long* __restrict__ acc) {
+    unsigned long long issued = 0, a_once = 0, b_once = 0;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < a.n_units; u += gridDim.x * blockDim.x) {
+        const ListUnit un = a.units[u];
+        const int cnt = a.grp_cnt[un.list];
+        if (cnt == 0) continue;
+        const int nqt = (cnt + LC_N - 1) / LC_N;
+        unsigned long long b_list = 0;
+        for (int qt = 0; qt < nqt; ++qt) b_list += (unsigned long long)a.n_kblocks * (cnt - qt * LC_N <= 32 ? LC_B_STAGE / 2 : LC_B_STAGE);
+        issued += (unsigned long long)nqt * a.n_kblocks * a_bytes + b_list;
+        a_once += (unsigned long long)a.n_kblocks * a_bytes;
+        if (u == 0 || a.units[u - 1].list != un.list) b_once += b_list;
+    }
+    atomicAdd(&acc[0], issued);
+    atomicAdd(&acc[1], a_once);
+    atomicAdd(&acc[2], b_once);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&acc[3], 1ull);
+}
+
 // ----------------------------------------------------------------------------- host side
 
 enum { WSC_B = 21, WSC_N = 22, WSC_K = 23 };
+
+static unsigned long long* g_traffic = nullptr;   // device accumulators of lc_traffic_kernel, per filter use (0 = lists, 1 = centres)
+static bool g_traffic_on = false;
 
 bool list_tc_supported(int elem, int key_metric, int k) {
     return (elem == VB_VECTOR || elem == VB_HALFVEC) && (key_metric == VB_L2_SQUARED || key_metric == VB_NEG_IP) && k >= 1 &&
@@ -508,8 +535,27 @@ int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, con
     list_tc_kernel<<<grid, LC_THREADS, LC_SMEM, s>>>(a);
     VB_CUDA(cudaGetLastError());
     count_launch();
+    if (g_traffic_on && g_traffic) {
+        lc_traffic_kernel<<<32, 256, 0, s>>>(a, level == 1 ? LC_A_PLANE : LC_A_STAGE, g_traffic + (one_list_all_queries ? 4 : 0));
+        VB_CUDA(cudaGetLastError());
+    }
     (void)rows;
     *qn_out = (const float*)d_qn;
+    return VB_OK;
+}
+
+int list_tc_traffic(int on, int64_t* out8) {
+    cudaStream_t s = ctx().stream;
+    if (!g_traffic) {
+        VB_CUDA(cudaMalloc(&g_traffic, 8 * sizeof(unsigned long long)));
+        VB_CUDA(cudaMemsetAsync(g_traffic, 0, 8 * sizeof(unsigned long long), s));
+    }
+    if (out8) {
+        VB_CUDA(cudaMemcpyAsync(out8, g_traffic, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        VB_CUDA(cudaStreamSynchronize(s));
+        VB_CUDA(cudaMemsetAsync(g_traffic, 0, 8 * sizeof(unsigned long long), s));
+    }
+    g_traffic_on = on != 0;
     return VB_OK;
 }
 
