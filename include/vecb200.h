@@ -85,14 +85,17 @@ int			vb_stream_wait_event(void *cuda_event);
 /*
  * Optional per-kernel timing with CUDA events on vb_stream(), used by bench.py for the
  * roofline of the dominant kernel (the events add ~1 us per bracketed launch).
- * Kernels: 0 = list/candidate scan (GetScanItems), 1 = centre scan (GetScanLists),
- * 2 = top-k select, 3 = k-means assign, 4 = HNSW search.
+ * Kernels: 0 = list/candidate scan (GetScanItems) incl. query grouping / packing, 1 = centre scan (GetScanLists),
+ * 2 = top-k select + exact re-score + certificate, 3 = k-means assign, 4 = HNSW search, 5 / 6 = the tensor-core filter
+ * kernel alone (lists / centres).
  */
 #define VB_PROF_SCAN_ITEMS 0
 #define VB_PROF_SCAN_LISTS 1
 #define VB_PROF_TOPK 2
 #define VB_PROF_ASSIGN 3
 #define VB_PROF_HNSW 4
+#define VB_PROF_LIST_TC 5		/* list_tc_kernel alone (the tensor-core filter pass over the probed lists) */
+#define VB_PROF_CENTRE_TC 6		/* the same kernel over the centre table (probe selection of query batches) */
 int			vb_prof_enable(int on);
 /* Synchronises, then returns accumulated milliseconds and bracketed launches since the last read of `kernel`. */
 int			vb_prof_read(int kernel, double *total_ms, int64_t *launches);
@@ -132,6 +135,8 @@ int			vb_table_append(vb_table *t, const void *rows, int64_t n);
 /* Append n rows that already live on the device (packed, unpadded layout). */
 int			vb_table_append_dev(vb_table *t, const void *rows_dev, int64_t n);
 int64_t		vb_table_rows(const vb_table *t);
+/* Read-only view of the resident rows: device pointer of row 0 and the padded row stride in bytes. */
+const void *vb_table_device_rows(const vb_table *t, size_t *stride_bytes);
 int			vb_table_free(vb_table *t);
 
 /*
@@ -227,6 +232,9 @@ int			vb_ivf_tc_traffic(int on, int64_t *out8);
  */
 int			vb_ivf_search_sharded_dev(vb_ivf *ix, const void *queries_dev, int64_t nq, int probes, int k,
 									  int64_t *out_ids_dev, float *out_dist_dev);
+/* The same with host buffers (queries in, int64 ids + float8 distances out; copies inside, synchronous). */
+int			vb_ivf_search_sharded(vb_ivf *ix, const void *queries, int64_t nq, int probes, int k,
+								  int64_t *out_ids, double *out_dist);
 
 /* --------------------------------------------------------------- communicator */
 

@@ -57,7 +57,7 @@ def launch_count() -> int:
     return int(load().vb_launch_count())
 
 
-PROF_SCAN_ITEMS, PROF_SCAN_LISTS, PROF_TOPK, PROF_ASSIGN, PROF_HNSW = range(5)
+PROF_SCAN_ITEMS, PROF_SCAN_LISTS, PROF_TOPK, PROF_ASSIGN, PROF_HNSW, PROF_LIST_TC, PROF_CENTRE_TC = range(7)
 
 
 def prof_enable(on=True):
@@ -201,6 +201,12 @@ class Table:
     def __len__(self):
         return int(load().vb_table_rows(self.h))
 
+    def device_rows(self):
+        """(device pointer of row 0, padded row stride in bytes): a read-only view of the resident rows"""
+        stride = C.c_size_t()
+        p = load().vb_table_device_rows(self.h, C.byref(stride))
+        return int(p or 0), int(stride.value)
+
     def exact_topk(self, metric, queries, k):
         """ORDER BY v <op> q LIMIT k without an index."""
         if _is_torch(queries):
@@ -334,6 +340,10 @@ class IvfflatIndex:
         _after_torch(queries_dev)
         _lib.check(load().vb_ivf_search_sharded_dev(self.h, _ptr(queries_dev), queries_dev.shape[0], int(probes), int(k),
                                                     _ptr(ids_dev), _ptr(dist_dev)))
+
+    def search_sharded_host_into(self, queries, k, probes, ids, dist):
+        """list-sharded search, host buffers in and out (int64 ids, float64 distances)"""
+        _lib.check(load().vb_ivf_search_sharded(self.h, _ptr(queries), queries.shape[0], int(probes), int(k), _ptr(ids), _ptr(dist)))
 
     def search_host_into(self, queries, k, probes, ids, dist):
         _lib.check(load().vb_ivf_search(self.h, _ptr(queries), queries.shape[0], int(probes), int(k), _ptr(ids), _ptr(dist)))

@@ -37,6 +37,7 @@ SIGNATURES = {
     "vb_table_append": (_i, [_vp, _vp, _i64]),
     "vb_table_append_dev": (_i, [_vp, _vp, _i64]),
     "vb_table_rows": (_i64, [_vp]),
+    "vb_table_device_rows": (_vp, [_vp, C.POINTER(C.c_size_t)]),
     "vb_table_free": (_i, [_vp]),
     "vb_exact_topk": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
     "vb_exact_topk_dev": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
@@ -56,6 +57,7 @@ SIGNATURES = {
     "vb_ivf_tc_fallbacks": (_i64, [_vp]),
     "vb_ivf_tc_traffic": (_i, [_i, _vp]),
     "vb_ivf_search_sharded_dev": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
+    "vb_ivf_search_sharded": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
     "vb_comm_unique_id": (_i, [_vp, C.c_size_t]),
     "vb_comm_init": (_i, [_vp, _i, _i]),
     "vb_comm_free": (_i, []),

@@ -571,6 +571,11 @@ int vb_table_append_dev(vb_table* t, const void* rows_dev, int64_t n) {
     return table_append_dev(t->t, rows_dev, n);
 }
 int64_t vb_table_rows(const vb_table* t) { return t ? t->t.n : 0; }
+const void* vb_table_device_rows(const vb_table* t, size_t* stride_bytes) {
+    if (!t) return nullptr;
+    if (stride_bytes) *stride_bytes = t->t.stride;
+    return t->t.d;
+}
 int vb_table_free(vb_table* t) {
     if (t) {
         table_free(t->t);
@@ -1079,6 +1084,28 @@ int vb_ivf_search_sharded_dev(vb_ivf* h, const void* queries_dev, int64_t nq, in
     VB_TRY(rc);
     ix.last_cand = -1;
     ix.last_bytes = nq;
+    return VB_OK;
+}
+
+int vb_ivf_search_sharded(vb_ivf* h, const void* queries, int64_t nq, int probes, int k, int64_t* out_ids, double* out_dist) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && h->ix.loaded && queries && out_ids && out_dist && k >= 1, "bad search arguments");
+    if (nq <= 0) return VB_OK;
+    Ivf& ix = h->ix;
+    Context& c = ctx();
+    const size_t raw = raw_row_bytes(ix.elem, ix.dim);
+    enum { WS_SH_Q = 18 };
+    void* d_q;
+    VB_TRY(workspace(WS_SH_Q, raw * (size_t)nq + (sizeof(int64_t) + sizeof(float)) * (size_t)nq * k + 64, &d_q));
+    int64_t* d_ids = (int64_t*)((uint8_t*)d_q + ((raw * (size_t)nq + 15) & ~(size_t)15));
+    float* d_dist = (float*)(d_ids + (size_t)nq * k);
+    VB_CUDA(cudaMemcpyAsync(d_q, queries, raw * (size_t)nq, cudaMemcpyHostToDevice, c.stream));
+    VB_TRY(vb_ivf_search_sharded_dev(h, d_q, nq, probes, k, d_ids, d_dist));
+    std::vector<float> hd((size_t)nq * k);
+    VB_CUDA(cudaMemcpyAsync(out_ids, d_ids, sizeof(int64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, c.stream));
+    VB_CUDA(cudaMemcpyAsync(hd.data(), d_dist, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, c.stream));
+    VB_CUDA(cudaStreamSynchronize(c.stream));
+    for (size_t i = 0; i < hd.size(); ++i) out_dist[i] = (double)hd[i];
     return VB_OK;
 }
 

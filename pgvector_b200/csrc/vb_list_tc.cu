@@ -409,7 +409,8 @@ __global__ void lc_traffic_kernel(LcArgs a, uint32_t a_bytes, unsigned long long
         unsigned long long b_list = 0;
         for (int qt = 0; qt < nqt; ++qt) b_list += (unsigned long long)a.n_kblocks * (cnt - qt * LC_N <= 32 ? LC_B_STAGE / 2 : LC_B_STAGE);
         issued += (unsigned long long)nqt * a.n_kblocks * a_bytes + b_list;
-        a_once += (unsigned long long)a.n_kblocks * a_bytes;
+        // a table tile that straddles two lists is visited by both units back to back: its second read comes from L2
+        if (!(u > 0 && a.units[u - 1].tile == un.tile && a.grp_cnt[a.units[u - 1].list] > 0)) a_once += (unsigned long long)a.n_kblocks * a_bytes;
         if (u == 0 || a.units[u - 1].list != un.list) b_once += b_list;
     }
     atomicAdd(&acc[0], issued);
@@ -532,7 +533,9 @@ int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, con
     a.uniform_nqt = one_list_all_queries ? (int)((nq * probes + LC_N - 1) / LC_N) : 0;
     a.n_jobs = a.uniform_nqt ? im.n_units * a.uniform_nqt : im.n_units;
     const int grid = std::max(1, std::min(a.n_jobs, c.sm_count));
+    prof_begin(one_list_all_queries ? VB_PROF_CENTRE_TC : VB_PROF_LIST_TC);
     list_tc_kernel<<<grid, LC_THREADS, LC_SMEM, s>>>(a);
+    prof_end(one_list_all_queries ? VB_PROF_CENTRE_TC : VB_PROF_LIST_TC);
     VB_CUDA(cudaGetLastError());
     count_launch();
     if (g_traffic_on && g_traffic) {

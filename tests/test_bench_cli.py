@@ -40,3 +40,16 @@ def test_product_arm_fails_loudly_without_a_gpu():
     p = _run(SMALL)
     assert p.returncode != 0
     assert not p.stdout.strip()          # no number is ever printed from a CPU path
+
+
+def test_reference_arm_of_the_other_configs():
+    """--config A (exact scan) and --config D (k-means build) also have a CPU arm that prints the contract's line"""
+    for extra, unit in ((["--config", "A", "--steps", "1", "--warmup", "0"], "queries/s"),
+                        (["--config", "D", "--dim", "16"], "rows/s")):
+        p = _run(["--impl", "reference"] + extra)
+        assert p.returncode == 0, p.stderr[-2000:]
+        lines = [l for l in p.stdout.splitlines() if l.strip()]
+        assert len(lines) == 1, p.stdout
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["unit"] == unit and d["value"] > 0
+        assert d["cpu_baseline"]["value"] == d["value"] and "workload" in d["config"]
