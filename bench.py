@@ -198,6 +198,8 @@ class Env:
         import pgvector_b200 as pv
         pv.init(self.local)
         pv.set_option("scan_impl", args.scan_impl)
+        if os.environ.get("VB_FUSED_REFINE") is not None:       # A/B switch of the fused select / re-score / certify kernel
+            pv.set_option("fused_refine", int(os.environ["VB_FUSED_REFINE"]))
         self.pv = pv
         self.stream = torch.cuda.ExternalStream(pv.stream_handle(), device=self.dev)
 
@@ -1032,7 +1034,7 @@ def run_hnsw(args):
             "roofline": {"bound": "hbm", "kernel": "hnsw_search_kernel", "achieved": moved / (kern / 1000) / 1e9, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                          "frac": moved / (kern / 1000) / 1e9 / peak, "traffic": moved,
                          "traffic_source": "n_dist (returned per query) x row bytes + one neighbour list per ~m distance evaluations (SURVEY 8d); gathers are 128-byte sectors",
-                         "n_dist_per_query": nd_mean, "avg_launch_ms": kern, "share_of_step": k_ms / ms},
+                         "n_dist_per_query": nd_mean, "avg_launch_ms": kern, "share_of_step": kern * args.steps / ms},
             "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": cores, "kind": "port",
                              "sample": f"{reps} batches of 2048 queries on the same graph, one query per thread (oracle port of src/hnswutils.c:824-987)"},
             "e2e": {"value": env.world * args.steps * B / (ms_h / 1000), "unit": "queries/s", "h2d_bytes_per_step": B * row_bytes, "d2h_bytes_per_step": B * (k * 16 + 8),
@@ -1153,12 +1155,7 @@ def run_d(args):
                                "ncclAllGather + ncclAllReduce per k-means++ centre, all inside libvecb200; assign is collective-free",
                            "l2_policy": "inputs larger than L2 (%d MB of rows per rank)" % (n_local * args.dim * 4 // 2**20)},
                 "phases_s": {"kmeans_pp_seeding": res["seed_s"], "lloyd": res["lloyd_s"], "lloyd_iterations": res["iters"], "assign": res["assign_s"]},
-                "roofline": {"bound": "tensor", "kernel": "assign_tc_kernel (tcgen05 split-bf16 GEMM + fused argmin)",
-                             "achieved": 3.0 * flops_assign / world / (a_ms / max(a_n, 1) / 1000.0) / 1e12 if a_n else None, "peak": tf_peak, "peak_source": peak_src,
-                             "unit": "TFLOP/s", "frac": (3.0 * flops_assign / world / (a_ms / max(a_n, 1) / 1000.0) / 1e12 / tf_peak) if a_n else None,
-                             "traffic": None, "note": "issued bf16 MMA flops (3 products per fp32-accurate term); useful flops are a third; the bracket covers every "
-                                                      "assign launch of a build (Lloyd iterations on the samples + the final pass over all rows)",
-                             "rows_rechecked_exactly_last_assign": res["rechecked"]},
+                "roofline": roofline_d(args, world, ns_local, a_ms, a_n, args.steps + args.warmup, tf_peak, peak_src, res),
                 "list_sizes": {"min": int(lens.min()), "mean": float(lens.mean()), "max": int(lens.max()), "empty": int((lens == 0).sum())},
                 "recall_at_10": recall, "cpu_baseline": None,
                 "e2e": {"value": args.rows / step_s, "unit": "rows/s", "h2d_bytes_per_step": args.lists * args.dim * 4, "d2h_bytes_per_step": args.lists * args.dim * 4 * 2,
@@ -1167,6 +1164,23 @@ def run_d(args):
         print(json.dumps(line))
     env.close()
     return 0
+
+
+def roofline_d(args, world, ns_local, a_ms, a_n, builds, tf_peak, peak_src, res):
+    """every bracketed assign launch of the timed + warm-up builds: one pass over the local samples per Lloyd iteration,
+    one pass over all local rows at the end; 2 x rows x lists x dim useful flops each, x 3 bf16 products issued"""
+    if not a_n:
+        return None
+    per_build = a_n / builds
+    rows_scored = (per_build - 1) * ns_local + args.rows / world          # per build, per rank
+    issued = 3.0 * 2.0 * rows_scored * args.lists * args.dim * builds
+    tf = issued / (a_ms / 1000.0) / 1e12
+    return {"bound": "tensor", "kernel": "assign_tc_kernel (tcgen05 split-bf16 GEMM + fused argmin) + exact re-check of flagged rows",
+            "achieved": tf, "peak": tf_peak, "peak_source": peak_src, "unit": "TFLOP/s", "frac": tf / tf_peak, "traffic": None,
+            "useful_tflops": tf / 3.0, "assign_launches_per_build": per_build, "ms_per_build_in_assign": a_ms / builds,
+            "note": "issued bf16 MMA flops (3 products per fp32-accurate term) over the CUDA-event time of every assign call of a build "
+                    "(Lloyd iterations on the samples + the final pass over all rows), exact re-checks included",
+            "rows_rechecked_exactly_last_assign": res["rechecked"]}
 
 
 def recall_d(env, args, comp, t_rows, res):
@@ -1229,7 +1243,7 @@ def table_rows_view(pv, table, n, dim, dev):
         raise RuntimeError("padded rows: no dense view")
 
     class _View:
-        __cuda_array_interface__ = {"shape": (n, dim), "typestr": "<f4", "data": (ptr, True), "version": 2}
+        __cuda_array_interface__ = {"shape": (n, dim), "typestr": "<f4", "data": (ptr, False), "version": 2}
 
     return torch.as_tensor(_View(), device=dev)
 

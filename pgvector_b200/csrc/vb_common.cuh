@@ -47,13 +47,14 @@ struct Context {
     cudaStream_t copy_stream = nullptr;
     int64_t launches = 0;
     int tc_level1 = 1;                 // batched list scan: try the hi-plane-only filter first (vb_set_option "tc_level1")
+    int fused_refine = 1;              // tensor-core filter: k' select + exact re-score + certificate in ONE kernel (0 = the three-kernel path)
     int scan_impl = 2;                 // 0 = LDG variant (vb_scan.cu), 1 = bulk-copy / TMA variant (vb_scan_bulk.cu), 2 = by table size
     int hnsw_build_fraction = 64;      // HNSW build: a batch is at most 1/fraction of the elements already inserted
     int hnsw_build_batch = 16384;      // ... and at most this many elements
     int64_t last_assign_flagged = -1;  // rows re-checked by the exact kernel in the last tensor-core assign (-1: exact path)
     // grow-only device workspace arenas (index = slot)
-    void* ws[24] = {nullptr};
-    size_t ws_bytes[24] = {0};
+    void* ws[32] = {nullptr};
+    size_t ws_bytes[32] = {0};
     // pinned staging
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -202,6 +203,10 @@ int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metr
                           float* out_key, int* fail_dev, int* n_failed_host, int level = 2);
 // traffic accounting of list_tc_kernel launches (profiling): enable / read-and-reset 8 counters (lists: 0-3, centres: 4-7)
 int list_tc_traffic(int on, int64_t* out8);
+int launch_list_tc_select_refine(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
+                                 int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
+                                 const float* dist, const int64_t* seg_begin, const int32_t* seg_len, const float* qn, int32_t* out_pos,
+                                 float* out_key, int* fail_dev, int* n_failed_host, int level = 2);
 int list_tile_rows();
 bool list_major_supported(int elem, int key_metric);
 int launch_list_major(const Table& rows, int key_metric, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists,

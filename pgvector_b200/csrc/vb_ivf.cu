@@ -223,11 +223,17 @@ static int ivf_select_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t 
         const float* qn = nullptr;
         VB_TRY(launch_list_tc(ix.centers, ix.ctc, km, qimg, qstride, nq, zero_lists, 1, pair_off, ix.lists, ix.d_centre_off, 1,
                               (float*)d_cdist, &qn, true));
-        VB_TRY(launch_segment_topk_v((const float*)d_cdist, sb, sl, nullptr, nullptr, nq, kp, pos_kp, key_kp));
         int n_failed = 0;
         if (!ix.defer_tc_check) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, sizeof(int), c.stream));
-        VB_TRY(launch_list_tc_refine(ix.centers, ix.ctc, km, qimg, qstride, nq, probes, kp, 1, zero_lists, pair_off, ix.d_centre_off, sl,
-                                     qn, pos_kp, key_kp, lists, ldist, ix.d_tc_fail, ix.defer_tc_check ? nullptr : &n_failed));
+        if (c.fused_refine) {
+            VB_TRY(launch_list_tc_select_refine(ix.centers, ix.ctc, km, qimg, qstride, nq, probes, kp, 1, zero_lists, pair_off, ix.d_centre_off,
+                                                (const float*)d_cdist, sb, sl, qn, lists, ldist, ix.d_tc_fail,
+                                                ix.defer_tc_check ? nullptr : &n_failed));
+        } else {
+            VB_TRY(launch_segment_topk_v((const float*)d_cdist, sb, sl, nullptr, nullptr, nq, kp, pos_kp, key_kp));
+            VB_TRY(launch_list_tc_refine(ix.centers, ix.ctc, km, qimg, qstride, nq, probes, kp, 1, zero_lists, pair_off, ix.d_centre_off, sl,
+                                         qn, pos_kp, key_kp, lists, ldist, ix.d_tc_fail, ix.defer_tc_check ? nullptr : &n_failed));
+        }
         prof_end(VB_PROF_SCAN_LISTS);
         ix.total_tc_failed += n_failed;
         if (n_failed == 0) {   // (deferred: optimistic, the caller checks the counter with its own synchronisation)
@@ -365,15 +371,21 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
         int32_t* pos_kp = (int32_t*)(key + (size_t)nq * k);
         float* key_kp = (float*)(pos_kp + (size_t)nq * kp);
         prof_begin(VB_PROF_TOPK);
-        VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, nullptr, nullptr, nq, kp, pos_kp, key_kp));
         int n_failed = 0;
         if (!ix.d_tc_fail) {
             VB_CUDA(cudaMalloc(&ix.d_tc_fail, 2 * sizeof(int)));
             VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, 2 * sizeof(int), c.stream));
         }
         if (!ix.defer_tc_check) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail + 1, 0, sizeof(int), c.stream));
-        VB_TRY(launch_list_tc_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off, seg_len, qn,
-                                     pos_kp, key_kp, pos, key, ix.d_tc_fail + 1, ix.defer_tc_check ? nullptr : &n_failed, level));
+        if (c.fused_refine) {
+            VB_TRY(launch_list_tc_select_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off,
+                                                (const float*)d_dist, seg_begin, seg_len, qn, pos, key, ix.d_tc_fail + 1,
+                                                ix.defer_tc_check ? nullptr : &n_failed, level));
+        } else {
+            VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, nullptr, nullptr, nq, kp, pos_kp, key_kp));
+            VB_TRY(launch_list_tc_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off, seg_len, qn,
+                                         pos_kp, key_kp, pos, key, ix.d_tc_fail + 1, ix.defer_tc_check ? nullptr : &n_failed, level));
+        }
         prof_end(VB_PROF_TOPK);
         ix.last_tc_failed = n_failed;
         ix.total_tc_failed += n_failed;
@@ -1019,7 +1031,7 @@ int vb_ivf_search_sharded_dev(vb_ivf* h, const void* queries_dev, int64_t nq, in
     VB_REQUIRE(P <= 4096, "sharded search: world * k must not exceed 4096");
     const int64_t chunk = (nq + world - 1) / world;
     const int64_t q0 = std::min<int64_t>(nq, (int64_t)rank * chunk), m = std::min<int64_t>(chunk, nq - q0);
-    enum { WS_SH_LISTS = 19, WS_SH_RES = 20 };
+    enum { WS_SH_LISTS = 24, WS_SH_RES = 25 };
     void *d_sh, *d_res;
     VB_TRY(workspace(WS_SH_LISTS, sizeof(int32_t) * (size_t)chunk * probes * (world + 1) + 64, &d_sh));
     int32_t* my_lists = (int32_t*)d_sh;                          // [chunk x probes]
@@ -1094,7 +1106,7 @@ int vb_ivf_search_sharded(vb_ivf* h, const void* queries, int64_t nq, int probes
     Ivf& ix = h->ix;
     Context& c = ctx();
     const size_t raw = raw_row_bytes(ix.elem, ix.dim);
-    enum { WS_SH_Q = 18 };
+    enum { WS_SH_Q = 26 };
     void* d_q;
     VB_TRY(workspace(WS_SH_Q, raw * (size_t)nq + (sizeof(int64_t) + sizeof(float)) * (size_t)nq * k + 64, &d_q));
     int64_t* d_ids = (int64_t*)((uint8_t*)d_q + ((raw * (size_t)nq + 15) & ~(size_t)15));

@@ -394,6 +394,198 @@ __global__ void certify_kernel(int64_t nq, int k, int kp, LcBound bound,
     }
 }
 
+// ---- the three steps after the approximate pass in ONE kernel (one warp per query) -----------------------------------
+//
+// select : the k' smallest approximate distances of the query's candidate run by (distance, position) -- the same
+//          composite key as segment_topk_kernel.  The warp keeps the k' best as a sorted list spread over its lanes
+//          (R = k' / 32 registers per lane, rank i at register i / 32, lane i % 32) and streams the run 32 candidates at
+//          a time; only candidates under the current k'-th key are inserted (~k' ln(n / k') insertions).
+// re-score: the candidates under the certificate threshold are a PREFIX of that sorted list; each is re-scored with
+//          the scan arithmetic (Acc<>, one row per warp pass, the loop of rescore_kernel), two rows in flight.
+// certify: rank by (exact distance, position), emit the first k, and check the certificate -- certify_kernel's rules.
+// Results are bit-identical to segment_topk_kernel + rescore_kernel + certify_kernel (tests compare the two paths).
+template <int R>
+struct WarpTopList {
+    uint64_t key[R];
+    __device__ __forceinline__ void fill(uint64_t v) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) key[r] = v;
+    }
+    // insert x (known to be smaller than the current last key); the displaced last key is dropped
+    __device__ __forceinline__ void insert(uint64_t x, int lane) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const unsigned gt = __ballot_sync(0xffffffffu, key[r] > x);
+            if (gt == 0) continue;                       // warp-uniform
+            const int first = __ffs(gt) - 1;
+            const uint64_t carry = __shfl_sync(0xffffffffu, key[r], 31);
+            const uint64_t up = __shfl_up_sync(0xffffffffu, key[r], 1);
+            if (lane > first) key[r] = up;
+            else if (lane == first) key[r] = x;
+            x = carry;
+        }
+    }
+    __device__ __forceinline__ uint64_t at(int i) const {   // rank i, warp-uniform i
+        uint64_t v = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (i / 32 == r) v = __shfl_sync(0xffffffffu, key[r], i % 32);
+        return v;
+    }
+};
+
+constexpr int SR_WARPS = 4;
+
+template <int ELEM, int METRIC, int R>
+__global__ void __launch_bounds__(SR_WARPS * 32) select_refine_kernel(const uint8_t* __restrict__ rows, size_t stride, int V,
+                                                                      const uint8_t* __restrict__ qimg, size_t qstride, int64_t nq, int k,
+                                                                      int kp, int probes, LcBound bound, const float* __restrict__ qn,
+                                                                      const float* __restrict__ dist, const int64_t* __restrict__ seg_begin,
+                                                                      const int32_t* __restrict__ seg_len,
+                                                                      const int32_t* __restrict__ probe_lists,
+                                                                      const int32_t* __restrict__ cand_off,
+                                                                      const int64_t* __restrict__ list_off, int32_t* __restrict__ out_pos,
+                                                                      float* __restrict__ out_key, int* __restrict__ n_failed) {
+    extern __shared__ uint4 sr_smem[];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int qvec = (int)(qstride / 16);
+    uint4* sq = sr_smem + (size_t)warp * qvec;
+    const int64_t q = blockIdx.x * (int64_t)SR_WARPS + warp;
+    if (q >= nq) return;
+    const uint4* gq = reinterpret_cast<const uint4*>(qimg + (size_t)q * qstride);
+    for (int i = lane; i < qvec; i += 32) sq[i] = gq[i];
+
+    // ---- select
+    const float* dp = dist + seg_begin[q];
+    const int n = seg_len[q];
+    WarpTopList<R> top;
+    top.fill(~0ull);
+    // the sentinel ~0ull sorts after every real key (position < 2^32 - 1), so the first k' candidates simply displace it
+    uint64_t thr = ~0ull;                                   // current k'-th key
+    const int kl = (kp - 1) % 32, kr = (kp - 1) / 32;
+    constexpr int UNR = 4;
+    for (int base = 0; base < n; base += 32 * UNR) {
+        float v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i = base + u * 32 + lane;
+            v[u] = i < n ? dp[i] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i = base + u * 32 + lane;
+            const uint64_t key = i < n ? (((uint64_t)orderable_key(v[u]) << 32) | (uint32_t)i) : ~0ull;
+            unsigned m = __ballot_sync(0xffffffffu, key < thr);
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const uint64_t x = __shfl_sync(0xffffffffu, key, j);
+                if (x < thr) {                              // warp-uniform
+                    top.insert(x, lane);
+                    uint64_t t = 0;
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        if (r == kr) t = __shfl_sync(0xffffffffu, top.key[r], kl);
+                    thr = t;
+                }
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---- threshold: (k-th smallest approximate distance) + 2 eps; the candidates under it are a prefix of the list
+    const float qnq = qn[q];
+    const int have = min(n, kp);                            // real entries in the list
+    const int kth = min(k, kp) - 1;
+    const uint64_t kth_key = top.at(kth);
+    const float kth_approx = kth_key == ~0ull ? __int_as_float(0x7F800000) : key_to_float((uint32_t)(kth_key >> 32));
+    const float T = kth_approx + 2.f * lc_eps(bound, qnq);
+    // entries of rank i: approx_i <= T  <=>  not (approx_i > T)   (NaN compares false: re-scored, like rescore_kernel)
+    float exact[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) exact[r] = __int_as_float(0x7F800000);
+    const int32_t* co = cand_off + q * (probes + 1);
+    for (int i0 = 0; i0 < have; i0 += 2) {
+        const uint64_t k0 = top.at(i0);
+        const uint64_t k1 = i0 + 1 < have ? top.at(i0 + 1) : ~0ull;
+        const float a0 = key_to_float((uint32_t)(k0 >> 32));
+        const float a1 = k1 == ~0ull ? 0.f : key_to_float((uint32_t)(k1 >> 32));
+        const bool do0 = !(a0 > T), do1 = k1 != ~0ull && !(a1 > T);
+        if (!do0 && !do1) continue;                         // (no early exit: NaN distances sort last and are re-scored too)
+        const uint4* rp[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int32_t ps = (int32_t)(uint32_t)(t == 0 ? k0 : k1);
+            int lo = 0, hi = probes;
+            if ((t == 0 ? do0 : do1)) {
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (co[mid] <= ps) lo = mid;
+                    else hi = mid;
+                }
+                while (lo + 1 < probes && co[lo + 1] <= ps) ++lo;   // empty lists share an offset
+                const int l = probe_lists[q * probes + lo];
+                rp[t] = reinterpret_cast<const uint4*>(rows + (size_t)(list_off[l] + (ps - co[lo])) * stride);
+            } else {
+                rp[t] = reinterpret_cast<const uint4*>(rows);
+            }
+        }
+        Acc<ELEM, METRIC> acc0, acc1;
+        if (do0 && do1) {
+#pragma unroll 4
+            for (int v = lane; v < V; v += 32) {
+                const uint4 x0 = __ldg(rp[0] + v), x1 = __ldg(rp[1] + v);
+                acc0.add(x0, sq, v);
+                acc1.add(x1, sq, v);
+            }
+        } else if (do0) {
+#pragma unroll 4
+            for (int v = lane; v < V; v += 32) acc0.add(__ldg(rp[0] + v), sq, v);
+        } else {
+#pragma unroll 4
+            for (int v = lane; v < V; v += 32) acc1.add(__ldg(rp[1] + v), sq, v);
+        }
+        acc0.template reduce<32>();
+        acc1.template reduce<32>();
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (do0 && i0 / 32 == r && lane == i0 % 32) exact[r] = (float)acc0.value();
+            if (do1 && (i0 + 1) / 32 == r && lane == (i0 + 1) % 32) exact[r] = (float)acc1.value();
+        }
+    }
+
+    // ---- order by (exact distance, position), emit the first k
+    uint64_t fin[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = r * 32 + lane;
+        const bool present = i < kp && top.key[r] != ~0ull;    // (ranks >= k' hold displaced leftovers, not candidates)
+        fin[r] = present ? (((uint64_t)orderable_key(exact[r]) << 32) | (uint32_t)top.key[r]) : (0xFFFFFFFF00000000ull | (uint32_t)i);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int rank = 0;
+#pragma unroll
+        for (int r2 = 0; r2 < R; ++r2)
+            for (int j = 0; j < 32; ++j) {
+                const uint64_t o = __shfl_sync(0xffffffffu, fin[r2], j);
+                rank += (r2 * 32 + j < kp) && o < fin[r];
+            }
+        const int i = r * 32 + lane;
+        if (i < kp && rank < k) {
+            const bool present = top.key[r] != ~0ull;
+            out_pos[q * k + rank] = present ? (int32_t)(uint32_t)fin[r] : -1;
+            out_key[q * k + rank] = present ? key_to_float((uint32_t)(fin[r] >> 32)) : __int_as_float(0x7F800000);
+        }
+    }
+    // ---- certificate: candidates beyond the k' exist -> the last of the k' must already be above the threshold
+    if (lane == 0) {
+        bool ok = true;
+        if (n > kp) ok = key_to_float((uint32_t)(thr >> 32)) > T;     // thr = the k'-th key; false for NaN
+        if (!ok) atomicAdd(n_failed, 1);
+    }
+}
+
 // Bytes one launch of list_tc_kernel moves, from the same job list the kernel walks (profiling only):
 //   [0] bytes requested by the bulk copies (every (unit, query tile, K block) stage: A tile + B tile),
 //   [1] distinct A bytes (each active (list, table tile) unit's planes once: re-reads by further query tiles of the
@@ -562,6 +754,33 @@ int list_tc_traffic(int on, int64_t* out8) {
     return VB_OK;
 }
 
+// |d~ - d_fp32| <= eps, in units of |x||q| for the product (x2 in the L2 form):
+//   representation: bf16 keeps 8 significant bits (unit roundoff 2^-8), so |x - x_hi| <= 2^-8 |x| and
+//     |x - x_hi - x_lo| <= 2^-16 |x|.  Level 2 drops x_lo.q_lo and the two residuals: 3 * 2^-16.  Level 1 also
+//     drops x_lo.q: 2^-8 + 2^-16.
+//   accumulation: one fp32 rounding of the TMEM accumulator per UMMA, (products per K step) * dim / 16 of them,
+//     <= 2^-23 each if the unit truncates; doubled to cover the alignment of the 16 products inside an UMMA.
+// The constants below are the values the GPU tests and benches of round 1 ran with (dim <= 1536); the formula takes
+// over for longer rows, where the accumulation term grows past them.
+// The fp32 norms, the final sum and the rounding of the exact fp32 distance it is compared with: 2^-16 (|x|^2 +
+// |q|^2) for L2, 2^-17 |x||q| for the inner product.
+static LcBound lc_make_bound(const Table& rows, const ListTcImage& im, int key_metric, int level) {
+    LcBound bound;
+    bound.is_l2 = key_metric == VB_L2_SQUARED;
+    const float steps = (float)(im.n_kblocks * (TC_K / 16));
+    const float rep = level == 1 ? 1.0f / 256.0f + 1.0f / 65536.0f : 3.0f / 65536.0f;
+    const float acc = 2.0f * (level == 1 ? 2.0f : 3.0f) * steps / 8388608.0f;
+    const float ip_unit = rep + acc;
+    float c_ip = level == 1 ? 1.0f / 256.0f + 1.0f / 8192.0f : 1.0f / 8192.0f;   // validated constants
+    c_ip = std::max(c_ip, ip_unit);
+    bound.c_dot = bound.is_l2 ? 2.0f * c_ip : c_ip + 1.0f / 131072.0f;
+    // norms and the exact fp32 distance each sum dim / 32 terms per lane plus a shuffle tree: 3 * (dim / 32 + 8) * 2^-24 of
+    // (|x|^2 + |q|^2) covers the two norms and the distance (<= 2 (|x|^2 + |q|^2)); 2^-16 up to ~2700 dimensions
+    bound.c_sum = std::max(1.0f / 65536.0f, 3.0f * ((float)rows.dim / 32.0f + 8.0f) / 16777216.0f);
+    bound.xmax = im.xmax;
+    return bound;
+}
+
 // steps 3 + 4: exact re-score of the selected candidates, final order, certificate.  The number of queries whose
 // certificate failed is ADDED to *fail_dev (a device counter the caller zeroes); with n_failed_host the counter is
 // also read back (one stream synchronisation), otherwise the caller checks it when it synchronises anyway.
@@ -578,29 +797,7 @@ int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metr
     uint8_t* failed = (uint8_t*)(exact + (size_t)nq * kp);
     const int V = (int)(rows.stride / 16);
     const unsigned grid = (unsigned)((nq * kp * 32 + 255) / 256);
-    // |d~ - d_fp32| <= eps, in units of |x||q| for the product (x2 in the L2 form):
-    //   representation: bf16 keeps 8 significant bits (unit roundoff 2^-8), so |x - x_hi| <= 2^-8 |x| and
-    //     |x - x_hi - x_lo| <= 2^-16 |x|.  Level 2 drops x_lo.q_lo and the two residuals: 3 * 2^-16.  Level 1 also
-    //     drops x_lo.q: 2^-8 + 2^-16.
-    //   accumulation: one fp32 rounding of the TMEM accumulator per UMMA, (products per K step) * dim / 16 of them,
-    //     <= 2^-23 each if the unit truncates; doubled to cover the alignment of the 16 products inside an UMMA.
-    // The constants below are the values the GPU tests and benches of round 1 ran with (dim <= 1536); the formula takes
-    // over for longer rows, where the accumulation term grows past them.
-    // The fp32 norms, the final sum and the rounding of the exact fp32 distance it is compared with: 2^-16 (|x|^2 +
-    // |q|^2) for L2, 2^-17 |x||q| for the inner product.
-    LcBound bound;
-    bound.is_l2 = key_metric == VB_L2_SQUARED;
-    const float steps = (float)(im.n_kblocks * (TC_K / 16));
-    const float rep = level == 1 ? 1.0f / 256.0f + 1.0f / 65536.0f : 3.0f / 65536.0f;
-    const float acc = 2.0f * (level == 1 ? 2.0f : 3.0f) * steps / 8388608.0f;
-    const float ip_unit = rep + acc;
-    float c_ip = level == 1 ? 1.0f / 256.0f + 1.0f / 8192.0f : 1.0f / 8192.0f;   // validated constants
-    c_ip = std::max(c_ip, ip_unit);
-    bound.c_dot = bound.is_l2 ? 2.0f * c_ip : c_ip + 1.0f / 131072.0f;
-    // norms and the exact fp32 distance each sum dim / 32 terms per lane plus a shuffle tree: 3 * (dim / 32 + 8) * 2^-24 of
-    // (|x|^2 + |q|^2) covers the two norms and the distance (<= 2 (|x|^2 + |q|^2)); 2^-16 up to ~2700 dimensions
-    bound.c_sum = std::max(1.0f / 65536.0f, 3.0f * ((float)rows.dim / 32.0f + 8.0f) / 16777216.0f);
-    bound.xmax = im.xmax;
+    const LcBound bound = lc_make_bound(rows, im, key_metric, level);
 #define VB_RS(E, M) rescore_kernel<E, M><<<grid, 256, 0, s>>>(rows.d, rows.stride, V, (const uint8_t*)qimg, qstride, nq, k, kp, probes, bound, qn, pos_kp, approx_kp, d_lists, cand_off, d_list_off, exact)
     if (rows.elem == VB_VECTOR) {
         if (key_metric == VB_L2_SQUARED) VB_RS(VB_VECTOR, VB_L2_SQUARED);
@@ -616,6 +813,50 @@ int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metr
     count_launch(2);
     if (n_failed_host) {
         VB_CUDA(cudaMemcpyAsync(n_failed_host, n_failed, sizeof(int), cudaMemcpyDeviceToHost, s));
+        VB_CUDA(cudaStreamSynchronize(s));
+    }
+    return VB_OK;
+}
+
+// steps 2 + 3 + 4 in one kernel (select_refine_kernel): k' select, exact re-score, final order, certificate
+int launch_list_tc_select_refine(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
+                                 int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
+                                 const float* dist, const int64_t* seg_begin, const int32_t* seg_len, const float* qn, int32_t* out_pos,
+                                 float* out_key, int* fail_dev, int* n_failed_host, int level) {
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    const LcBound bound = lc_make_bound(rows, im, key_metric, level);
+    const int V = (int)(rows.stride / 16);
+    const size_t smem = qstride * SR_WARPS;
+    const unsigned grid = (unsigned)((nq + SR_WARPS - 1) / SR_WARPS);
+    const int R = (kp + 31) / 32;
+#define VB_SR2(E, M, RR)                                                                                                              \
+    do {                                                                                                                              \
+        auto kern = select_refine_kernel<E, M, RR>;                                                                                   \
+        if (smem > 48 * 1024) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+        kern<<<grid, SR_WARPS * 32, smem, s>>>(rows.d, rows.stride, V, (const uint8_t*)qimg, qstride, nq, k, kp, probes, bound, qn, dist, \
+                                              seg_begin, seg_len, d_lists, cand_off, d_list_off, out_pos, out_key, fail_dev);         \
+    } while (0)
+#define VB_SR(E, M)                   \
+    do {                              \
+        if (R <= 1) VB_SR2(E, M, 1);  \
+        else if (R == 2) VB_SR2(E, M, 2); \
+        else VB_SR2(E, M, 4);         \
+    } while (0)
+    VB_REQUIRE(kp <= 128 && smem <= 200 * 1024, "select_refine: k' = %d / query image of %zu bytes not supported", kp, qstride);
+    if (rows.elem == VB_VECTOR) {
+        if (key_metric == VB_L2_SQUARED) VB_SR(VB_VECTOR, VB_L2_SQUARED);
+        else VB_SR(VB_VECTOR, VB_NEG_IP);
+    } else {
+        if (key_metric == VB_L2_SQUARED) VB_SR(VB_HALFVEC, VB_L2_SQUARED);
+        else VB_SR(VB_HALFVEC, VB_NEG_IP);
+    }
+#undef VB_SR
+#undef VB_SR2
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    if (n_failed_host) {
+        VB_CUDA(cudaMemcpyAsync(n_failed_host, fail_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
         VB_CUDA(cudaStreamSynchronize(s));
     }
     return VB_OK;

@@ -265,6 +265,85 @@ __global__ void __launch_bounds__(1024) lt_scan_kernel(const int32_t* __restrict
     }
 }
 
+// exclusive prefix sum by one CTA of 1024 threads (shared scratch supplied by the caller)
+__device__ __forceinline__ void lt_block_scan(const int32_t* __restrict__ cnt, int n, int32_t* __restrict__ begin, int32_t* warp_sum,
+                                              int32_t* carry) {
+    if (threadIdx.x == 0) *carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int32_t v = i < n ? cnt[i] : 0;
+        int32_t s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t u = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += u;
+        }
+        if (lane == 31) warp_sum[warp] = s;
+        __syncthreads();
+        if (warp == 0) {
+            int32_t w = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t u = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += u;
+            }
+            warp_sum[lane] = w;
+        }
+        __syncthreads();
+        const int32_t before = *carry + (warp ? warp_sum[warp - 1] : 0);
+        if (i < n) begin[i] = before + s - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) *carry = before + s;
+        __syncthreads();
+    }
+}
+
+// The whole grouping of a moderate batch in ONE launch of one CTA: count, scan, scatter, query tiles, scan -- counters
+// and cursors in shared memory (instead of a memset and five kernels with global atomics; a 2048-query batch has
+// 20 480 pairs = 20 per thread)
+__global__ void __launch_bounds__(1024) lt_group_kernel(const int32_t* __restrict__ probe_lists, int n_pairs, int probes,
+                                                        const int32_t* __restrict__ cand_off, int64_t cap, int n_lists, int gt_rows,
+                                                        int32_t* __restrict__ cnt, int32_t* __restrict__ begin,
+                                                        int32_t* __restrict__ gt_begin, int32_t* __restrict__ pair_q,
+                                                        int64_t* __restrict__ pair_out, int32_t* __restrict__ pair_list) {
+    extern __shared__ int32_t lg_smem[];
+    int32_t* scnt = lg_smem;             // [n_lists]
+    int32_t* scur = lg_smem + n_lists;   // [n_lists] begin, then the running cursor, then the tile counts
+    __shared__ int32_t warp_sum[32];
+    __shared__ int32_t carry;
+    for (int i = threadIdx.x; i < n_lists; i += 1024) scnt[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_pairs; i += 1024) {
+        const int l = probe_lists[i];
+        if (l >= 0) atomicAdd(&scnt[l], 1);
+    }
+    __syncthreads();
+    lt_block_scan(scnt, n_lists, scur, warp_sum, &carry);
+    for (int i = threadIdx.x; i < n_lists; i += 1024) {
+        cnt[i] = scnt[i];
+        begin[i] = scur[i];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_pairs; i += 1024) {
+        const int l = probe_lists[i];
+        if (l < 0) continue;
+        const int64_t q = i / probes;
+        const int p = i % probes;
+        const int slot = atomicAdd(&scur[l], 1);
+        pair_q[slot] = (int32_t)q;
+        pair_out[slot] = q * cap + cand_off[q * (probes + 1) + p];
+        pair_list[slot] = l;
+    }
+    if (gt_rows > 0) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_lists; i += 1024) scur[i] = (scnt[i] + gt_rows - 1) / gt_rows;
+        __syncthreads();
+        lt_block_scan(scur, n_lists, gt_begin, warp_sum, &carry);
+    }
+}
+
 __global__ void lt_scatter_kernel(const int32_t* __restrict__ probe_lists, int64_t n_pairs, int probes,
                                   const int32_t* __restrict__ cand_off, int64_t cap, const int32_t* __restrict__ begin,
                                   int32_t* __restrict__ cursor, int32_t* __restrict__ pair_q, int64_t* __restrict__ pair_out,
@@ -313,6 +392,18 @@ int build_query_groups(const int32_t* d_lists, int64_t nq, int probes, const int
     int32_t* tiles = g->begin + n_lists;
     g->gt_begin = tiles + n_lists;
     g->n_pairs = n_pairs;
+    if (n_pairs <= 131072 && n_lists <= 8192) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            VB_CUDA(cudaFuncSetAttribute(lt_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
+            attr_set = true;
+        }
+        lt_group_kernel<<<1, 1024, sizeof(int32_t) * 2 * (size_t)n_lists, s>>>(d_lists, (int)n_pairs, probes, cand_off, cap, n_lists, gt_rows, g->cnt,
+                                                                            g->begin, g->gt_begin, g->pair_q, g->pair_out, g->pair_list);
+        VB_CUDA(cudaGetLastError());
+        count_launch();
+        return VB_OK;
+    }
     VB_CUDA(cudaMemsetAsync(g->cnt, 0, sizeof(int32_t) * (size_t)n_lists * 2, s));
     const unsigned gp = (unsigned)((n_pairs + 255) / 256);
     lt_count_kernel<<<gp, 256, 0, s>>>(d_lists, n_pairs, g->cnt);

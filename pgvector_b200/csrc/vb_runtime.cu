@@ -342,7 +342,7 @@ int vb_shutdown(void) {
     vb::Context& c = vb::ctx();
     if (!c.inited) return VB_OK;
     cudaDeviceSynchronize();
-    for (int i = 0; i < 24; ++i) {
+    for (int i = 0; i < 32; ++i) {
         if (c.ws[i]) cudaFree(c.ws[i]);
         c.ws[i] = nullptr;
         c.ws_bytes[i] = 0;

@@ -165,3 +165,30 @@ def test_near_ties_at_long_rows(pv, dim, gap):
     if gap >= 1e-4:   # above fp32 summation noise the order is the oracle's too
         assert_same_neighbours(i0, d0, wi, wd, RTOL, min_positional=0.98, boundary=4)
         assert_same_neighbours(i3, d3, wi, wd, RTOL, min_positional=0.98, boundary=4)
+
+
+@pytest.mark.parametrize("k,probes", [(10, 10), (1, 3), (40, 10), (24, 7)])
+def test_fused_select_refine_equals_the_three_kernel_path(pv, headline, k, probes):
+    """select_refine_kernel (k' select + exact re-score + certificate in one warp-per-query kernel) returns bit for bit
+    what segment_topk_kernel + rescore_kernel + certify_kernel return, at both filter levels, incl. the counters"""
+    law, gix, oix, queries, _ = headline
+    out = {}
+    try:
+        pv.set_option("scan_impl", 4)
+        for level1 in (1, 0):
+            pv.set_option("tc_level1", level1)
+            for fused in (0, 1):
+                pv.set_option("fused_refine", fused)
+                f0, l0 = gix.tc_fallbacks(), gix.tc_level1_fallbacks()
+                ids, dist = gix.search(queries, k=k, probes=probes)
+                lists, ldist = gix.scan_lists(queries[:300], probes)
+                out[level1, fused] = (ids, dist, lists, ldist, gix.tc_fallbacks() - f0, gix.tc_level1_fallbacks() - l0)
+    finally:
+        pv.set_option("fused_refine", 1)
+        pv.set_option("tc_level1", 1)
+        pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
+    for level1 in (1, 0):
+        a, b = out[level1, 0], out[level1, 1]
+        for x, y in zip(a[:4], b[:4]):
+            assert np.array_equal(x, y), (level1, k, probes)
+        assert a[4:] == b[4:]
