@@ -1,10 +1,11 @@
 /*
- * pgstub/postgres.h -- a stand-in for the PostgreSQL server headers, just
- * complete enough to SYNTAX-CHECK pgvector_b200/ext/*.c together with the
- * reference's own ivfflat.h / hnsw.h / vector.h / halfvec.h
- * (gcc -fsyntax-only -Ipgstub -I/root/reference/src).  It is NOT PostgreSQL
- * code and is never linked; the real build uses the server's headers (PGXS).
- * Declarations follow the public PostgreSQL API (PG 17 signatures).
+ * pgstub/postgres.h -- a stand-in for the PostgreSQL server headers: complete enough to COMPILE
+ * the pgvector_b200/ext sources together with the reference's own ivfflat.h / hnsw.h / vector.h / halfvec.h
+ * (gcc -Ipgstub -I/root/reference/src), and -- with pgstub_runtime.c, which implements the handful of server
+ * functions the glue calls over in-memory page images -- to RUN it in the test harness (tests/harness).
+ * It is NOT PostgreSQL code and never ships; the real build uses the server's headers (PGXS).
+ * Declarations follow the public PostgreSQL API (PG 17 signatures); the page, item-pointer, index-tuple and
+ * varlena layouts are the on-disk ones (little endian), because the harness feeds the glue byte-exact page images.
  */
 #ifndef PGSTUB_POSTGRES_H
 #define PGSTUB_POSTGRES_H
@@ -82,10 +83,15 @@ extern int errcode(int); extern int errmsg(const char *, ...); extern int errdet
 extern void vb_stub_ereport(int, ...);
 #define ereport(level, rest) vb_stub_ereport(level, rest)
 extern void elog(int, const char *, ...);
-#define PG_TRY() do { {
-#define PG_FINALLY() } {
-#define PG_CATCH() } if (0) {
-#define PG_END_TRY() } } while (0)
+/* the structure of elog.h's PG_TRY: a chain of sigjmp_bufs; ereport(ERROR) longjmps to the innermost one */
+#include <setjmp.h>
+extern sigjmp_buf *PG_exception_stack;
+extern void pg_re_throw(void);
+#define PG_TRY() do { sigjmp_buf *_save_exception_stack = PG_exception_stack; sigjmp_buf _local_sigjmp_buf; bool _do_rethrow = false; \
+	if (sigsetjmp(_local_sigjmp_buf, 0) == 0) { PG_exception_stack = &_local_sigjmp_buf
+#define PG_CATCH() } else { PG_exception_stack = _save_exception_stack
+#define PG_FINALLY() } else _do_rethrow = true; { PG_exception_stack = _save_exception_stack
+#define PG_END_TRY() } if (_do_rethrow) pg_re_throw(); PG_exception_stack = _save_exception_stack; } while (0)
 #define CHECK_FOR_INTERRUPTS() ((void) 0)
 
 /* datum / fmgr */
@@ -96,7 +102,7 @@ extern void elog(int, const char *, ...);
 extern Datum Float8GetDatum(float8); extern float8 DatumGetFloat8(Datum);
 typedef struct FunctionCallInfoBaseData *FunctionCallInfo;
 typedef Datum (*PGFunction) (FunctionCallInfo fcinfo);
-typedef struct FmgrInfo { PGFunction fn_addr; Oid fn_oid; short fn_nargs; } FmgrInfo;
+struct FmgrInfo; typedef struct FmgrInfo { PGFunction fn_addr; Oid fn_oid; short fn_nargs; } FmgrInfo;
 #define PG_FUNCTION_ARGS FunctionCallInfo fcinfo
 #define PG_FUNCTION_INFO_V1(f) extern int pg_finfo_##f
 extern Datum PG_GETARG_DATUM_(FunctionCallInfo, int);
@@ -109,11 +115,17 @@ extern struct varlena *pg_detoast_datum(struct varlena *);
 extern Datum FunctionCall2Coll(FmgrInfo *, Oid, Datum, Datum); extern Datum FunctionCall1Coll(FmgrInfo *, Oid, Datum);
 extern Datum FunctionCall0Coll(FmgrInfo *, Oid); extern Datum DirectFunctionCall1Coll(PGFunction, Oid, Datum);
 extern Datum datumCopy(Datum, bool, int); extern bool datumIsEqual(Datum, Datum, bool, int);
+/* varlena headers, little endian (varatt.h): 4-byte header = length << 2; 1-byte header = (length << 1) | 1 */
 #define SET_VARSIZE(p, len) (*(uint32 *) (p) = ((uint32) (len)) << 2)
 #define VARSIZE(p) ((*(uint32 *) (p)) >> 2)
-#define VARSIZE_ANY(p) VARSIZE(p)
+#define VARATT_IS_SHORT(p) ((*(const uint8 *) (p) & 0x01) == 0x01)
+#define VARSIZE_SHORT(p) ((*(const uint8 *) (p) >> 1) & 0x7F)
+#define VARHDRSZ 4
+#define VARHDRSZ_SHORT 1
+#define VARDATA_SHORT(p) ((char *) (p) + 1)
+#define VARSIZE_ANY(p) (VARATT_IS_SHORT(p) ? VARSIZE_SHORT(p) : VARSIZE(p))
 #define VARATT_IS_COMPRESSED(p) false
-#define VARATT_IS_EXTENDED(p) false
+#define VARATT_IS_EXTENDED(p) VARATT_IS_SHORT(p)
 
 /* varbit */
 typedef struct { int32 vl_len_; int32 bit_len; uint8 bit_dat[FLEXIBLE_ARRAY_MEMBER]; } VarBit;
@@ -135,16 +147,19 @@ static inline bool ItemPointerIsValid(const ItemPointerData *p) { return p != NU
 typedef struct ItemIdData { unsigned lp_off:15, lp_flags:2, lp_len:15; } ItemIdData; typedef ItemIdData *ItemId;
 typedef struct PageHeaderData { char pad[24]; ItemIdData pd_linp[FLEXIBLE_ARRAY_MEMBER]; } PageHeaderData;
 #define SizeOfPageHeaderData 24
+#define PageGetContents(page) ((char *) (page) + MAXALIGN(SizeOfPageHeaderData))
 extern OffsetNumber PageGetMaxOffsetNumber(Page); extern ItemId PageGetItemId(Page, OffsetNumber);
 extern void *PageGetItem(Page, ItemId); extern char *PageGetSpecialPointer(Page); extern Size PageGetFreeSpace(Page);
 typedef struct IndexTupleData { ItemPointerData t_tid; unsigned short t_info; } IndexTupleData; typedef IndexTupleData *IndexTuple;
 #define MaxHeapTuplesPerPage 291
 
 /* relations, buffers */
-typedef struct TupleDescData *TupleDesc;
 typedef struct FormData_pg_attribute { Oid atttypid; int32 atttypmod; } FormData_pg_attribute; typedef FormData_pg_attribute *Form_pg_attribute;
+typedef struct TupleDescData { int natts; FormData_pg_attribute attrs[4]; } TupleDescData; typedef struct TupleDescData *TupleDesc;
 extern Form_pg_attribute TupleDescAttr(TupleDesc, int);
-typedef struct RelationData { Oid rd_id; Oid *rd_indcollation; void *rd_options; TupleDesc rd_att; } RelationData; typedef RelationData *Relation;
+typedef struct RelationData { Oid rd_id; Oid *rd_indcollation; void *rd_options; TupleDesc rd_att;
+	/* pgstub_runtime.c: the relation's pages (nblocks x BLCKSZ bytes) and the support functions the harness installed */
+	char *stub_pages; BlockNumber stub_nblocks; struct FmgrInfo *stub_procs[8]; } RelationData; typedef RelationData *Relation;
 #define RelationGetRelid(r) ((r)->rd_id)
 #define RelationGetDescr(r) ((r)->rd_att)
 extern BlockNumber RelationGetNumberOfBlocksInFork(Relation, ForkNumber);

@@ -34,15 +34,26 @@ typedef struct VbHnswCacheEntry
 
 static VbHnswCacheEntry * hnswCache = NULL;
 
+static void
+VbHnswDropImage(VbHnswImage * img)
+{
+	if (img->ix != NULL)
+		vb_hnsw_free(img->ix);
+	img->ix = NULL;
+	if (img->heaptids != NULL)
+		pfree(img->heaptids);
+	if (img->nheaptids != NULL)
+		pfree(img->nheaptids);
+	img->heaptids = NULL;
+	img->nheaptids = NULL;
+}
+
 void
 VbHnswInvalidate(Oid relid)
 {
 	for (VbHnswCacheEntry * e = hnswCache; e != NULL; e = e->next)
-		if (e->image.relid == relid && e->image.ix != NULL)
-		{
-			vb_hnsw_free(e->image.ix);
-			e->image.ix = NULL;
-		}
+		if (e->image.relid == relid)
+			VbHnswDropImage(&e->image);
 }
 
 /* open-addressing map index TID -> element number, built while walking the element pages */
@@ -139,7 +150,12 @@ VbHnswPack(Relation index, VbHnswImage * img)
 			Size		bytes;
 			const void *payload;
 
-			if (!HnswIsElementTuple(etup) || etup->deleted)
+			/*
+			 * Elements being deleted stay in the image: the reference still traverses them (CountElement is true for
+			 * scans, src/hnswutils.c:714-727) and only withholds their heap TIDs (heaptidsLength = 0 after
+			 * HnswLoadElementFromTuple) -- dropping them would cut the graph mid-vacuum.
+			 */
+			if (!HnswIsElementTuple(etup))
 				continue;
 			if (n == cap)
 			{
@@ -170,7 +186,7 @@ VbHnswPack(Relation index, VbHnswImage * img)
 			neighbortids[n] = etup->neighbortid;
 			ItemPointerSet(&selftids[n], blkno, offno);
 			nheaptids[n] = 0;
-			for (int i = 0; i < HNSW_HEAPTIDS; i++)
+			for (int i = 0; i < HNSW_HEAPTIDS && !etup->deleted; i++)
 			{
 				if (!ItemPointerIsValid(&etup->heaptids[i]))
 					break;
@@ -234,8 +250,25 @@ VbHnswPack(Relation index, VbHnswImage * img)
 		UnlockReleaseBuffer(buf);
 	}
 
+	if (n > 0 && entry < 0)
+	{
+		/* the meta page names an entry point the element pages do not hold (concurrent repair): CPU path for now */
+		MemoryContextSwitchTo(oldCtx);
+		MemoryContextDelete(packCtx);
+		return;
+	}
 	VB_CHECK(vb_hnsw_create(img->elem, img->metric, img->dimensions, m, &img->ix));
-	VB_CHECK(vb_hnsw_load(img->ix, rows.data, n, levels, nbr0, upper_off, upper, slots, entry));
+	{
+		int			rc = vb_hnsw_load(img->ix, rows.data, n, levels, nbr0, upper_off, upper, slots, entry);
+
+		if (rc != VB_OK)
+		{
+			VbHnswDropImage(img);	/* before raising: no device state across the longjmp */
+			ereport(ERROR,
+					(errcode(ERRCODE_EXTERNAL_ROUTINE_EXCEPTION),
+					 errmsg("vecb200: %s", vb_last_error())));
+		}
+	}
 
 	/* heap TIDs stay on the host: hnswgettuple expands elements into them */
 	img->n = n;
@@ -253,6 +286,7 @@ VbHnswGetImage(Relation index, FmgrInfo *procinfo)
 {
 	Oid			relid = RelationGetRelid(index);
 	BlockNumber nblocks = RelationGetNumberOfBlocks(index);
+	uint64		version = VbIndexVersion(index);
 	VbHnswCacheEntry *e;
 
 	for (e = hnswCache; e != NULL; e = e->next)
@@ -265,39 +299,33 @@ VbHnswGetImage(Relation index, FmgrInfo *procinfo)
 		e->next = hnswCache;
 		hnswCache = e;
 	}
-	if (e->image.ix != NULL && e->image.nblocks != nblocks)
-	{
-		vb_hnsw_free(e->image.ix);
-		e->image.ix = NULL;
-	}
+	if (e->image.ix != NULL && (e->image.nblocks != nblocks || e->image.version != version))
+		VbHnswDropImage(&e->image);
 	if (e->image.ix == NULL)
 	{
 		e->image.metric = VbMetricFromProc(procinfo, &e->image.elem);
 		e->image.dimensions = TupleDescAttr(RelationGetDescr(index), 0)->atttypmod;
 		e->image.nblocks = nblocks;
+		e->image.version = version;
 		VbHnswPack(index, &e->image);
 	}
-	return &e->image;
+	return e->image.ix != NULL ? &e->image : NULL;
 }
 
-/* scan-local results: elements nearest first, each expanded into its heap TIDs */
-typedef struct VbHnswScanState
-{
-	VbHnswImage *image;
-	int64	   *elements;
-	double	   *distances;
-	int			nelements;
-	int			cur;			/* current element */
-	int			curtid;			/* heap TIDs of the current element still to return (counts down) */
-}			VbHnswScanState;
-
 /* GetScanItems (src/hnswscan.c:25-56): one C ABI call, ef_search results nearest first */
-void
+bool
 VbHnswGetScanItems(IndexScanDesc scan, Datum value, int ef_search, VbHnswScanState * st)
 {
 	HnswScanOpaque so = (HnswScanOpaque) scan->opaque;
-	VbHnswImage *img = VbHnswGetImage(scan->indexRelation, so->support.procinfo);
+	VbHnswImage *img;
 	const void *q;
+
+	/* NULL query: every distance is 0 (src/hnswutils.c:555-556); the reference loop serves it */
+	if (DatumGetPointer(value) == NULL)
+		return false;
+	img = VbHnswGetImage(scan->indexRelation, so->support.procinfo);
+	if (img == NULL)
+		return false;
 
 	st->image = img;
 	st->elements = palloc(sizeof(int64) * (Size) ef_search);
@@ -306,8 +334,6 @@ VbHnswGetScanItems(IndexScanDesc scan, Datum value, int ef_search, VbHnswScanSta
 	st->cur = 0;
 	st->curtid = -1;
 
-	if (DatumGetPointer(value) == NULL)
-		elog(ERROR, "vecb200: NULL query is served by the CPU path");	/* caller keeps the reference loop for this case */
 	if (img->elem == VB_VECTOR)
 		q = DatumGetVector(value)->x;
 	else if (img->elem == VB_HALFVEC)
@@ -318,6 +344,7 @@ VbHnswGetScanItems(IndexScanDesc scan, Datum value, int ef_search, VbHnswScanSta
 	VB_CHECK(vb_hnsw_search(img->ix, q, 1, ef_search, ef_search, st->elements, st->distances, &so->tuples));
 	while (st->nelements < ef_search && st->elements[st->nelements] >= 0)
 		st->nelements++;
+	return true;
 }
 
 /* the loop of hnswgettuple (src/hnswscan.c:293-326): nearest element first, heap TIDs last-added first */

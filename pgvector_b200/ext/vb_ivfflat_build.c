@@ -92,7 +92,7 @@ bool
 VbIvfflatKmeans(Relation index, VectorArray samples, VectorArray centers, const IvfflatTypeInfo * typeInfo)
 {
 	FmgrInfo   *procinfo = index_getprocinfo(index, 1, IVFFLAT_KMEANS_DISTANCE_PROC);
-	int			elem;
+	int			elem = VB_VECTOR;
 	int			metric = VbKmeansMetricFromProc(procinfo, &elem);
 	int			dimensions = centers->dim;
 	int			k = centers->maxlen;

@@ -104,15 +104,55 @@ typedef struct VbIvfCacheEntry
 
 static VbIvfCacheEntry * ivfCache = NULL;
 
+static void
+VbIvfDropImage(VbIvfImage * img)
+{
+	if (img->ix != NULL)
+		vb_ivf_free(img->ix);
+	img->ix = NULL;
+	if (img->startPages != NULL)
+		pfree(img->startPages);
+	img->startPages = NULL;
+}
+
 void
 VbIvfInvalidate(Oid relid)
 {
 	for (VbIvfCacheEntry * e = ivfCache; e != NULL; e = e->next)
-		if (e->image.relid == relid && e->image.ix != NULL)
-		{
-			vb_ivf_free(e->image.ix);
-			e->image.ix = NULL;
-		}
+		if (e->image.relid == relid)
+			VbIvfDropImage(&e->image);
+}
+
+/* the version stamp in the meta page (block 0 of both AMs), see vb_glue.h */
+uint64
+VbIndexVersion(Relation index)
+{
+	Buffer		buf = ReadBuffer(index, 0);
+	uint64		version;
+
+	LockBuffer(buf, BUFFER_LOCK_SHARE);
+	memcpy(&version, BufferGetPage(buf) + MAXALIGN(SizeOfPageHeaderData) + VB_META_VERSION_OFFSET, sizeof(version));
+	UnlockReleaseBuffer(buf);
+	return version;
+}
+
+/*
+ * What aminsert / ambulkdelete / ambuild call after they changed the index (shown without the GenericXLog
+ * registration the AM wraps around every page change, src/ivfinsert.c:104-141 style).
+ */
+void
+VbBumpIndexVersion(Relation index)
+{
+	Buffer		buf = ReadBuffer(index, 0);
+	char	   *slot;
+	uint64		version;
+
+	LockBuffer(buf, BUFFER_LOCK_EXCLUSIVE);
+	slot = BufferGetPage(buf) + MAXALIGN(SizeOfPageHeaderData) + VB_META_VERSION_OFFSET;
+	memcpy(&version, slot, sizeof(version));
+	version++;
+	memcpy(slot, &version, sizeof(version));
+	UnlockReleaseBuffer(buf);
 }
 
 /*
@@ -215,7 +255,18 @@ VbIvfPack(Relation index, VbIvfImage * img)
 
 	/* hand the image to the device: pinned staging + DMA happen inside vb_ivf_load */
 	VB_CHECK(vb_ivf_create(img->elem, img->metric, img->dimensions, lists, &img->ix));
-	VB_CHECK(vb_ivf_load(img->ix, centers, offsets, rows.data, (const int64 *) ids.data));
+	{
+		int			rc = vb_ivf_load(img->ix, centers, offsets, rows.data, (const int64 *) ids.data);
+
+		if (rc != VB_OK)
+		{
+			/* release the handle BEFORE raising: no device state is held across the longjmp */
+			VbIvfDropImage(img);
+			ereport(ERROR,
+					(errcode(ERRCODE_EXTERNAL_ROUTINE_EXCEPTION),
+					 errmsg("vecb200: %s", vb_last_error())));
+		}
+	}
 
 	MemoryContextSwitchTo(oldCtx);
 	MemoryContextDelete(packCtx);
@@ -226,6 +277,7 @@ VbIvfGetImage(Relation index, FmgrInfo *procinfo, int dimensions)
 {
 	Oid			relid = RelationGetRelid(index);
 	BlockNumber nblocks = RelationGetNumberOfBlocks(index);
+	uint64		version = VbIndexVersion(index);
 	VbIvfCacheEntry *e;
 
 	for (e = ivfCache; e != NULL; e = e->next)
@@ -238,33 +290,19 @@ VbIvfGetImage(Relation index, FmgrInfo *procinfo, int dimensions)
 		e->next = ivfCache;
 		ivfCache = e;
 	}
-	/* stale (index grew) or never packed */
-	if (e->image.ix != NULL && e->image.nblocks != nblocks)
-	{
-		vb_ivf_free(e->image.ix);
-		e->image.ix = NULL;
-	}
+	/* stale (the index grew, or any backend inserted / vacuumed since the image was packed) or never packed */
+	if (e->image.ix != NULL && (e->image.nblocks != nblocks || e->image.version != version))
+		VbIvfDropImage(&e->image);
 	if (e->image.ix == NULL)
 	{
 		e->image.metric = VbMetricFromProc(procinfo, &e->image.elem);
 		e->image.dimensions = dimensions;
 		e->image.nblocks = nblocks;
+		e->image.version = version;
 		VbIvfPack(index, &e->image);
 	}
 	return &e->image;
 }
-
-/* scan-local state kept beside IvfflatScanOpaqueData (hung off so->lists' spare space in the patch) */
-typedef struct VbIvfScanState
-{
-	VbIvfImage *image;
-	int32	   *lists;			/* nearest-first list numbers [maxProbes] */
-	int			nlists;
-	int64	   *ids;			/* current batch, sorted by distance */
-	double	   *distances;
-	int64		nitems;
-	int64		next;
-}			VbIvfScanState;
 
 static inline const void *
 VbQueryPayload(VbIvfImage * img, Datum value)

@@ -1,6 +1,6 @@
-"""The extension-side glue (pgvector_b200/ext/*.c, PostgreSQL API) must at least parse against the
-reference's own headers.  PostgreSQL is not installed in this image, so the server headers are replaced
-by pgvector_b200/ext/pgstub (declarations only); this is a syntax/type check, not a run."""
+"""The extension-side glue (pgvector_b200/ext/*.c, PostgreSQL API) compiles warning-free against the reference's own
+headers (PostgreSQL is not installed in this image: the server headers are replaced by pgvector_b200/ext/pgstub) and
+calls only declared C ABI entry points.  tests/test_ext_harness.py RUNS the same files over synthesised index pages."""
 import os
 import subprocess
 
