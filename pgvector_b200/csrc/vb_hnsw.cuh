@@ -211,9 +211,35 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
             hnsw_score_batch<ELEM, METRIC, LPR>(g, sq, S.bid, cnt, S.bkey, lane);
             __syncwarp();
 
+            // Once R holds ef elements, a neighbour that is not nearer than R's last one cannot be admitted
+            // ("eDistance < f->distance || alwaysAdd", src/hnswutils.c:927-938): drop those before the sort, and skip
+            // the sort and the merge altogether when nothing is left -- the common case once the search has converged.
+            int cnt_in = cnt;
+            if (S.len == efl) {
+                const uint64_t wk = S.rk[efl - 1];
+                const uint32_t wi = S.ri[efl - 1];
+                const uint64_t k0 = lane < cnt ? S.bkey[lane] : 0;
+                const uint32_t i0 = lane < cnt ? S.bid[lane] : 0;
+                const bool keep = lane < cnt && ent_less(k0, i0, wk, wi);
+                const unsigned km = __ballot_sync(0xffffffffu, keep);
+                cnt_in = __popc(km);
+                if (cnt_in == 0) {
+                    if (first_inval < 32) break;
+                    continue;
+                }
+                if (cnt_in < cnt) {
+                    __syncwarp();
+                    if (keep) {
+                        const int p = __popc(km & ((1u << lane) - 1u));
+                        S.bkey[p] = k0;
+                        S.bid[p] = i0;
+                    }
+                    __syncwarp();
+                }
+            }
             // sort the batch by (key, id): bitonic over 32 lanes, empty lanes = +inf
-            uint64_t mk = lane < cnt ? S.bkey[lane] : ~0ull;
-            uint32_t mi = lane < cnt ? S.bid[lane] : 0x7fffffffu;
+            uint64_t mk = lane < cnt_in ? S.bkey[lane] : ~0ull;
+            uint32_t mi = lane < cnt_in ? S.bid[lane] : 0x7fffffffu;
 #pragma unroll
             for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
@@ -232,18 +258,18 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
                 }
             }
             __syncwarp();
-            if (lane < cnt) {
+            if (lane < cnt_in) {
                 S.bkey[lane] = mk;
                 S.bid[lane] = mi;
             }
             __syncwarp();
 
-            // merge R (len, sorted) with the batch (cnt, sorted) into the other buffer, keep efl
+            // merge R (len, sorted) with the batch (cnt_in, sorted) into the other buffer, keep efl
             const int len = S.len;
             for (int j = lane; j < len; j += 32) {
                 uint64_t kj = S.rk[j];
                 uint32_t ij = S.ri[j];
-                int lo = 0, hi = cnt;   // number of batch elements < R[j]
+                int lo = 0, hi = cnt_in;   // number of batch elements < R[j]
                 while (lo < hi) {
                     int mid = (lo + hi) >> 1;
                     if (ent_less(S.bkey[mid], S.bid[mid], kj, ij)) lo = mid + 1;
@@ -255,7 +281,7 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
                     S.ni[np] = ij;
                 }
             }
-            if (lane < cnt) {
+            if (lane < cnt_in) {
                 int lo = 0, hi = len;   // number of R elements < batch[lane]
                 while (lo < hi) {
                     int mid = (lo + hi) >> 1;
@@ -269,7 +295,7 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
                 }
             }
             __syncwarp();
-            S.len = min(efl, len + cnt);
+            S.len = min(efl, len + cnt_in);
             uint64_t* tk = S.rk;
             S.rk = S.nk;
             S.nk = tk;

@@ -1,0 +1,11 @@
+#!/bin/bash
+# gpurun with retries while the pod answers "transient" (busy): tools/gpurun_retry.sh <timeout> <command...>
+T=$1; shift
+for i in $(seq 1 12); do
+  out=$(/usr/local/graft/bin/gpurun --timeout "$T" -- "$@" 2>&1)
+  echo "$out" | tail -70
+  if ! echo "$out" | grep -q "status=transient"; then exit 0; fi
+  echo "[retry $i] pod busy, sleeping 150 s"
+  sleep 150
+done
+exit 3
