@@ -168,6 +168,18 @@ int			vb_ivf_load(vb_ivf *ix, const void *centers, const int64_t *list_offsets,
 int			vb_ivf_load_dev(vb_ivf *ix, const void *centers_dev, const int64_t *list_offsets_host,
 							const void *rows_dev, const int64_t *ids_dev);
 int64_t		vb_ivf_rows(const vb_ivf *ix);
+/*
+ * The same image, one list at a time -- the granularity the packer reads at (one entry-page chain per list,
+ * src/ivfscan.c:139-179), so the host never stages more than one list: vb_ivf_begin_load (centres), vb_ivf_load_list
+ * for the non-empty lists in ascending list order, vb_ivf_end_load.
+ * vb_ivf_replace_list swaps one list of a loaded image for new contents (an insert into that list, a vacuum of it):
+ * only that list crosses PCIe, the rows behind it are moved on the device, and the packed planes of the tensor-core
+ * filter are rebuilt on the device by the next batched scan.
+ */
+int			vb_ivf_begin_load(vb_ivf *ix, const void *centers);
+int			vb_ivf_load_list(vb_ivf *ix, int list, const void *rows, const int64_t *ids, int64_t n);
+int			vb_ivf_end_load(vb_ivf *ix);
+int			vb_ivf_replace_list(vb_ivf *ix, int list, const void *rows, const int64_t *ids, int64_t n);
 int			vb_ivf_free(vb_ivf *ix);
 
 /*

@@ -69,6 +69,7 @@ struct PgvHnsw
 	int64_t		entry;
 	uint64_t	rs0,
 				rs1;
+	const int32_t *levels_in;	/* caller-supplied level draws (NULL: drawn from the seed) */
 	uint32_t   *visited;		/* build-time epoch set */
 	uint32_t	epoch;
 	int64_t		visited_cap;
@@ -678,7 +679,7 @@ insert_row(PgvHnsw *g, int64_t row)
 {
 	int32_t		eid = (int32_t) g->n;
 	Element    *e = &g->el[eid];
-	int			level = (int) (-log(rnd_double(g)) * g->ml);	/* HnswInitElement (hnswutils.c:248-254) */
+	int			level = g->levels_in ? g->levels_in[row] : (int) (-log(rnd_double(g)) * g->ml);	/* HnswInitElement (hnswutils.c:248-254) */
 	int64_t		entryPoint = g->entry;
 
 	if (level > g->maxLevel)
@@ -741,6 +742,15 @@ pgv_hnsw_build(PgvHnsw *g, const void *rows, int64_t n)
 	g->epoch = 0;
 	for (int64_t i = 0; i < n; i++)
 		insert_row(g, i);
+}
+
+/* the same build with the level of every row given by the caller (the extension draws them from pg_prng) */
+void
+pgv_hnsw_build_levels(PgvHnsw *g, const void *rows, int64_t n, const int32_t *levels)
+{
+	g->levels_in = levels;
+	pgv_hnsw_build(g, rows, n);
+	g->levels_in = NULL;
 }
 
 int64_t

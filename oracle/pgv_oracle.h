@@ -135,6 +135,7 @@ PgvHnsw *pgv_hnsw_create(int elem, int metric, int dim, int m, int ef_constructi
 void	 pgv_hnsw_free(PgvHnsw *g);
 /* in-memory build insert (src/hnswbuild.c:437-480, hnswutils.c:1280-1357). rows must stay alive. */
 void	 pgv_hnsw_build(PgvHnsw *g, const void *rows, int64_t n);
+void	 pgv_hnsw_build_levels(PgvHnsw *g, const void *rows, int64_t n, const int32_t *levels);
 int64_t  pgv_hnsw_count(const PgvHnsw *g);
 int		 pgv_hnsw_entry(const PgvHnsw *g, int64_t *entry, int *entry_level);
 /* export: levels[n]; layer-0 neighbours [n][2m] (-1 padded) */

@@ -280,6 +280,30 @@ class IvfflatIndex:
         the cosine opclasses, identity otherwise."""
         return l2_normalize(q, self.elem) if self.normalize else q
 
+    def load_by_list(self, centers, lists):
+        """the same image loaded one list at a time: `lists` = iterable of (list number, rows, ids), ascending"""
+        centers = _host(self.elem, centers)
+        _lib.check(load().vb_ivf_begin_load(self.h, _ptr(centers)))
+        off = np.zeros(self.lists + 1, dtype=np.int64)
+        for l, rows, ids in lists:
+            rows = _host(self.elem, rows)
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+            _lib.check(load().vb_ivf_load_list(self.h, int(l), _ptr(rows), _ptr(ids), rows.shape[0]))
+            off[l + 1] = rows.shape[0]
+        _lib.check(load().vb_ivf_end_load(self.h))
+        self._off = np.concatenate([[0], np.cumsum(off[1:])]).astype(np.int64)
+        return self
+
+    def replace_list(self, l, rows, ids):
+        """swap one list of the loaded image (what an insert into / a vacuum of that list needs)"""
+        rows = _host(self.elem, rows)
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        _lib.check(load().vb_ivf_replace_list(self.h, int(l), _ptr(rows), _ptr(ids), rows.shape[0]))
+        delta = rows.shape[0] - int(self._off[l + 1] - self._off[l])
+        self._off = self._off.copy()
+        self._off[l + 1:] += delta
+        return self
+
     def scan_lists(self, queries, max_probes=None):
         """GetScanLists: nearest lists per query, ascending."""
         mp = int(max_probes or self.probes)

@@ -71,6 +71,11 @@ struct Ivf {
     int l1_cooldown = 0;              // batches left before level 1 is tried again after it failed
     int64_t last_tc_failed = 0, total_tc_failed = 0, total_l1_failed = 0;
     bool loaded = false;
+    // streaming load (vb_ivf_begin_load / vb_ivf_load_list / vb_ivf_end_load)
+    bool loading = false;
+    int next_list = 0;
+    std::vector<int64_t> h_ids;
+    std::vector<int64_t> pending_off;
 };
 
 // One CTA per query: candidate offsets of its probed lists and the chunk descriptors of the scan.
@@ -776,6 +781,110 @@ int vb_ivf_load_dev(vb_ivf* h, const void* centers_dev, const int64_t* list_offs
 }
 
 int64_t vb_ivf_rows(const vb_ivf* h) { return h ? h->ix.rows.n : 0; }
+
+// ---- list-at-a-time loading: the packer walks one entry-page chain at a time (src/ivfscan.c:139-179) and never holds
+// more than one list on the host
+
+int vb_ivf_begin_load(vb_ivf* h, const void* centers) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && centers, "null argument");
+    Ivf& ix = h->ix;
+    table_free(ix.centers);
+    table_free(ix.rows);
+    VB_TRY(table_append_host(ix.centers, centers, ix.lists));
+    ix.loaded = false;
+    ix.loading = true;
+    ix.next_list = 0;
+    ix.h_ids.clear();
+    ix.pending_off.assign((size_t)ix.lists + 1, 0);
+    return VB_OK;
+}
+
+int vb_ivf_load_list(vb_ivf* h, int list, const void* rows, const int64_t* ids, int64_t n) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && h->ix.loading, "vb_ivf_load_list outside vb_ivf_begin_load / vb_ivf_end_load");
+    Ivf& ix = h->ix;
+    VB_REQUIRE(list >= ix.next_list && list < ix.lists, "lists must arrive in ascending order (got %d, expected >= %d)", list, ix.next_list);
+    VB_REQUIRE(n >= 0 && (n == 0 || (rows && ids)), "null rows / ids");
+    for (int l = ix.next_list; l <= list; ++l) ix.pending_off[(size_t)l] = ix.rows.n;
+    if (n > 0) {
+        VB_TRY(table_append_host(ix.rows, rows, n));
+        ix.h_ids.insert(ix.h_ids.end(), ids, ids + n);
+    }
+    ix.next_list = list + 1;
+    ix.pending_off[(size_t)list + 1] = ix.rows.n;
+    return VB_OK;
+}
+
+int vb_ivf_end_load(vb_ivf* h) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && h->ix.loading, "vb_ivf_end_load without vb_ivf_begin_load");
+    Ivf& ix = h->ix;
+    for (int l = ix.next_list; l <= ix.lists; ++l) ix.pending_off[(size_t)l] = ix.rows.n;
+    ix.loading = false;
+    VB_TRY(ivf_set_offsets(ix, ix.pending_off.data()));
+    if (ix.d_ids) cudaFree(ix.d_ids);
+    ix.d_ids = nullptr;
+    const int64_t n = ix.rows.n;
+    if (n > 0) {
+        VB_CUDA(cudaMalloc(&ix.d_ids, sizeof(int64_t) * (size_t)n));
+        VB_CUDA(cudaMemcpy(ix.d_ids, ix.h_ids.data(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice));
+    }
+    ix.h_ids.clear();
+    ix.h_ids.shrink_to_fit();
+    ix.loaded = true;
+    return VB_OK;
+}
+
+// One list of a loaded image changed (insert into it, vacuum of it): only that list crosses PCIe; the rows behind it
+// move on the device, and the packed planes of the tensor-core filter are rebuilt on the device at the next batched scan.
+int vb_ivf_replace_list(vb_ivf* h, int list, const void* rows, const int64_t* ids, int64_t n) {
+    VB_TRY(require_init());
+    VB_REQUIRE(h && h->ix.loaded, "index not loaded");
+    Ivf& ix = h->ix;
+    VB_REQUIRE(list >= 0 && list < ix.lists && n >= 0 && (n == 0 || (rows && ids)), "bad list / rows");
+    Context& c = ctx();
+    const int64_t lo = ix.h_list_off[(size_t)list], hi = ix.h_list_off[(size_t)list + 1];
+    const int64_t total = ix.rows.n, tail = total - hi, new_total = lo + n + tail;
+    Table T;
+    T.elem = ix.rows.elem;
+    T.dim = ix.rows.dim;
+    T.stride = ix.rows.stride;
+    VB_TRY(table_reserve(T, std::max<int64_t>(new_total, 1)));
+    int64_t* new_ids = nullptr;
+    if (new_total > 0) VB_CUDA(cudaMalloc(&new_ids, sizeof(int64_t) * (size_t)new_total));
+    if (lo > 0) {
+        VB_CUDA(cudaMemcpyAsync(T.d, ix.rows.d, (size_t)lo * T.stride, cudaMemcpyDeviceToDevice, c.stream));
+        VB_CUDA(cudaMemcpyAsync(new_ids, ix.d_ids, sizeof(int64_t) * (size_t)lo, cudaMemcpyDeviceToDevice, c.stream));
+    }
+    T.n = lo;
+    int rc = n > 0 ? table_append_host(T, rows, n) : VB_OK;   // (synchronises the stream)
+    if (rc == VB_OK && n > 0 &&
+        cudaMemcpyAsync(new_ids + lo, ids, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, c.stream) != cudaSuccess)
+        rc = VB_ECUDA;
+    if (rc == VB_OK && tail > 0) {
+        if (cudaMemcpyAsync(T.d + (size_t)(lo + n) * T.stride, ix.rows.d + (size_t)hi * T.stride, (size_t)tail * T.stride,
+                            cudaMemcpyDeviceToDevice, c.stream) != cudaSuccess ||
+            cudaMemcpyAsync(new_ids + lo + n, ix.d_ids + hi, sizeof(int64_t) * (size_t)tail, cudaMemcpyDeviceToDevice, c.stream) != cudaSuccess)
+            rc = VB_ECUDA;
+    }
+    if (rc == VB_OK && cudaStreamSynchronize(c.stream) != cudaSuccess) rc = VB_ECUDA;
+    if (rc != VB_OK) {
+        table_free(T);
+        if (new_ids) cudaFree(new_ids);
+        if (rc == VB_ECUDA) set_error("vb_ivf_replace_list: device copy failed");
+        return rc;
+    }
+    T.n = new_total;
+    table_free(ix.rows);
+    ix.rows = T;
+    if (ix.d_ids) cudaFree(ix.d_ids);
+    ix.d_ids = new_ids;
+    std::vector<int64_t> off = ix.h_list_off;
+    const int64_t delta = n - (hi - lo);
+    for (int l = list + 1; l <= ix.lists; ++l) off[(size_t)l] += delta;
+    return ivf_set_offsets(ix, off.data());
+}
 
 int vb_ivf_free(vb_ivf* h) {
     if (!h) return VB_OK;

@@ -9,7 +9,7 @@ REF = "/root/reference/src"
 EXT = os.path.join(ROOT, "pgvector_b200", "ext")
 OUT = os.path.join(HERE, "_build")
 SRCS = [os.path.join(HERE, f) for f in ("harness_common.c", "harness_ivf.c", "harness_hnsw.c")] + \
-       [os.path.join(EXT, f) for f in ("vb_ivfflat_scan.c", "vb_ivfflat_build.c", "vb_hnsw_scan.c")] + \
+       [os.path.join(EXT, f) for f in ("vb_ivfflat_scan.c", "vb_ivfflat_build.c", "vb_hnsw_scan.c", "vb_hnsw_build.c")] + \
        [os.path.join(EXT, "pgstub", "pgstub_runtime.c")]
 FLAGS = ["-std=gnu11", "-O1", "-g", "-fPIC", "-shared", "-Wall", "-Werror", "-Wno-unused-function", "-Wno-comment",
          "-I" + os.path.join(EXT, "pgstub"), "-I" + REF, "-I" + os.path.join(ROOT, "include"), "-I" + EXT, "-I" + HERE]

@@ -11,11 +11,11 @@
 extern const char *pgstub_last_error(void);
 
 /* run `body` with an error trap: returns 0, or -1 with the message in pgstub_last_error() */
-#define H_TRAP(body) \
+#define H_TRAP(...) \
 	do { \
 		volatile int h_rc__ = 0; \
 		PG_TRY(); \
-		{ body; } \
+		{ __VA_ARGS__; } \
 		PG_CATCH(); \
 		{ h_rc__ = -1; } \
 		PG_END_TRY(); \

@@ -149,7 +149,7 @@ struct vb_hnsw
 	int			elem, metric, dim, m;
 	PgvHnsw    *g;
 	void	   *rows;
-	int32_t    *levels, *nbr0, *upper;
+	int32_t    *levels, *nbr0, *upper, *dup_of;
 	int64_t    *upper_off;
 	int64_t		n, entry, slots;
 };
@@ -210,6 +210,7 @@ vb_hnsw_free(vb_hnsw *h)
 		free(h->nbr0);
 		free(h->upper_off);
 		free(h->upper);
+		free(h->dup_of);
 		free(h);
 		mock_live_handles--;
 	}
@@ -250,6 +251,126 @@ vb_hnsw_search(vb_hnsw *h, const void *queries, int64_t nq, int ef, int k, int64
 			out_ndist[q] = nd;
 		free(ids);
 		free(d);
+	}
+	return VB_OK;
+}
+
+/* vb_hnsw_build on the oracle's serial build; the library numbers elements by ROW (a folded duplicate keeps its row
+ * number and points at its element through dup_of), the oracle numbers elements densely: translate */
+int
+vb_hnsw_build(vb_hnsw *h, const void *rows, int64_t n, int ef_construction, uint64_t seed, const int32_t *levels)
+{
+	size_t		rb = pgv_row_bytes(h->elem, h->dim);
+	PgvHnsw    *g = pgv_hnsw_create(h->elem, h->metric, h->dim, h->m, ef_construction, seed ? seed : 1);
+	int64_t		ne, slots, entry = -1, uslots = 0;
+	int			entry_level = 0, lm0 = 2 * h->m;
+	int32_t    *el, *en0, *eup, *nht;
+	int64_t    *euo, *erow, *ht;
+
+	if (mock_fail_next_load)
+	{
+		mock_fail_next_load = 0;
+		pgv_hnsw_free(g);
+		snprintf(mock_err, sizeof(mock_err), "mock: injected load failure");
+		return VB_ENOMEM;
+	}
+	h->rows = malloc(rb * (size_t) (n ? n : 1));
+	memcpy(h->rows, rows, rb * (size_t) n);
+	if (levels)
+		pgv_hnsw_build_levels(g, h->rows, n, levels);
+	else
+		pgv_hnsw_build(g, h->rows, n);
+	ne = pgv_hnsw_count(g);
+	el = malloc(sizeof(int32_t) * (size_t) (ne + 1));
+	en0 = malloc(sizeof(int32_t) * (size_t) (ne + 1) * lm0);
+	euo = malloc(sizeof(int64_t) * (size_t) (ne + 1));
+	pgv_hnsw_export_layer0(g, el, en0);
+	slots = pgv_hnsw_export_upper(g, euo, NULL);
+	eup = malloc(sizeof(int32_t) * (size_t) (slots + 1) * h->m);
+	pgv_hnsw_export_upper(g, euo, eup);
+	erow = malloc(sizeof(int64_t) * (size_t) (ne + 1));
+	nht = malloc(sizeof(int32_t) * (size_t) (ne + 1));
+	ht = malloc(sizeof(int64_t) * (size_t) (ne + 1) * 10);
+	pgv_hnsw_export_elements(g, erow, nht, ht);
+	pgv_hnsw_entry(g, &entry, &entry_level);
+	/* row-indexed arrays */
+	h->n = n;
+	h->levels = calloc((size_t) (n ? n : 1), sizeof(int32_t));
+	h->nbr0 = malloc(sizeof(int32_t) * (size_t) (n ? n : 1) * lm0);
+	h->upper_off = malloc(sizeof(int64_t) * (size_t) (n ? n : 1));
+	memset(h->nbr0, 0xFF, sizeof(int32_t) * (size_t) n * lm0);
+	{
+		int32_t    *dup = malloc(sizeof(int32_t) * (size_t) (n ? n : 1));
+
+		memset(dup, 0xFF, sizeof(int32_t) * (size_t) n);
+		for (int64_t e = 0; e < ne; e++)
+			for (int j = 1; j < nht[e]; j++)
+				dup[ht[e * 10 + j]] = (int32_t) erow[e];
+		h->upper = (int32_t *) dup;	/* parked; swapped below */
+	}
+	{
+		int32_t    *dup = h->upper;
+		int64_t		r;
+
+		if (levels)
+			for (r = 0; r < n; r++)
+				h->levels[r] = levels[r];
+		for (int64_t e = 0; e < ne; e++)
+			h->levels[erow[e]] = el[e];
+		for (r = 0; r < n; r++)
+		{
+			h->upper_off[r] = h->levels[r] > 0 ? uslots : -1;
+			uslots += h->levels[r];
+		}
+		h->upper = malloc(sizeof(int32_t) * (size_t) (uslots ? uslots : 1) * h->m);
+		memset(h->upper, 0xFF, sizeof(int32_t) * (size_t) uslots * h->m);
+		for (int64_t e = 0; e < ne; e++)
+		{
+			int64_t		row = erow[e];
+
+			for (int j = 0; j < lm0; j++)
+				h->nbr0[row * lm0 + j] = en0[e * lm0 + j] >= 0 ? (int32_t) erow[en0[e * lm0 + j]] : -1;
+			for (int lc = 1; lc <= el[e]; lc++)
+				for (int j = 0; j < h->m; j++)
+				{
+					int32_t		v = eup[(euo[e] + lc - 1) * h->m + j];
+
+					h->upper[(h->upper_off[row] + lc - 1) * h->m + j] = v >= 0 ? (int32_t) erow[v] : -1;
+				}
+		}
+		h->slots = uslots;
+		h->entry = entry >= 0 ? erow[entry] : -1;
+		h->dup_of = dup;
+	}
+	pgv_hnsw_free(g);
+	free(el); free(en0); free(euo); free(eup); free(erow); free(nht); free(ht);
+	return VB_OK;
+}
+
+int64_t vb_hnsw_rows(const vb_hnsw *h) { return h ? h->n : 0; }
+int64_t vb_hnsw_upper_slots(const vb_hnsw *h) { return h ? h->slots : 0; }
+
+int
+vb_hnsw_export(vb_hnsw *h, int32_t *levels, int32_t *nbr0, int64_t *upper_off, int32_t *upper, int64_t *entry, int32_t *dup_of)
+{
+	int64_t		n = h->n;
+
+	if (entry)
+		*entry = h->entry;
+	if (levels)
+		memcpy(levels, h->levels, sizeof(int32_t) * (size_t) n);
+	if (nbr0)
+		memcpy(nbr0, h->nbr0, sizeof(int32_t) * (size_t) n * 2 * h->m);
+	if (upper_off)
+		memcpy(upper_off, h->upper_off, sizeof(int64_t) * (size_t) n);
+	if (upper)
+		memcpy(upper, h->upper, sizeof(int32_t) * (size_t) h->slots * h->m);
+	if (dup_of)
+	{
+		if (h->dup_of)
+			memcpy(dup_of, h->dup_of, sizeof(int32_t) * (size_t) n);
+		else
+			memset(dup_of, 0xFF, sizeof(int32_t) * (size_t) n);
 	}
 	return VB_OK;
 }

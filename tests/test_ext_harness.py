@@ -332,3 +332,87 @@ def test_hnsw_elements_being_deleted_and_unmapped_entry_point():
     rel2, keep2 = H.open(bytes(b), 12, PROC[("vector", "l2")])
     got, _ = H.hnsw_scan(rel2, elem, rows[0], ef=40, max_items=10)
     assert got is None and H.lib.pgstub_pinned_buffers() == 0
+
+
+def _abi_build(H, elem, metric, dim, m, rows, efc, levels):
+    """the C ABI called directly (mock or real): vb_hnsw_create + vb_hnsw_build + vb_hnsw_export"""
+    L = H.lib
+    for f in (L.vb_hnsw_create, L.vb_hnsw_build, L.vb_hnsw_export, L.vb_hnsw_free):
+        f.restype = C.c_int
+    L.vb_hnsw_upper_slots.restype = C.c_int64
+    L.vb_hnsw_build.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint64, C.c_void_p]
+    L.vb_hnsw_upper_slots.argtypes = [C.c_void_p]
+    L.vb_hnsw_export.argtypes = [C.c_void_p] * 5 + [C.POINTER(C.c_int64), C.c_void_p]
+    L.vb_hnsw_free.argtypes = [C.c_void_p]
+    h = C.c_void_p()
+    assert L.vb_hnsw_create(elem, metric, dim, m, C.byref(h)) == 0
+    n = len(rows)
+    lv = np.ascontiguousarray(levels, dtype=np.int32)
+    assert L.vb_hnsw_build(h, np.ascontiguousarray(rows).ctypes.data_as(C.c_void_p), n, efc, 0, lv.ctypes.data_as(C.c_void_p)) == 0
+    slots = L.vb_hnsw_upper_slots(h)
+    out_l, nbr0 = np.empty(n, np.int32), np.empty((n, 2 * m), np.int32)
+    uo, up, dup = np.empty(n, np.int64), np.full((max(slots, 1), m), -1, np.int32), np.empty(n, np.int32)
+    entry = C.c_int64()
+    assert L.vb_hnsw_export(h, out_l.ctypes.data_as(C.c_void_p), nbr0.ctypes.data_as(C.c_void_p), uo.ctypes.data_as(C.c_void_p),
+                            up.ctypes.data_as(C.c_void_p), C.byref(entry), dup.ctypes.data_as(C.c_void_p)) == 0
+    L.vb_hnsw_free(h)
+    return out_l, nbr0, uo, up, entry.value, dup
+
+
+@_params
+@pytest.mark.parametrize("typ,metric,n,dim,m,dups", [("vector", "l2", 1500, 12, 8, 30), ("bit", "hamming", 1200, 128, 6, 0)])
+def test_hnsw_build_body_materialises_the_reference_graph(real, typ, metric, n, dim, m, dups):
+    """VbHnswBuildAdd / VbHnswBuildFinish: rows buffered by the build callback, graph built through the C ABI with the
+    levels the glue drew, and handed to the page writer as the in-memory structure InsertTupleInMemory leaves:
+    graph->head chain (newest first), neighbour arrays in stored order, duplicates as extra heap TIDs, entry point."""
+    H = Harness(real)
+    elem = ELEM[typ]
+    mt = {"l2": O.L2_SQUARED, "hamming": O.HAMMING}[metric]
+    x, _ = mixture(n, dim, 15, seed=n + m)
+    rows = O.binary_quantize(O.VECTOR, x) if elem == O.BIT else x
+    if dups:
+        rows = np.concatenate([rows, rows[:dups]])
+    nr = len(rows)
+    image, _ = P.ivfflat_image(O.VECTOR, 4, np.zeros((1, 4), np.float32), np.array([0, 0]), np.zeros((0, 4), np.float32), [])
+    rel, keep = H.open(image, dim, PROC[(typ, metric)])
+    max_level = 12
+    L = H.lib
+    L.h_hnsw_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p]
+    n_added, n_el, entry = C.c_int64(), C.c_int64(), C.c_int64()
+    lv = np.empty(nr, np.int32)
+    ht = np.full((nr, 10), -1, np.int64)
+    nht = np.empty(nr, np.int32)
+    nb0 = np.full((nr, 2 * m), -1, np.int64)
+    upp = np.full((nr, max_level, m), -1, np.int64)
+    rc = L.h_hnsw_build(rel, elem, dim, np.ascontiguousarray(rows).ctypes.data_as(C.c_void_p), nr, m, 40, 1 << 40, C.byref(n_added), C.byref(n_el),
+                        lv.ctypes.data_as(C.c_void_p), ht.ctypes.data_as(C.c_void_p), nht.ctypes.data_as(C.c_void_p),
+                        nb0.ctypes.data_as(C.c_void_p), upp.ctypes.data_as(C.c_void_p), max_level, C.byref(entry))
+    assert rc == 0, H.err()
+    assert n_added.value == nr and H.lib.pgstub_pinned_buffers() == 0
+    ne = n_el.value
+    tid = lambda r: P.tid_id(*P.heap_tid_of(int(r)))
+    row_of = {tid(r): r for r in range(nr)}
+    # the glue's level draws, per row, recovered from the elements (folded duplicates: any level, they carry no lists)
+    own = np.array([row_of[int(ht[e, 0])] for e in range(ne)])
+    assert np.all(np.diff(own) < 0), "graph->head chain is newest first (AddElementInMemory pushes at the head)"
+    levels = np.zeros(nr, np.int32)
+    levels[own] = lv[:ne]
+    want_l, want_n0, want_uo, want_up, want_entry, want_dup = _abi_build(H, elem, mt, dim, m, rows, 40, levels)
+    assert sorted(own.tolist()) == np.nonzero(want_dup < 0)[0].tolist()
+    assert int(entry.value) == tid(want_entry)
+    for e in range(ne):
+        r = own[e]
+        folded = sorted(np.nonzero(want_dup == r)[0].tolist())
+        assert [row_of[int(t)] for t in ht[e, :nht[e]]] == [r] + folded           # own TID first, duplicates in insertion order
+        got0 = [row_of[int(t)] for t in nb0[e] if t >= 0]
+        assert got0 == [int(v) for v in want_n0[r] if v >= 0]
+        for lc in range(1, lv[e] + 1):
+            gl = [row_of[int(t)] for t in upp[e, lc - 1] if t >= 0]
+            assert gl == [int(v) for v in want_up[want_uo[r] + lc - 1] if v >= 0], (e, lc)
+    if dups:
+        assert (want_dup >= 0).sum() >= dups // 2 and nht[:ne].max() >= 2
+    # the memory budget of the in-memory phase (src/hnswbuild.c:615-624): the buffer stops accepting rows
+    rc = L.h_hnsw_build(rel, elem, dim, np.ascontiguousarray(rows).ctypes.data_as(C.c_void_p), nr, m, 40, 200 * (P.row_bytes(elem, dim) + 6), C.byref(n_added),
+                        C.byref(n_el), lv.ctypes.data_as(C.c_void_p), ht.ctypes.data_as(C.c_void_p), nht.ctypes.data_as(C.c_void_p),
+                        nb0.ctypes.data_as(C.c_void_p), upp.ctypes.data_as(C.c_void_p), max_level, C.byref(entry))
+    assert rc == 0 and n_added.value == 200 and 0 < n_el.value <= 200

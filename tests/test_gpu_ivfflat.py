@@ -380,3 +380,49 @@ def test_device_pointer_variants_match_host_variants(pv, l2_index):
     h_ids, h_dist = pv.Table(O.VECTOR, 96).append(oix.rows).exact_topk(O.L2_SQUARED, queries[:20], 5)
     assert np.array_equal(e_ids.cpu().numpy(), h_ids)
     assert np.allclose(e_dist.cpu().numpy(), h_dist, rtol=1e-6)
+
+
+def test_list_at_a_time_load_and_replace_list(pv):
+    """vb_ivf_begin_load / vb_ivf_load_list / vb_ivf_end_load build the image vb_ivf_load builds, and
+    vb_ivf_replace_list swaps one list (growing, shrinking, emptying it) -- every scan kernel sees the new rows"""
+    import os
+    rows, centers = mixture(12000, 64, 24, seed=61)
+    queries, _ = mixture(300, 64, 24, seed=62)
+    assign = O.ivf_assign(O.VECTOR, O.L2_SQUARED, rows, centers, threads=8)
+    grouped, ids, offsets = build_ivf_arrays(rows, assign, 24)
+    whole = pv.IvfflatIndex("vector_l2_ops", 64, 24).load(centers, offsets, grouped, ids)
+    parts = [(l, grouped[offsets[l]:offsets[l + 1]], ids[offsets[l]:offsets[l + 1]]) for l in range(24) if offsets[l + 1] > offsets[l]]
+    piece = pv.IvfflatIndex("vector_l2_ops", 64, 24).load_by_list(centers, parts)
+    for impl in (0, 3, 4):
+        pv.set_option("scan_impl", impl)
+        a, b = whole.search(queries, k=10, probes=5), piece.search(queries, k=10, probes=5)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), impl
+    # replace three lists: one grows (rows moved in from list 9), list 9 shrinks accordingly, list 3 becomes empty
+    g2, i2, off2 = grouped.copy(), ids.copy(), offsets.copy()
+    cur = {l: (g2[off2[l]:off2[l + 1]].copy(), i2[off2[l]:off2[l + 1]].copy()) for l in range(24)}
+    take = len(cur[9][0]) // 2
+    cur[5] = (np.concatenate([cur[5][0], cur[9][0][:take]]), np.concatenate([cur[5][1], cur[9][1][:take]]))
+    cur[9] = (cur[9][0][take:], cur[9][1][take:])
+    moved3 = cur[3]
+    cur[3] = (cur[3][0][:0], cur[3][1][:0])
+    cur[4] = (np.concatenate([cur[4][0], moved3[0]]), np.concatenate([cur[4][1], moved3[1]]))
+    try:
+        pv.set_option("scan_impl", 4)
+        piece.search(queries, k=10, probes=5)          # the packed planes exist before the swap
+        for l in (5, 9, 3, 4):
+            piece.replace_list(l, cur[l][0], cur[l][1])
+        new_rows = np.concatenate([cur[l][0] for l in range(24)])
+        new_ids = np.concatenate([cur[l][1] for l in range(24)])
+        new_off = np.concatenate([[0], np.cumsum([len(cur[l][0]) for l in range(24)])]).astype(np.int64)
+        fresh = pv.IvfflatIndex("vector_l2_ops", 64, 24).load(centers, new_off, new_rows, new_ids)
+        oix = O.Ivf(O.VECTOR, O.L2_SQUARED, centers, new_off, new_rows, new_ids)
+        for impl in (0, 1, 3, 4):
+            pv.set_option("scan_impl", impl)
+            a, b = fresh.search(queries, k=10, probes=5), piece.search(queries, k=10, probes=5)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), impl
+        wi, wd = oix.search_batch(queries, 5, 10, threads=8)
+        assert np.allclose(b[1], wd, rtol=RTOL) and (b[0] == wi).mean() > 0.99
+    finally:
+        pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
+    with pytest.raises(pv.VecB200Error):
+        pv._lib.check(pv.load().vb_ivf_load_list(piece.h, 0, None, None, 0))      # outside begin / end
