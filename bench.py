@@ -1116,7 +1116,8 @@ def run_d(args):
         assign = pv.assign(t_rows, pv.L2_SQUARED, c_dev)
         pv.synchronize()
         t3 = time.perf_counter()
-        res.update(seed_s=t1 - t0, lloyd_s=t2 - t1, assign_s=t3 - t2, iters=iters, centers=c_dev, assign=assign, rechecked=pv.last_assign_rechecked())
+        res.update(seed_s=t1 - t0, lloyd_s=t2 - t1, assign_s=t3 - t2, iters=iters, centers=c_dev, assign=assign, rechecked=pv.last_assign_rechecked(),
+                   pp_stats=pv.kmeans_pp_stats())
 
     sampler = ClockSampler(env.local)
     if rank == 0:
@@ -1154,7 +1155,8 @@ def run_d(args):
                                f"rows and samples sharded over {world} rank(s); ncclAllReduce of centre sums / counts / change counter per Lloyd iteration, "
                                "ncclAllGather + ncclAllReduce per k-means++ centre, all inside libvecb200; assign is collective-free",
                            "l2_policy": "inputs larger than L2 (%d MB of rows per rank)" % (n_local * args.dim * 4 // 2**20)},
-                "phases_s": {"kmeans_pp_seeding": res["seed_s"], "lloyd": res["lloyd_s"], "lloyd_iterations": res["iters"], "assign": res["assign_s"]},
+                "phases_s": {"kmeans_pp_seeding": res["seed_s"], "lloyd": res["lloyd_s"], "lloyd_iterations": res["iters"], "assign": res["assign_s"],
+                             "kmeans_pp_samples_skipped_by_triangle_rule / stopped_by_bf16_bound / rescored_exactly": list(res["pp_stats"])},
                 "roofline": roofline_d(args, world, ns_local, a_ms, a_n, args.steps + args.warmup, tf_peak, peak_src, res),
                 "list_sizes": {"min": int(lens.min()), "mean": float(lens.mean()), "max": int(lens.max()), "empty": int((lens == 0).sum())},
                 "recall_at_10": recall, "cpu_baseline": None,

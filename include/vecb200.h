@@ -296,6 +296,14 @@ int			vb_kmeans_pp_init(vb_table *samples, int kmeans_metric, void *centers, int
  * centre is sample first_row (RandomInt() % numSamples, src/ivfkmeans.c:36); u[i], i < k - 1, is the RandomDouble()
  * of round i (src/ivfkmeans.c:78).  picked_out (may be NULL): the k chosen sample rows.
  */
+/*
+ * On large fp32 sample tables the seeding touches a sample only when its weight could change (triangle inequality over
+ * the chosen centres, then a bf16 lower bound; exact fp32 re-score for the rest -- the weights and the picks are
+ * those of the full pass).  out3: samples skipped by the triangle rule / stopped by the bf16 bound / re-scored
+ * exactly during the last seeding of this process (all zero when the plain pass ran).  Option "pp_filter": 0 = never,
+ * 1 = automatic (default), 2 = always.
+ */
+int			vb_kmeans_pp_stats(int64_t *out3);
 int			vb_kmeans_pp_init_draws(vb_table *samples, int kmeans_metric, void *centers, int k, int64_t first_row,
 									const double *u, int64_t *picked_out);
 /*

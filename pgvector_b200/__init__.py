@@ -437,6 +437,13 @@ def kmeans_pp_init(samples: Table, kmeans_metric, k, seed=42):
     return centers
 
 
+def kmeans_pp_stats():
+    """(skipped by the triangle rule, stopped by the bf16 bound, re-scored exactly) of the last k-means++ seeding"""
+    out = np.zeros(3, dtype=np.int64)
+    _lib.check(load().vb_kmeans_pp_stats(_ptr(out)))
+    return tuple(int(x) for x in out)
+
+
 def kmeans_pp_init_draws(samples: Table, kmeans_metric, k, first_row, u):
     """InitCenters (src/ivfkmeans.c:23-91) with the caller's draws; returns (centres, picked sample rows)."""
     raw = (samples.dim + 7) // 8 if samples.elem == BIT else samples.dim

@@ -72,6 +72,7 @@ SIGNATURES = {
     "vb_ivf_tc_level1_fallbacks": (_i64, [_vp]),
     "vb_kmeans": (_i, [_vp, _i, _vp, _i, _i, _u64, _vp, _vp, _vp]),
     "vb_kmeans_pp_init": (_i, [_vp, _i, _vp, _i, _u64]),
+    "vb_kmeans_pp_stats": (_i, [_vp]),
     "vb_kmeans_pp_init_draws": (_i, [_vp, _i, _vp, _i, _i64, _vp, _vp]),
     "vb_assign": (_i, [_vp, _i, _vp, _i, _vp]),
     "vb_assign_dev": (_i, [_vp, _i, _vp, _i, _vp]),

@@ -54,11 +54,14 @@ def build_library(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
+    # link beside the target and rename: a snapshot of the tree (gpurun) never sees a half-written library
+    tmp = LIB + ".tmp"
+    cmd = [NVCC, "-shared", "-o", tmp, *objs, "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    os.replace(tmp, LIB)
     return LIB
 
 

@@ -349,6 +349,10 @@ int vb_set_option(const char* name, int64_t value) {
         vb::ctx().tc_level1 = value != 0;
         return VB_OK;
     }
+    if (!strcmp(name, "pp_filter")) {
+        vb::ctx().pp_filter = (int)value;
+        return VB_OK;
+    }
     if (!strcmp(name, "fused_refine")) {
         vb::ctx().fused_refine = value != 0;
         return VB_OK;

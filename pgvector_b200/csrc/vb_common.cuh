@@ -47,6 +47,8 @@ struct Context {
     cudaStream_t copy_stream = nullptr;
     int64_t launches = 0;
     int tc_level1 = 1;                 // batched list scan: try the hi-plane-only filter first (vb_set_option "tc_level1")
+    int pp_filter = 1;                 // k-means++ on large fp32 sample tables: triangle-inequality + bf16 filters in front of the exact distances
+    unsigned long long pp_stats[3] = {0, 0, 0};   // last seeding: samples skipped by the triangle rule / stopped by the bf16 bound / re-scored exactly
     int fused_refine = 1;              // tensor-core filter: k' select + exact re-score + certificate in ONE kernel (0 = the three-kernel path)
     int scan_impl = 2;                 // 0 = LDG variant (vb_scan.cu), 1 = bulk-copy / TMA variant (vb_scan_bulk.cu), 2 = by table size
     int hnsw_build_fraction = 64;      // HNSW build: a batch is at most 1/fraction of the elements already inserted

@@ -8,6 +8,8 @@
 // fp32 reassociation.  It is compute bound on the CUDA cores (2 ops per element for L2);
 // the tensor-core (tcgen05) assign in vb_assign_tc.cu uses it to re-check near ties.
 #include "vb_common.cuh"
+#include "vb_distance.cuh"
+#include <cuda_bf16.h>
 
 #include <cub/cub.cuh>
 
@@ -724,6 +726,174 @@ __global__ void pp_gather_rows_kernel(const uint8_t* __restrict__ X, size_t stri
     for (size_t b = threadIdx.x; b < bytes; b += blockDim.x) dst[b] = src[b];
 }
 
+// ---- k-means++ distance pass with two exact filters (vector, L2) ------------------------------------------------------
+//
+// Round i needs w[j] = min(w[j], d(x_j, c_i)^2) for every sample; the reference computes all n distances
+// (src/ivfkmeans.c:48-65, with a TODO to use the triangle inequality).  Here a sample is touched only when its weight
+// could change:
+//   1. triangle inequality over the chosen centres: d(x, c_i) >= d(c_near, c_i) - d(x, c_near), so
+//      d(c_near(x), c_i) >= 2 sqrt(w(x)) leaves w(x) alone -- no row is read at all (needs near[j] and the i
+//      centre-to-centre distances of the round);
+//   2. a bf16 copy of the samples (half the bytes): d(x, c_i) >= d(x^, c_i) - |x - x^|, with |x - x^| stored per row.
+// Only the samples that pass both are re-scored from their fp32 rows with the scan arithmetic, so the weights -- and the
+// rows picked from the same draws -- are exactly those of the full pass (margins of 1e-5 cover fp32 rounding of the
+// filter quantities; they only ever send a sample to the exact path, never past it).
+struct PpFilter {
+    __nv_bfloat16* xb = nullptr;   // [n][words] bf16 copy of the samples (words = padded dimension)
+    float* ex = nullptr;           // [n] |x - x^| (upper bound)
+    int32_t* near = nullptr;       // [n] chosen centre currently nearest
+    float* dcc = nullptr;          // [k] distance of the newest centre to every earlier one (lower bounds)
+    uint8_t* cent = nullptr;       // [k][stride] chosen centre rows
+    unsigned long long* stats = nullptr;   // [3] samples skipped by (1), stopped by (2), re-scored exactly
+    int words = 0;
+};
+
+__global__ void pp_prepare_bf16_kernel(const uint8_t* __restrict__ X, size_t stride, int words, int64_t n, __nv_bfloat16* __restrict__ xb,
+                                       float* __restrict__ ex) {
+    const int64_t j = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32;
+    const int lane = threadIdx.x % 32;
+    if (j >= n) return;
+    const float* x = reinterpret_cast<const float*>(X + (size_t)j * stride);
+    __nv_bfloat16* o = xb + (size_t)j * words;
+    float err = 0.f;
+    for (int t = lane; t < words; t += 32) {
+        const float v = x[t];
+        const __nv_bfloat16 b = __float2bfloat16_rn(v);
+        o[t] = b;
+        const float d = v - __bfloat162float(b);
+        err = fmaf(d, d, err);
+    }
+    for (int o2 = 16; o2 > 0; o2 >>= 1) err += __shfl_xor_sync(0xffffffffu, err, o2);
+    if (lane == 0) ex[j] = sqrtf(err) * 1.0001f + 1e-30f;
+}
+
+// distance of the newest centre (fp32 row `cq`) to the earlier centres: one warp each, scan arithmetic
+__global__ void pp_dcc_kernel(const uint8_t* __restrict__ cent, size_t stride, int V, const uint8_t* __restrict__ cq, int i,
+                              float* __restrict__ dcc) {
+    const int t = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32);
+    const int lane = threadIdx.x % 32;
+    if (t >= i) return;
+    const uint4* rp = reinterpret_cast<const uint4*>(cent + (size_t)t * stride);
+    const uint4* sq = reinterpret_cast<const uint4*>(cq);
+    Acc<VB_VECTOR, VB_L2_SQUARED> acc;
+    for (int v = lane; v < V; v += 32) acc.add(__ldg(rp + v), sq, v);
+    acc.template reduce<32>();
+    if (lane == 0) dcc[t] = sqrtf((float)acc.value()) * (1.f - 1e-5f);
+}
+
+constexpr int PPF_WARPS = 8;
+__global__ void __launch_bounds__(PPF_WARPS * 32) pp_filtered_pass_kernel(const uint8_t* __restrict__ X, size_t stride, int V, PpFilter f,
+                                                                          const uint8_t* __restrict__ cq, int i, int64_t n,
+                                                                          float* __restrict__ w, double* __restrict__ wd) {
+    extern __shared__ uint4 ppf_sq[];   // the newest centre: V vectors
+    for (int v = threadIdx.x; v < V; v += blockDim.x) ppf_sq[v] = reinterpret_cast<const uint4*>(cq)[v];
+    __syncthreads();
+    const int lane = threadIdx.x % 32;
+    const int64_t j = blockIdx.x * (int64_t)PPF_WARPS + threadIdx.x / 32;
+    if (j >= n) return;
+    const float wj = w[j];
+    const float sj = sqrtf(wj);
+    if (i > 0) {
+        if (f.dcc[f.near[j]] >= 2.0002f * sj) {
+            if (lane == 0) atomicAdd(&f.stats[0], 1ull);
+            return;
+        }
+        // bf16 lower bound: 8 elements per 16-byte load
+        const uint4* xb = reinterpret_cast<const uint4*>(f.xb + (size_t)j * f.words);
+        const float* c = reinterpret_cast<const float*>(ppf_sq);
+        float acc = 0.f;
+        for (int v = lane; v < f.words / 8; v += 32) {
+            const uint4 b = __ldg(xb + v);
+            const uint32_t u[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const float lo = __uint_as_float(u[t] << 16), hi = __uint_as_float(u[t] & 0xFFFF0000u);
+                const float d0 = lo - c[v * 8 + 2 * t], d1 = hi - c[v * 8 + 2 * t + 1];
+                acc = fmaf(d0, d0, acc);
+                acc = fmaf(d1, d1, acc);
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (sqrtf(acc) * (1.f - 1e-5f) - f.ex[j] >= sj * (1.f + 1e-5f)) {
+            if (lane == 0) atomicAdd(&f.stats[1], 1ull);
+            return;
+        }
+    }
+    // exact: the scan kernels' arithmetic (one row per warp pass), then the reference's weight rule (src/ivfkmeans.c:59-69)
+    const uint4* rp = reinterpret_cast<const uint4*>(X + (size_t)j * stride);
+    Acc<VB_VECTOR, VB_L2_SQUARED> a;
+    for (int v = lane; v < V; v += 32) a.add(ldg_stream(rp + v), ppf_sq, v);
+    a.template reduce<32>();
+    if (lane == 0) {
+        atomicAdd(&f.stats[2], 1ull);
+        double distance = sqrt((double)(float)a.value());
+        distance *= distance;
+        if (distance < (double)wj) {
+            const float nw = (float)distance;
+            w[j] = nw;
+            wd[j] = (double)nw;
+            f.near[j] = i;
+        }
+    }
+}
+
+__global__ void pp_fill_f64_kernel(double* p, int64_t n, double v) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+enum { WSK_XB = 27, WSK_FLT = 28, WSK_CENT = 29 };
+
+static bool pp_filter_applies(const Table& X, int kmeans_metric, int k) {
+    // the filters pay off once the sample table is much larger than L2 and there are enough rounds to amortise the bf16 copy
+    if (!ctx().pp_filter || X.elem != VB_VECTOR || kmeans_metric != VB_L2 || X.stride % 32 != 0) return false;
+    return ctx().pp_filter == 2 || (k >= 64 && (size_t)X.n * X.stride >= ((size_t)256 << 20));   // 2 = forced (tests)
+}
+
+static int pp_filter_prepare(const Table& X, int k, double* d_wd, PpFilter* f) {
+    cudaStream_t s = ctx().stream;
+    const int64_t n = X.n;
+    f->words = (int)(X.stride / 4);
+    void *p_xb, *p_flt, *p_cent;
+    VB_TRY(workspace(WSK_XB, sizeof(__nv_bfloat16) * (size_t)n * f->words, &p_xb));
+    VB_TRY(workspace(WSK_FLT, (sizeof(float) + sizeof(int32_t)) * (size_t)n + sizeof(float) * (size_t)k + 64, &p_flt));
+    VB_TRY(workspace(WSK_CENT, X.stride * (size_t)k, &p_cent));
+    f->xb = (__nv_bfloat16*)p_xb;
+    f->ex = (float*)p_flt;
+    f->near = (int32_t*)(f->ex + n);
+    f->dcc = (float*)(f->near + n);
+    f->stats = (unsigned long long*)((uint8_t*)(f->dcc + k) + ((8 - ((uintptr_t)(f->dcc + k) & 7)) & 7));
+    f->cent = (uint8_t*)p_cent;
+    VB_CUDA(cudaMemsetAsync(f->near, 0, sizeof(int32_t) * (size_t)n, s));
+    VB_CUDA(cudaMemsetAsync(f->stats, 0, 3 * sizeof(unsigned long long), s));
+    pp_prepare_bf16_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, s>>>(X.d, X.stride, f->words, n, f->xb, f->ex);
+    pp_fill_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_wd, n, 3.402823466e+38);
+    VB_CUDA(cudaGetLastError());
+    count_launch(2);
+    return VB_OK;
+}
+
+// round i of the seeding on this process's samples: the newest centre's fp32 row is at crow (device, padded stride)
+static int pp_filter_round(const Table& X, const PpFilter& f, const uint8_t* crow, int i, float* d_w, double* d_wd) {
+    cudaStream_t s = ctx().stream;
+    const int V = (int)(X.stride / 16);
+    VB_CUDA(cudaMemcpyAsync(f.cent + (size_t)i * X.stride, crow, X.stride, cudaMemcpyDeviceToDevice, s));
+    if (i > 0) pp_dcc_kernel<<<(unsigned)((i * 32 + 255) / 256), 256, 0, s>>>(f.cent, X.stride, V, crow, i, f.dcc);
+    if (X.n > 0) {
+        const size_t smem = X.stride;
+        static bool attr = false;
+        if (!attr && smem > 48 * 1024) {
+            VB_CUDA(cudaFuncSetAttribute(pp_filtered_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            attr = true;
+        }
+        pp_filtered_pass_kernel<<<(unsigned)((X.n + PPF_WARPS - 1) / PPF_WARPS), PPF_WARPS * 32, smem, s>>>(X.d, X.stride, V, f, crow, i, X.n, d_w,
+                                                                                                          d_wd);
+    }
+    VB_CUDA(cudaGetLastError());
+    count_launch(2);
+    return VB_OK;
+}
+
 static double host_uniform(uint64_t* st) {
     uint64_t z = (*st += 0x9e3779b97f4a7c15ULL);
     z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
@@ -769,13 +939,20 @@ static int kmeans_pp(const Table& X, int kmeans_metric, void* centers_host, int 
     VB_CUDA(cudaMemcpyAsync(d_u, u.data(), sizeof(double) * (size_t)k, cudaMemcpyHostToDevice, s));
     VB_CUDA(cudaMemcpyAsync(d_picks, &first, sizeof(int64_t), cudaMemcpyHostToDevice, s));
     VB_CUDA(cudaStreamSynchronize(s));  // the host vectors above go out of use here
+    const bool filtered = pp_filter_applies(X, kmeans_metric, k);
+    PpFilter flt;
+    if (filtered) VB_TRY(pp_filter_prepare(X, k, (double*)d_wd, &flt));
     for (int i = 0; i + 1 < k; ++i) {
         // distance of every sample to the newest centre: the scan kernel with that row as the query
         pp_gather_rows_kernel<<<1, 256, 0, s>>>(X.d, X.stride, (const int64_t*)d_picks + i, X.stride, X.stride, (uint8_t*)d_qraw);
-        size_t qstride;
-        VB_TRY(upload_queries(X.elem, X.dim, d_qraw, 1, false, WSK_QIMG, &d_q, &qstride));
-        VB_TRY(launch_scan_regular(X, km, d_q, qstride, 1, n, (float*)d_key, n));
-        pp_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)d_key, kmeans_metric, n, (float*)d_w, (double*)d_wd);
+        if (filtered) {
+            VB_TRY(pp_filter_round(X, flt, (const uint8_t*)d_qraw, i, (float*)d_w, (double*)d_wd));
+        } else {
+            size_t qstride;
+            VB_TRY(upload_queries(X.elem, X.dim, d_qraw, 1, false, WSK_QIMG, &d_q, &qstride));
+            VB_TRY(launch_scan_regular(X, km, d_q, qstride, 1, n, (float*)d_key, n));
+            pp_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)d_key, kmeans_metric, n, (float*)d_w, (double*)d_wd);
+        }
         VB_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, (double*)d_wd, (double*)d_cum, (int)n, s));
         pp_pick_kernel<<<1, 1, 0, s>>>((const double*)d_cum, n, (const double*)d_u + i, (int64_t*)d_picks + i + 1);
         count_launch(4);
@@ -784,6 +961,8 @@ static int kmeans_pp(const Table& X, int kmeans_metric, void* centers_host, int 
     count_launch(1);
     VB_CUDA(cudaMemcpyAsync(centers_host, d_out, raw * (size_t)k, cudaMemcpyDeviceToHost, s));
     if (picked_out) VB_CUDA(cudaMemcpyAsync(picked_out, d_picks, sizeof(int64_t) * (size_t)k, cudaMemcpyDeviceToHost, s));
+    if (filtered) VB_CUDA(cudaMemcpyAsync(c.pp_stats, flt.stats, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    else c.pp_stats[0] = c.pp_stats[1] = c.pp_stats[2] = 0;
     VB_CUDA(cudaStreamSynchronize(s));
     VB_CUDA(cudaGetLastError());
     return VB_OK;
@@ -906,6 +1085,11 @@ static int kmeans_pp_sharded(const Table& X, int kmeans_metric, void* centers_ho
     int64_t first_contrib = first_local >= 0 ? first : 0;
     VB_CUDA(cudaMemcpyAsync(d_gpick, &first_contrib, sizeof(int64_t), cudaMemcpyHostToDevice, s));
     VB_CUDA(cudaStreamSynchronize(s));   // the host vectors above go out of use here
+    // (every rank decides alike: the slices of a sharded sample set have the same shape; a rank without samples skips the pass)
+    const bool filtered = n > 0 && ctx().pp_filter && X.elem == VB_VECTOR && kmeans_metric == VB_L2 && X.stride % 32 == 0 &&
+                          (ctx().pp_filter == 2 || (k >= 64 && (size_t)n_total * X.stride >= ((size_t)256 << 20)));
+    PpFilter flt;
+    if (filtered) VB_TRY(pp_filter_prepare(X, k, (double*)d_wd, &flt));
     for (int i = 0; i < k; ++i) {
         // centre i: the owner's row reaches every rank
         pp_contribute_row_kernel<<<4, 256, 0, s>>>(X.d, X.stride, d_pick, (uint32_t*)d_row, words);
@@ -915,10 +1099,14 @@ static int kmeans_pp_sharded(const Table& X, int kmeans_metric, void* centers_ho
         count_launch();
         if (i + 1 == k) break;
         if (n > 0) {
-            size_t qstride;
-            VB_TRY(upload_queries(X.elem, X.dim, d_row, 1, false, WSK_QIMG, &d_q, &qstride));
-            VB_TRY(launch_scan_regular(X, km, d_q, qstride, 1, n, (float*)d_key, n));
-            pp_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)d_key, kmeans_metric, n, (float*)d_w, (double*)d_wd);
+            if (filtered) {
+                VB_TRY(pp_filter_round(X, flt, (const uint8_t*)d_row, i, (float*)d_w, (double*)d_wd));
+            } else {
+                size_t qstride;
+                VB_TRY(upload_queries(X.elem, X.dim, d_row, 1, false, WSK_QIMG, &d_q, &qstride));
+                VB_TRY(launch_scan_regular(X, km, d_q, qstride, 1, n, (float*)d_key, n));
+                pp_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)d_key, kmeans_metric, n, (float*)d_w, (double*)d_wd);
+            }
             VB_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, (double*)d_wd, (double*)d_cum, (int)n, s));
             count_launch(2);
         }
@@ -956,6 +1144,12 @@ int vb_kmeans_pp_init(vb_table* samples, int kmeans_metric, void* centers, int k
     // with a communicator the samples are this rank's slice of a row-sharded sample set: every rank gets the same centres
     if (comm_world() > 1) return kmeans_pp_sharded(samples->t, kmeans_metric, centers, k, seed, nullptr);
     return kmeans_pp(samples->t, kmeans_metric, centers, k, seed);
+}
+
+int vb_kmeans_pp_stats(int64_t* out3) {
+    VB_REQUIRE(out3, "null argument");
+    for (int i = 0; i < 3; ++i) out3[i] = (int64_t)ctx().pp_stats[i];
+    return VB_OK;
 }
 
 int vb_kmeans_pp_init_draws(vb_table* samples, int kmeans_metric, void* centers, int k, int64_t first_row, const double* u,

@@ -31,14 +31,16 @@ def build(force=False):
     import oracle
     oracle.build()
     if force or not os.path.exists(mock) or os.path.getmtime(mock) < newest:
-        cmd = ["gcc", *FLAGS, "-o", mock, *SRCS, os.path.join(HERE, "mock_abi.c"),
+        cmd = ["gcc", *FLAGS, "-o", mock + ".tmp", *SRCS, os.path.join(HERE, "mock_abi.c"),
                "-L" + os.path.join(ROOT, "oracle"), "-l:liboracle.so", "-Wl,-rpath,$ORIGIN/../../../oracle", "-lm"]
         subprocess.run(cmd, check=True, capture_output=True, text=True)
+        os.replace(mock + ".tmp", mock)
     lib = os.path.join(ROOT, "pgvector_b200", "libvecb200.so")
     if os.path.exists(lib) and (force or not os.path.exists(real) or os.path.getmtime(real) < newest):
-        cmd = ["gcc", *FLAGS, "-o", real, *SRCS, "-L" + os.path.dirname(lib), "-l:libvecb200.so",
+        cmd = ["gcc", *FLAGS, "-o", real + ".tmp", *SRCS, "-L" + os.path.dirname(lib), "-l:libvecb200.so",
                "-Wl,-rpath,$ORIGIN/../../../pgvector_b200", "-lm"]
         subprocess.run(cmd, check=True, capture_output=True, text=True)
+        os.replace(real + ".tmp", real)
     return os.path.exists(mock), os.path.exists(real)
 
 

@@ -199,3 +199,34 @@ def test_assign_tolerance_grows_with_the_row_length(pv):
     assert pv.last_assign_rechecked() >= 0
     assert np.array_equal(got, exact)
     assert _assign_agreement(O.HALFVEC, O.L2_SQUARED, rows, centers, got, dim=dim) >= 0.999
+
+
+@pytest.mark.parametrize("law", ["mixture", "low_rank"])
+def test_filtered_seeding_picks_exactly_what_the_full_pass_picks(pv, law):
+    """k-means++ with the triangle-inequality and bf16 filters in front of the exact distances (option pp_filter):
+    the weights are those of the full pass, so from the same draws the same rows are picked -- equal to the unfiltered
+    GPU pass and to the oracle -- while most samples are never re-scored."""
+    n, dim, k = 30000, 128, 96
+    rng = np.random.default_rng(17)
+    if law == "mixture":
+        rows, _ = _data(O.VECTOR, n, dim, k, seed=5)
+    else:
+        frame = np.linalg.qr(rng.standard_normal((dim, 8)))[0].astype(np.float32)
+        rows = (rng.standard_normal((n, 8)).astype(np.float32) @ frame.T + 0.02 * rng.standard_normal((n, dim))).astype(np.float32)
+    first = int(rng.integers(0, n))
+    u = rng.random(k - 1)
+    t = pv.Table(O.VECTOR, dim).append(rows)
+    try:
+        pv.set_option("pp_filter", 0)
+        c0, p0 = pv.kmeans_pp_init_draws(t, O.L2, k, first, u)
+        assert pv.kmeans_pp_stats() == (0, 0, 0)
+        pv.set_option("pp_filter", 2)
+        c2, p2 = pv.kmeans_pp_init_draws(t, O.L2, k, first, u)
+        skipped, stopped, exact = pv.kmeans_pp_stats()
+    finally:
+        pv.set_option("pp_filter", 1)
+    assert np.array_equal(p2, p0) and np.array_equal(c2, c0)
+    assert skipped + stopped + exact == n * (k - 1)
+    assert exact < 0.5 * n * (k - 1), (skipped, stopped, exact)
+    want_c, want_p = O.kmeans_pp_init_draws(O.VECTOR, O.L2, rows, k, first, u)
+    assert np.array_equal(p2, want_p)
