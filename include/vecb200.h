@@ -124,6 +124,14 @@ int			vb_distance_batch(int elem, int metric, int dim, const void *q,
 int			vb_norm_batch(int elem, int dim, const void *rows, int64_t n, double *out);
 int			vb_l2_normalize_batch(int elem, int dim, const void *rows, int64_t n, void *out);
 int			vb_binary_quantize_batch(int elem, int dim, const void *rows, int64_t n, uint8_t *out);
+/*
+ * The casts that feed halfvec / bit indexes from vector columns (README "half-precision indexing"):
+ *   vb_vector_to_halfvec_batch  vector_to_halfvec (src/halfvec.c:540-555): Float4ToHalf, round to nearest even; a finite
+ *                               value that overflows fails with the reference's text: "<value>" is out of range for type halfvec
+ *   vb_halfvec_to_vector_batch  halfvec_to_vector (src/vector.c halfvec_to_vector): exact widening
+ */
+int			vb_vector_to_halfvec_batch(int dim, const void *rows, int64_t n, void *out);
+int			vb_halfvec_to_vector_batch(int dim, const void *rows, int64_t n, void *out);
 
 /* ------------------------------------------------------ resident row tables */
 
@@ -247,6 +255,14 @@ int			vb_ivf_search_sharded_dev(vb_ivf *ix, const void *queries_dev, int64_t nq,
 /* The same with host buffers (queries in, int64 ids + float8 distances out; copies inside, synchronous). */
 int			vb_ivf_search_sharded(vb_ivf *ix, const void *queries, int64_t nq, int probes, int k,
 								  int64_t *out_ids, double *out_dist);
+
+/*
+ * Exact (no index) top-k over a row-sharded table: every rank scans its own rows (vb_exact_topk_dev), the per-rank k
+ * nearest are all-gathered and merged by (distance, id).  id_offset = the global number of this rank's first row.
+ * Collective; every rank gets the full result.
+ */
+int			vb_exact_topk_sharded_dev(vb_table *t, int metric, const void *queries_dev, int64_t nq, int k, int64_t id_offset,
+									  int64_t *out_ids_dev, float *out_dist_dev);
 
 /* --------------------------------------------------------------- communicator */
 

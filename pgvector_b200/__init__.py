@@ -227,6 +227,17 @@ class Table:
         _lib.check(load().vb_exact_topk(self.h, metric, _ptr(queries), nq, k, _ptr(ids), _ptr(dist)))
         return ids, dist
 
+    def exact_topk_sharded(self, metric, queries_dev, k, id_offset):
+        """exact top-k over a row-sharded table (collective over the library's communicator); torch CUDA tensors"""
+        import torch
+        nq = queries_dev.shape[0]
+        ids = torch.empty((nq, k), dtype=torch.int64, device=queries_dev.device)
+        dist = torch.empty((nq, k), dtype=torch.float32, device=queries_dev.device)
+        _after_torch(queries_dev)
+        _lib.check(load().vb_exact_topk_sharded_dev(self.h, metric, _ptr(queries_dev), nq, k, int(id_offset), _ptr(ids), _ptr(dist)))
+        synchronize()
+        return ids, dist
+
     def free(self):
         if self.h:
             load().vb_table_free(self.h)
@@ -621,6 +632,31 @@ def l2_normalize(rows, elem=VECTOR):
         if "overflow" in str(e):
             raise OverflowError("value out of range: overflow") from None
         raise
+    return out[0] if single else out
+
+
+def vector_to_halfvec(rows):
+    """vector::halfvec (src/halfvec.c:540-555): RNE to half bit patterns; raises like the reference on overflow"""
+    rows = _host(VECTOR, rows)
+    single = rows.ndim == 1
+    r2 = np.ascontiguousarray(rows.reshape(1, -1) if single else rows)
+    out = np.empty(r2.shape, dtype=np.uint16)
+    try:
+        _lib.check(load().vb_vector_to_halfvec_batch(r2.shape[1], _ptr(r2), r2.shape[0], _ptr(out)))
+    except VecB200Error as e:
+        if "out of range for type halfvec" in str(e):
+            raise ValueError(str(e).split(": ", 1)[1]) from None
+        raise
+    return out[0] if single else out
+
+
+def halfvec_to_vector(rows):
+    """halfvec::vector: exact widening"""
+    rows = _host(HALFVEC, rows)
+    single = rows.ndim == 1
+    r2 = np.ascontiguousarray(rows.reshape(1, -1) if single else rows)
+    out = np.empty(r2.shape, dtype=np.float32)
+    _lib.check(load().vb_halfvec_to_vector_batch(r2.shape[1], _ptr(r2), r2.shape[0], _ptr(out)))
     return out[0] if single else out
 
 

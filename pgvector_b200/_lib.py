@@ -33,6 +33,8 @@ SIGNATURES = {
     "vb_norm_batch": (_i, [_i, _i, _vp, _i64, _vp]),
     "vb_l2_normalize_batch": (_i, [_i, _i, _vp, _i64, _vp]),
     "vb_binary_quantize_batch": (_i, [_i, _i, _vp, _i64, _vp]),
+    "vb_vector_to_halfvec_batch": (_i, [_i, _vp, _i64, _vp]),
+    "vb_halfvec_to_vector_batch": (_i, [_i, _vp, _i64, _vp]),
     "vb_table_create": (_i, [_i, _i, C.POINTER(_vp)]),
     "vb_table_append": (_i, [_vp, _vp, _i64]),
     "vb_table_append_dev": (_i, [_vp, _vp, _i64]),
@@ -62,6 +64,7 @@ SIGNATURES = {
     "vb_ivf_tc_traffic": (_i, [_i, _vp]),
     "vb_ivf_search_sharded_dev": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
     "vb_ivf_search_sharded": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp]),
+    "vb_exact_topk_sharded_dev": (_i, [_vp, _i, _vp, _i64, _i, _i64, _vp, _vp]),
     "vb_comm_unique_id": (_i, [_vp, C.c_size_t]),
     "vb_comm_init": (_i, [_vp, _i, _i]),
     "vb_comm_free": (_i, []),

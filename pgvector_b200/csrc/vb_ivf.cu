@@ -1208,6 +1208,41 @@ int vb_ivf_search_sharded_dev(vb_ivf* h, const void* queries_dev, int64_t nq, in
     return VB_OK;
 }
 
+__global__ void add_id_offset_kernel(int64_t* ids, int64_t n, int64_t offset) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n && ids[i] >= 0) ids[i] += offset;
+}
+
+// Exact (no index) top-k over a row-sharded table: every rank scans its own rows, the per-rank k nearest
+// are all-gathered and merged by (distance, id).  id_offset = the global number of this rank's row 0.
+int vb_exact_topk_sharded_dev(vb_table* t, int metric, const void* queries_dev, int64_t nq, int k, int64_t id_offset, int64_t* out_ids_dev,
+                              float* out_dist_dev) {
+    VB_TRY(require_init());
+    VB_REQUIRE(t && queries_dev && out_ids_dev && out_dist_dev && k >= 1, "bad arguments");
+    if (nq <= 0) return VB_OK;
+    Context& c = ctx();
+    const int world = comm_world();
+    int P = 2;
+    while (P < world * k) P <<= 1;
+    VB_REQUIRE(P <= 4096, "sharded exact scan: world * k must not exceed 4096");
+    enum { WS_SH_RES = 25 };
+    void* d_res;
+    const size_t res_ids = sizeof(int64_t) * (size_t)nq * k, res_dist = sizeof(float) * (size_t)nq * k;
+    VB_TRY(workspace(WS_SH_RES, (res_ids + res_dist) * (size_t)(world + 1) + 256, &d_res));
+    int64_t* my_ids = (int64_t*)d_res;
+    float* my_dist = (float*)((uint8_t*)d_res + res_ids);
+    int64_t* all_ids = (int64_t*)((uint8_t*)d_res + res_ids + res_dist);
+    float* all_dist = (float*)((uint8_t*)all_ids + res_ids * (size_t)world);
+    VB_TRY(vb_exact_topk_dev(t, metric, queries_dev, nq, k, my_ids, my_dist));
+    add_id_offset_kernel<<<(unsigned)((nq * k + 255) / 256), 256, 0, c.stream>>>(my_ids, nq * k, id_offset);
+    VB_TRY(comm_allgather(my_ids, all_ids, (int64_t)res_ids));
+    VB_TRY(comm_allgather(my_dist, all_dist, (int64_t)res_dist));
+    merge_ranks_kernel<<<(unsigned)nq, 128, (size_t)P * 8, c.stream>>>(all_ids, all_dist, world, nq, k, P, out_ids_dev, out_dist_dev);
+    VB_CUDA(cudaGetLastError());
+    count_launch(2);
+    return VB_OK;
+}
+
 int vb_ivf_search_sharded(vb_ivf* h, const void* queries, int64_t nq, int probes, int k, int64_t* out_ids, double* out_dist) {
     VB_TRY(require_init());
     VB_REQUIRE(h && h->ix.loaded && queries && out_ids && out_dist && k >= 1, "bad search arguments");

@@ -8,6 +8,9 @@
 #include "vb_common.cuh"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 namespace vb {
 
@@ -73,7 +76,49 @@ __global__ void binary_quantize_kernel(const uint8_t* __restrict__ in, size_t in
     out[(size_t)r * out_stride + b] = v;
 }
 
+// vector -> halfvec (vector_to_halfvec, src/halfvec.c:540-555): Float4ToHalf = round to nearest even, and a finite value
+// that becomes infinite is an error (src/halfutils.h:244-261); the first offender in row-major order is reported
+__global__ void to_half_kernel(const float* __restrict__ in, int64_t total, __half* __restrict__ out, unsigned long long* __restrict__ first_bad) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float x = in[i];
+    const __half h = __float2half_rn(x);
+    out[i] = h;
+    if (__hisinf(h) != 0 && !isinf(x)) atomicMin(first_bad, (unsigned long long)i);
+}
+__global__ void to_float_kernel(const __half* __restrict__ in, int64_t total, float* __restrict__ out) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < total) out[i] = __half2float(in[i]);
+}
+
 enum { WSO_IN = 17, WSO_OUT = 18, WSO_FLAG = 19 };
+
+// the shortest decimal that reads back as the same float, in PostgreSQL's float4 output style
+// (float_to_shortest_decimal_buf: fixed notation for exponents -4 .. 14, scientific otherwise)
+static void shortest_float(float v, char* buf, size_t cap) {
+    char tmp[64];
+    int digits = 9;
+    for (int p = 1; p <= 9; ++p) {
+        snprintf(tmp, sizeof(tmp), "%.*e", p - 1, (double)v);
+        if (strtof(tmp, nullptr) == v) {
+            digits = p;
+            break;
+        }
+    }
+    snprintf(tmp, sizeof(tmp), "%.*e", digits - 1, (double)v);
+    const int exp10 = atoi(strchr(tmp, 'e') + 1);
+    if (exp10 >= -4 && exp10 < 15) {
+        const int frac = digits - 1 - exp10;
+        snprintf(buf, cap, "%.*f", frac > 0 ? frac : 0, (double)v);
+    } else {
+        // mantissa without trailing zeros, exponent as e+NN
+        char mant[32];
+        size_t m = (size_t)(strchr(tmp, 'e') - tmp);
+        memcpy(mant, tmp, m);
+        mant[m] = 0;
+        snprintf(buf, cap, "%se%c%02d", mant, exp10 < 0 ? '-' : '+', exp10 < 0 ? -exp10 : exp10);
+    }
+}
 
 static int stage_in(int elem, int dim, const void* rows, int64_t n, void** d_in) {
     const size_t raw = raw_row_bytes(elem, dim);
@@ -150,6 +195,50 @@ int vb_binary_quantize_batch(int elem, int dim, const void* rows, int64_t n, uin
     VB_CUDA(cudaGetLastError());
     count_launch();
     VB_CUDA(cudaMemcpyAsync(out, d_out, nb * (size_t)n, cudaMemcpyDeviceToHost, s));
+    VB_CUDA(cudaStreamSynchronize(s));
+    return VB_OK;
+}
+
+int vb_vector_to_halfvec_batch(int dim, const void* rows, int64_t n, void* out) {
+    VB_TRY(require_init());
+    VB_REQUIRE(dim > 0 && (rows || n == 0) && out, "bad cast arguments");
+    if (n <= 0) return VB_OK;
+    cudaStream_t s = ctx().stream;
+    const int64_t total = n * dim;
+    void *d_in, *d_out, *d_flag;
+    VB_TRY(stage_in(VB_VECTOR, dim, rows, n, &d_in));
+    VB_TRY(workspace(WSO_OUT, sizeof(__half) * (size_t)total, &d_out));
+    VB_TRY(workspace(WSO_FLAG, 64, &d_flag));
+    VB_CUDA(cudaMemsetAsync(d_flag, 0xFF, sizeof(unsigned long long), s));
+    to_half_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const float*)d_in, total, (__half*)d_out, (unsigned long long*)d_flag);
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    unsigned long long bad = ~0ull;
+    VB_CUDA(cudaMemcpyAsync(out, d_out, sizeof(__half) * (size_t)total, cudaMemcpyDeviceToHost, s));
+    VB_CUDA(cudaMemcpyAsync(&bad, d_flag, sizeof(bad), cudaMemcpyDeviceToHost, s));
+    VB_CUDA(cudaStreamSynchronize(s));
+    if (bad != ~0ull) {
+        char num[64];
+        shortest_float(reinterpret_cast<const float*>(rows)[bad], num, sizeof(num));
+        set_error("\"%s\" is out of range for type halfvec", num);
+        return VB_EINVAL;
+    }
+    return VB_OK;
+}
+
+int vb_halfvec_to_vector_batch(int dim, const void* rows, int64_t n, void* out) {
+    VB_TRY(require_init());
+    VB_REQUIRE(dim > 0 && (rows || n == 0) && out, "bad cast arguments");
+    if (n <= 0) return VB_OK;
+    cudaStream_t s = ctx().stream;
+    const int64_t total = n * dim;
+    void *d_in, *d_out;
+    VB_TRY(stage_in(VB_HALFVEC, dim, rows, n, &d_in));
+    VB_TRY(workspace(WSO_OUT, sizeof(float) * (size_t)total, &d_out));
+    to_float_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>((const __half*)d_in, total, (float*)d_out);
+    VB_CUDA(cudaGetLastError());
+    count_launch();
+    VB_CUDA(cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, s));
     VB_CUDA(cudaStreamSynchronize(s));
     return VB_OK;
 }

@@ -63,3 +63,22 @@ def test_random_rows_match_oracle(pv, elem, dim):
         assert np.mean(got == want) > 0.999 and np.allclose(got, want, rtol=2e-7, atol=0)
     assert not got[7].any()
     assert np.array_equal(pv.binary_quantize(rows, elem), O.binary_quantize(elem, rows))
+
+
+def test_vector_to_halfvec_cast(pv):
+    """vector::halfvec (src/halfvec.c:540-555, Float4ToHalf src/halfutils.h:244-261): RNE, equal to the reference's own
+    converter bit for bit, and the reference's error text when a finite value does not fit (test/expected/cast.out:268-269)"""
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.standard_normal(5000) * 100, [0.0, -0.0, 65504.0, -65504.0, 65519.0, 5.9604645e-08, 2.9802322e-08, 1e-10, np.inf, -np.inf],
+                        rng.standard_normal(2000) * 1e-5]).astype(np.float32).reshape(-1, 2)
+    got = pv.vector_to_halfvec(x)
+    want = np.array([O.lib().pgv_float_to_half(float(v)) for v in x.ravel()], dtype=np.uint16).reshape(x.shape)
+    assert np.array_equal(got, want)
+    back = pv.halfvec_to_vector(got)
+    assert np.array_equal(back, want.view(np.float16).astype(np.float32))
+    with pytest.raises(ValueError, match='"65520" is out of range for type halfvec'):
+        pv.vector_to_halfvec(np.array([[1.0, 2.0], [65520.0, -65520.0]], dtype=np.float32))
+    with pytest.raises(ValueError, match=r'"-4e\+38" is out of range for type halfvec'):
+        pv.vector_to_halfvec(np.array([1.0, -4e38, 7e4], dtype=np.float32))
+    with pytest.raises(ValueError, match='"100000" is out of range for type halfvec'):
+        pv.vector_to_halfvec(np.array([1e5], dtype=np.float32))

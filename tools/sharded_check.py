@@ -126,6 +126,12 @@ def main():
         shard.search_sharded_host_into(q.cpu().numpy(), kk, probes, hi, hd)
         say(f"host-buffer sharded search == device variant (scan_impl {impl})", bool(np.array_equal(hi, ids.cpu().numpy())))
     pv.set_option("scan_impl", 2)
+    # 5. exact scan over row-sharded tables == exact scan over the whole table
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    tl = pv.Table(pv.VECTOR, dim).append(samples[lo:hi])
+    e_ids, e_d = tl.exact_topk_sharded(pv.L2_SQUARED, q[:128].contiguous(), 10, lo)
+    w_ids, w_d = tf.exact_topk(pv.L2_SQUARED, q[:128].contiguous(), 10)
+    say("sharded exact scan == single", bool((e_ids == w_ids).float().mean().item() > 0.999 and torch.allclose(e_d, w_d, rtol=1e-6)))
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     pv.comm_free()
