@@ -354,7 +354,7 @@ int vb_set_option(const char* name, int64_t value) {
         return VB_OK;
     }
     if (!strcmp(name, "fused_refine")) {
-        vb::ctx().fused_refine = value != 0;
+        vb::ctx().fused_refine = (int)value;
         return VB_OK;
     }
     if (!strcmp(name, "hnsw_build_fraction")) {

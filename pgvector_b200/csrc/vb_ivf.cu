@@ -230,10 +230,15 @@ static int ivf_select_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t 
                               (float*)d_cdist, &qn, true));
         int n_failed = 0;
         if (!ix.defer_tc_check) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, sizeof(int), c.stream));
-        if (c.fused_refine) {
+        if (c.fused_refine == 2) {
             VB_TRY(launch_list_tc_select_refine(ix.centers, ix.ctc, km, qimg, qstride, nq, probes, kp, 1, zero_lists, pair_off, ix.d_centre_off,
                                                 (const float*)d_cdist, sb, sl, qn, lists, ldist, ix.d_tc_fail,
                                                 ix.defer_tc_check ? nullptr : &n_failed));
+        } else if (c.fused_refine == 1) {
+            VB_TRY(launch_segment_topk_v((const float*)d_cdist, sb, sl, nullptr, nullptr, nq, kp, pos_kp, key_kp));
+            VB_TRY(launch_list_tc_select_refine(ix.centers, ix.ctc, km, qimg, qstride, nq, probes, kp, 1, zero_lists, pair_off, ix.d_centre_off,
+                                                (const float*)d_cdist, sb, sl, qn, lists, ldist, ix.d_tc_fail,
+                                                ix.defer_tc_check ? nullptr : &n_failed, 2, pos_kp, key_kp));
         } else {
             VB_TRY(launch_segment_topk_v((const float*)d_cdist, sb, sl, nullptr, nullptr, nq, kp, pos_kp, key_kp));
             VB_TRY(launch_list_tc_refine(ix.centers, ix.ctc, km, qimg, qstride, nq, probes, kp, 1, zero_lists, pair_off, ix.d_centre_off, sl,
@@ -382,10 +387,15 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
             VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, 2 * sizeof(int), c.stream));
         }
         if (!ix.defer_tc_check) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail + 1, 0, sizeof(int), c.stream));
-        if (c.fused_refine) {
+        if (c.fused_refine == 2) {
             VB_TRY(launch_list_tc_select_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off,
                                                 (const float*)d_dist, seg_begin, seg_len, qn, pos, key, ix.d_tc_fail + 1,
                                                 ix.defer_tc_check ? nullptr : &n_failed, level));
+        } else if (c.fused_refine == 1) {
+            VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, nullptr, nullptr, nq, kp, pos_kp, key_kp));
+            VB_TRY(launch_list_tc_select_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off,
+                                                (const float*)d_dist, seg_begin, seg_len, qn, pos, key, ix.d_tc_fail + 1,
+                                                ix.defer_tc_check ? nullptr : &n_failed, level, pos_kp, key_kp));
         } else {
             VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, nullptr, nullptr, nq, kp, pos_kp, key_kp));
             VB_TRY(launch_list_tc_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off, seg_len, qn,

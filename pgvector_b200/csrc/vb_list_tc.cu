@@ -445,7 +445,9 @@ __global__ void __launch_bounds__(SR_WARPS * 32) select_refine_kernel(const uint
                                                                       const int32_t* __restrict__ probe_lists,
                                                                       const int32_t* __restrict__ cand_off,
                                                                       const int64_t* __restrict__ list_off, int32_t* __restrict__ out_pos,
-                                                                      float* __restrict__ out_key, int* __restrict__ n_failed) {
+                                                                      float* __restrict__ out_key, int* __restrict__ n_failed,
+                                                                      const int32_t* __restrict__ pre_pos,
+                                                                      const float* __restrict__ pre_key) {
     extern __shared__ uint4 sr_smem[];
     const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
     const int qvec = (int)(qstride / 16);
@@ -464,7 +466,23 @@ __global__ void __launch_bounds__(SR_WARPS * 32) select_refine_kernel(const uint
     uint64_t thr = ~0ull;                                   // current k'-th key
     const int kl = (kp - 1) % 32, kr = (kp - 1) / 32;
     constexpr int UNR = 4;
-    for (int base = 0; base < n; base += 32 * UNR) {
+    if (pre_pos != nullptr) {
+        // the k' nearest were selected by segment_topk_kernel (sorted by (distance, position), -1 padded): load them
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int i = r * 32 + lane;
+            if (i < kp) {
+                const int32_t p = pre_pos[q * kp + i];
+                if (p >= 0) top.key[r] = ((uint64_t)orderable_key(pre_key[q * kp + i]) << 32) | (uint32_t)p;
+            }
+        }
+        uint64_t t = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r == kr) t = __shfl_sync(0xffffffffu, top.key[r], kl);
+        thr = t;
+    }
+    for (int base = 0; pre_pos == nullptr && base < n; base += 32 * UNR) {
         float v[UNR];
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
@@ -822,7 +840,8 @@ int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metr
 int launch_list_tc_select_refine(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
                                  int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
                                  const float* dist, const int64_t* seg_begin, const int32_t* seg_len, const float* qn, int32_t* out_pos,
-                                 float* out_key, int* fail_dev, int* n_failed_host, int level) {
+                                 float* out_key, int* fail_dev, int* n_failed_host, int level, const int32_t* pre_pos,
+                                 const float* pre_key) {
     Context& c = ctx();
     cudaStream_t s = c.stream;
     const LcBound bound = lc_make_bound(rows, im, key_metric, level);
@@ -835,7 +854,8 @@ int launch_list_tc_select_refine(const Table& rows, const ListTcImage& im, int k
         auto kern = select_refine_kernel<E, M, RR>;                                                                                   \
         if (smem > 48 * 1024) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
         kern<<<grid, SR_WARPS * 32, smem, s>>>(rows.d, rows.stride, V, (const uint8_t*)qimg, qstride, nq, k, kp, probes, bound, qn, dist, \
-                                              seg_begin, seg_len, d_lists, cand_off, d_list_off, out_pos, out_key, fail_dev);         \
+                                              seg_begin, seg_len, d_lists, cand_off, d_list_off, out_pos, out_key, fail_dev, pre_pos, \
+                                              pre_key);                                                                              \
     } while (0)
 #define VB_SR(E, M)                   \
     do {                              \

@@ -315,9 +315,15 @@ __global__ void __launch_bounds__(1024) lt_group_kernel(const int32_t* __restric
     __shared__ int32_t carry;
     for (int i = threadIdx.x; i < n_lists; i += 1024) scnt[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n_pairs; i += 1024) {
-        const int l = probe_lists[i];
-        if (l >= 0) atomicAdd(&scnt[l], 1);
+    // (8 independent loads per thread in flight: one CTA walking 20 k pairs one dependent load at a time took 42 us)
+    constexpr int U = 8;
+    for (int i0 = threadIdx.x; i0 < n_pairs; i0 += 1024 * U) {
+        int l[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) l[u] = i0 + u * 1024 < n_pairs ? probe_lists[i0 + u * 1024] : -1;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (l[u] >= 0) atomicAdd(&scnt[l[u]], 1);
     }
     __syncthreads();
     lt_block_scan(scnt, n_lists, scur, warp_sum, &carry);
@@ -326,15 +332,24 @@ __global__ void __launch_bounds__(1024) lt_group_kernel(const int32_t* __restric
         begin[i] = scur[i];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_pairs; i += 1024) {
-        const int l = probe_lists[i];
-        if (l < 0) continue;
-        const int64_t q = i / probes;
-        const int p = i % probes;
-        const int slot = atomicAdd(&scur[l], 1);
-        pair_q[slot] = (int32_t)q;
-        pair_out[slot] = q * cap + cand_off[q * (probes + 1) + p];
-        pair_list[slot] = l;
+    for (int i0 = threadIdx.x; i0 < n_pairs; i0 += 1024 * U) {
+        int l[U], co[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * 1024;
+            l[u] = i < n_pairs ? probe_lists[i] : -1;
+            co[u] = i < n_pairs ? cand_off[(i / probes) * (probes + 1) + i % probes] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (l[u] < 0) continue;
+            const int i = i0 + u * 1024;
+            const int q = i / probes;
+            const int slot = atomicAdd(&scur[l[u]], 1);
+            pair_q[slot] = q;
+            pair_out[slot] = (int64_t)q * cap + co[u];
+            pair_list[slot] = l[u];
+        }
     }
     if (gt_rows > 0) {
         __syncthreads();

@@ -282,9 +282,23 @@ __global__ void __launch_bounds__(TOPK_THREADS) segment_topk_kernel(const float*
             __syncthreads();
             const int shift = pass * 8;
             const uint64_t prefix = s_prefix, mask = s_mask;
-            for (uint32_t i = tid; i < n; i += TOPK_THREADS) {
-                uint64_t key = composite_key(kp[i], i);
-                if ((key & mask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+            // warp-aggregated histogram: candidate distances of one query share their leading bytes, so without
+            // aggregation every thread of the CTA hammers the same shared-memory counter (measured: ~110 us per launch
+            // for 2048 x 10 k keys, most of it serialised atomics)
+            for (uint32_t base = 0; base < n; base += TOPK_THREADS) {
+                const uint32_t i = base + tid;
+                uint64_t key = 0;
+                bool in = false;
+                if (i < n) {
+                    key = composite_key(kp[i], i);
+                    in = (key & mask) == prefix;
+                }
+                const unsigned act = __ballot_sync(0xffffffffu, in);
+                if (in) {
+                    const uint32_t bin = (uint32_t)(key >> shift) & 255u;
+                    const unsigned peers = __match_any_sync(act, bin);
+                    if ((tid & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+                }
             }
             __syncthreads();
             if (tid == 0) {

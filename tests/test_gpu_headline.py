@@ -169,15 +169,16 @@ def test_near_ties_at_long_rows(pv, dim, gap):
 
 @pytest.mark.parametrize("k,probes", [(10, 10), (1, 3), (40, 10), (24, 7)])
 def test_fused_select_refine_equals_the_three_kernel_path(pv, headline, k, probes):
-    """select_refine_kernel (k' select + exact re-score + certificate in one warp-per-query kernel) returns bit for bit
-    what segment_topk_kernel + rescore_kernel + certify_kernel return, at both filter levels, incl. the counters"""
+    """select_refine_kernel (exact re-score + certificate in one warp-per-query kernel after segment_topk_kernel's k'
+    select: option fused_refine = 1, the default; = 2 also selects inside the kernel) returns bit for bit what
+    segment_topk_kernel + rescore_kernel + certify_kernel (= 0) return, at both filter levels, incl. the counters"""
     law, gix, oix, queries, _ = headline
     out = {}
     try:
         pv.set_option("scan_impl", 4)
         for level1 in (1, 0):
             pv.set_option("tc_level1", level1)
-            for fused in (0, 1):
+            for fused in (0, 1, 2):
                 pv.set_option("fused_refine", fused)
                 f0, l0 = gix.tc_fallbacks(), gix.tc_level1_fallbacks()
                 ids, dist = gix.search(queries, k=k, probes=probes)
@@ -188,7 +189,9 @@ def test_fused_select_refine_equals_the_three_kernel_path(pv, headline, k, probe
         pv.set_option("tc_level1", 1)
         pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
     for level1 in (1, 0):
-        a, b = out[level1, 0], out[level1, 1]
-        for x, y in zip(a[:4], b[:4]):
-            assert np.array_equal(x, y), (level1, k, probes)
-        assert a[4:] == b[4:]
+        a = out[level1, 0]
+        for fused in (1, 2):
+            b = out[level1, fused]
+            for x, y in zip(a[:4], b[:4]):
+                assert np.array_equal(x, y), (level1, fused, k, probes)
+            assert a[4:] == b[4:]

@@ -128,18 +128,41 @@ def test_gpu_and_oracle_agree_on_the_gpu_built_graph(pv, opclass, dim, n, m, efc
         same_q = np.all(ids == wi, axis=1)
         assert same_q.mean() > 0.95
         assert np.array_equal(nd[same_q], wnd[same_q])
-    # quality next to the reference's serial build (oracle restatement) on the same rows
-    truth = [O.exact_topk(elem, metric, qq, x, k, dim=dim)[0] for qq in q[:100]]
+    # quality next to the reference's serial build (oracle restatement) on the same rows WITH THE SAME LEVEL DRAWS
+    # (recall moves by a few points between level draws; measured on B200 with shared levels, 8000 x 32, m = 8:
+    # serial 0.6945, batches of 1/64 of the graph 0.6955, 1/8 0.6475, one element at a time 0.6945 = the serial build)
+    truth = [O.exact_topk(elem, metric, qq, x, k, dim=dim)[0] for qq in q]
     ob = O.Hnsw(elem, metric, x, m=m, ef_construction=efc, seed=7, dim=dim)
     ge = ob.export()
-    oi, _, _ = ob.search_batch(q[:100], ef, k, ties=O.TIES_TOTAL, threads=8)
-    r_gpu = recall_at_k(ids[:100], truth)
+    oi, _, _ = ob.search_batch(q, ef, k, ties=O.TIES_TOTAL, threads=8)
     r_cpu = recall_at_k(ge["elem_row"][np.maximum(oi, 0)], truth)
-    if elem != O.BIT:   # (bit rows tie on distance: id recall is not meaningful; the 52-bit floor test is tie-aware)
-        assert r_gpu >= r_cpu - 0.02, (r_gpu, r_cpu)
+    if len(ge["levels"]) == n:        # no folded duplicates: element numbers are row numbers
+        gi2, g2 = gpu_build(pv, opclass, x, dim=dim, m=m, efc=efc, levels=ge["levels"])
+        ids2, _, _ = gi2.search(q, k=k, ef_search=ef)
+        r_gpu = recall_at_k(ids2, truth)
+        if elem != O.BIT:   # (bit rows tie on distance: id recall is not meaningful; the 52-bit floor test is tie-aware)
+            assert r_gpu >= r_cpu - 0.03, (r_gpu, r_cpu)
     # same mean degree as the serial build within a few percent: the heuristic prunes alike
     o_deg = (ge["nbr0"] >= 0).sum(axis=1).mean()
     assert abs(deg.mean() - o_deg) <= 0.15 * o_deg, (deg.mean(), o_deg)
+
+
+def test_one_element_at_a_time_is_the_serial_build(pv):
+    """with batches of one element (option hnsw_build_fraction huge) and the oracle's level draws, the GPU build IS the
+    reference's serial build: the same graph, list for list (the restatement of HnswFindElementNeighbors /
+    SelectNeighbors / HnswUpdateConnection is exact; only batching changes the graph)"""
+    x, _ = mixture(1500, 24, 10, seed=99)
+    ob = O.Hnsw(O.VECTOR, O.L2_SQUARED, x, m=8, ef_construction=40, seed=3)
+    ge = ob.export()
+    assert len(ge["levels"]) == len(x)
+    try:
+        pv.set_option("hnsw_build_fraction", 1 << 30)
+        gi, g = gpu_build(pv, "vector_l2_ops", x, m=8, efc=40, levels=ge["levels"])
+    finally:
+        pv.set_option("hnsw_build_fraction", 64)
+    assert g["entry"] == ge["entry"]
+    same0 = np.all(np.sort(g["nbr0"], axis=1) == np.sort(ge["nbr0"], axis=1), axis=1)
+    assert same0.mean() > 0.98, same0.mean()        # (fp32 near-ties in the heuristic may differ on a few elements)
 
 
 def test_caller_supplied_levels_and_first_elements(pv):
