@@ -1013,13 +1013,16 @@ def run_hnsw(args):
         recall = float((got_d[:nr] <= exd.cpu().numpy()[:, -1:].astype(np.float64)).mean())
     wi, wd, wnd = og.search_batch(q_h[:n_par], ef, k, ties=O.TIES_TOTAL, threads=cores)
     same_q = np.all(got_i == wi, axis=1)
-    t0 = time.perf_counter()
-    reps = 0
-    while time.perf_counter() - t0 < args.cpu_seconds / 2 or reps == 0:
-        lo = (reps * 2048) % max(1, args.queries - 2048 + 1)
-        og.search_batch(q_h[lo:lo + 2048], ef, k, ties=O.TIES_PG, threads=cores)
-        reps += 1
-    cpu_qps = reps * min(2048, args.queries) / (time.perf_counter() - t0)
+    cpu_base = None
+    if not args.no_cpu:
+        t0 = time.perf_counter()
+        reps = 0
+        while time.perf_counter() - t0 < args.cpu_seconds / 2 or reps == 0:
+            lo = (reps * 2048) % max(1, args.queries - 2048 + 1)
+            og.search_batch(q_h[lo:lo + 2048], ef, k, ties=O.TIES_PG, threads=cores)
+            reps += 1
+        cpu_base = {"value": reps * min(2048, args.queries) / (time.perf_counter() - t0), "unit": "queries/s", "cores": cores, "kind": "port",
+                    "sample": f"{reps} batches of 2048 queries on the same graph, one query per thread (oracle port of src/hnswutils.c:824-987)"}
     peak, _, peak_src = measured_peaks()
     qps = env.world * args.steps * B / (ms / 1000)
     kern = k_ms / max(k_n, 1)
@@ -1035,8 +1038,7 @@ def run_hnsw(args):
                          "frac": moved / (kern / 1000) / 1e9 / peak, "traffic": moved,
                          "traffic_source": "n_dist (returned per query) x row bytes + one neighbour list per ~m distance evaluations (SURVEY 8d); gathers are 128-byte sectors",
                          "n_dist_per_query": nd_mean, "avg_launch_ms": kern, "share_of_step": kern * args.steps / ms},
-            "cpu_baseline": {"value": cpu_qps, "unit": "queries/s", "cores": cores, "kind": "port",
-                             "sample": f"{reps} batches of 2048 queries on the same graph, one query per thread (oracle port of src/hnswutils.c:824-987)"},
+            "cpu_baseline": cpu_base,
             "e2e": {"value": env.world * args.steps * B / (ms_h / 1000), "unit": "queries/s", "h2d_bytes_per_step": B * row_bytes, "d2h_bytes_per_step": B * (k * 16 + 8),
                     "ms_per_step": ms_h / args.steps, "call": "vb_hnsw_search"},
             "gpu_launches": int(launches), "clocks": clocks,

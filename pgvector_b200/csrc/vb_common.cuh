@@ -46,6 +46,7 @@ struct Context {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     int64_t launches = 0;
+    uint64_t query_epoch = 0;          // bumped by every upload_queries(): caches keyed on a query image are valid for one batch only
     int tc_level1 = 1;                 // batched list scan: try the hi-plane-only filter first (vb_set_option "tc_level1")
     int pp_filter = 1;                 // k-means++ on large fp32 sample tables: triangle-inequality + bf16 filters in front of the exact distances
     unsigned long long pp_stats[3] = {0, 0, 0};   // last seeding: samples skipped by the triangle rule / stopped by the bf16 bound / re-scored exactly

@@ -123,11 +123,11 @@ static int hnsw_launch_t(const HnswDev& g, const void* qimg, size_t qstride, int
         kern<<<grid, HN_WARPS * 32, smem, s>>>(g, (const uint8_t*)qimg, qstride, nq, ef, k, vis, vis_cap, vis_upper, out_ids, out_f, out_d, \
                                                out_nd, overflow);                                                        \
     } while (0)
+    // lanes per row: a whole warp for rows of >= 512 bytes; short rows take few lanes each so that the <= 32 neighbours of
+    // one expansion are gathered in ONE pass (GROUPS * RPI >= 16 rows) instead of four dependent ones
     if (g.V >= 32) VB_HL(32);
-    else if (g.V >= 16) VB_HL(16);
-    else if (g.V >= 8) VB_HL(8);
-    else if (g.V >= 4) VB_HL(4);
-    else if (g.V >= 2) VB_HL(2);
+    else if (g.V >= 16) VB_HL(4);
+    else if (g.V >= 8) VB_HL(2);
     else VB_HL(1);
 #undef VB_HL
     VB_CUDA(cudaGetLastError());

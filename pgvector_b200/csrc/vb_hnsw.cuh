@@ -116,12 +116,26 @@ __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* 
             uint32_t e = bid[min(bi, cnt - 1)] & 0x7fffffffu;
             rp[i] = reinterpret_cast<const uint4*>(g.rows + (size_t)e * g.stride);
         }
+        // register double buffering: the loads of step v + LPR are issued before the arithmetic of step v, so 2 * RPI
+        // independent 128-bit gathers per lane are in flight instead of one dependent round trip per step
+        uint4 cur[RPI];
+        if (gl < g.V) {
+#pragma unroll
+            for (int i = 0; i < RPI; ++i) cur[i] = ldg_stream(rp[i] + gl);
+        }
         for (int v = gl; v < g.V; v += LPR) {
-            uint4 x[RPI];
+            uint4 nxt[RPI];
+            const int vn = v + LPR;
+            if (vn < g.V) {
 #pragma unroll
-            for (int i = 0; i < RPI; ++i) x[i] = ldg_stream(rp[i] + v);
+                for (int i = 0; i < RPI; ++i) nxt[i] = ldg_stream(rp[i] + vn);
+            }
 #pragma unroll
-            for (int i = 0; i < RPI; ++i) acc[i].add(x[i], sq, v);
+            for (int i = 0; i < RPI; ++i) acc[i].add(cur[i], sq, v);
+            if (vn < g.V) {
+#pragma unroll
+                for (int i = 0; i < RPI; ++i) cur[i] = nxt[i];
+            }
         }
 #pragma unroll
         for (int i = 0; i < RPI; ++i) {

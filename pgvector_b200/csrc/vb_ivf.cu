@@ -102,10 +102,11 @@ __global__ void __launch_bounds__(128) ivf_build_chunks_kernel(const int32_t* __
         co[probes] = off;
         seg_begin[q] = (int64_t)q * cap;
         seg_len[q] = off;
-        s_base = atomicAdd(n_chunks, nch);
+        s_base = chunks ? atomicAdd(n_chunks, nch) : 0;
         atomicAdd((unsigned long long*)cand_sum, (unsigned long long)off);
     }
     __syncthreads();
+    if (chunks == nullptr) return;   // the list-major kernels take the probe lists directly: no descriptors needed
     // emit descriptors; per-probe chunk base via a serial prefix held by each thread (probes is small)
     int base = s_base;
     for (int p = 0; p < probes; ++p) {
@@ -344,8 +345,12 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
         VB_CUDA(cudaMalloc(&ix.d_cand_sum, sizeof(int64_t)));
         VB_CUDA(cudaMemsetAsync(ix.d_cand_sum, 0, sizeof(int64_t), c.stream));
     }
-    ivf_build_chunks_kernel<<<(unsigned)nq, 128, 0, c.stream>>>(d_lists, probes, ix.d_list_off, rpc, cap, cand_off, seg_begin,
-                                                               seg_len, chunks, n_chunks, ix.d_cand_sum);
+    // chunk descriptors are for the per-query scan kernels only; batched scans (tensor-core filter, list-major) skip them
+    const bool per_query_scan = !(list_major_supported(ix.elem, key_metric(ix.metric)) && ix.n_tiles > 0 &&
+                                  (c.scan_impl >= 3 || (c.scan_impl == 2 && nq * probes >= 256)));
+    ivf_build_chunks_kernel<<<(unsigned)nq, per_query_scan ? 128 : 32, 0, c.stream>>>(d_lists, probes, ix.d_list_off, rpc, cap, cand_off, seg_begin,
+                                                                                      seg_len, per_query_scan ? chunks : nullptr, n_chunks,
+                                                                                      ix.d_cand_sum);
     VB_CUDA(cudaGetLastError());
     count_launch();
     VB_TRY(workspace(WS_DIST, sizeof(float) * (size_t)nq * cap, &d_dist));

@@ -711,13 +711,27 @@ int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, con
     VB_TRY(workspace(WSC_N, sizeof(float) * (size_t)nq + 64, &d_qn));
     // the query image is fp32 with the rows' padded dimension count for both element types
     const int qdim = (int)(qstride / 4);
-    row_sqnorm_kernel<VB_VECTOR><<<(unsigned)((nq * 32 + 255) / 256), 256, 0, s>>>((const uint8_t*)qimg, qstride, nq, qdim, (float*)d_qn,
-                                                                                  nq, 0.f);
+    {
+        // |q|^2 of the batch: the probe selection and the list scan of one batch see the same query image -- compute once
+        static const void* qn_img = nullptr;
+        static int64_t qn_nq = 0;
+        static uint64_t qn_epoch = ~0ull;
+        static void* qn_buf = nullptr;
+        if (!(qn_img == qimg && qn_nq == nq && qn_epoch == c.query_epoch && qn_buf == d_qn)) {
+            row_sqnorm_kernel<VB_VECTOR><<<(unsigned)((nq * 32 + 255) / 256), 256, 0, s>>>((const uint8_t*)qimg, qstride, nq, qdim, (float*)d_qn,
+                                                                                          nq, 0.f);
+            count_launch();
+            qn_img = qimg;
+            qn_nq = nq;
+            qn_epoch = c.query_epoch;
+            qn_buf = d_qn;
+        }
+    }
     const int64_t chunks = g.n_pairs * im.n_kblocks * 8;
     pack_groups_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, s>>>((const float*)qimg, qstride, qdim, im.n_kblocks, g.n_pairs,
                                                                         g.pair_q, g.pair_list, g.begin, g.gt_begin, (uint8_t*)d_B);
     VB_CUDA(cudaGetLastError());
-    count_launch(2);
+    count_launch();
     static bool attr_set = false;
     if (!attr_set) {
         VB_CUDA(cudaFuncSetAttribute(list_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LC_SMEM));

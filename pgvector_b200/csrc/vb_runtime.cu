@@ -193,6 +193,7 @@ __global__ void query_image_kernel(int elem, int dim, const uint8_t* __restrict_
 int upload_queries(int elem, int dim, const void* queries, int64_t nq, bool host, int ws_slot, void** out_dev,
                    size_t* qstride) {
     Context& c = ctx();
+    ++c.query_epoch;
     const size_t raw = raw_row_bytes(elem, dim);
     const size_t pad = padded_row_bytes(elem, dim);
     // image stride: fp32 per element for vector/halfvec (halfvec padded to 8 elements -> 32 B of floats)
