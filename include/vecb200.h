@@ -399,6 +399,25 @@ int			vb_hnsw_search(vb_hnsw *h, const void *queries, int64_t nq, int ef, int k,
 int			vb_hnsw_search_dev(vb_hnsw *h, const void *queries_dev, int64_t nq, int ef, int k,
 							   int64_t *out_ids_dev, float *out_dist_dev, int64_t *out_ndist_dev);
 
+/*
+ * hnsw.iterative_scan (src/hnswscan.c:62-87 ResumeScanItems, :228-340 hnswgettuple) for nq queries at once.  The
+ * handle owns what the reference keeps in HnswScanOpaqueData between batches: the visited set `v`, the `discarded`
+ * candidates (rejected neighbours and evicted results, src/hnswutils.c:929-937, 968-973) and the `tuples` counter.
+ * vb_hnsw_scan_next returns, per query, the next batch nearest first: out_ids / out_distances [nq x ef_search]
+ * (-1 / +inf padded), out_counts [nq]; the first call is GetScanItems (:25-56), every later one resumes from the
+ * ef_search nearest discarded candidates on the same visited set, and once a query's tuples counter has reached
+ * max_scan_tuples (hnsw.max_scan_tuples, src/hnsw.c:101-105) its remaining discarded candidates come back nearest
+ * first, ef_search at a time, without searching (:247-254).  out_counts[q] == 0: that scan is exhausted.
+ * The sequence is hnsw.iterative_scan = relaxed_order's; strict_order is the caller's filter on it (:316-322).
+ * work_mem * hnsw.scan_mem_multiplier (:247) is not modelled: map it onto max_scan_tuples.
+ */
+typedef struct vb_hnsw_scan vb_hnsw_scan;
+int			vb_hnsw_scan_begin(vb_hnsw *h, const void *queries, int64_t nq, int ef_search, int64_t max_scan_tuples,
+							   vb_hnsw_scan **out);
+int			vb_hnsw_scan_next(vb_hnsw_scan *scan, int64_t *out_ids, double *out_distances, int32_t *out_counts);
+int			vb_hnsw_scan_tuples(vb_hnsw_scan *scan, int64_t *out_tuples);	/* [nq] the tuples counters */
+int			vb_hnsw_scan_end(vb_hnsw_scan *scan);
+
 #ifdef __cplusplus
 }
 #endif

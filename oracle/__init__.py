@@ -161,6 +161,8 @@ def _declare(L):
     L.pgv_hnsw_import.argtypes = [i32, i32, i32, i32, vp, i64, vp, vp, vp, vp, i64, i32]
     L.pgv_hnsw_search.restype = i32
     L.pgv_hnsw_search.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    L.pgv_hnsw_iter_scan.restype = i64
+    L.pgv_hnsw_iter_scan.argtypes = [vp, vp, i32, i32, i64, i64, vp, vp, vp, vp]
     L.pgv_hnsw_search_batch.restype = None
     L.pgv_hnsw_search_batch.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp, vp, vp]
 
@@ -398,6 +400,19 @@ class Hnsw:
         nd = C.c_int64()
         n = L.pgv_hnsw_search(self.h, _p(q), ef, ties, _p(ids), _p(dist), C.byref(nd))
         return ids[:n], dist[:n], nd.value
+
+    def iter_scan(self, q, ef, max_scan_tuples=20000, max_out=1 << 20, ties=TIES_PG):
+        """the element sequence of an iterative scan in relaxed order (src/hnswscan.c:62-87, 228-340):
+        (ids, distances, batch number of each output [-1 = the drain after max_scan_tuples], tuples counter)"""
+        L = lib()
+        q = None if q is None else _rows(self.elem, q)
+        max_out = int(min(max_out, max(1, L.pgv_hnsw_count(self.h))))
+        ids = np.empty(max_out, dtype=np.int64)
+        dist = np.empty(max_out, dtype=np.float64)
+        batch = np.empty(max_out, dtype=np.int32)
+        nd = C.c_int64()
+        n = L.pgv_hnsw_iter_scan(self.h, _p(q), ef, ties, max_scan_tuples, max_out, _p(ids), _p(dist), _p(batch), C.byref(nd))
+        return ids[:n], dist[:n], batch[:n], nd.value
 
     def search_batch(self, queries, ef, k, ties=TIES_PG, threads=1):
         L = lib()

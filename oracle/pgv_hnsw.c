@@ -180,6 +180,16 @@ cmp_furthest(const ph_node *a, const ph_node *b, void *arg)
 	return key_cmp(x->distance, x->element, y->distance, y->element, *(int *) arg);
 }
 
+/* CompareNearestDiscardedCandidates (hnswutils.c:641-651): the discarded heap links candidates through w_node */
+static int
+cmp_nearest_discarded(const ph_node *a, const ph_node *b, void *arg)
+{
+	const SearchCand *x = ph_container(SearchCand, w_node, a);
+	const SearchCand *y = ph_container(SearchCand, w_node, b);
+
+	return -key_cmp(x->distance, x->element, y->distance, y->element, *(int *) arg);
+}
+
 static inline double
 elem_distance(const PgvHnsw *g, const void *q, int32_t e)
 {
@@ -202,8 +212,24 @@ typedef struct
  * epoch set; initVisited bumps the epoch.  tuples may be NULL.
  */
 static CandList
+search_layer_x(const PgvHnsw *g, const void *q, CandList ep, int ef, int lc, int tie_total,
+			   uint32_t *visited, uint32_t epoch, int64_t *tuples, Arena *arena, ph_heap *discarded, int initVisited);
+
+static CandList
 search_layer(const PgvHnsw *g, const void *q, CandList ep, int ef, int lc, int tie_total,
 			 uint32_t *visited, uint32_t epoch, int64_t *tuples, Arena *arena)
+{
+	return search_layer_x(g, q, ep, ef, lc, tie_total, visited, epoch, tuples, arena, NULL, 1);
+}
+
+/*
+ * discarded (may be NULL): the iterative scan's heap of candidates that were seen but are not in W -- rejected
+ * neighbours (hnswutils.c:929-937) and candidates evicted from W (:968-973).  initVisited = 0 resumes on the visited
+ * set of the previous call: entry points are neither re-added nor counted (:864-873).
+ */
+static CandList
+search_layer_x(const PgvHnsw *g, const void *q, CandList ep, int ef, int lc, int tie_total,
+			   uint32_t *visited, uint32_t epoch, int64_t *tuples, Arena *arena, ph_heap *discarded, int initVisited)
 {
 	ph_heap		C,
 				W;
@@ -220,9 +246,12 @@ search_layer(const PgvHnsw *g, const void *q, CandList ep, int ef, int lc, int t
 	{
 		SearchCand *sc = ep.items[i];
 
-		visited[sc->element] = epoch;
-		if (tuples)
-			(*tuples)++;
+		if (initVisited)
+		{
+			visited[sc->element] = epoch;
+			if (tuples)
+				(*tuples)++;
+		}
 		ph_add(&C, &sc->c_node);
 		ph_add(&W, &sc->w_node);
 		wlen++;
@@ -271,7 +300,14 @@ search_layer(const PgvHnsw *g, const void *q, CandList ep, int ef, int lc, int t
 
 			/* eDistance < f->distance || alwaysAdd (hnswutils.c:913-936) */
 			if (!(key_cmp(eDistance, eid, f->distance, f->element, total) < 0 || alwaysAdd))
+			{
+				if (discarded)
+				{
+					e = arena_new(arena, eid, eDistance);
+					ph_add(discarded, &e->w_node);
+				}
 				continue;
+			}
 			/* hnswutils.c:949-950 */
 			if (g->el[eid].level < lc)
 				continue;
@@ -282,7 +318,12 @@ search_layer(const PgvHnsw *g, const void *q, CandList ep, int ef, int lc, int t
 			wlen++;
 			/* No need to decrement wlen (hnswutils.c:962-974) */
 			if (wlen > ef)
-				ph_remove_first(&W);
+			{
+				SearchCand *d = ph_container(SearchCand, w_node, ph_remove_first(&W));
+
+				if (discarded)
+					ph_add(discarded, &d->w_node);
+			}
 		}
 	}
 
@@ -353,6 +394,95 @@ pgv_hnsw_search(const PgvHnsw *g, const void *q, int ef, int tie_mode, int64_t *
 
 	free(visited);
 	return n;
+}
+
+/*
+ * The iterative scan as hnswgettuple drives it (hnswscan.c:228-340, relaxed order; the strict mode is a filter on
+ * this sequence, :316-322): the first batch is GetScanItems with the discarded heap (:25-56), every further batch
+ * ResumeScanItems (:62-87) from the ef nearest discarded candidates on the same visited set; once the tuples counter
+ * has reached max_scan_tuples the remaining discarded candidates are returned nearest first (:247-254).  (The
+ * work_mem bound of :247 is not modelled.)  Emits up to max_out elements; out_batch[i] = the batch that produced
+ * output i (-1: the final drain).  Returns the number emitted; *tuples_out = the counter.
+ */
+int64_t
+pgv_hnsw_iter_scan(const PgvHnsw *g, const void *q, int ef, int tie_mode, int64_t max_scan_tuples, int64_t max_out,
+				   int64_t *out_ids, double *out_dist, int32_t *out_batch, int64_t *tuples_out)
+{
+	Arena		arena = {0};
+	CandList	ep,
+				w;
+	int64_t		tuples = 0,
+				n_out = 0;
+	int			total = tie_mode == PGV_TIES_TOTAL_ORDER;
+	uint32_t   *visited;
+	uint32_t	epoch = 0;
+	ph_heap		discarded;
+	int32_t		batch = 0;
+
+	if (tuples_out)
+		*tuples_out = 0;
+	if (g->entry < 0)
+		return 0;
+	visited = calloc((size_t) g->n, sizeof(uint32_t));
+	ph_init(&discarded, cmp_nearest_discarded, &total);
+	ep.items = malloc(sizeof(SearchCand *));
+	ep.items[0] = arena_new(&arena, (int32_t) g->entry, elem_distance(g, q, (int32_t) g->entry));
+	ep.n = 1;
+	for (int lc = g->el[g->entry].level; lc >= 1; lc--)
+	{
+		epoch++;
+		w = search_layer(g, q, ep, 1, lc, total, visited, epoch, NULL, &arena);
+		free(ep.items);
+		ep = w;
+	}
+	epoch++;
+	w = search_layer_x(g, q, ep, ef, 0, total, visited, epoch, &tuples, &arena, &discarded, 1);
+	free(ep.items);
+
+	for (;;)
+	{
+		/* hnswgettuple pops llast(w): nearest first */
+		for (int i = w.n - 1; i >= 0 && n_out < max_out; i--)
+		{
+			out_ids[n_out] = w.items[i]->element;
+			out_dist[n_out] = w.items[i]->distance;
+			out_batch[n_out] = batch;
+			n_out++;
+		}
+		free(w.items);
+		w.items = NULL;
+		w.n = 0;
+		if (n_out >= max_out || ph_is_empty(&discarded))
+			break;
+		if (tuples >= max_scan_tuples)
+		{
+			/* return the remaining candidates one at a time, nearest first */
+			while (!ph_is_empty(&discarded) && n_out < max_out)
+			{
+				SearchCand *sc = ph_container(SearchCand, w_node, ph_remove_first(&discarded));
+
+				out_ids[n_out] = sc->element;
+				out_dist[n_out] = sc->distance;
+				out_batch[n_out] = -1;
+				n_out++;
+			}
+			break;
+		}
+		/* ResumeScanItems: the next batch_size = ef nearest discarded candidates are the entry points */
+		ep.items = malloc(sizeof(SearchCand *) * (size_t) ef);
+		ep.n = 0;
+		for (int i = 0; i < ef && !ph_is_empty(&discarded); i++)
+			ep.items[ep.n++] = ph_container(SearchCand, w_node, ph_remove_first(&discarded));
+		batch++;
+		w = search_layer_x(g, q, ep, ef, 0, total, visited, epoch, &tuples, &arena, &discarded, 0);
+		free(ep.items);
+	}
+	free(w.items);
+	free(visited);
+	arena_free(&arena);
+	if (tuples_out)
+		*tuples_out = tuples;
+	return n_out;
 }
 
 void

@@ -156,6 +156,9 @@ PgvHnsw *pgv_hnsw_import(int elem, int metric, int dim, int m, const void *rows,
  * returns number of results (<= ef); n_dist = the `tuples` counter (hnswutils.c:872,905). */
 int pgv_hnsw_search(const PgvHnsw *g, const void *q, int ef, int tie_mode,
 					int64_t *out_ids, double *out_dist, int64_t *n_dist);
+/* iterative scan (src/hnswscan.c:62-87, 228-340; relaxed order): see pgv_hnsw.c */
+int64_t pgv_hnsw_iter_scan(const PgvHnsw *g, const void *q, int ef, int tie_mode, int64_t max_scan_tuples, int64_t max_out,
+						   int64_t *out_ids, double *out_dist, int32_t *out_batch, int64_t *tuples_out);
 void pgv_hnsw_search_batch(const PgvHnsw *g, const void *queries, int64_t nq, int ef, int tie_mode,
 						   int threads, int k, int64_t *out_ids, double *out_dist, int64_t *n_dist);
 

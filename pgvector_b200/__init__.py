@@ -553,6 +553,11 @@ class HnswIndex:
         _lib.check(load().vb_hnsw_search_dev(self.h, _ptr(queries_dev), queries_dev.shape[0], int(ef), int(k),
                                              _ptr(ids_dev), _ptr(dist_dev), _ptr(nd_dev)))
 
+    def iterative_scan(self, queries, ef_search=None, max_scan_tuples=20000):
+        """hnsw.iterative_scan for a batch of queries: an HnswScan whose next_batch() mirrors ResumeScanItems
+        (src/hnswscan.c:62-87); max_scan_tuples mirrors hnsw.max_scan_tuples (src/hnsw.c:101-105)."""
+        return HnswScan(self, queries, int(ef_search or self.ef_search), int(max_scan_tuples))
+
     def free(self):
         if self.h:
             load().vb_hnsw_free(self.h)
@@ -561,6 +566,67 @@ class HnswIndex:
     def __del__(self):
         try:
             self.free()
+        except Exception:
+            pass
+
+
+class HnswScan:
+    """One iterative index scan per query (src/hnswscan.c:228-340): next_batch() returns (ids, distances, counts) of
+    the next <= ef_search elements of every query, nearest first; counts == 0 marks an exhausted scan."""
+
+    def __init__(self, index, queries, ef, max_scan_tuples):
+        q = _host(index.elem, queries)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        self.index, self.nq, self.ef = index, q.shape[0], ef
+        h = C.c_void_p()
+        _lib.check(load().vb_hnsw_scan_begin(index.h, _ptr(q), self.nq, ef, max_scan_tuples, C.byref(h)))
+        self.h = h
+
+    def next_batch(self):
+        ids = np.empty((self.nq, self.ef), dtype=np.int64)
+        dist = np.empty((self.nq, self.ef), dtype=np.float64)
+        cnt = np.empty(self.nq, dtype=np.int32)
+        _lib.check(load().vb_hnsw_scan_next(self.h, _ptr(ids), _ptr(dist), _ptr(cnt)))
+        return ids, dist, cnt
+
+    def tuples(self):
+        t = np.empty(self.nq, dtype=np.int64)
+        _lib.check(load().vb_hnsw_scan_tuples(self.h, _ptr(t)))
+        return t
+
+    def tuples_of(self, query=0, strict=False, limit=None):
+        """what hnswgettuple hands the executor for one query, in order: (element, distance) pairs; strict mirrors
+        hnsw.iterative_scan = strict_order (elements nearer than one already returned are skipped, :316-322)"""
+        out = []
+        prev = -np.inf
+        while limit is None or len(out) < limit:
+            ids, dist, cnt = self.next_batch()
+            if cnt[query] == 0:
+                break
+            for j in range(int(cnt[query])):
+                d = float(dist[query, j])
+                if strict:
+                    if d < prev:
+                        continue
+                    prev = d
+                out.append((int(ids[query, j]), d))
+        return out if limit is None else out[:limit]
+
+    def close(self):
+        if self.h:
+            load().vb_hnsw_scan_end(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
         except Exception:
             pass
 

@@ -92,6 +92,10 @@ SIGNATURES = {
     "vb_hnsw_export": (_i, [_vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp]),
     "vb_hnsw_search": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "vb_hnsw_search_dev": (_i, [_vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "vb_hnsw_scan_begin": (_i, [_vp, _vp, _i64, _i, _i64, C.POINTER(_vp)]),
+    "vb_hnsw_scan_next": (_i, [_vp, _vp, _vp, _vp]),
+    "vb_hnsw_scan_tuples": (_i, [_vp, _vp]),
+    "vb_hnsw_scan_end": (_i, [_vp]),
 }
 
 

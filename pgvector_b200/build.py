@@ -11,6 +11,8 @@ LIB = os.path.join(HERE, "libvecb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+# extra -D definitions for A/B builds on the GPU box (e.g. VB_NVCC_DEFS="VB_HNSW_MINB=6")
+FLAGS += ["-D" + d for d in os.environ.get("VB_NVCC_DEFS", "").split()]
 
 
 def sources():

@@ -25,7 +25,7 @@ namespace vb {
 
 // One warp = one query at a time.
 template <int ELEM, int METRIC, int LPR>
-__global__ void __launch_bounds__(HN_WARPS * 32) hnsw_search_kernel(HnswDev g, const uint8_t* __restrict__ queries, size_t qstride,
+__global__ void VB_HNSW_BOUNDS hnsw_search_kernel(HnswDev g, const uint8_t* __restrict__ queries, size_t qstride,
                                                                     int64_t nq, int ef, int k, uint32_t* __restrict__ vis_all,
                                                                     uint32_t vis_cap, uint32_t vis_upper, int64_t* __restrict__ out_ids,
                                                                     float* __restrict__ out_f, double* __restrict__ out_d,
@@ -219,11 +219,17 @@ static int hnsw_search_impl(Hnsw& h, const void* queries, int64_t nq, int ef, in
     int resident = 0;
     VB_TRY(hnsw_launch(h, g, qimg, qstride, nq, ef, k, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, &resident));
     const int grid = (int)std::min<int64_t>(want_ctas, (int64_t)c.sm_count * std::max(1, resident));
-    // layer-0 table: generous for ef * 2m insertions per expansion wave; grows on overflow
-    uint32_t cap = 1u << 14;
-    while (cap < (uint32_t)(ef * h.m * 16) && cap < (1u << 22)) cap <<= 1;
+    // layer-0 table: a search visits a few multiples of ef elements (about 20 ef at m = 16), and the table may fill to
+    // half; it is cleared once per query, so it is sized tightly (the clears were 37 % of the round-1 kernel's DRAM
+    // traffic at 16 ef m) and grows on overflow -- the grown size is remembered per ef_search
+    uint32_t cap = 1u << 12;
+    while (cap < (uint32_t)(ef * h.m * 4) && cap < (1u << 22)) cap <<= 1;
+    if (h.vis_hint_ef == ef && h.vis_hint_cap > cap) cap = h.vis_hint_cap;
+    // the ef = 1 upper layers visit a few neighbour lists each
+    uint32_t vis_upper = 1024;
+    while (vis_upper < (uint32_t)(h.m * 16)) vis_upper <<= 1;
     for (int attempt = 0; attempt < 6; ++attempt) {
-        const uint32_t vis_upper = std::max<uint32_t>(2048u, cap / 8);
+        if (attempt > 0) vis_upper = std::max<uint32_t>(vis_upper, cap / 8);
         const uint32_t vis_cap = cap + vis_upper;
         const size_t need = (size_t)grid * HN_WARPS * vis_cap * sizeof(uint32_t);
         if (h.vis_bytes < need) {
@@ -251,6 +257,8 @@ static int hnsw_search_impl(Hnsw& h, const void* queries, int64_t nq, int ef, in
         VB_CUDA(cudaStreamSynchronize(s));
         if (!flag) break;
         cap <<= 2;   // visited table overflowed for some query: retry everything with a larger one
+        h.vis_hint_ef = ef;
+        h.vis_hint_cap = cap;
         VB_REQUIRE(attempt < 5, "hnsw: visited set overflow");
     }
     if (host) {

@@ -43,6 +43,8 @@ struct Hnsw {
     bool loaded = false;
     uint32_t* vis = nullptr;  // visited hash tables, one per resident warp
     size_t vis_bytes = 0;
+    int vis_hint_ef = 0;        // the last ef_search whose layer-0 table had to grow, and the size it grew to
+    uint32_t vis_hint_cap = 0;
     // build-side state (vb_hnsw_build.cu); nd0 / upper_d hold the distance stored with every neighbour
     // (HnswCandidate.distance, src/hnsw.h:143-148), dup_of the element a duplicate row was folded into
     float *nd0 = nullptr, *upper_d = nullptr;
@@ -53,6 +55,18 @@ struct Hnsw {
 void hnsw_release(Hnsw& h);
 
 constexpr int HN_WARPS = 4;             // queries (or inserted elements) per CTA
+
+// Resident CTAs per SM the register allocation aims for.  Without the second __launch_bounds__ argument ptxas picks a
+// target of its own per instantiation (56 .. 128 registers, the narrow-row ones with spills); the kernel waits on
+// dependent gathers, so resident warps matter more than a spill-free loop -- measured, see profiles/r2_hnsw_minb.md.
+#ifndef VB_HNSW_MINB
+#define VB_HNSW_MINB 6
+#endif
+#if VB_HNSW_MINB > 0
+#define VB_HNSW_BOUNDS __launch_bounds__(HN_WARPS * 32, VB_HNSW_MINB)
+#else
+#define VB_HNSW_BOUNDS __launch_bounds__(HN_WARPS * 32)
+#endif
 constexpr uint32_t VIS_EMPTY = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t hash_u32(uint32_t x) {
@@ -155,28 +169,163 @@ struct HnswWarpState {
     int len;
 };
 
+// The iterative scan's `discarded` heap (src/hnswscan.c:62-87, src/hnswutils.c:929-937, 968-973) as an append-only
+// array of one query: candidates that were seen but are not in R -- rejected neighbours and elements R evicted.
+struct HnswSink {
+    uint64_t* key;
+    uint32_t* id;
+    int len;            // may run past cap: the caller reports the overflow
+    int cap;
+    uint32_t inserted;  // entries in the (persistent) visited table
+};
+
+__device__ __forceinline__ void hnsw_sink_append(HnswSink& d, bool have, uint64_t k, uint32_t id, int lane) {
+    const unsigned m = __ballot_sync(0xffffffffu, have);
+    if (m == 0) return;
+    const int p = d.len + __popc(m & ((1u << lane) - 1u));
+    if (have && p < d.cap) {
+        d.key[p] = k;
+        d.id[p] = id & 0x7fffffffu;
+    }
+    d.len += __popc(m);
+}
+
+// R <- the efl nearest of R and the batch bkey / bid [0..cnt) (unsorted, unexpanded); everything that does not stay
+// goes to the sink when ITER.  Once R holds efl elements, an entry that is not nearer than R's last one cannot be
+// admitted ("eDistance < f->distance || alwaysAdd", src/hnswutils.c:927-938): those are dropped before the sort, and
+// the sort and the merge are skipped altogether when nothing is left -- the common case once a search has converged.
+template <bool ITER>
+__device__ __forceinline__ void hnsw_merge_batch(HnswWarpState& S, int cnt, int efl, int lane, HnswSink* sink) {
+    int cnt_in = cnt;
+    if (S.len == efl) {
+        const uint64_t wk = S.rk[efl - 1];
+        const uint32_t wi = S.ri[efl - 1];
+        const uint64_t k0 = lane < cnt ? S.bkey[lane] : 0;
+        const uint32_t i0 = lane < cnt ? S.bid[lane] : 0;
+        const bool keep = lane < cnt && ent_less(k0, i0, wk, wi);
+        const unsigned km = __ballot_sync(0xffffffffu, keep);
+        cnt_in = __popc(km);
+        if (ITER) hnsw_sink_append(*sink, lane < cnt && !keep, k0, i0, lane);
+        if (cnt_in == 0) return;
+        if (cnt_in < cnt) {
+            __syncwarp();
+            if (keep) {
+                const int p = __popc(km & ((1u << lane) - 1u));
+                S.bkey[p] = k0;
+                S.bid[p] = i0;
+            }
+            __syncwarp();
+        }
+    }
+    // sort the batch by (key, id): bitonic over 32 lanes, empty lanes = +inf
+    uint64_t mk = lane < cnt_in ? S.bkey[lane] : ~0ull;
+    uint32_t mi = lane < cnt_in ? S.bid[lane] : 0x7fffffffu;
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int st = size >> 1; st > 0; st >>= 1) {
+            uint64_t ok = __shfl_xor_sync(0xffffffffu, mk, st);
+            uint32_t oi = __shfl_xor_sync(0xffffffffu, mi, st);
+            bool up = (lane & size) == 0;
+            bool lower = (lane & st) == 0;
+            bool other_less = ent_less(ok, oi, mk, mi);
+            // keep min in the lower lane of an ascending pair, max otherwise
+            bool take = (lower == up) ? other_less : !other_less;
+            if (take) {
+                mk = ok;
+                mi = oi;
+            }
+        }
+    }
+    __syncwarp();
+    if (lane < cnt_in) {
+        S.bkey[lane] = mk;
+        S.bid[lane] = mi;
+    }
+    __syncwarp();
+
+    // merge R (len, sorted) with the batch (cnt_in, sorted) into the other buffer, keep efl
+    const int len = S.len;
+    for (int j0 = 0; j0 < len; j0 += 32) {
+        const int j = j0 + lane;
+        const bool act = j < len;
+        uint64_t kj = 0;
+        uint32_t ij = 0;
+        int np = 0;
+        if (act) {
+            kj = S.rk[j];
+            ij = S.ri[j];
+            int lo = 0, hi = cnt_in;   // number of batch elements < R[j]
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (ent_less(S.bkey[mid], S.bid[mid], kj, ij)) lo = mid + 1;
+                else hi = mid;
+            }
+            np = j + lo;
+            if (np < efl) {
+                S.nk[np] = kj;
+                S.ni[np] = ij;
+            }
+        }
+        if (ITER) hnsw_sink_append(*sink, act && np >= efl, kj, ij, lane);
+    }
+    {
+        int np = 0;
+        if (lane < cnt_in) {
+            int lo = 0, hi = len;   // number of R elements < batch[lane]
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (ent_less(S.rk[mid], S.ri[mid], mk, mi)) lo = mid + 1;
+                else hi = mid;
+            }
+            np = lane + lo;
+            if (np < efl) {
+                S.nk[np] = mk;
+                S.ni[np] = mi;     // unexpanded
+            }
+        }
+        if (ITER) hnsw_sink_append(*sink, lane < cnt_in && np >= efl, mk, mi, lane);
+    }
+    __syncwarp();
+    S.len = min(efl, len + cnt_in);
+    uint64_t* tk = S.rk;
+    S.rk = S.nk;
+    S.nk = tk;
+    uint32_t* ti = S.ri;
+    S.ri = S.ni;
+    S.ni = ti;
+}
+
 // HnswSearchLayer (src/hnswutils.c:824-987) at layer lc with ef = efl from the entry points already in R
 // (S.len of them, sorted).  tab / cap: this layer's visited table (cleared here, InitVisited :671-680).
 // ndist (may be null) accumulates the reference's `tuples` counter (:866-873, 905-906).  Returns false when the
 // visited table filled beyond half (the caller retries with a larger one).
-template <int ELEM, int METRIC, int LPR>
+// ITER: the iterative scan's variant -- everything seen and not kept goes to `sink`; init_visited = false resumes on
+// the visited table of the previous call (entry points are neither re-added nor counted, :864-873).
+template <int ELEM, int METRIC, int LPR, bool ITER = false>
 __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4* sq, int lc, int efl, int lane, HnswWarpState& S,
-                                                  uint32_t* tab, uint32_t cap, int64_t* ndist) {
+                                                  uint32_t* tab, uint32_t cap, int64_t* ndist, HnswSink* sink = nullptr,
+                                                  bool init_visited = true) {
     const int lm = lc == 0 ? 2 * g.m : g.m;
     const uint32_t mask = cap - 1;
-    for (uint32_t i = lane; i < cap; i += 32) tab[i] = VIS_EMPTY;
-    __syncwarp();
     uint32_t inserted = 0;
-    // entry points: visited, unexpanded; they count towards `tuples` (src/hnswutils.c:866-873)
-    if (S.len > efl) S.len = efl;   // ef shrinks only between an ef_construction layer and ... never; kept for safety
-    for (int i = lane; i < S.len; i += 32) {
-        S.ri[i] &= 0x7fffffffu;
-        vis_insert(tab, mask, S.ri[i]);
+    if (!ITER || init_visited) {
+        for (uint32_t i = lane; i < cap; i += 32) tab[i] = VIS_EMPTY;
+        __syncwarp();
+        // entry points: visited, unexpanded; they count towards `tuples` (src/hnswutils.c:866-873)
+        if (S.len > efl) S.len = efl;   // ef shrinks only between an ef_construction layer and ... never; kept for safety
+        for (int i = lane; i < S.len; i += 32) {
+            S.ri[i] &= 0x7fffffffu;
+            vis_insert(tab, mask, S.ri[i]);
+        }
+        inserted += (uint32_t)S.len;
+        if (ndist) *ndist += S.len;
+        __syncwarp();
+    } else {
+        inserted = sink->inserted;
     }
-    inserted += (uint32_t)S.len;
-    if (ndist) *ndist += S.len;
-    __syncwarp();
 
+    bool ok = true;
     for (;;) {
         // nearest unexpanded element of R
         int first = 0x7fffffff;
@@ -225,103 +374,17 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
             hnsw_score_batch<ELEM, METRIC, LPR>(g, sq, S.bid, cnt, S.bkey, lane);
             __syncwarp();
 
-            // Once R holds ef elements, a neighbour that is not nearer than R's last one cannot be admitted
-            // ("eDistance < f->distance || alwaysAdd", src/hnswutils.c:927-938): drop those before the sort, and skip
-            // the sort and the merge altogether when nothing is left -- the common case once the search has converged.
-            int cnt_in = cnt;
-            if (S.len == efl) {
-                const uint64_t wk = S.rk[efl - 1];
-                const uint32_t wi = S.ri[efl - 1];
-                const uint64_t k0 = lane < cnt ? S.bkey[lane] : 0;
-                const uint32_t i0 = lane < cnt ? S.bid[lane] : 0;
-                const bool keep = lane < cnt && ent_less(k0, i0, wk, wi);
-                const unsigned km = __ballot_sync(0xffffffffu, keep);
-                cnt_in = __popc(km);
-                if (cnt_in == 0) {
-                    if (first_inval < 32) break;
-                    continue;
-                }
-                if (cnt_in < cnt) {
-                    __syncwarp();
-                    if (keep) {
-                        const int p = __popc(km & ((1u << lane) - 1u));
-                        S.bkey[p] = k0;
-                        S.bid[p] = i0;
-                    }
-                    __syncwarp();
-                }
-            }
-            // sort the batch by (key, id): bitonic over 32 lanes, empty lanes = +inf
-            uint64_t mk = lane < cnt_in ? S.bkey[lane] : ~0ull;
-            uint32_t mi = lane < cnt_in ? S.bid[lane] : 0x7fffffffu;
-#pragma unroll
-            for (int size = 2; size <= 32; size <<= 1) {
-#pragma unroll
-                for (int st = size >> 1; st > 0; st >>= 1) {
-                    uint64_t ok = __shfl_xor_sync(0xffffffffu, mk, st);
-                    uint32_t oi = __shfl_xor_sync(0xffffffffu, mi, st);
-                    bool up = (lane & size) == 0;
-                    bool lower = (lane & st) == 0;
-                    bool other_less = ent_less(ok, oi, mk, mi);
-                    // keep min in the lower lane of an ascending pair, max otherwise
-                    bool take = (lower == up) ? other_less : !other_less;
-                    if (take) {
-                        mk = ok;
-                        mi = oi;
-                    }
-                }
-            }
-            __syncwarp();
-            if (lane < cnt_in) {
-                S.bkey[lane] = mk;
-                S.bid[lane] = mi;
-            }
-            __syncwarp();
-
-            // merge R (len, sorted) with the batch (cnt_in, sorted) into the other buffer, keep efl
-            const int len = S.len;
-            for (int j = lane; j < len; j += 32) {
-                uint64_t kj = S.rk[j];
-                uint32_t ij = S.ri[j];
-                int lo = 0, hi = cnt_in;   // number of batch elements < R[j]
-                while (lo < hi) {
-                    int mid = (lo + hi) >> 1;
-                    if (ent_less(S.bkey[mid], S.bid[mid], kj, ij)) lo = mid + 1;
-                    else hi = mid;
-                }
-                int np = j + lo;
-                if (np < efl) {
-                    S.nk[np] = kj;
-                    S.ni[np] = ij;
-                }
-            }
-            if (lane < cnt_in) {
-                int lo = 0, hi = len;   // number of R elements < batch[lane]
-                while (lo < hi) {
-                    int mid = (lo + hi) >> 1;
-                    if (ent_less(S.rk[mid], S.ri[mid], mk, mi)) lo = mid + 1;
-                    else hi = mid;
-                }
-                int np = lane + lo;
-                if (np < efl) {
-                    S.nk[np] = mk;
-                    S.ni[np] = mi;     // unexpanded
-                }
-            }
-            __syncwarp();
-            S.len = min(efl, len + cnt_in);
-            uint64_t* tk = S.rk;
-            S.rk = S.nk;
-            S.nk = tk;
-            uint32_t* ti = S.ri;
-            S.ri = S.ni;
-            S.ni = ti;
+            hnsw_merge_batch<ITER>(S, cnt, efl, lane, sink);
             if (first_inval < 32) break;
         }
         // keep the table at most half full; otherwise report and let the host retry with a larger one
-        if (inserted > cap / 2) return false;
+        if (inserted > cap / 2) {
+            ok = false;
+            break;
+        }
     }
-    return true;
+    if (ITER) sink->inserted = inserted;
+    return ok;
 }
 
 }  // namespace vb

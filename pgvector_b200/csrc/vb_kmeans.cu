@@ -718,6 +718,51 @@ __global__ void pp_pick_kernel(const double* __restrict__ cum, int64_t n, const 
     *picked = lo;
 }
 
+// pp_pick_kernel's search with 256 probes per step (three dependent steps for 2 * 10^5 samples instead of eighteen), then
+// the picked row is copied to `row_out` (16-byte words) by the same CTA: one launch per round instead of two.
+__global__ void __launch_bounds__(256) pp_pick_gather_kernel(const double* __restrict__ cum, int64_t n, const double* __restrict__ u,
+                                                             int64_t* __restrict__ picked, const uint8_t* __restrict__ X, size_t stride,
+                                                             uint8_t* __restrict__ row_out) {
+    __shared__ int64_t s_lo, s_hi;
+    __shared__ int s_first;
+    const int t = threadIdx.x;
+    const double choice = cum[n - 1] * u[0];
+    if (t == 0) {
+        s_lo = 0;
+        s_hi = n - 1;
+    }
+    __syncthreads();
+    for (;;) {
+        const int64_t lo = s_lo, hi = s_hi;   // the answer (smallest j with cum[j] >= choice, else n - 1) is in [lo, hi]
+        if (lo >= hi) break;
+        const int64_t step = (hi - lo + 255) / 256;
+        const int64_t p = min(hi, lo + (int64_t)t * step);
+        const bool ge = cum[p] >= choice;
+        if (t == 0) s_first = 256;
+        __syncthreads();
+        if (ge) atomicMin(&s_first, t);
+        __syncthreads();
+        const int first = s_first;
+        __syncthreads();
+        if (t == 0) {
+            if (first == 0) {
+                s_hi = lo;
+            } else if (first == 256) {
+                s_lo = min(hi, min(hi, lo + 255 * step) + 1);
+            } else {
+                s_lo = min(hi, lo + (int64_t)(first - 1) * step) + 1;
+                s_hi = min(hi, lo + (int64_t)first * step);
+            }
+        }
+        __syncthreads();
+    }
+    const int64_t row = s_lo;
+    if (t == 0) *picked = row;
+    const uint4* src = reinterpret_cast<const uint4*>(X + (size_t)row * stride);
+    uint4* dst = reinterpret_cast<uint4*>(row_out);
+    for (size_t v = t; v < stride / 16; v += 256) dst[v] = src[v];
+}
+
 // out[i] = first `bytes` bytes of row picks[i]; one block per picked row
 __global__ void pp_gather_rows_kernel(const uint8_t* __restrict__ X, size_t stride, const int64_t* __restrict__ picks, size_t bytes,
                                       size_t out_stride, uint8_t* __restrict__ out) {
@@ -785,8 +830,20 @@ constexpr int PPF_WARPS = 8;
 __global__ void __launch_bounds__(PPF_WARPS * 32) pp_filtered_pass_kernel(const uint8_t* __restrict__ X, size_t stride, int V, PpFilter f,
                                                                           const uint8_t* __restrict__ cq, int i, int64_t n,
                                                                           float* __restrict__ w, double* __restrict__ wd) {
-    extern __shared__ uint4 ppf_sq[];   // the newest centre: V vectors
-    for (int v = threadIdx.x; v < V; v += blockDim.x) ppf_sq[v] = reinterpret_cast<const uint4*>(cq)[v];
+    // the newest centre twice: as it is (V vectors, for the exact pass) and, for the bf16 pass, de-interleaved into the
+    // first and second float4 of every 8-element group -- lane v then reads c_a[v], c_b[v]: consecutive 16-byte words,
+    // conflict-free.  (Reading c[v * 8 + t] from the plain image is an 8-way bank conflict on every load; that, not
+    // HBM, bounded the first version of this kernel: ~190 us per round, the same as the unfiltered full read.)
+    extern __shared__ uint4 ppf_sq[];
+    float4* c_a = reinterpret_cast<float4*>(ppf_sq + V);
+    float4* c_b = c_a + V / 2;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        const uint4 x = reinterpret_cast<const uint4*>(cq)[v];
+        ppf_sq[v] = x;
+        const float4 f = make_float4(__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w));
+        if (v & 1) c_b[v >> 1] = f;
+        else c_a[v >> 1] = f;
+    }
     __syncthreads();
     const int lane = threadIdx.x % 32;
     const int64_t j = blockIdx.x * (int64_t)PPF_WARPS + threadIdx.x / 32;
@@ -800,18 +857,22 @@ __global__ void __launch_bounds__(PPF_WARPS * 32) pp_filtered_pass_kernel(const 
         }
         // bf16 lower bound: 8 elements per 16-byte load
         const uint4* xb = reinterpret_cast<const uint4*>(f.xb + (size_t)j * f.words);
-        const float* c = reinterpret_cast<const float*>(ppf_sq);
         float acc = 0.f;
         for (int v = lane; v < f.words / 8; v += 32) {
             const uint4 b = __ldg(xb + v);
-            const uint32_t u[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float lo = __uint_as_float(u[t] << 16), hi = __uint_as_float(u[t] & 0xFFFF0000u);
-                const float d0 = lo - c[v * 8 + 2 * t], d1 = hi - c[v * 8 + 2 * t + 1];
-                acc = fmaf(d0, d0, acc);
-                acc = fmaf(d1, d1, acc);
-            }
+            const float4 ca = c_a[v], cb = c_b[v];
+            const float d0 = __uint_as_float(b.x << 16) - ca.x, d1 = __uint_as_float(b.x & 0xFFFF0000u) - ca.y;
+            const float d2 = __uint_as_float(b.y << 16) - ca.z, d3 = __uint_as_float(b.y & 0xFFFF0000u) - ca.w;
+            const float d4 = __uint_as_float(b.z << 16) - cb.x, d5 = __uint_as_float(b.z & 0xFFFF0000u) - cb.y;
+            const float d6 = __uint_as_float(b.w << 16) - cb.z, d7 = __uint_as_float(b.w & 0xFFFF0000u) - cb.w;
+            acc = fmaf(d0, d0, acc);
+            acc = fmaf(d1, d1, acc);
+            acc = fmaf(d2, d2, acc);
+            acc = fmaf(d3, d3, acc);
+            acc = fmaf(d4, d4, acc);
+            acc = fmaf(d5, d5, acc);
+            acc = fmaf(d6, d6, acc);
+            acc = fmaf(d7, d7, acc);
         }
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (sqrtf(acc) * (1.f - 1e-5f) - f.ex[j] >= sj * (1.f + 1e-5f)) {
@@ -880,7 +941,7 @@ static int pp_filter_round(const Table& X, const PpFilter& f, const uint8_t* cro
     VB_CUDA(cudaMemcpyAsync(f.cent + (size_t)i * X.stride, crow, X.stride, cudaMemcpyDeviceToDevice, s));
     if (i > 0) pp_dcc_kernel<<<(unsigned)((i * 32 + 255) / 256), 256, 0, s>>>(f.cent, X.stride, V, crow, i, f.dcc);
     if (X.n > 0) {
-        const size_t smem = X.stride;
+        const size_t smem = 2 * X.stride;
         static bool attr = false;
         if (!attr && smem > 48 * 1024) {
             VB_CUDA(cudaFuncSetAttribute(pp_filtered_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -942,9 +1003,10 @@ static int kmeans_pp(const Table& X, int kmeans_metric, void* centers_host, int 
     const bool filtered = pp_filter_applies(X, kmeans_metric, k);
     PpFilter flt;
     if (filtered) VB_TRY(pp_filter_prepare(X, k, (double*)d_wd, &flt));
+    pp_gather_rows_kernel<<<1, 256, 0, s>>>(X.d, X.stride, (const int64_t*)d_picks, X.stride, X.stride, (uint8_t*)d_qraw);
+    count_launch(1);
     for (int i = 0; i + 1 < k; ++i) {
-        // distance of every sample to the newest centre: the scan kernel with that row as the query
-        pp_gather_rows_kernel<<<1, 256, 0, s>>>(X.d, X.stride, (const int64_t*)d_picks + i, X.stride, X.stride, (uint8_t*)d_qraw);
+        // distance of every sample to the newest centre (its row is in d_qraw): the scan kernel with that row as the query
         if (filtered) {
             VB_TRY(pp_filter_round(X, flt, (const uint8_t*)d_qraw, i, (float*)d_w, (double*)d_wd));
         } else {
@@ -954,8 +1016,9 @@ static int kmeans_pp(const Table& X, int kmeans_metric, void* centers_host, int 
             pp_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const float*)d_key, kmeans_metric, n, (float*)d_w, (double*)d_wd);
         }
         VB_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, tmp_bytes, (double*)d_wd, (double*)d_cum, (int)n, s));
-        pp_pick_kernel<<<1, 1, 0, s>>>((const double*)d_cum, n, (const double*)d_u + i, (int64_t*)d_picks + i + 1);
-        count_launch(4);
+        pp_pick_gather_kernel<<<1, 256, 0, s>>>((const double*)d_cum, n, (const double*)d_u + i, (int64_t*)d_picks + i + 1, X.d, X.stride,
+                                                (uint8_t*)d_qraw);
+        count_launch(3);
     }
     pp_gather_rows_kernel<<<(unsigned)k, 256, 0, s>>>(X.d, X.stride, (const int64_t*)d_picks, raw, raw, (uint8_t*)d_out);
     count_launch(1);

@@ -153,3 +153,106 @@ def test_empty_and_single_element_index(pv):
     gi2.load(np.array([[1, 2, 3]], np.float32), np.zeros(1, np.int32), nbr0, np.full(1, -1, np.int64), np.zeros((0, 16), np.int32), 0)
     ids, dist, nd = gi2.search(np.array([[1, 2, 4]], np.float32), k=3, ef_search=10)
     assert list(ids[0]) == [0, -1, -1] and dist[0][0] == 1.0 and nd[0] == 1
+
+
+# ------------------------------------------------------------------------------------------------ iterative scan
+
+def scan_all(gi, queries, ef, max_scan_tuples, max_batches=10 ** 6):
+    """drive an HnswScan to exhaustion: per query the concatenated (ids, distances, batch sizes)"""
+    nq = len(queries)
+    ids = [[] for _ in range(nq)]
+    dist = [[] for _ in range(nq)]
+    sizes = [[] for _ in range(nq)]
+    with gi.iterative_scan(queries, ef_search=ef, max_scan_tuples=max_scan_tuples) as sc:
+        for _ in range(max_batches):
+            bi, bd, cnt = sc.next_batch()
+            if not cnt.any():
+                break
+            for q in range(nq):
+                c = int(cnt[q])
+                if c:
+                    ids[q].extend(bi[q, :c].tolist())
+                    dist[q].extend(bd[q, :c].tolist())
+                    sizes[q].append(c)
+                assert np.all(bi[q, c:] == -1)
+        tuples = sc.tuples()
+    return ids, dist, sizes, tuples
+
+
+@pytest.mark.parametrize("ef,max_tuples", [(40, 10 ** 9), (40, 3000), (10, 500), (100, 20000)])
+def test_iterative_scan_matches_oracle(l2_graph, ef, max_tuples):
+    """hnsw.iterative_scan = relaxed_order (src/hnswscan.c:62-87, 228-340): the element sequence of every batch
+    (GetScanItems, then ResumeScanItems from the discarded candidates on the same visited set, then the drain past
+    hnsw.max_scan_tuples) equals the total-order oracle's, element for element, with the same tuples counter."""
+    og, gi, g, rows, queries = l2_graph
+    queries = queries[:24]
+    ids, dist, sizes, tuples = scan_all(gi, queries, ef, max_tuples)
+    same = 0
+    for q in range(len(queries)):
+        wi, wd, wb, wt = og.iter_scan(queries[q], ef, max_scan_tuples=max_tuples, ties=O.TIES_TOTAL)
+        got = np.array(ids[q])
+        assert len(set(ids[q])) == len(ids[q])                      # an element is returned once
+        if len(got) == len(wi) and np.array_equal(got, wi):
+            same += 1
+            assert np.allclose(dist[q], wd, rtol=RTOL)
+            assert int(tuples[q]) == wt
+            # batch boundaries: the searched batches as the oracle cut them, the drain in ef-sized pieces
+            searched = [int((wb == b).sum()) for b in range(int(wb.max()) + 1)] if len(wb) else []
+            assert sizes[q][:len(searched)] == searched
+        # the first batch is the plain scan
+        pi, pd, _ = gi.search(queries[q], k=ef, ef_search=ef)
+        n0 = sizes[q][0]
+        assert np.array_equal(got[:n0], pi[0][:n0])
+        if max_tuples >= 10 ** 9:
+            assert len(rows) - 5 <= len(got) == len(wi)             # everything reachable is enumerated
+        else:
+            # test/t/043_hnsw_iterative_scan.pl: about max_scan_tuples elements come back in total
+            assert max_tuples <= len(got) <= max_tuples + 100 * ef + 200
+    # fp32 summation order can flip a near tie and send one walk elsewhere; it must be rare
+    assert same >= len(queries) - 2, same
+
+
+def test_iterative_scan_strict_order_and_limit(l2_graph):
+    """strict_order drops elements nearer than one already returned (src/hnswscan.c:316-322); a LIMIT stops pulling"""
+    og, gi, g, rows, queries = l2_graph
+    with gi.iterative_scan(queries[:1], ef_search=20, max_scan_tuples=2000) as sc:
+        got = sc.tuples_of(0, strict=True)
+    d = np.array([x[1] for x in got])
+    assert len(got) > 20 and np.all(np.diff(d) >= 0)
+    wi, wd, _, _ = og.iter_scan(queries[0], 20, max_scan_tuples=2000, ties=O.TIES_TOTAL)
+    keep, prev = [], -np.inf
+    for e, x in zip(wi, wd):
+        if x >= prev:
+            keep.append(int(e))
+            prev = x
+    assert [x[0] for x in got] == keep
+    with gi.iterative_scan(queries[:1], ef_search=20, max_scan_tuples=2000) as sc:
+        assert [x[0] for x in sc.tuples_of(0, limit=55)] == [int(e) for e in wi[:55]]
+
+
+def test_iterative_scan_small_and_filtered(pv):
+    """fewer elements than ef_search; a filter that keeps 1 row in 50 finds its LIMIT through resumed batches
+    (the WHERE i % 10000 = 0 ... LIMIT 11 shape of test/t/043_hnsw_iterative_scan.pl)"""
+    rng = np.random.default_rng(5)
+    rows = rng.random((30, 3)).astype(np.float32)
+    og, gi, g = build_pair(pv, "vector_l2_ops", rows, m=4, efc=16)
+    ids, dist, sizes, tuples = scan_all(gi, rows[:2], 40, 20000)
+    for q in range(2):
+        wi, _, _, wt = og.iter_scan(rows[q], 40, ties=O.TIES_TOTAL)
+        assert ids[q] == wi.tolist() and int(tuples[q]) == wt
+    rows = rng.random((20000, 3)).astype(np.float32)
+    og, gi, g = build_pair(pv, "vector_l2_ops", rows, m=8, efc=32)
+    er = g["elem_row"]
+    q = rows[7]
+    with gi.iterative_scan(q, ef_search=40, max_scan_tuples=20000) as sc:
+        hits = []
+        while len(hits) < 11:
+            bi, bd, cnt = sc.next_batch()
+            if cnt[0] == 0:
+                break
+            hits += [int(er[e]) for e in bi[0, :cnt[0]] if er[e] % 50 == 0]
+    assert len(hits) >= 11
+    # the nearest filtered rows are found (relaxed order: compare as sets against the exact answer)
+    d = ((rows[::50] - q) ** 2).sum(1)
+    exact = set((np.argsort(d)[:5] * 50).tolist())
+    assert len(exact & set(hits)) >= 4

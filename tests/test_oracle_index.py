@@ -142,3 +142,31 @@ def test_bit_kmeans_majority_centres():
         if len(mem):
             want = np.packbits((mem.mean(0) > 0.5).astype(np.uint8))
             assert np.array_equal(c[j], want)
+
+
+def test_hnsw_iterative_scan_restatement():
+    """pgv_hnsw_iter_scan (src/hnswscan.c:62-87, 228-340): batch 0 is the plain scan; resumed batches never repeat an
+    element and enumerate everything reachable; past hnsw.max_scan_tuples about that many elements have come
+    back (test/t/043_hnsw_iterative_scan.pl: the number of matches of a 1-in-10000 filter is max_scan_tuples / 10000
+    +- 2) and the drain is nearest first; the pairing-heap and total-order tie modes agree on float data."""
+    rows, _ = mixture(6000, 16, 20, seed=5)
+    queries, _ = mixture(8, 16, 20, seed=6)
+    g = O.Hnsw(O.VECTOR, O.L2_SQUARED, rows, m=8, ef_construction=32, seed=3)
+    for q in queries:
+        i0, d0, nd0 = g.search(q, 40, O.TIES_PG)
+        ids, dist, batch, nd = g.iter_scan(q, 40, max_scan_tuples=10 ** 9, ties=O.TIES_PG)
+        assert np.array_equal(ids[:len(i0)], i0) and np.array_equal(dist[:len(i0)], d0)
+        assert len(rows) - 5 <= len(ids) == len(set(ids.tolist())) == nd     # (pruning can leave an element without in-edges)
+        for b in range(int(batch.max()) + 1):
+            assert np.all(np.diff(dist[batch == b]) >= 0) and (batch == b).sum() <= 40
+        ids_t, _, batch_t, nd_t = g.iter_scan(q, 40, max_scan_tuples=10 ** 9, ties=O.TIES_TOTAL)
+        if len(np.unique(dist)) == len(dist):       # (two equal fp32 distances among 6000 do happen; the modes may then differ)
+            assert np.array_equal(ids, ids_t) and np.array_equal(batch, batch_t) and nd == nd_t
+        else:
+            assert sorted(ids.tolist()) == sorted(ids_t.tolist())
+        for limit in (500, 2000):
+            ids2, dist2, batch2, nd2 = g.iter_scan(q, 40, max_scan_tuples=limit, ties=O.TIES_PG)
+            assert limit <= len(ids2) == nd2 <= limit + 1500
+            assert np.all(np.diff(dist2[batch2 == -1]) >= 0)
+            n_same = int((batch2 >= 0).sum())
+            assert np.array_equal(ids2[:n_same], ids[:n_same])
