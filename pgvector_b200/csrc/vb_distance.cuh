@@ -32,6 +32,21 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
     return __uint_as_float(u);
 }
 
+// sm_100 mixed-precision scalar arithmetic (PTX ISA 8.6, FHFMA / FHADD in SASS): an fp16 operand is widened inside the
+// instruction, either half of a 32-bit register is addressable (.H1), so a halfvec element costs no conversion.
+// float(a) * float(b) is exact in fp32 (22-bit product) and the addition rounds once: bit-identical to
+// fmaf(__half2float(a), __half2float(b), c); likewise float(a) - c.
+__device__ __forceinline__ float fh_fma(uint16_t a, uint16_t b, float c) {
+    float d;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float fh_sub(uint16_t a, float c) {
+    float d;
+    asm("sub.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(a), "f"(c));
+    return d;
+}
+
 template <int ELEM, int METRIC>
 struct Acc {
     // fp metrics: a = main sum, b = |row|^2, c = |query|^2 (cosine only)
@@ -53,6 +68,29 @@ struct Acc {
             fc = fmaf(q, q, fc);
         }
     }
+    // halfvec element (raw bits) against an fp32 query element
+    __device__ __forceinline__ void add_hf(uint16_t x, float q) {
+        if (METRIC == VB_L2_SQUARED) {
+            float d = fh_sub(x, q);
+            fa = fmaf(d, d, fa);
+        } else if (METRIC == VB_L1) {
+            fa += fabsf(fh_sub(x, q));
+        } else {
+            add_f(__half2float(__ushort_as_half(x)), q);
+        }
+    }
+    // halfvec element against a halfvec query element (both raw bits)
+    __device__ __forceinline__ void add_hh(uint16_t x, uint16_t q) {
+        if (METRIC == VB_NEG_IP) {
+            fa = fh_fma(x, q, fa);
+        } else if (METRIC == VB_COSINE) {
+            fa = fh_fma(x, q, fa);
+            fb = fh_fma(x, x, fb);
+            fc = fh_fma(q, q, fc);
+        } else {
+            add_hf(x, __half2float(__ushort_as_half(q)));
+        }
+    }
     // one 16-byte row vector against the query image in shared memory
     __device__ __forceinline__ void add(uint4 r, const uint4* sq, int v) {
         if (ELEM == VB_VECTOR) {
@@ -63,18 +101,14 @@ struct Acc {
             add_f(__uint_as_float(r.w), __uint_as_float(q.w));
         } else if (ELEM == VB_HALFVEC) {
             uint4 q0 = sq[2 * v], q1 = sq[2 * v + 1];
-            float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
-            float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
-            float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&r.z));
-            float2 x3 = __half22float2(*reinterpret_cast<const __half2*>(&r.w));
-            add_f(x0.x, __uint_as_float(q0.x));
-            add_f(x0.y, __uint_as_float(q0.y));
-            add_f(x1.x, __uint_as_float(q0.z));
-            add_f(x1.y, __uint_as_float(q0.w));
-            add_f(x2.x, __uint_as_float(q1.x));
-            add_f(x2.y, __uint_as_float(q1.y));
-            add_f(x3.x, __uint_as_float(q1.z));
-            add_f(x3.y, __uint_as_float(q1.w));
+            add_hf((uint16_t)(r.x & 0xffffu), __uint_as_float(q0.x));
+            add_hf((uint16_t)(r.x >> 16), __uint_as_float(q0.y));
+            add_hf((uint16_t)(r.y & 0xffffu), __uint_as_float(q0.z));
+            add_hf((uint16_t)(r.y >> 16), __uint_as_float(q0.w));
+            add_hf((uint16_t)(r.z & 0xffffu), __uint_as_float(q1.x));
+            add_hf((uint16_t)(r.z >> 16), __uint_as_float(q1.y));
+            add_hf((uint16_t)(r.w & 0xffffu), __uint_as_float(q1.z));
+            add_hf((uint16_t)(r.w >> 16), __uint_as_float(q1.w));
         } else {
             uint4 q = sq[v];
             if (METRIC == VB_HAMMING) {
@@ -89,18 +123,14 @@ struct Acc {
     // halfvec row vector against 8 query elements kept as packed halves (the fp32 image of a halfvec query
     // holds exact conversions of halves, so converting back and forth changes nothing)
     __device__ __forceinline__ void add_h(uint4 r, uint4 qh) {
-        float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), q0 = __half22float2(*reinterpret_cast<const __half2*>(&qh.x));
-        float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&r.y)), q1 = __half22float2(*reinterpret_cast<const __half2*>(&qh.y));
-        float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&r.z)), q2 = __half22float2(*reinterpret_cast<const __half2*>(&qh.z));
-        float2 x3 = __half22float2(*reinterpret_cast<const __half2*>(&r.w)), q3 = __half22float2(*reinterpret_cast<const __half2*>(&qh.w));
-        add_f(x0.x, q0.x);
-        add_f(x0.y, q0.y);
-        add_f(x1.x, q1.x);
-        add_f(x1.y, q1.y);
-        add_f(x2.x, q2.x);
-        add_f(x2.y, q2.y);
-        add_f(x3.x, q3.x);
-        add_f(x3.y, q3.y);
+        add_hh((uint16_t)(r.x & 0xffffu), (uint16_t)(qh.x & 0xffffu));
+        add_hh((uint16_t)(r.x >> 16), (uint16_t)(qh.x >> 16));
+        add_hh((uint16_t)(r.y & 0xffffu), (uint16_t)(qh.y & 0xffffu));
+        add_hh((uint16_t)(r.y >> 16), (uint16_t)(qh.y >> 16));
+        add_hh((uint16_t)(r.z & 0xffffu), (uint16_t)(qh.z & 0xffffu));
+        add_hh((uint16_t)(r.z >> 16), (uint16_t)(qh.z >> 16));
+        add_hh((uint16_t)(r.w & 0xffffu), (uint16_t)(qh.w & 0xffffu));
+        add_hh((uint16_t)(r.w >> 16), (uint16_t)(qh.w >> 16));
     }
     template <int LPR>
     __device__ __forceinline__ void reduce() {

@@ -93,14 +93,28 @@ __device__ __forceinline__ bool ent_less(uint64_t ka, uint32_t ia, uint64_t kb, 
     return ka < kb || (ka == kb && (ia & 0x7fffffffu) < (ib & 0x7fffffffu));
 }
 
-// a table row as the "query image" the Acc<> arithmetic reads from shared memory: vector and bit rows as they
-// are, halfvec rows widened to fp32 (exact, HalfToFloat4)
-template <int ELEM>
+// The "query image" the Acc<> arithmetic reads from shared memory.  vector and bit: the value as it is.  halfvec: widened
+// to fp32 (exact, HalfToFloat4) for L2 / L1, whose subtraction takes an fp32 operand -- but kept as packed halves for the
+// inner product, where one FHFMA per element multiplies two halves into the fp32 sum (half the shared-memory reads, no
+// conversions; bit-identical to the widened arithmetic, see fh_fma).
+template <int ELEM, int METRIC>
+struct HnswImage {
+    static constexpr bool packed = ELEM == VB_HALFVEC && METRIC == VB_NEG_IP;
+};
+
+template <int ELEM, int METRIC>
+__device__ __forceinline__ void hnsw_acc_add(Acc<ELEM, METRIC>& acc, uint4 r, const uint4* sq, int v) {
+    if (HnswImage<ELEM, METRIC>::packed) acc.add_h(r, sq[v]);
+    else acc.add(r, sq, v);
+}
+
+// a table row as the image
+template <int ELEM, int METRIC>
 __device__ __forceinline__ void load_row_image(const uint8_t* row, int V, uint4* img, int lane) {
     const uint4* rp = reinterpret_cast<const uint4*>(row);
     for (int v = lane; v < V; v += 32) {
         const uint4 r = __ldg(rp + v);
-        if (ELEM == VB_HALFVEC) {
+        if (ELEM == VB_HALFVEC && !HnswImage<ELEM, METRIC>::packed) {
             const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
             const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
             const float2 x2 = __half22float2(*reinterpret_cast<const __half2*>(&r.z));
@@ -110,6 +124,25 @@ __device__ __forceinline__ void load_row_image(const uint8_t* row, int V, uint4*
         } else {
             img[v] = r;
         }
+    }
+}
+
+// a query of the batch as the image: gq = what upload_queries() wrote (halfvec queries widened to fp32, qvec 16-byte
+// words); V = 16-byte words of a table row
+template <int ELEM, int METRIC>
+__device__ __forceinline__ void load_query_image(const uint4* gq, int qvec, int V, uint4* img, int lane) {
+    if (HnswImage<ELEM, METRIC>::packed) {
+        for (int v = lane; v < V; v += 32) {
+            const uint4 a = gq[2 * v], b = gq[2 * v + 1];
+            const __half2 h0 = __floats2half2_rn(__uint_as_float(a.x), __uint_as_float(a.y));
+            const __half2 h1 = __floats2half2_rn(__uint_as_float(a.z), __uint_as_float(a.w));
+            const __half2 h2 = __floats2half2_rn(__uint_as_float(b.x), __uint_as_float(b.y));
+            const __half2 h3 = __floats2half2_rn(__uint_as_float(b.z), __uint_as_float(b.w));
+            img[v] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+        }
+    } else {
+        for (int i = lane; i < qvec; i += 32) img[i] = gq[i];
     }
 }
 
@@ -131,24 +164,28 @@ __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* 
             rp[i] = reinterpret_cast<const uint4*>(g.rows + (size_t)e * g.stride);
         }
         // register double buffering: the loads of step v + LPR are issued before the arithmetic of step v, so 2 * RPI
-        // independent 128-bit gathers per lane are in flight instead of one dependent round trip per step
-        uint4 cur[RPI];
+        // independent 128-bit gathers per lane are in flight instead of one dependent round trip per step.  Two named
+        // buffers alternate (no register copies between steps).
+        uint4 bufa[RPI], bufb[RPI];
         if (gl < g.V) {
 #pragma unroll
-            for (int i = 0; i < RPI; ++i) cur[i] = ldg_stream(rp[i] + gl);
+            for (int i = 0; i < RPI; ++i) bufa[i] = ldg_stream(rp[i] + gl);
         }
-        for (int v = gl; v < g.V; v += LPR) {
-            uint4 nxt[RPI];
-            const int vn = v + LPR;
-            if (vn < g.V) {
+        for (int v = gl; v < g.V; v += 2 * LPR) {
+            const int v1 = v + LPR, v2 = v + 2 * LPR;
+            if (v1 < g.V) {
 #pragma unroll
-                for (int i = 0; i < RPI; ++i) nxt[i] = ldg_stream(rp[i] + vn);
+                for (int i = 0; i < RPI; ++i) bufb[i] = ldg_stream(rp[i] + v1);
             }
 #pragma unroll
-            for (int i = 0; i < RPI; ++i) acc[i].add(cur[i], sq, v);
-            if (vn < g.V) {
+            for (int i = 0; i < RPI; ++i) hnsw_acc_add<ELEM, METRIC>(acc[i], bufa[i], sq, v);
+            if (v1 < g.V) {
+                if (v2 < g.V) {
 #pragma unroll
-                for (int i = 0; i < RPI; ++i) cur[i] = nxt[i];
+                    for (int i = 0; i < RPI; ++i) bufa[i] = ldg_stream(rp[i] + v2);
+                }
+#pragma unroll
+                for (int i = 0; i < RPI; ++i) hnsw_acc_add<ELEM, METRIC>(acc[i], bufb[i], sq, v1);
             }
         }
 #pragma unroll

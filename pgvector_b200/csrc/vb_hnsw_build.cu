@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_insert_kernel(BuildDev b, 
 
     for (int w = gwarp; w < b.B; w += nwarps) {
         const int e = b.b0 + w;
-        load_row_image<ELEM>(g.rows + (size_t)e * g.stride, g.V, sq, lane);
+        load_row_image<ELEM, METRIC>(g.rows + (size_t)e * g.stride, g.V, sq, lane);
         __syncwarp();
         const int level = g.levels[e];
 
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_insert_kernel(BuildDev b, 
         {
             Acc<ELEM, METRIC> acc;
             const uint4* rp = reinterpret_cast<const uint4*>(g.rows + (size_t)g.entry * g.stride);
-            for (int v = lane; v < g.V; v += 32) acc.add(ldg_stream(rp + v), sq, v);
+            for (int v = lane; v < g.V; v += 32) hnsw_acc_add<ELEM, METRIC>(acc, ldg_stream(rp + v), sq, v);
             acc.template reduce<32>();
             if (lane == 0) {
                 S.rk[0] = orderable_key64(acc.value());
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_insert_kernel(BuildDev b, 
                     if (lane == 0) sel[nR] = i;
                     ++nR;
                     if (nR == lm || i + 1 >= len) break;
-                    load_row_image<ELEM>(g.rows + (size_t)(wi[i] & 0x7fffffffu) * g.stride, g.V, img, lane);
+                    load_row_image<ELEM, METRIC>(g.rows + (size_t)(wi[i] & 0x7fffffffu) * g.stride, g.V, img, lane);
                     __syncwarp();
                     prune_against<ELEM, METRIC, LPR>(
                         g, img, i + 1, len, dead, bid, bj, bkey, lane, [&](int j) { return wi[j] & 0x7fffffffu; },
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_update_kernel(BuildDev b, 
                 if (dead[c]) continue;
                 ++nAcc;
                 if (nAcc == lm || c == n - 1) break;
-                load_row_image<ELEM>(g.rows + (size_t)(uint32_t)ck[c] * g.stride, g.V, img, lane);
+                load_row_image<ELEM, METRIC>(g.rows + (size_t)(uint32_t)ck[c] * g.stride, g.V, img, lane);
                 __syncwarp();
                 prune_against<ELEM, METRIC, LPR>(
                     g, img, c + 1, n, dead, bid, bj, bkey, lane, [&](int j) { return (uint32_t)ck[j]; },

@@ -76,7 +76,7 @@ __global__ void VB_HNSW_BOUNDS hnsw_iter_kernel(HnswDev g, IterDev it, const uin
             continue;
         }
         const uint4* gq = reinterpret_cast<const uint4*>(queries + (size_t)q * qstride);
-        for (int i = lane; i < qvec; i += 32) sq[i] = gq[i];
+        load_query_image<ELEM, METRIC>(gq, qvec, g.V, sq, lane);
         __syncwarp();
 
         HnswWarpState S;
@@ -102,7 +102,7 @@ __global__ void VB_HNSW_BOUNDS hnsw_iter_kernel(HnswDev g, IterDev it, const uin
             {
                 Acc<ELEM, METRIC> acc;
                 const uint4* rp = reinterpret_cast<const uint4*>(g.rows + (size_t)g.entry * g.stride);
-                for (int v = lane; v < g.V; v += 32) acc.add(ldg_stream(rp + v), sq, v);
+                for (int v = lane; v < g.V; v += 32) hnsw_acc_add<ELEM, METRIC>(acc, ldg_stream(rp + v), sq, v);
                 acc.template reduce<32>();
                 if (lane == 0) {
                     S.rk[0] = orderable_key64(acc.value());

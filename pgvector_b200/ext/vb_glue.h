@@ -124,10 +124,15 @@ typedef struct VbHnswScanState
 	int			nelements;
 	int			cur;			/* current element */
 	int			curtid;			/* heap TIDs of the current element still to return (counts down) */
+	/* hnsw.iterative_scan (src/hnswscan.c:62-87, 236-262): the library keeps v / discarded / tuples in this handle */
+	vb_hnsw_scan *iter;
+	int			batch;			/* ef_search: elements per batch */
+	double		previousDistance;	/* strict_order (src/hnswscan.c:316-322) */
 }			VbHnswScanState;
 
 /* false: this scan must be served by the reference's CPU loop (NULL query, or a graph the image cannot represent) */
 extern bool VbHnswGetScanItems(IndexScanDesc scan, Datum value, int ef_search, VbHnswScanState * st);
 extern bool VbHnswNextItem(IndexScanDesc scan, VbHnswScanState * st);
+extern void VbHnswEndScan(VbHnswScanState * st);	/* hnswrescan / hnswendscan: releases the iterative scan's handle */
 
 #endif

@@ -16,6 +16,7 @@
 #include "access/relscan.h"
 #include "common/hashfn.h"
 #include "storage/bufmgr.h"
+#include "utils/float.h"
 #include "utils/memutils.h"
 #include "utils/rel.h"
 #include "utils/varbit.h"
@@ -341,10 +342,36 @@ VbHnswGetScanItems(IndexScanDesc scan, Datum value, int ef_search, VbHnswScanSta
 	else
 		q = VARBITS(DatumGetVarBitP(value));
 
+	st->iter = NULL;
+	st->batch = ef_search;
+	st->previousDistance = -get_float8_infinity();
+	if (hnsw_iterative_scan != HNSW_ITERATIVE_SCAN_OFF)
+	{
+		int32		count = 0;
+
+		/* the first batch is GetScanItems with the discarded heap (src/hnswscan.c:55) */
+		VB_CHECK(vb_hnsw_scan_begin(img->ix, q, 1, ef_search, hnsw_max_scan_tuples, &st->iter));
+		if (vb_hnsw_scan_next(st->iter, st->elements, st->distances, &count) != VB_OK)
+		{
+			VbHnswEndScan(st);
+			ereport(ERROR, (errcode(ERRCODE_EXTERNAL_ROUTINE_EXCEPTION), errmsg("vecb200: %s", vb_last_error())));
+		}
+		st->nelements = count;
+		(void) vb_hnsw_scan_tuples(st->iter, &so->tuples);
+		return true;
+	}
 	VB_CHECK(vb_hnsw_search(img->ix, q, 1, ef_search, ef_search, st->elements, st->distances, &so->tuples));
 	while (st->nelements < ef_search && st->elements[st->nelements] >= 0)
 		st->nelements++;
 	return true;
+}
+
+void
+VbHnswEndScan(VbHnswScanState * st)
+{
+	if (st->iter != NULL)
+		vb_hnsw_scan_end(st->iter);
+	st->iter = NULL;
 }
 
 /* the loop of hnswgettuple (src/hnswscan.c:293-326): nearest element first, heap TIDs last-added first */
@@ -353,12 +380,45 @@ VbHnswNextItem(IndexScanDesc scan, VbHnswScanState * st)
 {
 	VbHnswImage *img = st->image;
 
-	while (st->cur < st->nelements)
+	for (;;)
 	{
-		int64		e = st->elements[st->cur];
+		int64		e;
 
+		if (st->cur >= st->nelements)
+		{
+			int32		count = 0;
+
+			/* W is consumed: resume from the discarded candidates, or stop (src/hnswscan.c:236-262) */
+			if (st->iter == NULL)
+				return false;
+			if (vb_hnsw_scan_next(st->iter, st->elements, st->distances, &count) != VB_OK)
+			{
+				VbHnswEndScan(st);
+				ereport(ERROR, (errcode(ERRCODE_EXTERNAL_ROUTINE_EXCEPTION), errmsg("vecb200: %s", vb_last_error())));
+			}
+			st->nelements = count;
+			st->cur = 0;
+			st->curtid = -1;
+			(void) vb_hnsw_scan_tuples(st->iter, &((HnswScanOpaque) scan->opaque)->tuples);
+			if (count == 0)
+			{
+				VbHnswEndScan(st);
+				return false;
+			}
+		}
+		e = st->elements[st->cur];
 		if (st->curtid < 0)
+		{
 			st->curtid = img->nheaptids[e];
+			/* strict_order: an element nearer than one already returned is dropped (src/hnswscan.c:316-322) */
+			if (hnsw_iterative_scan == HNSW_ITERATIVE_SCAN_STRICT && st->curtid > 0)
+			{
+				if (st->distances[st->cur] < st->previousDistance)
+					st->curtid = 0;
+				else
+					st->previousDistance = st->distances[st->cur];
+			}
+		}
 		if (st->curtid == 0)
 		{
 			st->cur++;
@@ -370,5 +430,4 @@ VbHnswNextItem(IndexScanDesc scan, VbHnswScanState * st)
 		scan->xs_recheckorderby = false;
 		return true;
 	}
-	return false;
 }

@@ -43,6 +43,17 @@ HnswGetMetaPageInfo(Relation index, int *m, HnswElement * entryPoint)
 	UnlockReleaseBuffer(buf);
 }
 
+/* the GUCs of src/hnsw.c:28-37, 96-105 the glue reads */
+int			hnsw_iterative_scan = HNSW_ITERATIVE_SCAN_OFF;
+int			hnsw_max_scan_tuples = 20000;
+
+void
+h_hnsw_set_iterative(int mode, int max_scan_tuples)
+{
+	hnsw_iterative_scan = mode;
+	hnsw_max_scan_tuples = max_scan_tuples;
+}
+
 /* the loop of hnswgettuple (src/hnswscan.c:189-331) with the GPU call patched in; -2 = "serve on the CPU path" */
 int
 h_hnsw_scan(HRelation * h, int elem, const void *query_payload, int ef_search, int64 max_items, int64 *out_tids, int64 *n_out,
@@ -68,6 +79,7 @@ h_hnsw_scan(HRelation * h, int elem, const void *query_payload, int ef_search, i
 		{
 			while (n < max_items && VbHnswNextItem(&scan, &st))
 				out_tids[n++] = VbTidToId(&scan.xs_heaptid);
+			VbHnswEndScan(&st);		/* hnswendscan */
 			*n_out = n;
 			*tuples = so.tuples;
 		}

@@ -255,6 +255,81 @@ vb_hnsw_search(vb_hnsw *h, const void *queries, int64_t nq, int ef, int k, int64
 	return VB_OK;
 }
 
+/* the iterative scan on the oracle's (single query): the whole sequence is produced up front and handed out batch by
+ * batch -- the searched batches as the oracle cut them, the drain past max_scan_tuples ef_search at a time */
+struct vb_hnsw_scan
+{
+	int			ef;
+	int64_t		n,
+				next,
+				tuples;
+	int64_t    *ids;
+	double	   *dist;
+	int32_t    *batch;
+};
+
+int
+vb_hnsw_scan_begin(vb_hnsw *h, const void *queries, int64_t nq, int ef_search, int64_t max_scan_tuples, vb_hnsw_scan **out)
+{
+	vb_hnsw_scan *sc;
+	int64_t		cap = h->n > 0 ? h->n : 1;
+
+	if (nq != 1)
+		return VB_EINVAL;
+	sc = calloc(1, sizeof(*sc));
+	sc->ef = ef_search;
+	sc->ids = malloc(sizeof(int64_t) * (size_t) cap);
+	sc->dist = malloc(sizeof(double) * (size_t) cap);
+	sc->batch = malloc(sizeof(int32_t) * (size_t) cap);
+	sc->n = h->g ? pgv_hnsw_iter_scan(h->g, queries, ef_search, PGV_TIES_TOTAL_ORDER, max_scan_tuples, cap, sc->ids, sc->dist, sc->batch,
+									  &sc->tuples) : 0;
+	mock_live_handles++;
+	*out = sc;
+	return VB_OK;
+}
+
+int
+vb_hnsw_scan_next(vb_hnsw_scan *sc, int64_t *out_ids, double *out_distances, int32_t *out_counts)
+{
+	int			c = 0;
+
+	while (sc->next < sc->n && c < sc->ef && (c == 0 || sc->batch[sc->next] == sc->batch[sc->next - 1]))
+	{
+		out_ids[c] = sc->ids[sc->next];
+		out_distances[c] = sc->dist[sc->next];
+		c++;
+		sc->next++;
+	}
+	for (int i = c; i < sc->ef; i++)
+	{
+		out_ids[i] = -1;
+		out_distances[i] = 1.0 / 0.0;
+	}
+	out_counts[0] = c;
+	return VB_OK;
+}
+
+int
+vb_hnsw_scan_tuples(vb_hnsw_scan *sc, int64_t *out_tuples)
+{
+	out_tuples[0] = sc->tuples;
+	return VB_OK;
+}
+
+int
+vb_hnsw_scan_end(vb_hnsw_scan *sc)
+{
+	if (sc)
+	{
+		free(sc->ids);
+		free(sc->dist);
+		free(sc->batch);
+		free(sc);
+		mock_live_handles--;
+	}
+	return VB_OK;
+}
+
 /* vb_hnsw_build on the oracle's serial build; the library numbers elements by ROW (a folded duplicate keeps its row
  * number and points at its element through dup_of), the oracle numbers elements densely: translate */
 int

@@ -44,6 +44,7 @@ class Harness:
         L.h_ivf_assign.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.pgstub_pinned_buffers.restype = C.c_int
         L.pgstub_buffer_reads.restype = C.c_long
+        L.h_hnsw_set_iterative.argtypes = [C.c_int, C.c_int]
         if not real:
             L.mock_live.restype = C.c_int
             L.mock_ivf_rows.restype = C.c_int64
@@ -303,6 +304,60 @@ def test_hnsw_packer_and_scan(real, typ, metric, n, dim, m, dups):
     # NULL query: served by the reference loop
     got, _ = H.hnsw_scan(rel, elem, None, ef=40, max_items=10)
     assert got is None
+    H.lib.h_hnsw_invalidate(rel)
+
+
+@_params
+@pytest.mark.parametrize("typ,metric,n,dim,m,dups", [("vector", "l2", 2500, 16, 8, 40), ("halfvec", "ip", 1500, 40, 16, 0)])
+def test_hnsw_iterative_scan_through_the_glue(real, typ, metric, n, dim, m, dups):
+    """hnsw.iterative_scan (src/hnswscan.c:62-87, 236-262) through VbHnswGetScanItems / VbHnswNextItem: relaxed order
+    returns the oracle's sequence (batch after batch, then the drain past hnsw.max_scan_tuples), strict order drops the
+    elements nearer than one already returned (:316-322), a LIMIT stops pulling, and hnswendscan frees the handle."""
+    H = Harness(real)
+    elem, mt, rows, og, g = hnsw_case(typ, metric, n, dim, m, seed=n + dim, dups=dups)
+    ne = len(g["levels"])
+    erows = rows[g["elem_row"]]
+    heaptids = [list(g["heaptids"][e][:g["n_heaptids"][e]]) for e in range(ne)]
+    image, info = P.hnsw_image(elem, dim, m, erows, g["levels"], g["nbr0"], g["upper_off"], g["upper"], g["entry"], heaptids=heaptids,
+                               write_order=range(ne))
+    rel, keep = H.open(image, dim, PROC[(typ, metric)])
+    tids = lambda elems: [P.tid_id(*P.heap_tid_of(int(r))) for e in elems for r in reversed(heaptids[e])]
+    H.hnsw_scan(rel, elem, rows[0], ef=20, max_items=5)                          # (packs the image: one library handle)
+    live0 = H.lib.mock_live() if not real else 0
+    rng = np.random.default_rng(4)
+    try:
+        for qi in rng.integers(0, len(rows), 6):
+            q = rows[qi]
+            for max_tuples in (10 ** 6, 600):
+                H.lib.h_hnsw_set_iterative(1, max_tuples)                      # relaxed_order
+                got, tuples = H.hnsw_scan(rel, elem, q, ef=20, max_items=10 ** 6)
+                wi, wd, wb, wt = og.iter_scan(q, 20, max_scan_tuples=max_tuples, ties=O.TIES_TOTAL)
+                want = tids(wi)
+                assert len(got) == len(set(got.tolist()))
+                if real:
+                    assert abs(len(got) - len(want)) <= 40 and len(set(got.tolist()) & set(want)) >= 0.97 * len(want)
+                else:
+                    assert list(got) == want and tuples == wt
+                if max_tuples == 10 ** 6:
+                    assert len(got) >= 0.9 * len(rows)                         # every reachable row comes back once
+                got10, _ = H.hnsw_scan(rel, elem, q, ef=20, max_items=55)      # LIMIT 55: three batches are enough
+                assert len(got10) == 55 and (real or list(got10) == want[:55])
+            H.lib.h_hnsw_set_iterative(2, 600)                                 # strict_order
+            got, _ = H.hnsw_scan(rel, elem, q, ef=20, max_items=10 ** 6)
+            wi, wd, wb, wt = og.iter_scan(q, 20, max_scan_tuples=600, ties=O.TIES_TOTAL)
+            keep_e, prev = [], -np.inf
+            for e, d in zip(wi, wd):
+                if d >= prev:
+                    keep_e.append(int(e))
+                    prev = d
+            if not real:
+                assert list(got) == tids(keep_e)
+            assert 20 <= len(got) <= len(tids(wi))
+    finally:
+        H.lib.h_hnsw_set_iterative(0, 20000)
+    if not real:
+        assert H.lib.mock_live() == live0                                      # every scan handle was released
+    assert H.lib.pgstub_pinned_buffers() == 0
     H.lib.h_hnsw_invalidate(rel)
 
 
