@@ -254,32 +254,51 @@ __device__ __forceinline__ void hnsw_merge_batch(HnswWarpState& S, int cnt, int 
             __syncwarp();
         }
     }
-    // sort the batch by (key, id): bitonic over 32 lanes, empty lanes = +inf
+    // sort the batch by (key, id).  A converged search admits one or two neighbours per expansion: up to 8 survivors are
+    // ranked by counting (each lane counts the entries before its own: cnt_in broadcasts), more go through a bitonic
+    // network over the 32 lanes (empty lanes = +inf).
     uint64_t mk = lane < cnt_in ? S.bkey[lane] : ~0ull;
     uint32_t mi = lane < cnt_in ? S.bid[lane] : 0x7fffffffu;
+    if (cnt_in <= 8) {
+        int rank = 0;
+        for (int j = 0; j < cnt_in; ++j) {
+            const uint64_t kj = __shfl_sync(0xffffffffu, mk, j);
+            const uint32_t ij = __shfl_sync(0xffffffffu, mi, j);
+            rank += ent_less(kj, ij, mk, mi) ? 1 : 0;
+        }
+        __syncwarp();
+        if (lane < cnt_in) {
+            S.bkey[rank] = mk;
+            S.bid[rank] = mi;
+        }
+        __syncwarp();
+        mk = lane < cnt_in ? S.bkey[lane] : ~0ull;
+        mi = lane < cnt_in ? S.bid[lane] : 0x7fffffffu;
+    } else {
 #pragma unroll
-    for (int size = 2; size <= 32; size <<= 1) {
+        for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
-        for (int st = size >> 1; st > 0; st >>= 1) {
-            uint64_t ok = __shfl_xor_sync(0xffffffffu, mk, st);
-            uint32_t oi = __shfl_xor_sync(0xffffffffu, mi, st);
-            bool up = (lane & size) == 0;
-            bool lower = (lane & st) == 0;
-            bool other_less = ent_less(ok, oi, mk, mi);
-            // keep min in the lower lane of an ascending pair, max otherwise
-            bool take = (lower == up) ? other_less : !other_less;
-            if (take) {
-                mk = ok;
-                mi = oi;
+            for (int st = size >> 1; st > 0; st >>= 1) {
+                uint64_t ok = __shfl_xor_sync(0xffffffffu, mk, st);
+                uint32_t oi = __shfl_xor_sync(0xffffffffu, mi, st);
+                bool up = (lane & size) == 0;
+                bool lower = (lane & st) == 0;
+                bool other_less = ent_less(ok, oi, mk, mi);
+                // keep min in the lower lane of an ascending pair, max otherwise
+                bool take = (lower == up) ? other_less : !other_less;
+                if (take) {
+                    mk = ok;
+                    mi = oi;
+                }
             }
         }
+        __syncwarp();
+        if (lane < cnt_in) {
+            S.bkey[lane] = mk;
+            S.bid[lane] = mi;
+        }
+        __syncwarp();
     }
-    __syncwarp();
-    if (lane < cnt_in) {
-        S.bkey[lane] = mk;
-        S.bid[lane] = mi;
-    }
-    __syncwarp();
 
     // merge R (len, sorted) with the batch (cnt_in, sorted) into the other buffer, keep efl
     const int len = S.len;

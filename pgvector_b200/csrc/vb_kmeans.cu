@@ -827,74 +827,98 @@ __global__ void pp_dcc_kernel(const uint8_t* __restrict__ cent, size_t stride, i
 }
 
 constexpr int PPF_WARPS = 8;
+// Persistent CTAs (the centre image is staged once per CTA, not once per 8 rows); a warp takes 32 consecutive samples at
+// a time: the triangle test runs one sample per lane (coalesced reads of w / near, no row touched), the survivors are
+// then visited one after the other by the whole warp for the bf16 bound and, if that cannot decide, the exact fp32
+// distance.
 __global__ void __launch_bounds__(PPF_WARPS * 32) pp_filtered_pass_kernel(const uint8_t* __restrict__ X, size_t stride, int V, PpFilter f,
                                                                           const uint8_t* __restrict__ cq, int i, int64_t n,
                                                                           float* __restrict__ w, double* __restrict__ wd) {
     // the newest centre twice: as it is (V vectors, for the exact pass) and, for the bf16 pass, de-interleaved into the
     // first and second float4 of every 8-element group -- lane v then reads c_a[v], c_b[v]: consecutive 16-byte words,
-    // conflict-free.  (Reading c[v * 8 + t] from the plain image is an 8-way bank conflict on every load; that, not
-    // HBM, bounded the first version of this kernel: ~190 us per round, the same as the unfiltered full read.)
+    // conflict-free.  (Reading c[v * 8 + t] from the plain image is an 8-way bank conflict on every load.)
     extern __shared__ uint4 ppf_sq[];
     float4* c_a = reinterpret_cast<float4*>(ppf_sq + V);
     float4* c_b = c_a + V / 2;
     for (int v = threadIdx.x; v < V; v += blockDim.x) {
         const uint4 x = reinterpret_cast<const uint4*>(cq)[v];
         ppf_sq[v] = x;
-        const float4 f = make_float4(__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w));
-        if (v & 1) c_b[v >> 1] = f;
-        else c_a[v >> 1] = f;
+        const float4 c = make_float4(__uint_as_float(x.x), __uint_as_float(x.y), __uint_as_float(x.z), __uint_as_float(x.w));
+        if (v & 1) c_b[v >> 1] = c;
+        else c_a[v >> 1] = c;
     }
     __syncthreads();
     const int lane = threadIdx.x % 32;
-    const int64_t j = blockIdx.x * (int64_t)PPF_WARPS + threadIdx.x / 32;
-    if (j >= n) return;
-    const float wj = w[j];
-    const float sj = sqrtf(wj);
-    if (i > 0) {
-        if (f.dcc[f.near[j]] >= 2.0002f * sj) {
-            if (lane == 0) atomicAdd(&f.stats[0], 1ull);
-            return;
+    const int64_t gwarp = blockIdx.x * (int64_t)PPF_WARPS + threadIdx.x / 32;
+    const int64_t nwarps = gridDim.x * (int64_t)PPF_WARPS;
+    const int groups = f.words / 8;
+    unsigned long long n_tri = 0, n_bf = 0, n_exact = 0;   // warp-uniform tallies, one atomic per warp at the end
+    for (int64_t base = gwarp * 32; base < n; base += nwarps * 32) {
+        const int64_t jl = base + lane;
+        float wl = 0.f;
+        bool pass = false;
+        if (jl < n) {
+            wl = w[jl];
+            pass = i == 0 || !(f.dcc[f.near[jl]] >= 2.0002f * sqrtf(wl));
         }
-        // bf16 lower bound: 8 elements per 16-byte load
-        const uint4* xb = reinterpret_cast<const uint4*>(f.xb + (size_t)j * f.words);
-        float acc = 0.f;
-        for (int v = lane; v < f.words / 8; v += 32) {
-            const uint4 b = __ldg(xb + v);
-            const float4 ca = c_a[v], cb = c_b[v];
-            const float d0 = __uint_as_float(b.x << 16) - ca.x, d1 = __uint_as_float(b.x & 0xFFFF0000u) - ca.y;
-            const float d2 = __uint_as_float(b.y << 16) - ca.z, d3 = __uint_as_float(b.y & 0xFFFF0000u) - ca.w;
-            const float d4 = __uint_as_float(b.z << 16) - cb.x, d5 = __uint_as_float(b.z & 0xFFFF0000u) - cb.y;
-            const float d6 = __uint_as_float(b.w << 16) - cb.z, d7 = __uint_as_float(b.w & 0xFFFF0000u) - cb.w;
-            acc = fmaf(d0, d0, acc);
-            acc = fmaf(d1, d1, acc);
-            acc = fmaf(d2, d2, acc);
-            acc = fmaf(d3, d3, acc);
-            acc = fmaf(d4, d4, acc);
-            acc = fmaf(d5, d5, acc);
-            acc = fmaf(d6, d6, acc);
-            acc = fmaf(d7, d7, acc);
-        }
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (sqrtf(acc) * (1.f - 1e-5f) - f.ex[j] >= sj * (1.f + 1e-5f)) {
-            if (lane == 0) atomicAdd(&f.stats[1], 1ull);
-            return;
+        unsigned todo = __ballot_sync(0xffffffffu, pass);
+        n_tri += (unsigned)__popc(__ballot_sync(0xffffffffu, jl < n)) - (unsigned)__popc(todo);
+        while (todo) {
+            const int r = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int64_t j = base + r;
+            const float wj = __shfl_sync(0xffffffffu, wl, r);
+            const float sj = sqrtf(wj);
+            if (i > 0) {
+                // bf16 lower bound: 8 elements per 16-byte load
+                const uint4* xb = reinterpret_cast<const uint4*>(f.xb + (size_t)j * f.words);
+                float acc = 0.f;
+#pragma unroll 2
+                for (int v = lane; v < groups; v += 32) {
+                    const uint4 b = __ldg(xb + v);
+                    const float4 ca = c_a[v], cb = c_b[v];
+                    const float d0 = __uint_as_float(b.x << 16) - ca.x, d1 = __uint_as_float(b.x & 0xFFFF0000u) - ca.y;
+                    const float d2 = __uint_as_float(b.y << 16) - ca.z, d3 = __uint_as_float(b.y & 0xFFFF0000u) - ca.w;
+                    const float d4 = __uint_as_float(b.z << 16) - cb.x, d5 = __uint_as_float(b.z & 0xFFFF0000u) - cb.y;
+                    const float d6 = __uint_as_float(b.w << 16) - cb.z, d7 = __uint_as_float(b.w & 0xFFFF0000u) - cb.w;
+                    acc = fmaf(d0, d0, acc);
+                    acc = fmaf(d1, d1, acc);
+                    acc = fmaf(d2, d2, acc);
+                    acc = fmaf(d3, d3, acc);
+                    acc = fmaf(d4, d4, acc);
+                    acc = fmaf(d5, d5, acc);
+                    acc = fmaf(d6, d6, acc);
+                    acc = fmaf(d7, d7, acc);
+                }
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (sqrtf(acc) * (1.f - 1e-5f) - f.ex[j] >= sj * (1.f + 1e-5f)) {
+                    ++n_bf;
+                    continue;
+                }
+            }
+            // exact: the scan kernels' arithmetic (one row per warp pass), then the reference's weight rule (src/ivfkmeans.c:59-69)
+            const uint4* rp = reinterpret_cast<const uint4*>(X + (size_t)j * stride);
+            Acc<VB_VECTOR, VB_L2_SQUARED> a;
+#pragma unroll 4
+            for (int v = lane; v < V; v += 32) a.add(ldg_stream(rp + v), ppf_sq, v);
+            a.template reduce<32>();
+            ++n_exact;
+            if (lane == 0) {
+                double distance = sqrt((double)(float)a.value());
+                distance *= distance;
+                if (distance < (double)wj) {
+                    const float nw = (float)distance;
+                    w[j] = nw;
+                    wd[j] = (double)nw;
+                    f.near[j] = i;
+                }
+            }
         }
     }
-    // exact: the scan kernels' arithmetic (one row per warp pass), then the reference's weight rule (src/ivfkmeans.c:59-69)
-    const uint4* rp = reinterpret_cast<const uint4*>(X + (size_t)j * stride);
-    Acc<VB_VECTOR, VB_L2_SQUARED> a;
-    for (int v = lane; v < V; v += 32) a.add(ldg_stream(rp + v), ppf_sq, v);
-    a.template reduce<32>();
     if (lane == 0) {
-        atomicAdd(&f.stats[2], 1ull);
-        double distance = sqrt((double)(float)a.value());
-        distance *= distance;
-        if (distance < (double)wj) {
-            const float nw = (float)distance;
-            w[j] = nw;
-            wd[j] = (double)nw;
-            f.near[j] = i;
-        }
+        if (n_tri) atomicAdd(&f.stats[0], n_tri);
+        if (n_bf) atomicAdd(&f.stats[1], n_bf);
+        if (n_exact) atomicAdd(&f.stats[2], n_exact);
     }
 }
 
@@ -947,7 +971,14 @@ static int pp_filter_round(const Table& X, const PpFilter& f, const uint8_t* cro
             VB_CUDA(cudaFuncSetAttribute(pp_filtered_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             attr = true;
         }
-        pp_filtered_pass_kernel<<<(unsigned)((X.n + PPF_WARPS - 1) / PPF_WARPS), PPF_WARPS * 32, smem, s>>>(X.d, X.stride, V, f, crow, i, X.n, d_w,
+        const int64_t want = (X.n + PPF_WARPS * 32 - 1) / (PPF_WARPS * 32);
+        static int resident = 0;   // CTAs per SM at this shared-memory size (one wave: the kernel is persistent)
+        if (resident == 0) {
+            VB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, pp_filtered_pass_kernel, PPF_WARPS * 32, smem));
+            resident = std::max(1, resident);
+        }
+        const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)ctx().sm_count * resident);
+        pp_filtered_pass_kernel<<<grid, PPF_WARPS * 32, smem, s>>>(X.d, X.stride, V, f, crow, i, X.n, d_w,
                                                                                                           d_wd);
     }
     VB_CUDA(cudaGetLastError());
