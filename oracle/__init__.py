@@ -46,11 +46,21 @@ def build(force: bool = False) -> None:
     if have and not force and all(os.path.getmtime(s) <= os.path.getmtime(so) for s in srcs):
         if os.path.exists(os.path.join(HERE, "_ref", "libpgvref.so")) or not os.path.exists("/root/reference/src"):
             return
-    if os.path.exists(so) and not have:
-        os.remove(so)
-    subprocess.run(["make", "-C", HERE, "-s", "all"], check=True, capture_output=True)
-    with open(stamp_path, "w") as f:
-        f.write(stamp)
+    # several processes (one per GPU under torchrun) may get here together: one builds, the others wait for the lock
+    # and find the library up to date; the library is linked beside its final name and renamed
+    import fcntl
+    with open(os.path.join(HERE, ".build_lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        have = os.path.exists(so) and os.path.exists(stamp_path) and open(stamp_path).read() == stamp
+        if have and not force and all(os.path.getmtime(s) <= os.path.getmtime(so) for s in srcs):
+            if os.path.exists(os.path.join(HERE, "_ref", "libpgvref.so")) or not os.path.exists("/root/reference/src"):
+                return
+        tmp = so + ".tmp"
+        subprocess.run(["make", "-C", HERE, "-s", "-B", "liboracle.so", "OUT=" + tmp], check=True, capture_output=True)
+        os.replace(tmp, so)
+        subprocess.run(["make", "-C", HERE, "-s", "ref"], check=True, capture_output=True)
+        with open(stamp_path, "w") as f:
+            f.write(stamp)
 
 
 _lib = None

@@ -46,6 +46,7 @@ struct Context {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;
     int64_t launches = 0;
+    int slab_select = 1;               // selection from the filter's slab minima (0: full radix selection of every run)
     uint64_t query_epoch = 0;          // bumped by every upload_queries(): caches keyed on a query image are valid for one batch only
     int tc_level1 = 1;                 // batched list scan: try the hi-plane-only filter first (vb_set_option "tc_level1")
     int pp_filter = 1;                 // k-means++ on large fp32 sample tables: triangle-inequality + bf16 filters in front of the exact distances
@@ -175,10 +176,20 @@ struct QueryGroups {
     int32_t* pair_q;     // [pairs] query number
     int32_t* pair_list;  // [pairs] list number
     int64_t* pair_out;   // [pairs] offset of the pair's candidate run in the distance buffer
+    int32_t* pair_sbase; // [pairs] first entry of the pair's run in the slab-minimum array (slab_base(), cap_s > 0 only)
     int64_t n_pairs;
 };
+// Slab minima of the tensor-core filter: a slab = 32 table-aligned rows of one (query, probe) pair's list; the filter's
+// epilogue stores min d~ over the slab next to the dense d~ array, and the selection reads only the slabs that can hold
+// one of the k' nearest.  Layout: query q owns cap_s = cap / 32 + 2 probes + 2 entries; probe p's run starts at
+// q cap_s + cand_off[q][p] / 32 + 2 p (a list of len rows spans at most len / 32 + 2 slabs, so runs never overlap) and
+// slab (r >> 5) - (list_off[l] >> 5) of the list is entry number that of the run.
+__host__ __device__ inline int64_t slab_cap(int64_t cap, int probes) { return (cap >> 5) + 2 * (int64_t)probes + 2; }
+__host__ __device__ inline int64_t slab_base(int64_t q, int64_t cap_s, int32_t cand_off, int p) {
+    return q * cap_s + (cand_off >> 5) + 2 * p;
+}
 int build_query_groups(const int32_t* d_lists, int64_t nq, int probes, const int32_t* cand_off, int64_t cap, int n_lists, int gt_rows,
-                       QueryGroups* g);
+                       QueryGroups* g, int64_t cap_s = 0);
 // tensor-core filter of the batched list scan (vb_list_tc.cu)
 struct ListUnit {
     int32_t list;
@@ -200,7 +211,12 @@ int list_tc_prepare(const Table& rows, ListTcImage* im);
 void list_tc_release(ListTcImage* im);
 int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
                    const int32_t* d_lists, int probes, const int32_t* cand_off, int64_t cap, const int64_t* d_list_off, int n_lists,
-                   float* out, const float** qn_out, bool one_list_all_queries = false, int level = 2);
+                   float* out, const float** qn_out, bool one_list_all_queries = false, int level = 2, float* smin = nullptr,
+                   int64_t cap_s = 0);
+// the k' nearest of every query's candidate run from the slab minima (same output as launch_segment_topk_v)
+int launch_slab_select(const float* dist, const float* smin, int64_t nq, int probes, const int32_t* probe_lists, const int32_t* cand_off,
+                       const int64_t* list_off, int64_t cap, int64_t cap_s, const int64_t* seg_begin, const int32_t* seg_len, int kp,
+                       int32_t* out_pos, float* out_key);
 int launch_list_tc_refine(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
                           int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
                           const int32_t* seg_len, const float* qn, const int32_t* pos_kp, const float* approx_kp, int32_t* out_pos,

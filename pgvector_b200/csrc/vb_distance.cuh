@@ -47,6 +47,18 @@ __device__ __forceinline__ float fh_sub(uint16_t a, float c) {
     return d;
 }
 
+// the same read marked evict-first in L2 (random row gathers of a graph walk: each row is used once, and the lines it would
+// displace -- the per-query visited tables, the neighbour lists -- are re-used)
+__device__ __forceinline__ uint4 ldg_gather(const uint4* p) {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+
 template <int ELEM, int METRIC>
 struct Acc {
     // fp metrics: a = main sum, b = |row|^2, c = |query|^2 (cosine only)

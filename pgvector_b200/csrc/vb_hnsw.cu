@@ -220,10 +220,11 @@ static int hnsw_search_impl(Hnsw& h, const void* queries, int64_t nq, int ef, in
     VB_TRY(hnsw_launch(h, g, qimg, qstride, nq, ef, k, nullptr, 0, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, &resident));
     const int grid = (int)std::min<int64_t>(want_ctas, (int64_t)c.sm_count * std::max(1, resident));
     // layer-0 table: a search visits a few multiples of ef elements (about 20 ef at m = 16), and the table may fill to
-    // half; it is cleared once per query, so it is sized tightly (the clears were 37 % of the round-1 kernel's DRAM
-    // traffic at 16 ef m) and grows on overflow -- the grown size is remembered per ef_search
+    // three quarters.  It is sized tightly: the tables of all resident warps together should stay in L2 (3552 warps x
+    // 64 KB did not: every visited probe of the 10 M-row bit graph went to DRAM, ncu r2_hnsw_E), and the per-query clear
+    // is proportional to it.  It grows on overflow -- the grown size is remembered per ef_search.
     uint32_t cap = 1u << 12;
-    while (cap < (uint32_t)(ef * h.m * 4) && cap < (1u << 22)) cap <<= 1;
+    while (cap < (uint32_t)(ef * h.m * 2) && cap < (1u << 22)) cap <<= 1;
     if (h.vis_hint_ef == ef && h.vis_hint_cap > cap) cap = h.vis_hint_cap;
     // the ef = 1 upper layers visit a few neighbour lists each
     uint32_t vis_upper = 1024;

@@ -146,6 +146,17 @@ __device__ __forceinline__ void load_query_image(const uint4* gq, int qvec, int 
     }
 }
 
+#ifndef VB_HNSW_EVICT_FIRST
+#define VB_HNSW_EVICT_FIRST 1
+#endif
+__device__ __forceinline__ uint4 hnsw_row_ld(const uint4* p) {
+#if VB_HNSW_EVICT_FIRST
+    return ldg_gather(p);
+#else
+    return ldg_stream(p);
+#endif
+}
+
 // distances of the image `sq` to the rows bid[0..cnt): GROUPS rows per pass (LPR lanes per row), RPI passes in flight.
 // bkey[i] = orderable key of the float8 the opclass's proc 1 returns.
 template <int ELEM, int METRIC, int LPR>
@@ -169,20 +180,20 @@ __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* 
         uint4 bufa[RPI], bufb[RPI];
         if (gl < g.V) {
 #pragma unroll
-            for (int i = 0; i < RPI; ++i) bufa[i] = ldg_stream(rp[i] + gl);
+            for (int i = 0; i < RPI; ++i) bufa[i] = hnsw_row_ld(rp[i] + gl);
         }
         for (int v = gl; v < g.V; v += 2 * LPR) {
             const int v1 = v + LPR, v2 = v + 2 * LPR;
             if (v1 < g.V) {
 #pragma unroll
-                for (int i = 0; i < RPI; ++i) bufb[i] = ldg_stream(rp[i] + v1);
+                for (int i = 0; i < RPI; ++i) bufb[i] = hnsw_row_ld(rp[i] + v1);
             }
 #pragma unroll
             for (int i = 0; i < RPI; ++i) hnsw_acc_add<ELEM, METRIC>(acc[i], bufa[i], sq, v);
             if (v1 < g.V) {
                 if (v2 < g.V) {
 #pragma unroll
-                    for (int i = 0; i < RPI; ++i) bufa[i] = ldg_stream(rp[i] + v2);
+                    for (int i = 0; i < RPI; ++i) bufa[i] = hnsw_row_ld(rp[i] + v2);
                 }
 #pragma unroll
                 for (int i = 0; i < RPI; ++i) hnsw_acc_add<ELEM, METRIC>(acc[i], bufb[i], sq, v1);
@@ -355,7 +366,7 @@ __device__ __forceinline__ void hnsw_merge_batch(HnswWarpState& S, int cnt, int 
 // HnswSearchLayer (src/hnswutils.c:824-987) at layer lc with ef = efl from the entry points already in R
 // (S.len of them, sorted).  tab / cap: this layer's visited table (cleared here, InitVisited :671-680).
 // ndist (may be null) accumulates the reference's `tuples` counter (:866-873, 905-906).  Returns false when the
-// visited table filled beyond half (the caller retries with a larger one).
+// visited table filled beyond three quarters (the caller retries with a larger one).
 // ITER: the iterative scan's variant -- everything seen and not kept goes to `sink`; init_visited = false resumes on
 // the visited table of the previous call (entry points are neither re-added nor counted, :864-873).
 template <int ELEM, int METRIC, int LPR, bool ITER = false>
@@ -433,8 +444,8 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
             hnsw_merge_batch<ITER>(S, cnt, efl, lane, sink);
             if (first_inval < 32) break;
         }
-        // keep the table at most half full; otherwise report and let the host retry with a larger one
-        if (inserted > cap / 2) {
+        // keep the table at most three quarters full; otherwise report and let the host retry with a larger one
+        if (inserted > cap - cap / 4) {
             ok = false;
             break;
         }

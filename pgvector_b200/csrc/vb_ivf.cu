@@ -14,7 +14,7 @@ namespace vb {
 // workspace slots
 enum { WS_QIMG = 0, WS_DIST = 1, WS_CDIST = 2, WS_PROBES = 3, WS_CHUNKS = 4, WS_SEG = 5, WS_POS = 6, WS_OUT = 7 };
 // 8..11 are used by the CUB sort path in vb_scan.cu
-enum { WS_MISC = 12, WS_OUT2 = 13 };
+enum { WS_MISC = 12, WS_OUT2 = 13, WS_SMIN = 31 };
 
 __global__ void regular_segments_kernel(int64_t nseg, int64_t stride, int32_t len, int64_t* begin, int32_t* lens) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -377,8 +377,15 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
         ix.last_list_level = level;
         const int kp = list_tc_kp(k, level);
         const float* qn = nullptr;
+        // slab minima for the selection (vb_common.cuh slab_base): with them the k' nearest are found from 32 k' candidates
+        // per query instead of the whole run
+        const int64_t cap_s = slab_cap(cap, probes);
+        const bool slabs = c.slab_select && c.fused_refine != 2 && kp <= 128 && nq * cap_s < (int64_t)INT32_MAX &&
+                           (size_t)cap_s * 4 + 20 * 1024 <= 160 * 1024;
+        void* d_smin = nullptr;
+        if (slabs) VB_TRY(workspace(WS_SMIN, sizeof(float) * (size_t)nq * cap_s, &d_smin));
         VB_TRY(launch_list_tc(ix.rows, ix.tc, km, qimg, qstride, nq, d_lists, probes, cand_off, cap, ix.d_list_off, ix.lists,
-                              (float*)d_dist, &qn, false, level));
+                              (float*)d_dist, &qn, false, level, (float*)d_smin, cap_s));
         prof_end(VB_PROF_SCAN_ITEMS);
         VB_TRY(workspace(WS_POS, (sizeof(int32_t) + sizeof(float)) * (size_t)nq * (k + kp), &d_pos));
         int32_t* pos = (int32_t*)d_pos;
@@ -397,12 +404,20 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
                                                 (const float*)d_dist, seg_begin, seg_len, qn, pos, key, ix.d_tc_fail + 1,
                                                 ix.defer_tc_check ? nullptr : &n_failed, level));
         } else if (c.fused_refine == 1) {
-            VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, nullptr, nullptr, nq, kp, pos_kp, key_kp));
+            if (slabs)
+                VB_TRY(launch_slab_select((const float*)d_dist, (const float*)d_smin, nq, probes, d_lists, cand_off, ix.d_list_off, cap,
+                                          cap_s, seg_begin, seg_len, kp, pos_kp, key_kp));
+            else
+                VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, nullptr, nullptr, nq, kp, pos_kp, key_kp));
             VB_TRY(launch_list_tc_select_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off,
                                                 (const float*)d_dist, seg_begin, seg_len, qn, pos, key, ix.d_tc_fail + 1,
                                                 ix.defer_tc_check ? nullptr : &n_failed, level, pos_kp, key_kp));
         } else {
-            VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, nullptr, nullptr, nq, kp, pos_kp, key_kp));
+            if (slabs)
+                VB_TRY(launch_slab_select((const float*)d_dist, (const float*)d_smin, nq, probes, d_lists, cand_off, ix.d_list_off, cap,
+                                          cap_s, seg_begin, seg_len, kp, pos_kp, key_kp));
+            else
+                VB_TRY(launch_segment_topk_v((const float*)d_dist, seg_begin, seg_len, nullptr, nullptr, nq, kp, pos_kp, key_kp));
             VB_TRY(launch_list_tc_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off, seg_len, qn,
                                          pos_kp, key_kp, pos, key, ix.d_tc_fail + 1, ix.defer_tc_check ? nullptr : &n_failed, level));
         }

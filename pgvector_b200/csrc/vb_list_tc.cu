@@ -70,6 +70,8 @@ struct LcArgs {
     const float* xn;           // |x|^2 per table row
     const float* qn;           // |q|^2 per query of the batch
     float* out;
+    float* smin;               // slab minima (slab_base(), vb_common.cuh) or nullptr
+    const int32_t* pair_sbase;
     int n_kblocks;
     int is_l2;
     int hi_only;               // level 1: only the hi plane of the rows is read and multiplied (x_hi . (q_hi + q_lo))
@@ -223,6 +225,9 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
             const bool valid_row = r_table >= lo && r_table < hi;
             const float xnr = valid_row && a.is_l2 ? a.xn[r_table] : 0.f;
             const int gb = a.grp_begin[un.list];
+            // this warp's 32 rows are one table-aligned slab of the list (if any of them belongs to it)
+            const bool slabs = a.smin != nullptr && __ballot_sync(0xffffffffu, valid_row) != 0;
+            const int slab_local = (int)((((int64_t)un.tile * LC_M + qr * 32) >> 5) - (lo >> 5));
             for (int qt = jb.q_lo; qt < jb.q_hi; ++qt, ++tile) {
                 const int as = tile & 1;
                 const uint32_t aph = (tile >> 1) & 1;
@@ -247,15 +252,25 @@ __global__ void __launch_bounds__(LC_THREADS, 1) list_tc_kernel(LcArgs a) {
                         my_out = a.pair_out[gb + myc];
                         if (a.is_l2) my_qn = a.qn[a.pair_q[gb + myc]];
                     }
+                    float my_min = __int_as_float(0x7F800000);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const int64_t po = __shfl_sync(0xffffffffu, my_out, j);
                         const float qn = __shfl_sync(0xffffffffu, my_qn, j);
+                        float val = __int_as_float(0x7F800000);
                         if (col0 + j < cnt && valid_row) {
                             const float dot = __uint_as_float(acc[j]);
-                            a.out[po + (r_table - lo)] = a.is_l2 ? fmaf(-2.f, dot, xnr + qn) : -dot;
+                            val = a.is_l2 ? fmaf(-2.f, dot, xnr + qn) : -dot;
+                            a.out[po + (r_table - lo)] = val;
+                        }
+                        if (slabs) {
+                            // minimum of column j over the warp's 32 rows (one CREDUX), kept by lane j
+                            float m;
+                            asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(m) : "f"(val));
+                            if (lane == j) my_min = m;
                         }
                     }
+                    if (slabs && myc < cnt) a.smin[a.pair_sbase[gb + myc] + slab_local] = my_min;
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -700,11 +715,11 @@ void list_tc_release(ListTcImage* im) {
 // approximate pass: fills `out` (the per-query candidate runs) with d~
 int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
                    const int32_t* d_lists, int probes, const int32_t* cand_off, int64_t cap, const int64_t* d_list_off, int n_lists,
-                   float* out, const float** qn_out, bool one_list_all_queries, int level) {
+                   float* out, const float** qn_out, bool one_list_all_queries, int level, float* smin, int64_t cap_s) {
     Context& c = ctx();
     cudaStream_t s = c.stream;
     QueryGroups g{};
-    VB_TRY(build_query_groups(d_lists, nq, probes, cand_off, cap, n_lists, LC_N, &g));
+    VB_TRY(build_query_groups(d_lists, nq, probes, cand_off, cap, n_lists, LC_N, &g, smin ? cap_s : 0));
     const int64_t max_gtiles = g.n_pairs / LC_N + n_lists + 1;
     void *d_B, *d_qn;
     VB_TRY(workspace(WSC_B, (size_t)max_gtiles * im.n_kblocks * LC_B_STAGE, &d_B));
@@ -751,6 +766,8 @@ int launch_list_tc(const Table& rows, const ListTcImage& im, int key_metric, con
     a.xn = im.xn;
     a.qn = (const float*)d_qn;
     a.out = out;
+    a.smin = smin;
+    a.pair_sbase = g.pair_sbase;
     a.n_kblocks = im.n_kblocks;
     a.is_l2 = key_metric == VB_L2_SQUARED;
     a.hi_only = level == 1;

@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(1024) lt_group_kernel(const int32_t* __restric
                                                         const int32_t* __restrict__ cand_off, int64_t cap, int n_lists, int gt_rows,
                                                         int32_t* __restrict__ cnt, int32_t* __restrict__ begin,
                                                         int32_t* __restrict__ gt_begin, int32_t* __restrict__ pair_q,
-                                                        int64_t* __restrict__ pair_out, int32_t* __restrict__ pair_list) {
+                                                        int64_t* __restrict__ pair_out, int32_t* __restrict__ pair_list,
+                                                        int32_t* __restrict__ pair_sbase, int64_t cap_s) {
     extern __shared__ int32_t lg_smem[];
     int32_t* scnt = lg_smem;             // [n_lists]
     int32_t* scur = lg_smem + n_lists;   // [n_lists] begin, then the running cursor, then the tile counts
@@ -349,6 +350,7 @@ __global__ void __launch_bounds__(1024) lt_group_kernel(const int32_t* __restric
             pair_q[slot] = q;
             pair_out[slot] = (int64_t)q * cap + co[u];
             pair_list[slot] = l[u];
+            if (cap_s) pair_sbase[slot] = (int32_t)slab_base(q, cap_s, co[u], i % probes);
         }
     }
     if (gt_rows > 0) {
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(1024) lt_group_kernel(const int32_t* __restric
 __global__ void lt_scatter_kernel(const int32_t* __restrict__ probe_lists, int64_t n_pairs, int probes,
                                   const int32_t* __restrict__ cand_off, int64_t cap, const int32_t* __restrict__ begin,
                                   int32_t* __restrict__ cursor, int32_t* __restrict__ pair_q, int64_t* __restrict__ pair_out,
-                                  int32_t* __restrict__ pair_list) {
+                                  int32_t* __restrict__ pair_list, int32_t* __restrict__ pair_sbase, int64_t cap_s) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n_pairs) return;
     const int l = probe_lists[i];
@@ -373,6 +375,7 @@ __global__ void lt_scatter_kernel(const int32_t* __restrict__ probe_lists, int64
     pair_q[slot] = (int32_t)q;
     pair_out[slot] = q * cap + cand_off[q * (probes + 1) + p];
     pair_list[slot] = l;
+    if (cap_s) pair_sbase[slot] = (int32_t)slab_base(q, cap_s, cand_off[q * (probes + 1) + p], p);
 }
 
 // tiles[l] = ceil(cnt[l] / rows_per_tile): the number of query tiles of each list (input of a second prefix sum)
@@ -390,13 +393,14 @@ enum { WSL_GROUPS = 20 };
 // Group the (query, probe) pairs of a batch by list.  gt_rows > 0 additionally numbers the query tiles of
 // gt_rows queries over all lists (tensor-core path: one packed B tile per query tile).
 int build_query_groups(const int32_t* d_lists, int64_t nq, int probes, const int32_t* cand_off, int64_t cap, int n_lists, int gt_rows,
-                       QueryGroups* g) {
+                       QueryGroups* g, int64_t cap_s) {
     Context& c = ctx();
     cudaStream_t s = c.stream;
     const int64_t n_pairs = nq * probes;
     VB_REQUIRE(n_pairs < (int64_t)INT32_MAX, "too many (query, probe) pairs");
     void* d_ws;
-    const size_t ints = (size_t)n_lists * 5 + (size_t)n_pairs * 2;
+    VB_REQUIRE(nq * cap_s < (int64_t)INT32_MAX, "slab-minimum array too large (%lld queries)", (long long)nq);
+    const size_t ints = (size_t)n_lists * 5 + (size_t)n_pairs * 3;
     VB_TRY(workspace(WSL_GROUPS, sizeof(int64_t) * (size_t)n_pairs + sizeof(int32_t) * ints + 64, &d_ws));
     g->pair_out = (int64_t*)d_ws;
     g->pair_q = (int32_t*)(g->pair_out + n_pairs);
@@ -406,6 +410,7 @@ int build_query_groups(const int32_t* d_lists, int64_t nq, int probes, const int
     g->begin = cursor + n_lists;
     int32_t* tiles = g->begin + n_lists;
     g->gt_begin = tiles + n_lists;
+    g->pair_sbase = g->gt_begin + n_lists;
     g->n_pairs = n_pairs;
     if (n_pairs <= 131072 && n_lists <= 8192) {
         static bool attr_set = false;
@@ -414,7 +419,8 @@ int build_query_groups(const int32_t* d_lists, int64_t nq, int probes, const int
             attr_set = true;
         }
         lt_group_kernel<<<1, 1024, sizeof(int32_t) * 2 * (size_t)n_lists, s>>>(d_lists, (int)n_pairs, probes, cand_off, cap, n_lists, gt_rows, g->cnt,
-                                                                            g->begin, g->gt_begin, g->pair_q, g->pair_out, g->pair_list);
+                                                                            g->begin, g->gt_begin, g->pair_q, g->pair_out, g->pair_list,
+                                                                            g->pair_sbase, cap_s);
         VB_CUDA(cudaGetLastError());
         count_launch();
         return VB_OK;
@@ -423,7 +429,8 @@ int build_query_groups(const int32_t* d_lists, int64_t nq, int probes, const int
     const unsigned gp = (unsigned)((n_pairs + 255) / 256);
     lt_count_kernel<<<gp, 256, 0, s>>>(d_lists, n_pairs, g->cnt);
     lt_scan_kernel<<<1, 1024, 0, s>>>(g->cnt, n_lists, g->begin);
-    lt_scatter_kernel<<<gp, 256, 0, s>>>(d_lists, n_pairs, probes, cand_off, cap, g->begin, cursor, g->pair_q, g->pair_out, g->pair_list);
+    lt_scatter_kernel<<<gp, 256, 0, s>>>(d_lists, n_pairs, probes, cand_off, cap, g->begin, cursor, g->pair_q, g->pair_out, g->pair_list,
+                                         g->pair_sbase, cap_s);
     count_launch(3);
     if (gt_rows > 0) {
         lt_tiles_kernel<<<(unsigned)((n_lists + 255) / 256), 256, 0, s>>>(g->cnt, n_lists, gt_rows, tiles);

@@ -257,8 +257,10 @@ __global__ void __launch_bounds__(TOPK_THREADS) segment_topk_kernel(const float*
                                                                     const int64_t* __restrict__ seg_begin,
                                                                     const int32_t* __restrict__ seg_len, int k,
                                                                     int kpow2, int32_t* __restrict__ out_pos,
-                                                                    float* __restrict__ out_key) {
+                                                                    float* __restrict__ out_key,
+                                                                    const int32_t* __restrict__ only_flagged) {
     extern __shared__ uint64_t sel[];  // kpow2 entries
+    if (only_flagged != nullptr && only_flagged[blockIdx.x] == 0) return;   // (the slab selection's overflow path)
     __shared__ uint32_t hist[256];
     __shared__ uint64_t s_prefix, s_mask;
     __shared__ uint32_t s_kk, s_done, s_count;
@@ -363,6 +365,182 @@ __global__ void __launch_bounds__(TOPK_THREADS) segment_topk_kernel(const float*
     }
 }
 
+// ---- the k' nearest of a candidate run from the slab minima of the tensor-core filter -------------------------------------
+//
+// The filter's epilogue stores, beside the dense d~ array, min d~ of every slab (32 table-aligned rows of one probed list,
+// slab_base() in vb_common.cuh).  tau = the k'-th smallest slab minimum is an upper bound of the k'-th smallest d~ (k'
+// distinct candidates are <= tau), so the k' nearest all lie in slabs whose minimum is <= tau: exactly k' slabs when the
+// minima are distinct -- 32 k' candidates are read per query instead of the whole run (100 k at the headline shape, where
+// the eight radix passes of segment_topk_kernel over 2048 such runs took 190 us).
+// One CTA per query: (1) the run's slab minima into shared memory, (2) radix-select tau, (3) gather the candidates <= tau
+// of the qualifying slabs, (4) sort by (d~, position), emit k'.  More candidates than the buffer holds (massive ties)
+// flags the query for segment_topk_kernel.  Output: identical to segment_topk_kernel's.
+constexpr int SS_THREADS = 256;
+constexpr int SS_CAND = 2048;
+
+__global__ void __launch_bounds__(SS_THREADS) slab_select_kernel(const float* __restrict__ dist, const float* __restrict__ smin, int probes,
+                                                                 const int32_t* __restrict__ probe_lists,
+                                                                 const int32_t* __restrict__ cand_off, const int64_t* __restrict__ list_off,
+                                                                 int64_t cap, int64_t cap_s, int n_slab_max, int k,
+                                                                 int32_t* __restrict__ out_pos, float* __restrict__ out_key,
+                                                                 int32_t* __restrict__ flagged) {
+    extern __shared__ uint64_t ss_smem[];
+    uint64_t* cand = ss_smem;                                             // [SS_CAND]
+    uint32_t* skey = reinterpret_cast<uint32_t*>(cand + SS_CAND);         // [n_slab_max] orderable slab minima
+    int32_t* s_off = reinterpret_cast<int32_t*>(skey + n_slab_max);       // [probes + 1] first slab of every probe
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_mask, s_kk, s_done, s_count;
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int32_t* co = cand_off + (int64_t)q * (probes + 1);
+    const int32_t* pl = probe_lists + (int64_t)q * probes;
+    if (tid == 0) {
+        int off = 0;
+        for (int p = 0; p < probes; ++p) {
+            s_off[p] = off;
+            const int l = pl[p];
+            if (l >= 0) {
+                const int64_t lo = list_off[l], hi = list_off[l + 1];
+                if (hi > lo) off += (int)(((hi - 1) >> 5) - (lo >> 5) + 1);
+            }
+        }
+        s_off[probes] = off;
+        s_count = 0;
+        flagged[q] = 0;
+    }
+    __syncthreads();
+    const int S = s_off[probes];
+    for (int p = 0; p < probes; ++p) {
+        const int ns = s_off[p + 1] - s_off[p];
+        const float* sp = smin + slab_base(q, cap_s, co[p], p);
+        for (int j = tid; j < ns; j += SS_THREADS) skey[s_off[p] + j] = orderable_key(sp[j]);
+    }
+    __syncthreads();
+    // ---- tau: the k-th smallest slab minimum (everything when there are at most k slabs)
+    uint32_t tau = 0xFFFFFFFFu;
+    if (S > k) {
+        if (tid == 0) {
+            s_prefix = 0;
+            s_mask = 0;
+            s_kk = (uint32_t)k;
+            s_done = 0;
+        }
+        __syncthreads();
+        for (int pass = 3; pass >= 0; --pass) {
+            hist[tid] = 0;
+            __syncthreads();
+            const int shift = pass * 8;
+            const uint32_t prefix = s_prefix, mask = s_mask;
+            for (int i = tid; i < S; i += SS_THREADS) {
+                const uint32_t key = skey[i];
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                uint32_t kk = s_kk, cum = 0;
+                int b = 0;
+                for (; b < 256; ++b) {
+                    if (cum + hist[b] >= kk) break;
+                    cum += hist[b];
+                }
+                s_prefix = prefix | ((uint32_t)b << shift);
+                s_mask = mask | (0xFFu << shift);
+                s_kk = kk - cum;
+            }
+            __syncthreads();
+        }
+        tau = s_prefix;   // exactly the k-th smallest key (ties included by the <= below)
+    }
+    // ---- gather: one warp per qualifying slab, lane = row of the slab
+    const int warp = tid / 32, lane = tid % 32;
+    const float* dq = dist + (int64_t)q * cap;
+    for (int p = 0; p < probes; ++p) {
+        const int ns = s_off[p + 1] - s_off[p];
+        if (ns == 0) continue;
+        const int l = pl[p];
+        const int64_t lo = list_off[l], hi = list_off[l + 1];
+        const int64_t slab0 = lo >> 5;
+        for (int j = warp; j < ns; j += SS_THREADS / 32) {
+            if (skey[s_off[p] + j] > tau) continue;          // warp-uniform
+            const int64_t r = ((slab0 + j) << 5) + lane;
+            if (r >= lo && r < hi) {
+                const uint32_t pos = (uint32_t)(co[p] + (int32_t)(r - lo));
+                const uint32_t ok = orderable_key(dq[pos]);
+                if (ok <= tau) {
+                    const uint32_t slot = atomicAdd(&s_count, 1u);
+                    if (slot < (uint32_t)SS_CAND) cand[slot] = ((uint64_t)ok << 32) | pos;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t n = s_count;
+    if (n > (uint32_t)SS_CAND) {
+        if (tid == 0) flagged[q] = 1;
+        return;
+    }
+    // ---- sort by (d~, position) and emit
+    int npow2 = 2;
+    while ((uint32_t)npow2 < n) npow2 <<= 1;
+    for (int i = (int)n + tid; i < npow2; i += SS_THREADS) cand[i] = ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= npow2; size <<= 1) {
+        for (int st = size >> 1; st > 0; st >>= 1) {
+            for (int i = tid; i < npow2; i += SS_THREADS) {
+                const int j = i ^ st;
+                if (j > i) {
+                    const uint64_t x = cand[i], y = cand[j];
+                    const bool up = (i & size) == 0;
+                    if ((x > y) == up) {
+                        cand[i] = y;
+                        cand[j] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < k; i += SS_THREADS) {
+        if ((uint32_t)i < n) {
+            const uint64_t key = cand[i];
+            out_pos[(int64_t)q * k + i] = (int32_t)(uint32_t)key;
+            out_key[(int64_t)q * k + i] = key_to_float((uint32_t)(key >> 32));
+        } else {
+            out_pos[(int64_t)q * k + i] = -1;
+            out_key[(int64_t)q * k + i] = __int_as_float(0x7F800000);
+        }
+    }
+}
+
+enum { WSS_FLAG = 30 };
+
+int launch_slab_select(const float* dist, const float* smin, int64_t nq, int probes, const int32_t* probe_lists, const int32_t* cand_off,
+                       const int64_t* list_off, int64_t cap, int64_t cap_s, const int64_t* seg_begin, const int32_t* seg_len, int kp,
+                       int32_t* out_pos, float* out_key) {
+    if (nq == 0) return VB_OK;
+    cudaStream_t s = ctx().stream;
+    VB_REQUIRE(kp <= TOPK_MAX_K, "slab selection: k' too large");
+    void* d_flag;
+    VB_TRY(workspace(WSS_FLAG, sizeof(int32_t) * (size_t)nq, &d_flag));
+    const size_t smem = (size_t)SS_CAND * 8 + (size_t)cap_s * 4 + (size_t)(probes + 1) * 4;
+    VB_REQUIRE(smem <= 200 * 1024, "slab selection: %zu bytes of shared memory", smem);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        VB_CUDA(cudaFuncSetAttribute(slab_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    slab_select_kernel<<<(unsigned)nq, SS_THREADS, smem, s>>>(dist, smin, probes, probe_lists, cand_off, list_off, cap, cap_s, (int)cap_s, kp,
+                                                            out_pos, out_key, (int32_t*)d_flag);
+    // queries whose candidates did not fit (ties by the thousand) take the full selection
+    int kpow2 = 2;
+    while (kpow2 < kp) kpow2 <<= 1;
+    segment_topk_kernel<<<(unsigned)nq, TOPK_THREADS, (size_t)kpow2 * 8, s>>>(dist, seg_begin, seg_len, kp, kpow2, out_pos, out_key,
+                                                                            (const int32_t*)d_flag);
+    VB_CUDA(cudaGetLastError());
+    count_launch(2);
+    return VB_OK;
+}
+
 // --- large k / "sort everything": composite keys + CUB segmented radix sort (not the hot path:
 //     the keys are 0.07 % of the bytes the scan kernel streams)
 __global__ void build_composite_kernel(const float* __restrict__ keys, const int64_t* __restrict__ seg_begin,
@@ -403,7 +581,7 @@ int launch_segment_topk_v(const float* keys, const int64_t* seg_begin_dev, const
         int kpow2 = 2;
         while (kpow2 < k) kpow2 <<= 1;
         segment_topk_kernel<<<(unsigned)nseg, TOPK_THREADS, (size_t)kpow2 * 8, s>>>(keys, seg_begin_dev, seg_len_dev, k,
-                                                                                 kpow2, out_pos, out_key);
+                                                                                 kpow2, out_pos, out_key, nullptr);
         VB_CUDA(cudaGetLastError());
         count_launch();
         return VB_OK;

@@ -195,3 +195,57 @@ def test_fused_select_refine_equals_the_three_kernel_path(pv, headline, k, probe
             for x, y in zip(a[:4], b[:4]):
                 assert np.array_equal(x, y), (level1, fused, k, probes)
             assert a[4:] == b[4:]
+
+
+@pytest.mark.parametrize("k,probes", [(10, 10), (1, 3), (40, 20)])
+def test_selection_from_slab_minima_equals_the_full_selection(pv, headline, k, probes):
+    """The filter's epilogue stores the minimum d~ of every 32-row slab; the k' nearest are then selected from the slabs
+    whose minimum is under the k'-th smallest slab minimum (vb_scan.cu slab_select_kernel) instead of a radix selection
+    over the whole candidate run.  Same candidates, same order: outputs are bit-identical, at both filter levels and
+    with either refine path."""
+    law, ix, oix, queries, _ = headline
+    qs = queries[:300]
+    out = {}
+    try:
+        pv.set_option("scan_impl", 4)
+        for level1 in (1, 0):
+            pv.set_option("tc_level1", level1)
+            for fused in (1, 0):
+                pv.set_option("fused_refine", fused)
+                for slab in (0, 1):
+                    pv.set_option("slab_select", slab)
+                    f0 = ix.tc_fallbacks()
+                    out[(level1, fused, slab)] = ix.search(qs, k=k, probes=probes) + (ix.tc_fallbacks() - f0,)
+    finally:
+        pv.set_option("slab_select", 1)
+        pv.set_option("fused_refine", 1)
+        pv.set_option("tc_level1", 1)
+        pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
+    for level1 in (1, 0):
+        for fused in (1, 0):
+            i0, d0, f0 = out[(level1, fused, 0)]
+            i1, d1, f1 = out[(level1, fused, 1)]
+            assert np.array_equal(i0, i1) and np.array_equal(d0, d1) and f0 == f1
+
+
+def test_selection_from_slab_minima_with_ties_by_the_thousand(pv):
+    """5000 copies of one row: every slab minimum ties, more candidates qualify than the selection's buffer holds, and the
+    flagged queries go through the full selection -- results still equal the exact scan's (ids by position order)"""
+    rng = np.random.default_rng(11)
+    dim = 64
+    base = rng.standard_normal((3000, dim)).astype(np.float32)
+    dup = np.repeat(base[:1], 5000, axis=0)
+    rows = np.concatenate([dup, base])
+    ix, oix = build(pv, rows, 4, seed=2)
+    qs = np.concatenate([base[:1] + 0.01, base[5:40]]).astype(np.float32)
+    try:
+        pv.set_option("scan_impl", 4)
+        got_i, got_d = ix.search(qs, k=10, probes=4)
+        pv.set_option("scan_impl", 3)
+        want_i, want_d = ix.search(qs, k=10, probes=4)
+    finally:
+        pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
+    assert np.allclose(got_d, want_d, rtol=1e-5, atol=1e-6)
+    # among exact ties the order is by position in the list; both paths apply it
+    assert np.array_equal(got_i[1:], want_i[1:])
+    assert set(got_i[0].tolist()) <= set(range(5000))

@@ -85,8 +85,17 @@ def main():
     c_sh, it_sh = pv.kmeans(t, pv.L2, want, max_iter=30)
     pv.comm_free()
     c_one, it_one = pv.kmeans(tf, pv.L2, want, max_iter=30)
-    err = float(np.max(np.abs(c_sh - c_one)))
-    say("k-means sharded ~ single", err < 1e-3 and abs(it_sh - it_one) <= 2, f"max |dc| {err:.2e}, iterations {it_sh} vs {it_one}")
+    # partial sums are added in rank order, not in sample order: one borderline sample may change cluster, which moves
+    # two centres by ~|x| / members; everything else must agree and the objective must be the same
+    dc = np.max(np.abs(c_sh - c_one), axis=1)
+
+    def objective(cent):
+        d = (samples ** 2).sum(1)[:, None] - 2.0 * samples @ cent.T + (cent ** 2).sum(1)[None, :]
+        return float(d.min(1).sum())
+    o_sh, o_one = objective(c_sh.astype(np.float64)), objective(c_one.astype(np.float64))
+    say("k-means sharded ~ single", float((dc < 1e-3).mean()) >= 0.9 and abs(o_sh - o_one) <= 1e-4 * o_one and abs(it_sh - it_one) <= 2,
+        f"centres within 1e-3: {int((dc < 1e-3).sum())}/{k}, max |dc| {dc.max():.2e}, objective {o_sh:.6g} vs {o_one:.6g}, "
+        f"iterations {it_sh} vs {it_one}")
 
     # 4. list-sharded search (a fresh communicator: the id was consumed)
     ident = [pv.comm_unique_id() if rank == 0 else None]
