@@ -19,7 +19,11 @@
  *   - "host" pointers are ordinary process memory; "_dev" variants take device
  *     pointers valid on the library's current device.  Work is enqueued on the
  *     library stream (vb_stream()); host-buffer variants synchronise before
- *     returning, _dev variants do not.
+ *     returning.  _dev variants return with their work enqueued, with two stated
+ *     exceptions: the batched vb_ivf_search*_dev read ONE 8-byte pair of certificate
+ *     counters per sub-batch of queries (the tensor-core filter re-runs an
+ *     uncertified batch exactly before the results may be used), and
+ *     vb_hnsw_search_dev reads one overflow flag per call (visited-table growth).
  *   - rows are row-major and contiguous in the caller's buffers (vector: dim
  *     fp32; halfvec: dim IEEE binary16; bit: (dim+7)/8 bytes, MSB first, tail
  *     bits zero -- exactly the payload of Vector.x (src/vector.h:18-24),

@@ -231,7 +231,9 @@ static int ivf_select_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t 
                               (float*)d_cdist, &qn, true));
         int n_failed = 0;
         if (!ix.defer_tc_check) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, sizeof(int), c.stream));
-        if (c.fused_refine == 2) {
+        // a run of a few thousand centre distances is selected inside the refine kernel (one warp streams it in a few
+        // steps: cheaper than a launch of the CTA-per-query radix selection, 43 us for 2048 x 1000); long runs are not
+        if (c.fused_refine == 2 || (c.fused_refine == 1 && ix.lists <= 4096)) {
             VB_TRY(launch_list_tc_select_refine(ix.centers, ix.ctc, km, qimg, qstride, nq, probes, kp, 1, zero_lists, pair_off, ix.d_centre_off,
                                                 (const float*)d_cdist, sb, sl, qn, lists, ldist, ix.d_tc_fail,
                                                 ix.defer_tc_check ? nullptr : &n_failed));

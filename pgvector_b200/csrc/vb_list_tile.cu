@@ -300,15 +300,13 @@ __device__ __forceinline__ void lt_block_scan(const int32_t* __restrict__ cnt, i
     }
 }
 
-// The whole grouping of a moderate batch in ONE launch of one CTA: count, scan, scatter, query tiles, scan -- counters
-// and cursors in shared memory (instead of a memset and five kernels with global atomics; a 2048-query batch has
-// 20 480 pairs = 20 per thread)
+// Counting, both prefix sums and the query-tile numbering of a moderate batch in ONE launch of one CTA -- counters in
+// shared memory (instead of a memset and four kernels with global atomics; a 2048-query batch has 20 480 pairs = 20 per
+// thread); lt_scatter_kernel then places the pairs
 __global__ void __launch_bounds__(1024) lt_group_kernel(const int32_t* __restrict__ probe_lists, int n_pairs, int probes,
                                                         const int32_t* __restrict__ cand_off, int64_t cap, int n_lists, int gt_rows,
                                                         int32_t* __restrict__ cnt, int32_t* __restrict__ begin,
-                                                        int32_t* __restrict__ gt_begin, int32_t* __restrict__ pair_q,
-                                                        int64_t* __restrict__ pair_out, int32_t* __restrict__ pair_list,
-                                                        int32_t* __restrict__ pair_sbase, int64_t cap_s) {
+                                                        int32_t* __restrict__ gt_begin, int32_t* __restrict__ cursor) {
     extern __shared__ int32_t lg_smem[];
     int32_t* scnt = lg_smem;             // [n_lists]
     int32_t* scur = lg_smem + n_lists;   // [n_lists] begin, then the running cursor, then the tile counts
@@ -333,26 +331,9 @@ __global__ void __launch_bounds__(1024) lt_group_kernel(const int32_t* __restric
         begin[i] = scur[i];
     }
     __syncthreads();
-    for (int i0 = threadIdx.x; i0 < n_pairs; i0 += 1024 * U) {
-        int l[U], co[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * 1024;
-            l[u] = i < n_pairs ? probe_lists[i] : -1;
-            co[u] = i < n_pairs ? cand_off[(i / probes) * (probes + 1) + i % probes] : 0;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (l[u] < 0) continue;
-            const int i = i0 + u * 1024;
-            const int q = i / probes;
-            const int slot = atomicAdd(&scur[l[u]], 1);
-            pair_q[slot] = q;
-            pair_out[slot] = (int64_t)q * cap + co[u];
-            pair_list[slot] = l[u];
-            if (cap_s) pair_sbase[slot] = (int32_t)slab_base(q, cap_s, co[u], i % probes);
-        }
-    }
+    // (the scatter is lt_scatter_kernel's: 80 k scattered 4-byte stores through ONE SM's store path took ~40 us of this
+    // kernel's 48; spread over the GPU they take a few)
+    for (int i = threadIdx.x; i < n_lists; i += 1024) cursor[i] = 0;
     if (gt_rows > 0) {
         __syncthreads();
         for (int i = threadIdx.x; i < n_lists; i += 1024) scur[i] = (scnt[i] + gt_rows - 1) / gt_rows;
@@ -419,10 +400,11 @@ int build_query_groups(const int32_t* d_lists, int64_t nq, int probes, const int
             attr_set = true;
         }
         lt_group_kernel<<<1, 1024, sizeof(int32_t) * 2 * (size_t)n_lists, s>>>(d_lists, (int)n_pairs, probes, cand_off, cap, n_lists, gt_rows, g->cnt,
-                                                                            g->begin, g->gt_begin, g->pair_q, g->pair_out, g->pair_list,
-                                                                            g->pair_sbase, cap_s);
+                                                                            g->begin, g->gt_begin, cursor);
+        lt_scatter_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, s>>>(d_lists, n_pairs, probes, cand_off, cap, g->begin, cursor, g->pair_q,
+                                                                          g->pair_out, g->pair_list, g->pair_sbase, cap_s);
         VB_CUDA(cudaGetLastError());
-        count_launch();
+        count_launch(2);
         return VB_OK;
     }
     VB_CUDA(cudaMemsetAsync(g->cnt, 0, sizeof(int32_t) * (size_t)n_lists * 2, s));
