@@ -224,7 +224,7 @@ static int hnsw_search_impl(Hnsw& h, const void* queries, int64_t nq, int ef, in
     // 64 KB did not: every visited probe of the 10 M-row bit graph went to DRAM, ncu r2_hnsw_E), and the per-query clear
     // is proportional to it.  It grows on overflow -- the grown size is remembered per ef_search.
     uint32_t cap = 1u << 12;
-    while (cap < (uint32_t)(ef * h.m * 2) && cap < (1u << 22)) cap <<= 1;
+    while (cap < (uint32_t)(ef * h.m * (VB_AB_VIS ? 2 : 4)) && cap < (1u << 22)) cap <<= 1;
     if (h.vis_hint_ef == ef && h.vis_hint_cap > cap) cap = h.vis_hint_cap;
     // the ef = 1 upper layers visit a few neighbour lists each
     uint32_t vis_upper = 1024;

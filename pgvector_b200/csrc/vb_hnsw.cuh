@@ -99,7 +99,10 @@ __device__ __forceinline__ bool ent_less(uint64_t ka, uint32_t ia, uint64_t kb, 
 // conversions; bit-identical to the widened arithmetic, see fh_fma).
 template <int ELEM, int METRIC>
 struct HnswImage {
-    static constexpr bool packed = ELEM == VB_HALFVEC && METRIC == VB_NEG_IP;
+#ifndef VB_AB_PACKED
+#define VB_AB_PACKED 1
+#endif
+    static constexpr bool packed = VB_AB_PACKED && ELEM == VB_HALFVEC && METRIC == VB_NEG_IP;
 };
 
 template <int ELEM, int METRIC>
@@ -149,6 +152,16 @@ __device__ __forceinline__ void load_query_image(const uint4* gq, int qvec, int 
 #ifndef VB_HNSW_EVICT_FIRST
 #define VB_HNSW_EVICT_FIRST 1
 #endif
+// A/B switches of the round-2 changes (tools/gpu_session7.sh measures each against the others; see profiles/r2_hnsw_ab.md)
+#ifndef VB_AB_PINGPONG
+#define VB_AB_PINGPONG 1
+#endif
+#ifndef VB_AB_RANKSORT
+#define VB_AB_RANKSORT 1
+#endif
+#ifndef VB_AB_INPLACE
+#define VB_AB_INPLACE 1
+#endif
 __device__ __forceinline__ uint4 hnsw_row_ld(const uint4* p) {
 #if VB_HNSW_EVICT_FIRST
     return ldg_gather(p);
@@ -174,6 +187,7 @@ __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* 
             uint32_t e = bid[min(bi, cnt - 1)] & 0x7fffffffu;
             rp[i] = reinterpret_cast<const uint4*>(g.rows + (size_t)e * g.stride);
         }
+#if VB_AB_PINGPONG
         // register double buffering: the loads of step v + LPR are issued before the arithmetic of step v, so 2 * RPI
         // independent 128-bit gathers per lane are in flight instead of one dependent round trip per step.  Two named
         // buffers alternate (no register copies between steps).
@@ -199,6 +213,27 @@ __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* 
                 for (int i = 0; i < RPI; ++i) hnsw_acc_add<ELEM, METRIC>(acc[i], bufb[i], sq, v1);
             }
         }
+#else
+        uint4 cur[RPI];
+        if (gl < g.V) {
+#pragma unroll
+            for (int i = 0; i < RPI; ++i) cur[i] = hnsw_row_ld(rp[i] + gl);
+        }
+        for (int v = gl; v < g.V; v += LPR) {
+            uint4 nxt[RPI];
+            const int vn = v + LPR;
+            if (vn < g.V) {
+#pragma unroll
+                for (int i = 0; i < RPI; ++i) nxt[i] = hnsw_row_ld(rp[i] + vn);
+            }
+#pragma unroll
+            for (int i = 0; i < RPI; ++i) hnsw_acc_add<ELEM, METRIC>(acc[i], cur[i], sq, v);
+            if (vn < g.V) {
+#pragma unroll
+                for (int i = 0; i < RPI; ++i) cur[i] = nxt[i];
+            }
+        }
+#endif
 #pragma unroll
         for (int i = 0; i < RPI; ++i) {
             acc[i].template reduce<LPR>();
@@ -270,7 +305,7 @@ __device__ __forceinline__ void hnsw_merge_batch(HnswWarpState& S, int cnt, int 
     // network over the 32 lanes (empty lanes = +inf).
     uint64_t mk = lane < cnt_in ? S.bkey[lane] : ~0ull;
     uint32_t mi = lane < cnt_in ? S.bid[lane] : 0x7fffffffu;
-    if (cnt_in <= 8) {
+    if (VB_AB_RANKSORT && cnt_in <= 8) {
         int rank = 0;
         for (int j = 0; j < cnt_in; ++j) {
             const uint64_t kj = __shfl_sync(0xffffffffu, mk, j);
@@ -311,6 +346,7 @@ __device__ __forceinline__ void hnsw_merge_batch(HnswWarpState& S, int cnt, int 
         __syncwarp();
     }
 
+#if VB_AB_INPLACE
     // merge the batch (cnt_in, sorted) into R (len, sorted) IN PLACE, keeping efl.  Every element's final position is
     // its index plus the number of elements of the other sequence before it.  The batch's positions are computed first
     // (R still untouched); R is then shifted right chunk by chunk from the END -- a chunk's elements are read by all
@@ -373,6 +409,58 @@ __device__ __forceinline__ void hnsw_merge_batch(HnswWarpState& S, int cnt, int 
     __syncwarp();
     S.len = min(efl, len + cnt_in);
 }
+#else
+    const int len = S.len;
+    for (int j0 = 0; j0 < len; j0 += 32) {
+        const int j = j0 + lane;
+        const bool act = j < len;
+        uint64_t kj = 0;
+        uint32_t ij = 0;
+        int np = 0;
+        if (act) {
+            kj = S.rk[j];
+            ij = S.ri[j];
+            int lo = 0, hi = cnt_in;   // number of batch elements < R[j]
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (ent_less(S.bkey[mid], S.bid[mid], kj, ij)) lo = mid + 1;
+                else hi = mid;
+            }
+            np = j + lo;
+            if (np < efl) {
+                S.nk[np] = kj;
+                S.ni[np] = ij;
+            }
+        }
+        if (ITER) hnsw_sink_append(*sink, act && np >= efl, kj, ij, lane);
+    }
+    {
+        int np = 0;
+        if (lane < cnt_in) {
+            int lo = 0, hi = len;   // number of R elements < batch[lane]
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (ent_less(S.rk[mid], S.ri[mid], mk, mi)) lo = mid + 1;
+                else hi = mid;
+            }
+            np = lane + lo;
+            if (np < efl) {
+                S.nk[np] = mk;
+                S.ni[np] = mi;     // unexpanded
+            }
+        }
+        if (ITER) hnsw_sink_append(*sink, lane < cnt_in && np >= efl, mk, mi, lane);
+    }
+    __syncwarp();
+    S.len = min(efl, len + cnt_in);
+    uint64_t* tk = S.rk;
+    S.rk = S.nk;
+    S.nk = tk;
+    uint32_t* ti = S.ri;
+    S.ri = S.ni;
+    S.ni = ti;
+}
+#endif
 
 // HnswSearchLayer (src/hnswutils.c:824-987) at layer lc with ef = efl from the entry points already in R
 // (S.len of them, sorted).  tab / cap: this layer's visited table (cleared here, InitVisited :671-680).
@@ -456,7 +544,10 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
             if (first_inval < 32) break;
         }
         // keep the table at most three quarters full; otherwise report and let the host retry with a larger one
-        if (inserted > cap - cap / 4) {
+#ifndef VB_AB_VIS
+#define VB_AB_VIS 1
+#endif
+        if (inserted > (VB_AB_VIS ? cap - cap / 4 : cap / 2)) {
             ok = false;
             break;
         }

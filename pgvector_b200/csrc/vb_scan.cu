@@ -394,17 +394,24 @@ __global__ void __launch_bounds__(SS_THREADS) slab_select_kernel(const float* __
     const int tid = threadIdx.x;
     const int32_t* co = cand_off + (int64_t)q * (probes + 1);
     const int32_t* pl = probe_lists + (int64_t)q * probes;
+    // slabs per probe (the list bounds are independent loads: one thread per probe), then their prefix sums
+    for (int p = tid; p < probes; p += SS_THREADS) {
+        const int l = pl[p];
+        int ns = 0;
+        if (l >= 0) {
+            const int64_t lo = list_off[l], hi = list_off[l + 1];
+            if (hi > lo) ns = (int)(((hi - 1) >> 5) - (lo >> 5) + 1);
+        }
+        s_off[p + 1] = ns;
+    }
+    __syncthreads();
     if (tid == 0) {
         int off = 0;
+        s_off[0] = 0;
         for (int p = 0; p < probes; ++p) {
-            s_off[p] = off;
-            const int l = pl[p];
-            if (l >= 0) {
-                const int64_t lo = list_off[l], hi = list_off[l + 1];
-                if (hi > lo) off += (int)(((hi - 1) >> 5) - (lo >> 5) + 1);
-            }
+            off += s_off[p + 1];
+            s_off[p + 1] = off;
         }
-        s_off[probes] = off;
         s_count = 0;
         flagged[q] = 0;
     }
@@ -436,16 +443,36 @@ __global__ void __launch_bounds__(SS_THREADS) slab_select_kernel(const float* __
                 if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
             }
             __syncthreads();
-            if (tid == 0) {
-                uint32_t kk = s_kk, cum = 0;
-                int b = 0;
-                for (; b < 256; ++b) {
-                    if (cum + hist[b] >= kk) break;
-                    cum += hist[b];
+            if (tid < 32) {
+                // the bin holding the kk-th key: every lane sums 8 bins, a warp scan finds the lane, the lane its bin
+                const uint32_t kk = s_kk;
+                uint32_t h[8], mine = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    h[t] = hist[tid * 8 + t];
+                    mine += h[t];
                 }
-                s_prefix = prefix | ((uint32_t)b << shift);
-                s_mask = mask | (0xFFu << shift);
-                s_kk = kk - cum;
+                uint32_t incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += u;
+                }
+                const unsigned reach = __ballot_sync(0xffffffffu, incl >= kk);
+                const int owner = __ffs(reach) - 1;      // (kk <= the number of keys under the prefix: always found)
+                if (tid == owner) {
+                    uint32_t cum = incl - mine;
+                    int b = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        if (cum + h[t] >= kk) break;
+                        cum += h[t];
+                        ++b;
+                    }
+                    s_prefix = prefix | ((uint32_t)(tid * 8 + b) << shift);
+                    s_mask = mask | (0xFFu << shift);
+                    s_kk = kk - cum;
+                }
             }
             __syncthreads();
         }

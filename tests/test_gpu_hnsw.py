@@ -207,7 +207,7 @@ def test_iterative_scan_matches_oracle(l2_graph, ef, max_tuples):
             assert sizes[q][:len(searched)] == searched
         # thousands of elements ordered by fp32 distances: a summation-order flip between two nearly equal ones is
         # expected somewhere in a long scan, so long scans are compared as sets / prefixes as well
-        n3 = int(np.sum(wb < 3) if np.any(wb >= 3) else len(wb))
+        n3 = int(np.sum((wb >= 0) & (wb < 3)))                      # (the searched batches 0..2; -1 marks the drain)
         prefix_same += int(np.array_equal(got[:n3], wi[:n3]))
         overlap.append(len(set(ids[q]) & set(wi.tolist())) / max(1, len(wi)))
         if len(got) == len(wi):
