@@ -200,6 +200,8 @@ class Env:
         pv.set_option("scan_impl", args.scan_impl)
         if os.environ.get("VB_FUSED_REFINE") is not None:       # A/B switch of the fused select / re-score / certify kernel
             pv.set_option("fused_refine", int(os.environ["VB_FUSED_REFINE"]))
+        if os.environ.get("VB_HNSW_L2") is not None:            # A/B switch of the persisting-L2 window over the HNSW visited tables
+            pv.set_option("hnsw_l2_persist", int(os.environ["VB_HNSW_L2"]))
         if os.environ.get("VB_SLAB_SELECT") is not None:        # A/B switch of the selection from slab minima
             pv.set_option("slab_select", int(os.environ["VB_SLAB_SELECT"]))
         self.pv = pv

@@ -357,6 +357,10 @@ int vb_set_option(const char* name, int64_t value) {
         vb::ctx().fused_refine = (int)value;
         return VB_OK;
     }
+    if (!strcmp(name, "hnsw_l2_persist")) {
+        vb::ctx().hnsw_l2_persist = value != 0;
+        return VB_OK;
+    }
     if (!strcmp(name, "slab_select")) {
         vb::ctx().slab_select = value != 0;
         return VB_OK;

@@ -56,6 +56,7 @@ struct Context {
     int scan_impl = 2;                 // 0 = LDG variant (vb_scan.cu), 1 = bulk-copy / TMA variant (vb_scan_bulk.cu), 2 = by table size
     int hnsw_build_fraction = 64;      // HNSW build: a batch is at most 1/fraction of the elements already inserted
     int hnsw_build_batch = 16384;      // ... and at most this many elements
+    int hnsw_l2_persist = 1;           // HNSW scans: keep the visited tables in the persisting part of L2
     int64_t last_assign_flagged = -1;  // rows re-checked by the exact kernel in the last tensor-core assign (-1: exact path)
     // grow-only device workspace arenas (index = slot)
     void* ws[32] = {nullptr};

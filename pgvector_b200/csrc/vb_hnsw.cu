@@ -164,6 +164,37 @@ static int hnsw_launch(const Hnsw& h, const HnswDev& g, const void* qimg, size_t
 
 enum { WSH_QIMG = 0, WSH_OUT = 7, WSH_FLAG = 12 };
 
+// The visited tables are the only data of a graph walk that is re-used (32 probes per expansion, every one a random
+// 32-byte sector); rows and neighbour lists stream past once.  Marking the tables' range persisting in L2 keeps the
+// probes out of DRAM (ncu r2_hnsw_E2: L2 hit rate 23 %, 3.4 GB of DRAM write-backs per launch without it).
+static void hnsw_l2_window(cudaStream_t s, void* base, size_t bytes, bool on) {
+    static int max_window = -1, max_persist = -1;
+    if (max_window < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        if (max_persist > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+        cudaGetLastError();
+    }
+    if (max_window <= 0 || max_persist <= 0) return;
+    cudaStreamAttrValue v{};
+    if (on) {
+        const size_t win = std::min(bytes, (size_t)max_window);
+        v.accessPolicyWindow.base_ptr = base;
+        v.accessPolicyWindow.num_bytes = win;
+        v.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)win);
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } else {
+        v.accessPolicyWindow.num_bytes = 0;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);
+    cudaGetLastError();
+}
+
 static int hnsw_search_impl(Hnsw& h, const void* queries, int64_t nq, int ef, int k, bool host, int64_t* out_ids, float* out_f,
                             double* out_d, int64_t* out_nd) {
     VB_REQUIRE(h.loaded, "hnsw index not loaded");
@@ -247,15 +278,22 @@ static int hnsw_search_impl(Hnsw& h, const void* queries, int64_t nq, int ef, in
             h.vis_bytes = need;
         }
         VB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
+        if (c.hnsw_l2_persist) hnsw_l2_window(s, h.vis, need, true);
         prof_begin(VB_PROF_HNSW);
-        VB_TRY(hnsw_launch(h, g, qimg, qstride, nq, ef, k, h.vis, vis_cap, vis_upper, grid, d_ids, d_f, d_d, d_nd, (int*)d_flag));
+        const int lrc = hnsw_launch(h, g, qimg, qstride, nq, ef, k, h.vis, vis_cap, vis_upper, grid, d_ids, d_f, d_d, d_nd, (int*)d_flag);
         prof_end(VB_PROF_HNSW);
+        if (c.hnsw_l2_persist) hnsw_l2_window(s, nullptr, 0, false);
+        VB_TRY(lrc);
         if (!host && attempt == 0) {
             // device variant stays asynchronous unless the table was too small; check lazily
         }
         int flag = 0;
         VB_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s));
         VB_CUDA(cudaStreamSynchronize(s));
+        if (c.hnsw_l2_persist) {
+            cudaCtxResetPersistingL2Cache();   // the walk is over: hand the set-aside lines back to everybody
+            cudaGetLastError();
+        }
         if (!flag) break;
         cap <<= 2;   // visited table overflowed for some query: retry everything with a larger one
         h.vis_hint_ef = ef;
