@@ -59,6 +59,7 @@ __global__ void VB_HNSW_BOUNDS hnsw_search_kernel(HnswDev g, const uint8_t* __re
         S.ri = idA;
         S.nk = keyB;
         S.ni = idB;
+        S.vcn = 2 * ef;
         S.bkey = bkey;
         S.bid = bid;
         S.len = 0;

@@ -162,6 +162,9 @@ __device__ __forceinline__ void load_query_image(const uint4* gq, int qvec, int 
 #ifndef VB_AB_INPLACE
 #define VB_AB_INPLACE 1
 #endif
+#ifndef VB_AB_VCACHE
+#define VB_AB_VCACHE 0
+#endif
 __device__ __forceinline__ uint4 hnsw_row_ld(const uint4* p) {
 #if VB_HNSW_EVICT_FIRST
     return ldg_gather(p);
@@ -250,6 +253,7 @@ struct HnswWarpState {
     uint64_t* bkey;       // [32]
     uint32_t* bid;        // [32]
     int len;
+    int vcn;              // entries of the visited cache (the unused second key buffer: 2 ef words), 0 = none
 };
 
 // The iterative scan's `discarded` heap (src/hnswscan.c:62-87, src/hnswutils.c:929-937, 968-973) as an append-only
@@ -475,6 +479,9 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
     const int lm = lc == 0 ? 2 * g.m : g.m;
     const uint32_t mask = cap - 1;
     uint32_t inserted = 0;
+    uint32_t* vc = reinterpret_cast<uint32_t*>(S.nk);
+    const int vcn = (VB_AB_VCACHE && VB_AB_INPLACE) ? S.vcn : 0;
+    for (int i = lane; i < vcn; i += 32) vc[i] = VIS_EMPTY;
     if (!ITER || init_visited) {
         for (uint32_t i = lane; i < cap; i += 32) tab[i] = VIS_EMPTY;
         __syncwarp();
@@ -522,7 +529,16 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
             unsigned inval = ~vmask;
             int first_inval = inval ? __ffs(inval) - 1 : 32;
             valid = valid && lane < first_inval;
-            bool fresh = valid && vis_insert(tab, mask, (uint32_t)nid);
+            // a small exact cache of recently visited ids in shared memory: a hit is a visited element for certain and
+            // saves the probe of the global table (60 % of the neighbours of an expansion are visited already)
+            bool known = false;
+            uint32_t vslot = 0;
+            if (VB_AB_VCACHE && VB_AB_INPLACE && vcn > 0 && valid) {
+                vslot = (uint32_t)(((uint64_t)hash_u32((uint32_t)nid ^ 0x9e3779b9u) * (uint32_t)vcn) >> 32);
+                known = vc[vslot] == (uint32_t)nid;
+            }
+            bool fresh = valid && !known && vis_insert(tab, mask, (uint32_t)nid);
+            if (VB_AB_VCACHE && VB_AB_INPLACE && vcn > 0 && valid) vc[vslot] = (uint32_t)nid;
             inserted += (uint32_t)__popc(__ballot_sync(0xffffffffu, fresh));
             // elements below this layer are skipped (src/hnswutils.c:949-950)
             if (fresh && lc > 0 && g.levels[nid] < lc) fresh = false;

@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(HN_WARPS * 32) hnsw_insert_kernel(BuildDev b, 
         S.ri = idA;
         S.nk = keyB;
         S.ni = idB;
+        S.vcn = 0;
         S.bkey = bkey;
         S.bid = bid;
         // entry point (HnswEntryCandidate, src/hnswutils.c:609-621)

@@ -84,6 +84,7 @@ __global__ void VB_HNSW_BOUNDS hnsw_iter_kernel(HnswDev g, IterDev it, const uin
         S.ri = idA;
         S.nk = keyB;
         S.ni = idB;
+        S.vcn = 2 * ef;
         S.bkey = bkey;
         S.bid = bid;
         S.len = 0;
