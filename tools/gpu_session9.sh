@@ -16,8 +16,8 @@ except Exception as e:
     print("B failed", e)
 PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r2_launches_B.csv python bench.py --no-extras --no-cpu --no-recall --law rank16 --steps 2 --warmup 1 > $O/r2_ncu_launches_B.log 2>&1; echo "launch list exit $?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:list_tc_kernel -s 4 -c 1 -o $O/r2_listtc -f python bench.py --no-extras --no-cpu --no-recall --law rank16 --steps 2 --warmup 1 > $O/r2_ncu_listtc.log 2>&1; echo "ncu list_tc exit $?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_bulk_kernel -s 2 -c 1 -o $O/r2_scanbulk -f python bench.py --scan-impl 1 --no-extras --no-cpu --no-recall --law rank16 --steps 2 --warmup 1 > $O/r2_ncu_scanbulk.log 2>&1; echo "ncu scan_bulk exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:list_tc_kernel -s 2 -c 2 -o $O/r2_listtc -f python bench.py --no-extras --no-cpu --no-recall --law rank16 --steps 2 --warmup 1 > $O/r2_ncu_listtc.log 2>&1; echo "ncu list_tc exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_bulk_kernel -s 1 -c 2 -o $O/r2_scanbulk -f python bench.py --scan-impl 1 --no-extras --no-cpu --no-recall --law rank16 --steps 2 --warmup 1 > $O/r2_ncu_scanbulk.log 2>&1; echo "ncu scan_bulk exit $?"
 timeout 1800 python -m pytest tests -m gpu -q --timeout=900 --durations=12 > $O/r2_tests.log 2>&1
 echo "pytest exit $?" >> $O/r2_tests.log; tail -22 $O/r2_tests.log
 timeout 900 python bench.py --config C > $O/r2_bench_C.json 2> $O/r2_bench_C.err; echo "C exit $?"; tail -2 $O/r2_bench_C.err; cut -c1-1500 $O/r2_bench_C.json
