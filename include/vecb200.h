@@ -162,6 +162,43 @@ int			vb_exact_topk(vb_table *t, int metric, const void *queries, int64_t nq, in
 int			vb_exact_topk_dev(vb_table *t, int metric, const void *queries_dev, int64_t nq, int k,
 							  int64_t *out_ids_dev, float *out_dist_dev);
 
+/* ---------------------------------------------------------------- sparsevec */
+
+/*
+ * sparsevec (src/sparsevec.h:21-32): dim, nnz, indices[nnz] (0-based, ascending), values[nnz].  A batch of rows is CSR:
+ * row r = entries row_off[r] .. row_off[r+1] of idx[] / val[] (row_off[0] = 0).  All host buffers.
+ *
+ *   vb_sparsevec_distance_batch      out[r] = metric(row r, q) as the float8 of sparsevec's l2_distance /
+ *                                    l2_squared_distance / inner_product / negative_inner_product / cosine_distance /
+ *                                    l1_distance (src/sparsevec.c:826-1057); metric = VB_L2, VB_L2_SQUARED, VB_IP, VB_NEG_IP,
+ *                                    VB_COSINE, VB_L1.  dim != q_dim fails with CheckDims' text ("different sparsevec
+ *                                    dimensions %d and %d", src/sparsevec.c:44-51); q_nnz < 0 = NULL query, all zeros.
+ *   vb_sparsevec_norm_batch          l2_norm (src/sparsevec.c:1062-1077), fp64 sums
+ *   vb_sparsevec_l2_normalize_batch  l2_normalize (src/sparsevec.c:1082-1150): quotients that round to zero are dropped, so
+ *                                    the result has its own offsets; out_idx / out_val need room for row_off[n] entries;
+ *                                    an infinite quotient fails with "value out of range: overflow"
+ */
+int			vb_sparsevec_distance_batch(int metric, int dim, int q_dim, int32_t q_nnz, const int32_t *q_idx, const float *q_val,
+										int64_t n, const int64_t *row_off, const int32_t *idx, const float *val, double *out);
+int			vb_sparsevec_norm_batch(int64_t n, const int64_t *row_off, const float *val, double *out);
+int			vb_sparsevec_l2_normalize_batch(int64_t n, const int64_t *row_off, const int32_t *idx, const float *val,
+											int64_t *out_row_off, int32_t *out_idx, float *out_val);
+
+typedef struct vb_sparse_table vb_sparse_table;	/* n sparsevec rows resident in HBM as CSR */
+
+int			vb_sparse_table_create(int dim, vb_sparse_table **out);
+int			vb_sparse_table_append(vb_sparse_table *t, int64_t n, const int64_t *row_off, const int32_t *idx, const float *val);
+int64_t		vb_sparse_table_rows(const vb_sparse_table *t);
+int64_t		vb_sparse_table_nnz(const vb_sparse_table *t);
+int			vb_sparse_table_free(vb_sparse_table *t);
+/*
+ * Exact (no index) top-k of nq sparsevec queries (CSR: q_off[nq+1], q_idx, q_val) over the table: the sequential-scan plan
+ * "ORDER BY v <op> q LIMIT k" for <-> (VB_L2), <#> (VB_NEG_IP), <=> (VB_COSINE), <+> (VB_L1); k <= 2048.
+ * out_ids = row numbers (append order, -1 padded), out_dist = the operator's float8; ties: smaller row number first.
+ */
+int			vb_sparse_exact_topk(vb_sparse_table *t, int metric, int q_dim, int64_t nq, const int64_t *q_off, const int32_t *q_idx,
+								 const float *q_val, int k, int64_t *out_ids, double *out_dist);
+
 /* ---------------------------------------------------------------- IVFFlat */
 
 typedef struct vb_ivf vb_ivf;	/* device image of one ivfflat index: centres + rows grouped by list + ids */

@@ -176,6 +176,17 @@ def _declare(L):
     L.pgv_hnsw_search_batch.restype = None
     L.pgv_hnsw_search_batch.argtypes = [vp, vp, i64, i32, i32, i32, i32, vp, vp, vp]
 
+    L.pgv_sparse_distance.restype = dbl
+    L.pgv_sparse_distance.argtypes = [i32, i32, vp, vp, i32, vp, vp]
+    L.pgv_sparse_distance_f64.restype = dbl
+    L.pgv_sparse_distance_f64.argtypes = [i32, i32, vp, vp, i32, vp, vp]
+    L.pgv_sparse_l2_norm.restype = dbl
+    L.pgv_sparse_l2_norm.argtypes = [i32, vp]
+    L.pgv_sparse_l2_normalize.restype = i32
+    L.pgv_sparse_l2_normalize.argtypes = [i32, vp, vp, vp, vp]
+    L.pgv_sparse_distance_batch.restype = None
+    L.pgv_sparse_distance_batch.argtypes = [i32, i32, vp, vp, i64, vp, vp, vp, vp]
+
 
 # ----------------------------------------------------------------- helpers
 
@@ -258,6 +269,49 @@ def exact_topk(elem, metric, q, rows, k, dim=None):
     dist = np.empty(k, dtype=np.float64)
     L.pgv_exact_topk(elem, metric, d, _p(q), _p(rows), rows.shape[0], k, _p(ids), _p(dist))
     return ids, dist
+
+
+# ----------------------------------------------------------------- sparsevec (pgv_sparse.c)
+
+def _sp(v):
+    """(indices, values) -> contiguous int32 / float32 arrays (indices ascending, 0-based)"""
+    idx = np.ascontiguousarray(v[0], dtype=np.int32)
+    val = np.ascontiguousarray(v[1], dtype=np.float32)
+    assert idx.shape == val.shape and idx.ndim == 1
+    return idx, val
+
+
+def sparse_distance(metric, a, b, f64=False):
+    """a, b = (indices, values); the float8 of sparsevec's l2_distance / inner_product / ... (src/sparsevec.c:826-1057)"""
+    (ai, ax), (bi, bx) = _sp(a), _sp(b)
+    fn = lib().pgv_sparse_distance_f64 if f64 else lib().pgv_sparse_distance
+    return fn(metric, ai.size, _p(ai), _p(ax), bi.size, _p(bi), _p(bx))
+
+
+def sparse_l2_norm(a):
+    _, ax = _sp(a)
+    return lib().pgv_sparse_l2_norm(ax.size, _p(ax))
+
+
+def sparse_l2_normalize(a):
+    ai, ax = _sp(a)
+    oi, ox = np.empty_like(ai), np.empty_like(ax)
+    n = lib().pgv_sparse_l2_normalize(ai.size, _p(ai), _p(ax), _p(oi), _p(ox))
+    if n < 0:
+        raise OverflowError("value out of range: overflow")
+    return oi[:n].copy(), ox[:n].copy()
+
+
+def sparse_distance_batch(metric, q, row_off, idx, val):
+    """one query against CSR rows: out[r] = distance(row r, q)"""
+    qi, qx = _sp(q)
+    row_off = np.ascontiguousarray(row_off, dtype=np.int64)
+    idx = np.ascontiguousarray(idx, dtype=np.int32)
+    val = np.ascontiguousarray(val, dtype=np.float32)
+    n = row_off.size - 1
+    out = np.empty(n, dtype=np.float64)
+    lib().pgv_sparse_distance_batch(metric, qi.size, _p(qi), _p(qx), n, _p(row_off), _p(idx), _p(val), _p(out))
+    return out
 
 
 def ivf_set_tie_mode(total_order: bool):

@@ -69,6 +69,20 @@ void pgv_distance_batch(int elem, int metric, int dim, const void *q,
 void pgv_exact_topk(int elem, int metric, int dim, const void *q, const void *rows,
 					int64_t n, int k, int64_t *out_ids, double *out_dist);
 
+/* ---- pgv_sparse.c ------------------------------------------------------ */
+/* sparsevec = (dim, nnz, indices[nnz] ascending 0-based, values[nnz]) (src/sparsevec.h:21-32).  The float8 the SQL
+ * function returns (src/sparsevec.c:826-1057); metrics: L2_SQUARED, L2, IP, NEG_IP, COSINE, L1 */
+double pgv_sparse_distance(int metric, int a_nnz, const int32_t *a_idx, const float *a_val,
+						   int b_nnz, const int32_t *b_idx, const float *b_val);
+double pgv_sparse_distance_f64(int metric, int a_nnz, const int32_t *a_idx, const float *a_val,
+							   int b_nnz, const int32_t *b_idx, const float *b_val);
+double pgv_sparse_l2_norm(int nnz, const float *val);	/* src/sparsevec.c:1062-1077 */
+/* src/sparsevec.c:1082-1150; returns the result's nnz, or -1 for float_overflow_error() */
+int    pgv_sparse_l2_normalize(int nnz, const int32_t *idx, const float *val, int32_t *out_idx, float *out_val);
+/* one query against n CSR rows: out[r] = distance(row r, q) */
+void   pgv_sparse_distance_batch(int metric, int q_nnz, const int32_t *q_idx, const float *q_val, int64_t n,
+								 const int64_t *row_off, const int32_t *idx, const float *val, double *out);
+
 /* ---- pgv_ivfflat.c ----------------------------------------------------- */
 typedef struct PgvIvfIndex
 {

@@ -20,7 +20,9 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
+from . import sparsevec  # noqa: F401  (sparsevec functions, CSR tables and the exact scan over them)
 from ._lib import VecB200Error, load  # noqa: F401
+from .sparsevec import SparseRows, SparseTable, SparseVector  # noqa: F401
 
 VECTOR, HALFVEC, BIT = 0, 1, 2
 L2_SQUARED, NEG_IP, COSINE, L1, HAMMING, JACCARD, L2, IP, SPHERICAL = range(9)

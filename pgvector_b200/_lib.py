@@ -35,6 +35,15 @@ SIGNATURES = {
     "vb_binary_quantize_batch": (_i, [_i, _i, _vp, _i64, _vp]),
     "vb_vector_to_halfvec_batch": (_i, [_i, _vp, _i64, _vp]),
     "vb_halfvec_to_vector_batch": (_i, [_i, _vp, _i64, _vp]),
+    "vb_sparsevec_distance_batch": (_i, [_i, _i, _i, C.c_int32, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "vb_sparsevec_norm_batch": (_i, [_i64, _vp, _vp, _vp]),
+    "vb_sparsevec_l2_normalize_batch": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vb_sparse_table_create": (_i, [_i, C.POINTER(_vp)]),
+    "vb_sparse_table_append": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "vb_sparse_table_rows": (_i64, [_vp]),
+    "vb_sparse_table_nnz": (_i64, [_vp]),
+    "vb_sparse_table_free": (_i, [_vp]),
+    "vb_sparse_exact_topk": (_i, [_vp, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp]),
     "vb_table_create": (_i, [_i, _i, C.POINTER(_vp)]),
     "vb_table_append": (_i, [_vp, _vp, _i64]),
     "vb_table_append_dev": (_i, [_vp, _vp, _i64]),

@@ -3,9 +3,10 @@
 
 Run HERE (dev container, /root/reference present):
     python tests/golden/make_golden.py
-It reads /root/reference/test/expected/{vector_type,halfvec,bit}.out (psql
+It reads /root/reference/test/expected/{vector_type,halfvec,bit,sparsevec}.out (psql
 echo of each statement followed by its result), keeps the statements on the
-distance hot path and writes tests/golden/distance_kat.json.
+distance hot path and writes tests/golden/distance_kat.json
+(and tests/golden/sparsevec_kat.json).
 It also transcribes the tiny index-level orderings of
 test/expected/{ivfflat_*,hnsw_*}.out into tests/golden/index_orderings.json.
 Nothing here is executed on the GPU box; the JSON files are committed.
@@ -113,9 +114,14 @@ def main():
     cases += parse_out(os.path.join(exp, "vector_type.out"), "vector")
     cases += parse_out(os.path.join(exp, "halfvec.out"), "halfvec")
     cases += parse_out(os.path.join(exp, "bit.out"), "bit")
+    sparse = parse_out(os.path.join(exp, "sparsevec.out"), "sparsevec")
     with open(os.path.join(OUT, "distance_kat.json"), "w") as f:
         json.dump(dict(generated_by="tests/golden/make_golden.py", reference="pgvector @ e48241b (v0.8.6+)",
                        cases=cases), f, indent=1)
+    # sparsevec goes to its own file: the literals are '{index:value,...}/dim' with 1-based indices
+    with open(os.path.join(OUT, "sparsevec_kat.json"), "w") as f:
+        json.dump(dict(generated_by="tests/golden/make_golden.py", reference="pgvector @ e48241b (v0.8.6+)",
+                       cases=sparse), f, indent=1)
     blocks = []
     for name in ("ivfflat_vector", "ivfflat_halfvec", "ivfflat_bit", "hnsw_vector", "hnsw_halfvec", "hnsw_bit"):
         p = os.path.join(exp, name + ".out")
@@ -123,7 +129,11 @@ def main():
             blocks += parse_orderings(p)
     with open(os.path.join(OUT, "index_orderings.json"), "w") as f:
         json.dump(dict(generated_by="tests/golden/make_golden.py", blocks=blocks), f, indent=1)
-    print(f"{len(cases)} known-answer cases, {len(blocks)} index ordering blocks")
+    sp_blocks = parse_orderings(os.path.join(exp, "hnsw_sparsevec.out"))
+    with open(os.path.join(OUT, "sparsevec_orderings.json"), "w") as f:
+        json.dump(dict(generated_by="tests/golden/make_golden.py", blocks=sp_blocks), f, indent=1)
+    print(f"{len(sp_blocks)} sparsevec ordering blocks")
+    print(f"{len(cases)} known-answer cases, {len(sparse)} sparsevec cases, {len(blocks)} index ordering blocks")
 
 
 if __name__ == "__main__":
