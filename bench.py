@@ -108,9 +108,14 @@ def host_threads():
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    # Sampled every 200 ms (the period of the profiling recipe).  A query is not free: with `-lms 20` and power.draw in
+    # the list the end-to-end step of config B measured 1.69 ms under the sampler against 0.98 ms without it
+    # (profiles/r2_diag_e2e.json) -- the driver serialises the query with the process's copies and synchronisations.
+    # power.draw (the slow sensor read) is not used by the line, so it is not queried; the placeholder keeps the columns.
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks.mem,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    PERIOD_MS = 200
 
     def __init__(self, index=0):
         self.samples = []
@@ -120,7 +125,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.PERIOD_MS)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -466,7 +471,7 @@ def measure_ivf(env, args, law, centers, offsets, grouped, order, full, queries)
     for i in range(args.warmup):
         step_dev(i)
     env.barrier()
-    for i in range(300 if args.scan_impl >= 2 and full else 3):     # load for the clock sampler (nvidia-smi needs ~0.3 s)
+    for i in range(600 if args.scan_impl >= 2 and full else 3):     # load for the clock sampler (nvidia-smi reports every 200 ms)
         step_dev(i)
     env.barrier()
     pv.prof_enable(True)
