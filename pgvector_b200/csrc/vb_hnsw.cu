@@ -112,6 +112,9 @@ static int hnsw_launch_t(const HnswDev& g, const void* qimg, size_t qstride, int
     const size_t smem = per_warp * HN_WARPS;
     VB_REQUIRE(smem <= 200 * 1024, "ef_search %d with this dimension needs %zu bytes of shared memory per CTA", ef, smem);
     cudaStream_t s = ctx().stream;
+#ifndef VB_AB_LPR_V8
+#define VB_AB_LPR_V8 2   /* lanes per row for 128-byte rows (bit(1024)); 8 = one 16-byte word per lane, 32 rows in one round trip */
+#endif
 #define VB_HL(LPR)                                                                                                        \
     do {                                                                                                                  \
         auto kern = hnsw_search_kernel<ELEM, METRIC, LPR>;                                                                \
@@ -128,6 +131,7 @@ static int hnsw_launch_t(const HnswDev& g, const void* qimg, size_t qstride, int
     // one expansion are gathered in ONE pass (GROUPS * RPI >= 16 rows) instead of four dependent ones
     if (g.V >= 32) VB_HL(32);
     else if (g.V >= 16) VB_HL(4);
+    else if (g.V == 8 && VB_AB_LPR_V8 == 8) VB_HL(8);
     else if (g.V >= 8) VB_HL(2);
     else VB_HL(1);
 #undef VB_HL

@@ -165,6 +165,16 @@ __device__ __forceinline__ void load_query_image(const uint4* gq, int qvec, int 
 #ifndef VB_AB_VCACHE
 #define VB_AB_VCACHE 0
 #endif
+// rows in flight per lane group for rows narrower than a warp pass (bit(1024): 8 lanes per row, one 16-byte word per lane):
+// 2 = 8 rows per pass, 4 = 16, 8 = 32 (a whole expansion in one round trip of the gather)
+#ifndef VB_AB_RPI_NARROW
+#define VB_AB_RPI_NARROW 2
+#endif
+// prefetch (into L2) the layer-0 neighbour list of every element that is about to be admitted to R: it is read when the
+// element is expanded, many expansions later, and would otherwise be a dependent DRAM round trip at the top of the loop
+#ifndef VB_AB_NBRPF
+#define VB_AB_NBRPF 0
+#endif
 __device__ __forceinline__ uint4 hnsw_row_ld(const uint4* p) {
 #if VB_HNSW_EVICT_FIRST
     return ldg_gather(p);
@@ -179,7 +189,10 @@ template <int ELEM, int METRIC, int LPR>
 __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* sq, const uint32_t* bid, int cnt, uint64_t* bkey,
                                                  int lane) {
     constexpr int GROUPS = 32 / LPR;
-    constexpr int RPI = (LPR == 32) ? 4 : 2;   // (8 in flight measured the same: 821 k vs 816 k queries/s, at 128 registers)
+    // LPR == 8 is launched only for rows of exactly 8 words (bit(1024)): one word per lane, 8 rows per lane group, so the
+    // <= 32 rows of an expansion are ONE round trip with every load in flight
+    constexpr bool ONE_WORD = LPR == 8;
+    constexpr int RPI = (LPR == 32) ? 4 : ONE_WORD ? 8 : VB_AB_RPI_NARROW;   // (LPR 32: 8 in flight measured the same: 821 k vs 816 k queries/s, at 128 registers)
     const int grp = lane / LPR, gl = lane % LPR;
     for (int b0 = 0; b0 < cnt; b0 += GROUPS * RPI) {
         Acc<ELEM, METRIC> acc[RPI];
@@ -190,6 +203,13 @@ __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* 
             uint32_t e = bid[min(bi, cnt - 1)] & 0x7fffffffu;
             rp[i] = reinterpret_cast<const uint4*>(g.rows + (size_t)e * g.stride);
         }
+        if constexpr (ONE_WORD) {
+            uint4 w[RPI];
+#pragma unroll
+            for (int i = 0; i < RPI; ++i) w[i] = hnsw_row_ld(rp[i] + gl);
+#pragma unroll
+            for (int i = 0; i < RPI; ++i) hnsw_acc_add<ELEM, METRIC>(acc[i], w[i], sq, gl);
+        } else {
 #if VB_AB_PINGPONG
         // register double buffering: the loads of step v + LPR are issued before the arithmetic of step v, so 2 * RPI
         // independent 128-bit gathers per lane are in flight instead of one dependent round trip per step.  Two named
@@ -237,6 +257,7 @@ __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* 
             }
         }
 #endif
+        }
 #pragma unroll
         for (int i = 0; i < RPI; ++i) {
             acc[i].template reduce<LPR>();
@@ -555,6 +576,12 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
 
             hnsw_score_batch<ELEM, METRIC, LPR>(g, sq, S.bid, cnt, S.bkey, lane);
             __syncwarp();
+#if VB_AB_NBRPF
+            if (lc == 0 && lane < cnt) {
+                const bool admit = S.len < efl || ent_less(S.bkey[lane], S.bid[lane], S.rk[efl - 1], S.ri[efl - 1]);
+                if (admit) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.nbr0 + (size_t)(S.bid[lane] & 0x7fffffffu) * lm));
+            }
+#endif
 
             hnsw_merge_batch<ITER>(S, cnt, efl, lane, sink);
             if (first_inval < 32) break;
