@@ -1214,6 +1214,9 @@ static int kmeans_pp_sharded(const Table& X, int kmeans_metric, void* centers_ho
     VB_TRY(comm_allreduce(d_gpick, k, 2));
     VB_CUDA(cudaMemcpyAsync(centers_host, d_out, raw * (size_t)k, cudaMemcpyDeviceToHost, s));
     if (picked_out) VB_CUDA(cudaMemcpyAsync(picked_out, d_gpick, sizeof(int64_t) * (size_t)k, cudaMemcpyDeviceToHost, s));
+    // this rank's filter tallies (vb_kmeans_pp_stats; the caller sums them over the ranks if it wants the totals)
+    if (filtered) VB_CUDA(cudaMemcpyAsync(c.pp_stats, flt.stats, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    else c.pp_stats[0] = c.pp_stats[1] = c.pp_stats[2] = 0;
     VB_CUDA(cudaStreamSynchronize(s));
     VB_CUDA(cudaGetLastError());
     return VB_OK;
