@@ -474,8 +474,10 @@ def measure_ivf(env, args, law, centers, offsets, grouped, order, full, queries)
     for i in range(600 if args.scan_impl >= 2 and full else 3):     # load for the clock sampler (nvidia-smi reports every 200 ms)
         step_dev(i)
     env.barrier()
+    # The timed region carries the per-kernel event brackets (the roofline's kernel time is measured over it); the
+    # traffic accounting -- an extra kernel per filter launch that walks the launch's job list -- runs over two
+    # identical steps AFTER it (it cost 4-7 % of `value` inside, profiles/r2_diag_e2e_v2.json).
     pv.prof_enable(True)
-    pv.tc_traffic(True, read=True)
     for p in (pv.PROF_SCAN_ITEMS, pv.PROF_SCAN_LISTS, pv.PROF_TOPK, pv.PROF_LIST_TC, pv.PROF_CENTRE_TC):
         pv.prof_read(p)
     l0 = pv.launch_count()
@@ -489,8 +491,12 @@ def measure_ivf(env, args, law, centers, offsets, grouped, order, full, queries)
     launches = pv.launch_count() - l0
     prof = {name: pv.prof_read(p) for name, p in (("scan_items", pv.PROF_SCAN_ITEMS), ("scan_lists", pv.PROF_SCAN_LISTS),
                                                    ("topk", pv.PROF_TOPK), ("list_tc", pv.PROF_LIST_TC), ("centre_tc", pv.PROF_CENTRE_TC))}
-    traffic = pv.tc_traffic(False, read=True)
     pv.prof_enable(False)
+    pv.tc_traffic(True, read=True)
+    for i in range(2):
+        step_dev(args.warmup + args.steps - 1 - i)      # the last batches of the timed region again
+    pv.synchronize()
+    traffic = pv.tc_traffic(False, read=True)
     cand_last = ix.last_candidates()                    # this rank's candidates in the last step
     cand_all = int(env.sum_over_ranks(cand_last))
     qps = args.steps * B / (ms / 1000.0)

@@ -113,7 +113,7 @@ static int hnsw_launch_t(const HnswDev& g, const void* qimg, size_t qstride, int
     VB_REQUIRE(smem <= 200 * 1024, "ef_search %d with this dimension needs %zu bytes of shared memory per CTA", ef, smem);
     cudaStream_t s = ctx().stream;
 #ifndef VB_AB_LPR_V8
-#define VB_AB_LPR_V8 2   /* lanes per row for 128-byte rows (bit(1024)); 8 = one 16-byte word per lane, 32 rows in one round trip */
+#define VB_AB_LPR_V8 8   /* lanes per row for 128-byte rows (bit(1024)); 8 = one 16-byte word per lane, 32 rows in one round trip */
 #endif
 #define VB_HL(LPR)                                                                                                        \
     do {                                                                                                                  \

@@ -175,6 +175,10 @@ __device__ __forceinline__ void load_query_image(const uint4* gq, int qvec, int 
 #ifndef VB_AB_NBRPF
 #define VB_AB_NBRPF 0
 #endif
+// narrow rows: score all listed neighbours while their visited probes are in flight (see hnsw_search_layer)
+#ifndef VB_AB_SPEC
+#define VB_AB_SPEC 1
+#endif
 __device__ __forceinline__ uint4 hnsw_row_ld(const uint4* p) {
 #if VB_HNSW_EVICT_FIRST
     return ldg_gather(p);
@@ -189,11 +193,34 @@ template <int ELEM, int METRIC, int LPR>
 __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* sq, const uint32_t* bid, int cnt, uint64_t* bkey,
                                                  int lane) {
     constexpr int GROUPS = 32 / LPR;
-    // LPR == 8 is launched only for rows of exactly 8 words (bit(1024)): one word per lane, 8 rows per lane group, so the
-    // <= 32 rows of an expansion are ONE round trip with every load in flight
-    constexpr bool ONE_WORD = LPR == 8;
-    constexpr int RPI = (LPR == 32) ? 4 : ONE_WORD ? 8 : VB_AB_RPI_NARROW;   // (LPR 32: 8 in flight measured the same: 821 k vs 816 k queries/s, at 128 registers)
+    constexpr int RPI = (LPR == 32) ? 4 : VB_AB_RPI_NARROW;   // (LPR 32: 8 in flight measured the same: 821 k vs 816 k queries/s, at 128 registers)
     const int grp = lane / LPR, gl = lane % LPR;
+    if constexpr (LPR == 8) {
+        // rows of at most 8 words (bit(1024) = 128 bytes): one word per lane and 8 rows per lane group, so the <= 32 rows of
+        // an expansion are ONE round trip with every load in flight (the generic path below walks a row in steps of LPR words
+        // with two steps in flight)
+        if (g.V <= 8) {
+            constexpr int R1 = 8;
+            for (int b0 = 0; b0 < cnt; b0 += GROUPS * R1) {
+                Acc<ELEM, METRIC> acc[R1];
+                uint4 w[R1];
+#pragma unroll
+                for (int i = 0; i < R1; ++i) {
+                    const int bi = b0 + i * GROUPS + grp;
+                    const uint32_t e = bid[min(bi, cnt - 1)] & 0x7fffffffu;
+                    w[i] = gl < g.V ? hnsw_row_ld(reinterpret_cast<const uint4*>(g.rows + (size_t)e * g.stride) + gl) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int i = 0; i < R1; ++i) {
+                    if (gl < g.V) hnsw_acc_add<ELEM, METRIC>(acc[i], w[i], sq, gl);
+                    acc[i].template reduce<LPR>();
+                    const int bi = b0 + i * GROUPS + grp;
+                    if (gl == 0 && bi < cnt) bkey[bi] = orderable_key64(acc[i].value());
+                }
+            }
+            return;
+        }
+    }
     for (int b0 = 0; b0 < cnt; b0 += GROUPS * RPI) {
         Acc<ELEM, METRIC> acc[RPI];
         const uint4* rp[RPI];
@@ -203,13 +230,6 @@ __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* 
             uint32_t e = bid[min(bi, cnt - 1)] & 0x7fffffffu;
             rp[i] = reinterpret_cast<const uint4*>(g.rows + (size_t)e * g.stride);
         }
-        if constexpr (ONE_WORD) {
-            uint4 w[RPI];
-#pragma unroll
-            for (int i = 0; i < RPI; ++i) w[i] = hnsw_row_ld(rp[i] + gl);
-#pragma unroll
-            for (int i = 0; i < RPI; ++i) hnsw_acc_add<ELEM, METRIC>(acc[i], w[i], sq, gl);
-        } else {
 #if VB_AB_PINGPONG
         // register double buffering: the loads of step v + LPR are issued before the arithmetic of step v, so 2 * RPI
         // independent 128-bit gathers per lane are in flight instead of one dependent round trip per step.  Two named
@@ -257,7 +277,6 @@ __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* 
             }
         }
 #endif
-        }
 #pragma unroll
         for (int i = 0; i < RPI; ++i) {
             acc[i].template reduce<LPR>();
@@ -558,13 +577,67 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
                 vslot = (uint32_t)(((uint64_t)hash_u32((uint32_t)nid ^ 0x9e3779b9u) * (uint32_t)vcn) >> 32);
                 known = vc[vslot] == (uint32_t)nid;
             }
+            int cnt;
+            if constexpr (VB_AB_SPEC && LPR <= 8) {
+                // Narrow rows (< 512 bytes; bit(1024) = 128): every listed neighbour is scored SPECULATIVELY while its visited
+                // probe is in flight -- the probe (a random atomic on a table that lives in L2 / DRAM) and the row gather
+                // are two dependent round trips otherwise, and the rows of the ~60 % already-visited neighbours cost less
+                // than the wait.  The distances of the non-fresh ones are dropped; results, `tuples` and the visited set
+                // are exactly those of the ordered version.
+                const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                const int cnt_all = __popc(vm);
+                if (cnt_all == 0) {
+                    if (first_inval < 32) break;
+                    continue;
+                }
+                const int pos_all = __popc(vm & ((1u << lane) - 1u));
+                uint32_t hs = 0, old = 0;
+                if (valid) {
+                    S.bid[pos_all] = (uint32_t)nid;
+                    hs = hash_u32((uint32_t)nid) & mask;
+                    old = atomicCAS(&tab[hs], VIS_EMPTY, (uint32_t)nid);     // issued here, consumed after the scoring
+                }
+                __syncwarp();
+                hnsw_score_batch<ELEM, METRIC, LPR>(g, sq, S.bid, cnt_all, S.bkey, lane);
+                __syncwarp();
+                bool fresh = false;
+                if (valid) {
+                    for (;;) {   // the rest of the probe sequence (collisions are rare below 3/4 load)
+                        if (old == VIS_EMPTY) {
+                            fresh = true;
+                            break;
+                        }
+                        if (old == (uint32_t)nid) break;
+                        hs = (hs + 1) & mask;
+                        old = atomicCAS(&tab[hs], VIS_EMPTY, (uint32_t)nid);
+                    }
+                }
+                inserted += (uint32_t)__popc(__ballot_sync(0xffffffffu, fresh));
+                if (fresh && lc > 0 && g.levels[nid] < lc) fresh = false;   // src/hnswutils.c:949-950
+                const unsigned fm = __ballot_sync(0xffffffffu, fresh);
+                cnt = __popc(fm);
+                if (cnt == 0) {
+                    if (first_inval < 32) break;
+                    continue;
+                }
+                if (ndist) *ndist += cnt;
+                // keep the fresh entries of (bkey, bid), in list order
+                const uint64_t mykey = valid ? S.bkey[pos_all] : 0ull;
+                __syncwarp();
+                const int pos = __popc(fm & ((1u << lane) - 1u));
+                if (fresh) {
+                    S.bkey[pos] = mykey;
+                    S.bid[pos] = (uint32_t)nid;
+                }
+                __syncwarp();
+            } else {
             bool fresh = valid && !known && vis_insert(tab, mask, (uint32_t)nid);
             if (VB_AB_VCACHE && VB_AB_INPLACE && vcn > 0 && valid) vc[vslot] = (uint32_t)nid;
             inserted += (uint32_t)__popc(__ballot_sync(0xffffffffu, fresh));
             // elements below this layer are skipped (src/hnswutils.c:949-950)
             if (fresh && lc > 0 && g.levels[nid] < lc) fresh = false;
             unsigned fm = __ballot_sync(0xffffffffu, fresh);
-            const int cnt = __popc(fm);
+            cnt = __popc(fm);
             if (cnt == 0) {
                 if (first_inval < 32) break;
                 continue;
@@ -576,6 +649,7 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
 
             hnsw_score_batch<ELEM, METRIC, LPR>(g, sq, S.bid, cnt, S.bkey, lane);
             __syncwarp();
+            }
 #if VB_AB_NBRPF
             if (lc == 0 && lane < cnt) {
                 const bool admit = S.len < efl || ent_less(S.bkey[lane], S.bid[lane], S.rk[efl - 1], S.ri[efl - 1]);

@@ -450,6 +450,9 @@ struct WarpTopList {
 };
 
 constexpr int SR_WARPS = 4;
+#ifndef VB_SR_PARALLEL_ADDR
+#define VB_SR_PARALLEL_ADDR 1
+#endif
 
 template <int ELEM, int METRIC, int R>
 __global__ void __launch_bounds__(SR_WARPS * 32) select_refine_kernel(const uint8_t* __restrict__ rows, size_t stride, int V,
@@ -538,6 +541,30 @@ __global__ void __launch_bounds__(SR_WARPS * 32) select_refine_kernel(const uint
 #pragma unroll
     for (int r = 0; r < R; ++r) exact[r] = __int_as_float(0x7F800000);
     const int32_t* co = cand_off + q * (probes + 1);
+#if VB_SR_PARALLEL_ADDR
+    // Row address of every listed candidate, one candidate per lane (R per lane): position -> probe (binary search of the
+    // query's candidate offsets) -> list -> row.  That is five dependent loads; done inside the re-score loop they were
+    // paid once per PAIR of candidates, ahead of the row reads, by the whole warp.
+    const uint8_t* rowp[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int i = r * 32 + lane;
+        const uint64_t ki = top.key[r];
+        rowp[r] = rows;
+        if (i < have && ki != ~0ull) {
+            const int32_t ps = (int32_t)(uint32_t)ki;
+            int lo = 0, hi = probes;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (co[mid] <= ps) lo = mid;
+                else hi = mid;
+            }
+            while (lo + 1 < probes && co[lo + 1] <= ps) ++lo;   // empty lists share an offset
+            const int l = probe_lists[q * probes + lo];
+            rowp[r] = rows + (size_t)(list_off[l] + (ps - co[lo])) * stride;
+        }
+    }
+#endif
     for (int i0 = 0; i0 < have; i0 += 2) {
         const uint64_t k0 = top.at(i0);
         const uint64_t k1 = i0 + 1 < have ? top.at(i0 + 1) : ~0ull;
@@ -546,6 +573,17 @@ __global__ void __launch_bounds__(SR_WARPS * 32) select_refine_kernel(const uint
         const bool do0 = !(a0 > T), do1 = k1 != ~0ull && !(a1 > T);
         if (!do0 && !do1) continue;                         // (no early exit: NaN distances sort last and are re-scored too)
         const uint4* rp[2];
+#if VB_SR_PARALLEL_ADDR
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int it = min(i0 + t, R * 32 - 1);         // (warp-uniform; the clamp only guards the shuffle of an absent k1)
+            unsigned long long a = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                if (it / 32 == r) a = __shfl_sync(0xffffffffu, (unsigned long long)rowp[r], it % 32);
+            rp[t] = reinterpret_cast<const uint4*>((t == 0 ? do0 : do1) ? (const uint8_t*)a : rows);
+        }
+#else
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
             const int32_t ps = (int32_t)(uint32_t)(t == 0 ? k0 : k1);
@@ -563,6 +601,7 @@ __global__ void __launch_bounds__(SR_WARPS * 32) select_refine_kernel(const uint
                 rp[t] = reinterpret_cast<const uint4*>(rows);
             }
         }
+#endif
         Acc<ELEM, METRIC> acc0, acc1;
         if (do0 && do1) {
 #pragma unroll 4

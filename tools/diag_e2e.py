@@ -94,6 +94,31 @@ def main():
     # 5. plain host call, pinned and pageable queries
     timed("search_host_pinned", lambda i: ix.search_host_into(q_np[i % 4], k, args.probes, ids_h, dist_h))
     timed("search_host_pageable", lambda i: ix.search_host_into(q_pageable[i % 4], k, args.probes, ids_h, dist_h))
+    # 6. the same loops with bench.py's clock sampler (nvidia-smi -lms) running beside them, and with the profiling brackets on
+    sampler = bench.ClockSampler(env.local)
+    sampler.start()
+    time.sleep(0.5)
+    n[0] = 0
+    ix.prefetch_queries(q_np[0], 0)
+    timed("pipelined_with_clock_sampler", piped)
+    timed("search_dev_with_clock_sampler", lambda i: ix.search_into(qb[i % nb], k, args.probes, ids_dev, dist_dev))
+    out["sampler"] = sampler.stop()
+    time.sleep(0.3)
+    n[0] = 0
+    ix.prefetch_queries(q_np[0], 0)
+    timed("pipelined_after_sampler_stopped", piped)
+    pv.prof_enable(True)
+    timed("search_dev_with_prof_brackets", lambda i: ix.search_into(qb[i % nb], k, args.probes, ids_dev, dist_dev))
+    pv.tc_traffic(True, read=True)
+    timed("search_dev_with_prof_brackets_and_traffic_accounting", lambda i: ix.search_into(qb[i % nb], k, args.probes, ids_dev, dist_dev))
+    pv.tc_traffic(False, read=True)
+    pv.prof_enable(False)
+    # 7. bench-like order: 700 device steps first, then the pipelined loop with 100 steps
+    for i in range(700):
+        ix.search_into(qb[i % nb], k, args.probes, ids_dev, dist_dev)
+    n[0] = 0
+    ix.prefetch_queries(q_np[0], 0)
+    timed("pipelined_after_700_device_steps", piped, steps=100, warm=3)
     print(json.dumps(out, indent=1))
     env.close()
 
