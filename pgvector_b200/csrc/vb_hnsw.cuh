@@ -175,9 +175,11 @@ __device__ __forceinline__ void load_query_image(const uint4* gq, int qvec, int 
 #ifndef VB_AB_NBRPF
 #define VB_AB_NBRPF 0
 #endif
-// narrow rows: score all listed neighbours while their visited probes are in flight (see hnsw_search_layer)
+// narrow rows: score all listed neighbours while their visited probes are in flight (see hnsw_search_layer).  Measured on
+// config E (10M x bit(1024), ef_search 200): 724 k queries/s with it, 758 k without -- the 60 % of wasted scorings cost more
+// than the overlapped round trip saves; kept as a switch (profiles/r2_ab_hnsw_spec.md)
 #ifndef VB_AB_SPEC
-#define VB_AB_SPEC 1
+#define VB_AB_SPEC 0
 #endif
 __device__ __forceinline__ uint4 hnsw_row_ld(const uint4* p) {
 #if VB_HNSW_EVICT_FIRST
