@@ -51,8 +51,9 @@ struct Context {
     int tc_level1 = 1;                 // batched list scan: try the hi-plane-only filter first (vb_set_option "tc_level1")
     int pp_filter = 1;                 // k-means++ on large fp32 sample tables: triangle-inequality + bf16 filters in front of the exact distances
     unsigned long long pp_stats[3] = {0, 0, 0};   // last seeding: samples skipped by the triangle rule / stopped by the bf16 bound / re-scored exactly
-    int fused_refine = 1;              // tensor-core filter, after the k' select: 1 = exact re-score + certificate in one warp-per-query kernel,
-                                       // 0 = rescore_kernel + certify_kernel, 2 = the select runs inside that kernel too
+    int fused_refine = 3;              // tensor-core filter, after the k' select: 3 = select + exact re-score + certificate with one CTA per query,
+                                       // 1 = re-score + certificate in one warp-per-query kernel fed by the selection kernel,
+                                       // 0 = rescore_kernel + certify_kernel, 2 = the select runs inside the warp-per-query kernel too
     int scan_impl = 2;                 // 0 = LDG variant (vb_scan.cu), 1 = bulk-copy / TMA variant (vb_scan_bulk.cu), 2 = by table size
     int hnsw_build_fraction = 64;      // HNSW build: a batch is at most 1/fraction of the elements already inserted
     int hnsw_build_batch = 16384;      // ... and at most this many elements
@@ -229,6 +230,11 @@ int launch_list_tc_select_refine(const Table& rows, const ListTcImage& im, int k
                                  const float* dist, const int64_t* seg_begin, const int32_t* seg_len, const float* qn, int32_t* out_pos,
                                  float* out_key, int* fail_dev, int* n_failed_host, int level = 2, const int32_t* pre_pos = nullptr,
                                  const float* pre_key = nullptr);
+// the same three steps with one CTA per query (selection CTA-wide, re-score on eight warps); smin == nullptr: short runs
+int launch_list_tc_cta_refine(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
+                              int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
+                              const float* dist, const float* smin, int64_t cap, int64_t cap_s, const int32_t* seg_len, const float* qn,
+                              int32_t* out_pos, float* out_key, int* fail_dev, int level = 2);
 int list_tile_rows();
 bool list_major_supported(int elem, int key_metric);
 int launch_list_major(const Table& rows, int key_metric, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists,

@@ -233,11 +233,19 @@ static int ivf_select_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t 
         if (!ix.defer_tc_check) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, sizeof(int), c.stream));
         // a run of a few thousand centre distances is selected inside the refine kernel (one warp streams it in a few
         // steps: cheaper than a launch of the CTA-per-query radix selection, 43 us for 2048 x 1000); long runs are not
-        if (c.fused_refine == 2 || (c.fused_refine == 1 && ix.lists <= 4096)) {
+        if (c.fused_refine == 3 && ix.lists <= 2048) {
+            // one CTA per query: the run of centre distances is short enough to be selected directly
+            VB_TRY(launch_list_tc_cta_refine(ix.centers, ix.ctc, km, qimg, qstride, nq, probes, kp, 1, zero_lists, pair_off, ix.d_centre_off,
+                                             (const float*)d_cdist, nullptr, ix.lists, 0, sl, qn, lists, ldist, ix.d_tc_fail, 2));
+            if (!ix.defer_tc_check) {
+                VB_CUDA(cudaMemcpyAsync(&n_failed, ix.d_tc_fail, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+                VB_CUDA(cudaStreamSynchronize(c.stream));
+            }
+        } else if (c.fused_refine == 2 || (c.fused_refine != 0 && ix.lists <= 4096)) {
             VB_TRY(launch_list_tc_select_refine(ix.centers, ix.ctc, km, qimg, qstride, nq, probes, kp, 1, zero_lists, pair_off, ix.d_centre_off,
                                                 (const float*)d_cdist, sb, sl, qn, lists, ldist, ix.d_tc_fail,
                                                 ix.defer_tc_check ? nullptr : &n_failed));
-        } else if (c.fused_refine == 1) {
+        } else if (c.fused_refine != 0) {
             VB_TRY(launch_segment_topk_v((const float*)d_cdist, sb, sl, nullptr, nullptr, nq, kp, pos_kp, key_kp));
             VB_TRY(launch_list_tc_select_refine(ix.centers, ix.ctc, km, qimg, qstride, nq, probes, kp, 1, zero_lists, pair_off, ix.d_centre_off,
                                                 (const float*)d_cdist, sb, sl, qn, lists, ldist, ix.d_tc_fail,
@@ -401,11 +409,21 @@ static int ivf_scan_topk(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, 
             VB_CUDA(cudaMemsetAsync(ix.d_tc_fail, 0, 2 * sizeof(int), c.stream));
         }
         if (!ix.defer_tc_check) VB_CUDA(cudaMemsetAsync(ix.d_tc_fail + 1, 0, sizeof(int), c.stream));
-        if (c.fused_refine == 2) {
+        if (c.fused_refine == 3 && slabs && !ix.force_level2) {
+            // one CTA per query: slab selection, re-score on eight warps, ranking, certificate (a selection that overflows
+            // counts as uncertified: the repeat of the batch takes the kernels below)
+            VB_TRY(launch_list_tc_cta_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off,
+                                             (const float*)d_dist, (const float*)d_smin, cap, cap_s, seg_len, qn, pos, key, ix.d_tc_fail + 1,
+                                             level));
+            if (!ix.defer_tc_check) {
+                VB_CUDA(cudaMemcpyAsync(&n_failed, ix.d_tc_fail + 1, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+                VB_CUDA(cudaStreamSynchronize(c.stream));
+            }
+        } else if (c.fused_refine == 2) {
             VB_TRY(launch_list_tc_select_refine(ix.rows, ix.tc, km, qimg, qstride, nq, k, kp, probes, d_lists, cand_off, ix.d_list_off,
                                                 (const float*)d_dist, seg_begin, seg_len, qn, pos, key, ix.d_tc_fail + 1,
                                                 ix.defer_tc_check ? nullptr : &n_failed, level));
-        } else if (c.fused_refine == 1) {
+        } else if (c.fused_refine == 1 || c.fused_refine == 3) {
             if (slabs)
                 VB_TRY(launch_slab_select((const float*)d_dist, (const float*)d_smin, nq, probes, d_lists, cand_off, ix.d_list_off, cap,
                                           cap_s, seg_begin, seg_len, kp, pos_kp, key_kp));

@@ -32,6 +32,7 @@
 // Roofline: HBM -- one pass over the packed hi planes (level 1: 2 bytes per row element) or both planes (level 2:
 // 4 bytes) of the probed lists per batch.
 #include "vb_tc.cuh"
+#include "vb_slab_select.cuh"
 #include "vb_distance.cuh"
 
 #include <algorithm>
@@ -658,6 +659,102 @@ __global__ void __launch_bounds__(SR_WARPS * 32) select_refine_kernel(const uint
     }
 }
 
+// Steps 2 + 3 + 4 with ONE CTA per query (cta_refine_kernel): the selection is CTA-wide (slab minima, or the whole run
+// when it is short: the distances of a query to every centre), the candidates under the certificate threshold are then
+// re-scored by the CTA's eight warps in parallel (one row per warp at a time; select_refine_kernel walks them two at a
+// time on a single warp), ranked and certified.  Same arithmetic, same tie rule, same outputs as select_refine_kernel;
+// a query whose selection overflows its buffer (ties by the thousand) counts as uncertified and the batch is repeated
+// on the kernels above.
+template <int ELEM, int METRIC>
+__global__ void __launch_bounds__(SS_THREADS) cta_refine_kernel(const uint8_t* __restrict__ rows, size_t stride, int V,
+                                                                const uint8_t* __restrict__ qimg, size_t qstride, int k, int kp, int probes,
+                                                                LcBound bound, const float* __restrict__ qn, const float* __restrict__ dist,
+                                                                const float* __restrict__ smin, int64_t cap, int64_t cap_s,
+                                                                const int32_t* __restrict__ seg_len, const int32_t* __restrict__ probe_lists,
+                                                                const int32_t* __restrict__ cand_off, const int64_t* __restrict__ list_off,
+                                                                int32_t* __restrict__ out_pos, float* __restrict__ out_key,
+                                                                int* __restrict__ n_failed) {
+    extern __shared__ uint64_t cr_smem[];
+    uint64_t* cand = cr_smem;                                                   // [SS_CAND]
+    uint64_t* fin = cand + SS_CAND;                                             // [kp] final keys
+    const uint8_t** rowp = reinterpret_cast<const uint8_t**>(fin + kp);         // [kp] row addresses
+    uint4* sq = reinterpret_cast<uint4*>(rowp + kp + (kp & 1));                 // [qvec] query image (16-byte aligned)
+    const int qvec = (int)(qstride / 16);
+    float* exact = reinterpret_cast<float*>(sq + qvec);                         // [kp]
+    uint32_t* skey = reinterpret_cast<uint32_t*>(exact + kp);                   // [cap_s] (slab path only)
+    int32_t* s_off = reinterpret_cast<int32_t*>(skey + (smin ? cap_s : 0));     // [probes + 1]
+    const int q = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
+    const uint4* gq = reinterpret_cast<const uint4*>(qimg + (size_t)q * qstride);
+    for (int i = tid; i < qvec; i += SS_THREADS) sq[i] = gq[i];
+    const int n_run = seg_len[q];
+    int n;
+    if (smin) n = slab_select_cta(dist, smin, probes, probe_lists, cand_off, list_off, cap, cap_s, q, kp, cand, skey, s_off);
+    else n = direct_select_cta(dist + (int64_t)q * cap, n_run, cand);
+    if (n < 0) {
+        // not selected here: the query reports as uncertified (outputs are rewritten by the repeat of the batch)
+        if (tid == 0) atomicAdd(n_failed, 1);
+        return;
+    }
+    const int have = min(n, kp);
+    // ---- threshold: (k-th smallest approximate distance) + 2 eps
+    const int kth = min(k, kp) - 1;
+    const uint64_t kth_key = kth < have ? cand[kth] : ~0ull;
+    const float kth_approx = kth_key == ~0ull ? __int_as_float(0x7F800000) : key_to_float((uint32_t)(kth_key >> 32));
+    const float T = kth_approx + 2.f * lc_eps(bound, qn[q]);
+    const uint64_t thr = kp - 1 < have ? cand[kp - 1] : ~0ull;                    // the k'-th key
+    // ---- row address of every listed candidate (one per thread)
+    const int32_t* co = cand_off + (int64_t)q * (probes + 1);
+    for (int i = tid; i < kp; i += SS_THREADS) {
+        exact[i] = __int_as_float(0x7F800000);
+        rowp[i] = rows;
+        if (i < have) {
+            const int32_t ps = (int32_t)(uint32_t)cand[i];
+            int lo = 0, hi = probes;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (co[mid] <= ps) lo = mid;
+                else hi = mid;
+            }
+            while (lo + 1 < probes && co[lo + 1] <= ps) ++lo;   // empty lists share an offset
+            const int l = probe_lists[(int64_t)q * probes + lo];
+            rowp[i] = rows + (size_t)(list_off[l] + (ps - co[lo])) * stride;
+        }
+    }
+    __syncthreads();
+    // ---- exact re-score of the candidates with approx <= T (NaN compares false: re-scored too), one row per warp
+    for (int i = warp; i < have; i += SS_THREADS / 32) {
+        const float a = key_to_float((uint32_t)(cand[i] >> 32));
+        if (a > T) continue;                                 // warp-uniform
+        const uint4* rp = reinterpret_cast<const uint4*>(rowp[i]);
+        Acc<ELEM, METRIC> acc;
+#pragma unroll 4
+        for (int v = lane; v < V; v += 32) acc.add(__ldg(rp + v), sq, v);
+        acc.template reduce<32>();
+        if (lane == 0) exact[i] = (float)acc.value();
+    }
+    __syncthreads();
+    // ---- order by (exact distance, position), emit the first k
+    for (int i = tid; i < kp; i += SS_THREADS)
+        fin[i] = i < have ? (((uint64_t)orderable_key(exact[i]) << 32) | (uint32_t)cand[i]) : (0xFFFFFFFF00000000ull | (uint32_t)i);
+    __syncthreads();
+    for (int i = tid; i < kp; i += SS_THREADS) {
+        const uint64_t mine = fin[i];
+        int rank = 0;
+        for (int j = 0; j < kp; ++j) rank += fin[j] < mine;
+        if (rank < k) {
+            const bool present = i < have;
+            out_pos[(int64_t)q * k + rank] = present ? (int32_t)(uint32_t)mine : -1;
+            out_key[(int64_t)q * k + rank] = present ? key_to_float((uint32_t)(mine >> 32)) : __int_as_float(0x7F800000);
+        }
+    }
+    // ---- certificate: candidates beyond the k' exist -> the last of the k' must already be above the threshold
+    if (tid == 0 && n_run > kp) {
+        const bool ok = key_to_float((uint32_t)(thr >> 32)) > T;     // false for NaN
+        if (!ok) atomicAdd(n_failed, 1);
+    }
+}
+
 // Bytes one launch of list_tc_kernel moves, from the same job list the kernel walks (profiling only):
 //   [0] bytes requested by the bulk copies (every (unit, query tile, K block) stage: A tile + B tile),
 //   [1] distinct A bytes (each active (list, table tile) unit's planes once: re-reads by further query tiles of the
@@ -949,6 +1046,39 @@ int launch_list_tc_select_refine(const Table& rows, const ListTcImage& im, int k
         VB_CUDA(cudaMemcpyAsync(n_failed_host, fail_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
         VB_CUDA(cudaStreamSynchronize(s));
     }
+    return VB_OK;
+}
+
+// steps 2 + 3 + 4 with one CTA per query; smin == nullptr: the run is short (<= SS_CAND) and selected directly
+int launch_list_tc_cta_refine(const Table& rows, const ListTcImage& im, int key_metric, const void* qimg, size_t qstride, int64_t nq,
+                              int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
+                              const float* dist, const float* smin, int64_t cap, int64_t cap_s, const int32_t* seg_len, const float* qn,
+                              int32_t* out_pos, float* out_key, int* fail_dev, int level) {
+    if (nq == 0) return VB_OK;
+    Context& c = ctx();
+    cudaStream_t s = c.stream;
+    const LcBound bound = lc_make_bound(rows, im, key_metric, level);
+    const int V = (int)(rows.stride / 16);
+    const size_t smem = (size_t)SS_CAND * 8 + (size_t)kp * 8 + (size_t)(kp + (kp & 1)) * 8 + qstride + (size_t)kp * 4 +
+                        (smin ? (size_t)cap_s * 4 : 0) + (size_t)(probes + 1) * 4 + 16;
+    VB_REQUIRE(kp <= 256 && smem <= 200 * 1024 && (smin || cap <= SS_CAND), "cta_refine: k' = %d / %zu bytes of shared memory not supported", kp, smem);
+#define VB_CR(E, M)                                                                                                              \
+    do {                                                                                                                         \
+        auto kern = cta_refine_kernel<E, M>;                                                                                     \
+        if (smem > 48 * 1024) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        kern<<<(unsigned)nq, SS_THREADS, smem, s>>>(rows.d, rows.stride, V, (const uint8_t*)qimg, qstride, k, kp, probes, bound, qn, dist, smin, \
+                                                   cap, cap_s, seg_len, d_lists, cand_off, d_list_off, out_pos, out_key, fail_dev);   \
+    } while (0)
+    if (rows.elem == VB_VECTOR) {
+        if (key_metric == VB_L2_SQUARED) VB_CR(VB_VECTOR, VB_L2_SQUARED);
+        else VB_CR(VB_VECTOR, VB_NEG_IP);
+    } else {
+        if (key_metric == VB_L2_SQUARED) VB_CR(VB_HALFVEC, VB_L2_SQUARED);
+        else VB_CR(VB_HALFVEC, VB_NEG_IP);
+    }
+#undef VB_CR
+    VB_CUDA(cudaGetLastError());
+    count_launch();
     return VB_OK;
 }
 

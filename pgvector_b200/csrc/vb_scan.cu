@@ -15,6 +15,7 @@
 // each thread keeps RPI * UNROLL independent LDG.128 outstanding.
 #include "vb_common.cuh"
 #include "vb_distance.cuh"
+#include "vb_slab_select.cuh"
 
 #include <cub/cub.cuh>
 
@@ -375,9 +376,6 @@ __global__ void __launch_bounds__(TOPK_THREADS) segment_topk_kernel(const float*
 // One CTA per query: (1) the run's slab minima into shared memory, (2) radix-select tau, (3) gather the candidates <= tau
 // of the qualifying slabs, (4) sort by (d~, position), emit k'.  More candidates than the buffer holds (massive ties)
 // flags the query for segment_topk_kernel.  Output: identical to segment_topk_kernel's.
-constexpr int SS_THREADS = 256;
-constexpr int SS_CAND = 2048;
-
 __global__ void __launch_bounds__(SS_THREADS) slab_select_kernel(const float* __restrict__ dist, const float* __restrict__ smin, int probes,
                                                                  const int32_t* __restrict__ probe_lists,
                                                                  const int32_t* __restrict__ cand_off, const int64_t* __restrict__ list_off,
@@ -388,147 +386,13 @@ __global__ void __launch_bounds__(SS_THREADS) slab_select_kernel(const float* __
     uint64_t* cand = ss_smem;                                             // [SS_CAND]
     uint32_t* skey = reinterpret_cast<uint32_t*>(cand + SS_CAND);         // [n_slab_max] orderable slab minima
     int32_t* s_off = reinterpret_cast<int32_t*>(skey + n_slab_max);       // [probes + 1] first slab of every probe
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t s_prefix, s_mask, s_kk, s_done, s_count;
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
-    const int32_t* co = cand_off + (int64_t)q * (probes + 1);
-    const int32_t* pl = probe_lists + (int64_t)q * probes;
-    // slabs per probe (the list bounds are independent loads: one thread per probe), then their prefix sums
-    for (int p = tid; p < probes; p += SS_THREADS) {
-        const int l = pl[p];
-        int ns = 0;
-        if (l >= 0) {
-            const int64_t lo = list_off[l], hi = list_off[l + 1];
-            if (hi > lo) ns = (int)(((hi - 1) >> 5) - (lo >> 5) + 1);
-        }
-        s_off[p + 1] = ns;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int off = 0;
-        s_off[0] = 0;
-        for (int p = 0; p < probes; ++p) {
-            off += s_off[p + 1];
-            s_off[p + 1] = off;
-        }
-        s_count = 0;
-        flagged[q] = 0;
-    }
-    __syncthreads();
-    const int S = s_off[probes];
-    for (int p = 0; p < probes; ++p) {
-        const int ns = s_off[p + 1] - s_off[p];
-        const float* sp = smin + slab_base(q, cap_s, co[p], p);
-        for (int j = tid; j < ns; j += SS_THREADS) skey[s_off[p] + j] = orderable_key(sp[j]);
-    }
-    __syncthreads();
-    // ---- tau: the k-th smallest slab minimum (everything when there are at most k slabs)
-    uint32_t tau = 0xFFFFFFFFu;
-    if (S > k) {
-        if (tid == 0) {
-            s_prefix = 0;
-            s_mask = 0;
-            s_kk = (uint32_t)k;
-            s_done = 0;
-        }
-        __syncthreads();
-        for (int pass = 3; pass >= 0; --pass) {
-            hist[tid] = 0;
-            __syncthreads();
-            const int shift = pass * 8;
-            const uint32_t prefix = s_prefix, mask = s_mask;
-            for (int i = tid; i < S; i += SS_THREADS) {
-                const uint32_t key = skey[i];
-                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            if (tid < 32) {
-                // the bin holding the kk-th key: every lane sums 8 bins, a warp scan finds the lane, the lane its bin
-                const uint32_t kk = s_kk;
-                uint32_t h[8], mine = 0;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    h[t] = hist[tid * 8 + t];
-                    mine += h[t];
-                }
-                uint32_t incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (tid >= o) incl += u;
-                }
-                const unsigned reach = __ballot_sync(0xffffffffu, incl >= kk);
-                const int owner = __ffs(reach) - 1;      // (kk <= the number of keys under the prefix: always found)
-                if (tid == owner) {
-                    uint32_t cum = incl - mine;
-                    int b = 0;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        if (cum + h[t] >= kk) break;
-                        cum += h[t];
-                        ++b;
-                    }
-                    s_prefix = prefix | ((uint32_t)(tid * 8 + b) << shift);
-                    s_mask = mask | (0xFFu << shift);
-                    s_kk = kk - cum;
-                }
-            }
-            __syncthreads();
-        }
-        tau = s_prefix;   // exactly the k-th smallest key (ties included by the <= below)
-    }
-    // ---- gather: one warp per qualifying slab, lane = row of the slab
-    const int warp = tid / 32, lane = tid % 32;
-    const float* dq = dist + (int64_t)q * cap;
-    for (int p = 0; p < probes; ++p) {
-        const int ns = s_off[p + 1] - s_off[p];
-        if (ns == 0) continue;
-        const int l = pl[p];
-        const int64_t lo = list_off[l], hi = list_off[l + 1];
-        const int64_t slab0 = lo >> 5;
-        for (int j = warp; j < ns; j += SS_THREADS / 32) {
-            if (skey[s_off[p] + j] > tau) continue;          // warp-uniform
-            const int64_t r = ((slab0 + j) << 5) + lane;
-            if (r >= lo && r < hi) {
-                const uint32_t pos = (uint32_t)(co[p] + (int32_t)(r - lo));
-                const uint32_t ok = orderable_key(dq[pos]);
-                if (ok <= tau) {
-                    const uint32_t slot = atomicAdd(&s_count, 1u);
-                    if (slot < (uint32_t)SS_CAND) cand[slot] = ((uint64_t)ok << 32) | pos;
-                }
-            }
-        }
-    }
-    __syncthreads();
-    const uint32_t n = s_count;
-    if (n > (uint32_t)SS_CAND) {
-        if (tid == 0) flagged[q] = 1;
-        return;
-    }
-    // ---- sort by (d~, position) and emit
-    int npow2 = 2;
-    while ((uint32_t)npow2 < n) npow2 <<= 1;
-    for (int i = (int)n + tid; i < npow2; i += SS_THREADS) cand[i] = ~0ull;
-    __syncthreads();
-    for (int size = 2; size <= npow2; size <<= 1) {
-        for (int st = size >> 1; st > 0; st >>= 1) {
-            for (int i = tid; i < npow2; i += SS_THREADS) {
-                const int j = i ^ st;
-                if (j > i) {
-                    const uint64_t x = cand[i], y = cand[j];
-                    const bool up = (i & size) == 0;
-                    if ((x > y) == up) {
-                        cand[i] = y;
-                        cand[j] = x;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
+    const int n = slab_select_cta(dist, smin, probes, probe_lists, cand_off, list_off, cap, cap_s, q, k, cand, skey, s_off);
+    if (tid == 0) flagged[q] = n < 0 ? 1 : 0;
+    if (n < 0) return;
     for (int i = tid; i < k; i += SS_THREADS) {
-        if ((uint32_t)i < n) {
+        if (i < n) {
             const uint64_t key = cand[i];
             out_pos[(int64_t)q * k + i] = (int32_t)(uint32_t)key;
             out_key[(int64_t)q * k + i] = key_to_float((uint32_t)(key >> 32));

@@ -1,0 +1,176 @@
+// vb_slab_select.cuh -- CTA-wide selection of the k' nearest of one query's candidate run, shared by
+// slab_select_kernel (vb_scan.cu) and cta_refine_kernel (vb_list_tc.cu).
+//
+// The tensor-core filter's epilogue stores, beside the dense d~ array, min d~ of every slab (32 table-aligned rows of one
+// probed list, slab_base() in vb_common.cuh).  tau = the k'-th smallest slab minimum is an upper bound of the k'-th
+// smallest d~ (k' distinct candidates are <= tau), so the k' nearest all lie in slabs whose minimum is <= tau: exactly k'
+// slabs when the minima are distinct -- 32 k' candidates are read per query instead of the whole run.
+#pragma once
+
+#include "vb_common.cuh"
+#include "vb_distance.cuh"
+
+namespace vb {
+
+constexpr int SS_THREADS = 256;
+constexpr int SS_CAND = 2048;
+
+// cand[0 .. npow2) sorted ascending by (d~, position); entries past n are ~0ull.  All SS_THREADS threads call it.
+__device__ __forceinline__ void ss_sort_cand(uint64_t* cand, uint32_t n) {
+    const int tid = threadIdx.x;
+    int npow2 = 2;
+    while ((uint32_t)npow2 < n) npow2 <<= 1;
+    for (int i = (int)n + tid; i < npow2; i += SS_THREADS) cand[i] = ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= npow2; size <<= 1) {
+        for (int st = size >> 1; st > 0; st >>= 1) {
+            for (int i = tid; i < npow2; i += SS_THREADS) {
+                const int j = i ^ st;
+                if (j > i) {
+                    const uint64_t x = cand[i], y = cand[j];
+                    const bool up = (i & size) == 0;
+                    if ((x > y) == up) {
+                        cand[i] = y;
+                        cand[j] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// The candidates of query q that can be among its k nearest by d~: (1) the run's slab minima into shared memory,
+// (2) radix-select tau, (3) gather the candidates <= tau of the qualifying slabs, (4) sort.  Returns their number n
+// (cand[0 .. n) sorted, n >= min(k, run length)), or -1 when more than SS_CAND qualify (ties by the thousand).
+// skey: [cap_s] words, s_off: [probes + 1] words of shared memory.
+__device__ __forceinline__ int slab_select_cta(const float* __restrict__ dist, const float* __restrict__ smin, int probes,
+                                               const int32_t* __restrict__ probe_lists, const int32_t* __restrict__ cand_off,
+                                               const int64_t* __restrict__ list_off, int64_t cap, int64_t cap_s, int q, int k,
+                                               uint64_t* cand, uint32_t* skey, int32_t* s_off) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_mask, s_kk, s_done, s_count;
+    const int tid = threadIdx.x;
+    const int32_t* co = cand_off + (int64_t)q * (probes + 1);
+    const int32_t* pl = probe_lists + (int64_t)q * probes;
+    // slabs per probe (the list bounds are independent loads: one thread per probe), then their prefix sums
+    for (int p = tid; p < probes; p += SS_THREADS) {
+        const int l = pl[p];
+        int ns = 0;
+        if (l >= 0) {
+            const int64_t lo = list_off[l], hi = list_off[l + 1];
+            if (hi > lo) ns = (int)(((hi - 1) >> 5) - (lo >> 5) + 1);
+        }
+        s_off[p + 1] = ns;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int off = 0;
+        s_off[0] = 0;
+        for (int p = 0; p < probes; ++p) {
+            off += s_off[p + 1];
+            s_off[p + 1] = off;
+        }
+        s_count = 0;
+    }
+    __syncthreads();
+    const int S = s_off[probes];
+    for (int p = 0; p < probes; ++p) {
+        const int ns = s_off[p + 1] - s_off[p];
+        const float* sp = smin + slab_base(q, cap_s, co[p], p);
+        for (int j = tid; j < ns; j += SS_THREADS) skey[s_off[p] + j] = orderable_key(sp[j]);
+    }
+    __syncthreads();
+    // ---- tau: the k-th smallest slab minimum (everything when there are at most k slabs)
+    uint32_t tau = 0xFFFFFFFFu;
+    if (S > k) {
+        if (tid == 0) {
+            s_prefix = 0;
+            s_mask = 0;
+            s_kk = (uint32_t)k;
+            s_done = 0;
+        }
+        __syncthreads();
+        for (int pass = 3; pass >= 0; --pass) {
+            hist[tid] = 0;
+            __syncthreads();
+            const int shift = pass * 8;
+            const uint32_t prefix = s_prefix, mask = s_mask;
+            for (int i = tid; i < S; i += SS_THREADS) {
+                const uint32_t key = skey[i];
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid < 32) {
+                // the bin holding the kk-th key: every lane sums 8 bins, a warp scan finds the lane, the lane its bin
+                const uint32_t kk = s_kk;
+                uint32_t h[8], mine = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    h[t] = hist[tid * 8 + t];
+                    mine += h[t];
+                }
+                uint32_t incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += u;
+                }
+                const unsigned reach = __ballot_sync(0xffffffffu, incl >= kk);
+                const int owner = __ffs(reach) - 1;      // (kk <= the number of keys under the prefix: always found)
+                if (tid == owner) {
+                    uint32_t cum = incl - mine;
+                    int b = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        if (cum + h[t] >= kk) break;
+                        cum += h[t];
+                        ++b;
+                    }
+                    s_prefix = prefix | ((uint32_t)(tid * 8 + b) << shift);
+                    s_mask = mask | (0xFFu << shift);
+                    s_kk = kk - cum;
+                }
+            }
+            __syncthreads();
+        }
+        tau = s_prefix;   // exactly the k-th smallest key (ties included by the <= below)
+    }
+    // ---- gather: one warp per qualifying slab, lane = row of the slab
+    const int warp = tid / 32, lane = tid % 32;
+    const float* dq = dist + (int64_t)q * cap;
+    for (int p = 0; p < probes; ++p) {
+        const int ns = s_off[p + 1] - s_off[p];
+        if (ns == 0) continue;
+        const int l = pl[p];
+        const int64_t lo = list_off[l], hi = list_off[l + 1];
+        const int64_t slab0 = lo >> 5;
+        for (int j = warp; j < ns; j += SS_THREADS / 32) {
+            if (skey[s_off[p] + j] > tau) continue;          // warp-uniform
+            const int64_t r = ((slab0 + j) << 5) + lane;
+            if (r >= lo && r < hi) {
+                const uint32_t pos = (uint32_t)(co[p] + (int32_t)(r - lo));
+                const uint32_t ok = orderable_key(dq[pos]);
+                if (ok <= tau) {
+                    const uint32_t slot = atomicAdd(&s_count, 1u);
+                    if (slot < (uint32_t)SS_CAND) cand[slot] = ((uint64_t)ok << 32) | pos;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t n = s_count;
+    if (n > (uint32_t)SS_CAND) return -1;
+    ss_sort_cand(cand, n);
+    return (int)n;
+}
+
+// a short run (n <= SS_CAND candidates, e.g. the distances of one query to every centre): all of it, sorted
+__device__ __forceinline__ int direct_select_cta(const float* __restrict__ dq, int n, uint64_t* cand) {
+    for (int i = threadIdx.x; i < n; i += SS_THREADS) cand[i] = ((uint64_t)orderable_key(dq[i]) << 32) | (uint32_t)i;
+    __syncthreads();
+    ss_sort_cand(cand, (uint32_t)n);
+    return n;
+}
+
+}  // namespace vb

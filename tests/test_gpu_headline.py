@@ -169,28 +169,29 @@ def test_near_ties_at_long_rows(pv, dim, gap):
 
 @pytest.mark.parametrize("k,probes", [(10, 10), (1, 3), (40, 10), (24, 7)])
 def test_fused_select_refine_equals_the_three_kernel_path(pv, headline, k, probes):
-    """select_refine_kernel (exact re-score + certificate in one warp-per-query kernel after segment_topk_kernel's k'
-    select: option fused_refine = 1, the default; = 2 also selects inside the kernel) returns bit for bit what
-    segment_topk_kernel + rescore_kernel + certify_kernel (= 0) return, at both filter levels, incl. the counters"""
+    """cta_refine_kernel (option fused_refine = 3, the default: selection, exact re-score, ranking and certificate with one
+    CTA per query) and select_refine_kernel (= 1: one warp per query after the selection kernel; = 2: it also selects)
+    return bit for bit what segment_topk_kernel + rescore_kernel + certify_kernel (= 0) return, at both filter levels,
+    incl. the counters"""
     law, gix, oix, queries, _ = headline
     out = {}
     try:
         pv.set_option("scan_impl", 4)
         for level1 in (1, 0):
             pv.set_option("tc_level1", level1)
-            for fused in (0, 1, 2):
+            for fused in (0, 1, 2, 3):
                 pv.set_option("fused_refine", fused)
                 f0, l0 = gix.tc_fallbacks(), gix.tc_level1_fallbacks()
                 ids, dist = gix.search(queries, k=k, probes=probes)
                 lists, ldist = gix.scan_lists(queries[:300], probes)
                 out[level1, fused] = (ids, dist, lists, ldist, gix.tc_fallbacks() - f0, gix.tc_level1_fallbacks() - l0)
     finally:
-        pv.set_option("fused_refine", 1)
+        pv.set_option("fused_refine", 3)
         pv.set_option("tc_level1", 1)
         pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
     for level1 in (1, 0):
         a = out[level1, 0]
-        for fused in (1, 2):
+        for fused in (1, 2, 3):
             b = out[level1, fused]
             for x, y in zip(a[:4], b[:4]):
                 assert np.array_equal(x, y), (level1, fused, k, probes)
@@ -210,7 +211,7 @@ def test_selection_from_slab_minima_equals_the_full_selection(pv, headline, k, p
         pv.set_option("scan_impl", 4)
         for level1 in (1, 0):
             pv.set_option("tc_level1", level1)
-            for fused in (1, 0):
+            for fused in (3, 1, 0):
                 pv.set_option("fused_refine", fused)
                 for slab in (0, 1):
                     pv.set_option("slab_select", slab)
@@ -218,11 +219,11 @@ def test_selection_from_slab_minima_equals_the_full_selection(pv, headline, k, p
                     out[(level1, fused, slab)] = ix.search(qs, k=k, probes=probes) + (ix.tc_fallbacks() - f0,)
     finally:
         pv.set_option("slab_select", 1)
-        pv.set_option("fused_refine", 1)
+        pv.set_option("fused_refine", 3)
         pv.set_option("tc_level1", 1)
         pv.set_option("scan_impl", int(os.environ.get("VB_TEST_SCAN_IMPL", "2")))
     for level1 in (1, 0):
-        for fused in (1, 0):
+        for fused in (3, 1, 0):
             i0, d0, f0 = out[(level1, fused, 0)]
             i1, d1, f1 = out[(level1, fused, 1)]
             assert np.array_equal(i0, i1) and np.array_equal(d0, d1) and f0 == f1
@@ -230,14 +231,15 @@ def test_selection_from_slab_minima_equals_the_full_selection(pv, headline, k, p
 
 def test_selection_from_slab_minima_with_ties_by_the_thousand(pv):
     """5000 copies of one row: every slab minimum ties, more candidates qualify than the selection's buffer holds, and the
-    flagged queries go through the full selection -- results still equal the exact scan's (ids by position order)"""
+    flagged queries go through the full selection (the CTA-per-query kernel reports them as uncertified and the batch is
+    repeated on the selection kernels) -- results still equal the exact scan's (ids by position order)"""
     rng = np.random.default_rng(11)
     dim = 64
     base = rng.standard_normal((3000, dim)).astype(np.float32)
     dup = np.repeat(base[:1], 5000, axis=0)
     rows = np.concatenate([dup, base])
     ix, oix = build(pv, rows, 4, seed=2)
-    qs = np.concatenate([base[:1] + 0.01, base[5:40]]).astype(np.float32)
+    qs = np.concatenate([base[:1] + 0.01, base[5:105]]).astype(np.float32)     # 101 queries x 4 probes: a batched scan
     try:
         pv.set_option("scan_impl", 4)
         got_i, got_d = ix.search(qs, k=10, probes=4)
