@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(SS_THREADS) cta_refine_kernel(const uint8_t* _
     uint64_t* cand = cr_smem;                                                   // [SS_CAND]
     uint64_t* fin = cand + SS_CAND;                                             // [kp] final keys
     const uint8_t** rowp = reinterpret_cast<const uint8_t**>(fin + kp);         // [kp] row addresses
-    uint4* sq = reinterpret_cast<uint4*>(rowp + kp + (kp & 1));                 // [qvec] query image (16-byte aligned)
+    uint4* sq = reinterpret_cast<uint4*>(rowp + kp);                            // [qvec] query image (cand, fin and rowp are 16 kp + 16384 bytes: aligned)
     const int qvec = (int)(qstride / 16);
     float* exact = reinterpret_cast<float*>(sq + qvec);                         // [kp]
     uint32_t* skey = reinterpret_cast<uint32_t*>(exact + kp);                   // [cap_s] (slab path only)
@@ -1059,7 +1059,7 @@ int launch_list_tc_cta_refine(const Table& rows, const ListTcImage& im, int key_
     cudaStream_t s = c.stream;
     const LcBound bound = lc_make_bound(rows, im, key_metric, level);
     const int V = (int)(rows.stride / 16);
-    const size_t smem = (size_t)SS_CAND * 8 + (size_t)kp * 8 + (size_t)(kp + (kp & 1)) * 8 + qstride + (size_t)kp * 4 +
+    const size_t smem = (size_t)SS_CAND * 8 + (size_t)kp * 16 + qstride + (size_t)kp * 4 +
                         (smin ? (size_t)cap_s * 4 : 0) + (size_t)(probes + 1) * 4 + 16;
     VB_REQUIRE(kp <= 256 && smem <= 200 * 1024 && (smin || cap <= SS_CAND), "cta_refine: k' = %d / %zu bytes of shared memory not supported", kp, smem);
 #define VB_CR(E, M)                                                                                                              \
