@@ -680,17 +680,16 @@ __global__ void __launch_bounds__(SS_THREADS) cta_refine_kernel(const uint8_t* _
     const uint8_t** rowp = reinterpret_cast<const uint8_t**>(fin + kp);         // [kp] row addresses
     uint4* sq = reinterpret_cast<uint4*>(rowp + kp);                            // [qvec] query image (cand, fin and rowp are 16 kp + 16384 bytes: aligned)
     const int qvec = (int)(qstride / 16);
-    float* exact = reinterpret_cast<float*>(sq + qvec);                         // [kp]
-    uint32_t* skey = reinterpret_cast<uint32_t*>(exact + kp);                   // [cap_s] (slab path only)
-    int32_t* s_off = reinterpret_cast<int32_t*>(skey + (smin ? cap_s : 0));     // [probes + 1]
+    void* work = sq + qvec;                                                     // the selection's work area (16-byte aligned)
+    float* exact = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(work) + (smin ? ss_select_smem_bytes(cap_s, probes) : (size_t)cap * 4));   // [kp]
     const int q = blockIdx.x;
     const int tid = threadIdx.x, warp = tid / 32, lane = tid % 32;
     const uint4* gq = reinterpret_cast<const uint4*>(qimg + (size_t)q * qstride);
     for (int i = tid; i < qvec; i += SS_THREADS) sq[i] = gq[i];
     const int n_run = seg_len[q];
     int n;
-    if (smin) n = slab_select_cta(dist, smin, probes, probe_lists, cand_off, list_off, cap, cap_s, q, kp, cand, skey, s_off);
-    else n = direct_select_cta(dist + (int64_t)q * cap, n_run, cand);
+    if (smin) n = slab_select_cta(dist, smin, probes, probe_lists, cand_off, list_off, cap, cap_s, q, kp, cand, work);
+    else n = direct_select_cta(dist + (int64_t)q * cap, n_run, kp, cand, work);
     if (n < 0) {
         // not selected here: the query reports as uncertified (outputs are rewritten by the repeat of the batch)
         if (tid == 0) atomicAdd(n_failed, 1);
@@ -1059,8 +1058,8 @@ int launch_list_tc_cta_refine(const Table& rows, const ListTcImage& im, int key_
     cudaStream_t s = c.stream;
     const LcBound bound = lc_make_bound(rows, im, key_metric, level);
     const int V = (int)(rows.stride / 16);
-    const size_t smem = (size_t)SS_CAND * 8 + (size_t)kp * 16 + qstride + (size_t)kp * 4 +
-                        (smin ? (size_t)cap_s * 4 : 0) + (size_t)(probes + 1) * 4 + 16;
+    const size_t smem = (size_t)SS_CAND * 8 + (size_t)kp * 16 + qstride + (smin ? ss_select_smem_bytes(cap_s, probes) : (size_t)cap * 4) +
+                        (size_t)kp * 4 + 16;
     VB_REQUIRE(kp <= 256 && smem <= 200 * 1024 && (smin || cap <= SS_CAND), "cta_refine: k' = %d / %zu bytes of shared memory not supported", kp, smem);
 #define VB_CR(E, M)                                                                                                              \
     do {                                                                                                                         \

@@ -383,12 +383,10 @@ __global__ void __launch_bounds__(SS_THREADS) slab_select_kernel(const float* __
                                                                  int32_t* __restrict__ out_pos, float* __restrict__ out_key,
                                                                  int32_t* __restrict__ flagged) {
     extern __shared__ uint64_t ss_smem[];
-    uint64_t* cand = ss_smem;                                             // [SS_CAND]
-    uint32_t* skey = reinterpret_cast<uint32_t*>(cand + SS_CAND);         // [n_slab_max] orderable slab minima
-    int32_t* s_off = reinterpret_cast<int32_t*>(skey + n_slab_max);       // [probes + 1] first slab of every probe
+    uint64_t* cand = ss_smem;                                             // [SS_CAND], then the selection's work area
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
-    const int n = slab_select_cta(dist, smin, probes, probe_lists, cand_off, list_off, cap, cap_s, q, k, cand, skey, s_off);
+    const int n = slab_select_cta(dist, smin, probes, probe_lists, cand_off, list_off, cap, cap_s, q, k, cand, cand + SS_CAND);
     if (tid == 0) flagged[q] = n < 0 ? 1 : 0;
     if (n < 0) return;
     for (int i = tid; i < k; i += SS_THREADS) {
@@ -413,7 +411,7 @@ int launch_slab_select(const float* dist, const float* smin, int64_t nq, int pro
     VB_REQUIRE(kp <= TOPK_MAX_K, "slab selection: k' too large");
     void* d_flag;
     VB_TRY(workspace(WSS_FLAG, sizeof(int32_t) * (size_t)nq, &d_flag));
-    const size_t smem = (size_t)SS_CAND * 8 + (size_t)cap_s * 4 + (size_t)(probes + 1) * 4;
+    const size_t smem = (size_t)SS_CAND * 8 + ss_select_smem_bytes(cap_s, probes);
     VB_REQUIRE(smem <= 200 * 1024, "slab selection: %zu bytes of shared memory", smem);
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {

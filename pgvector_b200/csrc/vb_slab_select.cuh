@@ -40,16 +40,84 @@ __device__ __forceinline__ void ss_sort_cand(uint64_t* cand, uint32_t n) {
     }
 }
 
+// the k-th smallest of the S orderable keys in shared memory (k <= S): four 8-bit radix passes over a 256-bin histogram
+__device__ __forceinline__ uint32_t ss_radix_kth(const uint32_t* keys, int S, int k) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_mask, s_kk;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_prefix = 0;
+        s_mask = 0;
+        s_kk = (uint32_t)k;
+    }
+    __syncthreads();
+    for (int pass = 3; pass >= 0; --pass) {
+        hist[tid] = 0;
+        __syncthreads();
+        const int shift = pass * 8;
+        const uint32_t prefix = s_prefix, mask = s_mask;
+        for (int i = tid; i < S; i += SS_THREADS) {
+            const uint32_t key = keys[i];
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // the bin holding the kk-th key: every lane sums 8 bins, a warp scan finds the lane, the lane its bin
+            const uint32_t kk = s_kk;
+            uint32_t h[8], mine = 0;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                h[t] = hist[tid * 8 + t];
+                mine += h[t];
+            }
+            uint32_t incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += u;
+            }
+            const unsigned reach = __ballot_sync(0xffffffffu, incl >= kk);
+            const int owner = __ffs(reach) - 1;      // (kk <= the number of keys under the prefix: always found)
+            if (tid == owner) {
+                uint32_t cum = incl - mine;
+                int b = 0;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    if (cum + h[t] >= kk) break;
+                    cum += h[t];
+                    ++b;
+                }
+                s_prefix = prefix | ((uint32_t)(tid * 8 + b) << shift);
+                s_mask = mask | (0xFFu << shift);
+                s_kk = kk - cum;
+            }
+        }
+        __syncthreads();
+    }
+    return s_prefix;   // exactly the k-th smallest key
+}
+
+// shared memory the selection needs beside cand[SS_CAND]: slab keys + the list of qualifying slabs (2 cap_s words), and
+// per probe: first slab (probes + 1), candidate offset, list bounds
+__host__ __device__ inline size_t ss_select_smem_bytes(int64_t cap_s, int probes) {
+    return (size_t)cap_s * 8 + (size_t)(2 * probes + 2) * 4 + (size_t)probes * 16 + 16;
+}
+
 // The candidates of query q that can be among its k nearest by d~: (1) the run's slab minima into shared memory,
-// (2) radix-select tau, (3) gather the candidates <= tau of the qualifying slabs, (4) sort.  Returns their number n
-// (cand[0 .. n) sorted, n >= min(k, run length)), or -1 when more than SS_CAND qualify (ties by the thousand).
-// skey: [cap_s] words, s_off: [probes + 1] words of shared memory.
+// (2) radix-select tau, (3) list the qualifying slabs, then gather their candidates <= tau with every load independent
+// (one candidate per thread and step), (4) sort.  Returns their number n (cand[0 .. n) sorted, n >= min(k, run length)),
+// or -1 when more than SS_CAND qualify (ties by the thousand).  `work`: ss_select_smem_bytes() of shared memory, 8-byte aligned.
 __device__ __forceinline__ int slab_select_cta(const float* __restrict__ dist, const float* __restrict__ smin, int probes,
                                                const int32_t* __restrict__ probe_lists, const int32_t* __restrict__ cand_off,
                                                const int64_t* __restrict__ list_off, int64_t cap, int64_t cap_s, int q, int k,
-                                               uint64_t* cand, uint32_t* skey, int32_t* s_off) {
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t s_prefix, s_mask, s_kk, s_done, s_count;
+                                               uint64_t* cand, void* work) {
+    __shared__ uint32_t s_count, s_nq;
+    int64_t* s_lo = reinterpret_cast<int64_t*>(work);                     // [probes] list bounds
+    int64_t* s_hi = s_lo + probes;
+    uint32_t* skey = reinterpret_cast<uint32_t*>(s_hi + probes);          // [cap_s] orderable slab minima
+    uint32_t* qlist = skey + cap_s;                                       // [cap_s] qualifying slabs
+    int32_t* s_off = reinterpret_cast<int32_t*>(qlist + cap_s);           // [probes + 1] first slab of every probe
+    int32_t* s_co = s_off + probes + 1;                                   // [probes] first candidate of every probe
     const int tid = threadIdx.x;
     const int32_t* co = cand_off + (int64_t)q * (probes + 1);
     const int32_t* pl = probe_lists + (int64_t)q * probes;
@@ -57,10 +125,15 @@ __device__ __forceinline__ int slab_select_cta(const float* __restrict__ dist, c
     for (int p = tid; p < probes; p += SS_THREADS) {
         const int l = pl[p];
         int ns = 0;
+        int64_t lo = 0, hi = 0;
         if (l >= 0) {
-            const int64_t lo = list_off[l], hi = list_off[l + 1];
+            lo = list_off[l];
+            hi = list_off[l + 1];
             if (hi > lo) ns = (int)(((hi - 1) >> 5) - (lo >> 5) + 1);
         }
+        s_lo[p] = lo;
+        s_hi[p] = hi;
+        s_co[p] = co[p];
         s_off[p + 1] = ns;
     }
     __syncthreads();
@@ -72,89 +145,42 @@ __device__ __forceinline__ int slab_select_cta(const float* __restrict__ dist, c
             s_off[p + 1] = off;
         }
         s_count = 0;
+        s_nq = 0;
     }
     __syncthreads();
     const int S = s_off[probes];
     for (int p = 0; p < probes; ++p) {
         const int ns = s_off[p + 1] - s_off[p];
-        const float* sp = smin + slab_base(q, cap_s, co[p], p);
+        const float* sp = smin + slab_base(q, cap_s, s_co[p], p);
         for (int j = tid; j < ns; j += SS_THREADS) skey[s_off[p] + j] = orderable_key(sp[j]);
     }
     __syncthreads();
     // ---- tau: the k-th smallest slab minimum (everything when there are at most k slabs)
     uint32_t tau = 0xFFFFFFFFu;
-    if (S > k) {
-        if (tid == 0) {
-            s_prefix = 0;
-            s_mask = 0;
-            s_kk = (uint32_t)k;
-            s_done = 0;
-        }
-        __syncthreads();
-        for (int pass = 3; pass >= 0; --pass) {
-            hist[tid] = 0;
-            __syncthreads();
-            const int shift = pass * 8;
-            const uint32_t prefix = s_prefix, mask = s_mask;
-            for (int i = tid; i < S; i += SS_THREADS) {
-                const uint32_t key = skey[i];
-                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            if (tid < 32) {
-                // the bin holding the kk-th key: every lane sums 8 bins, a warp scan finds the lane, the lane its bin
-                const uint32_t kk = s_kk;
-                uint32_t h[8], mine = 0;
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    h[t] = hist[tid * 8 + t];
-                    mine += h[t];
-                }
-                uint32_t incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (tid >= o) incl += u;
-                }
-                const unsigned reach = __ballot_sync(0xffffffffu, incl >= kk);
-                const int owner = __ffs(reach) - 1;      // (kk <= the number of keys under the prefix: always found)
-                if (tid == owner) {
-                    uint32_t cum = incl - mine;
-                    int b = 0;
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        if (cum + h[t] >= kk) break;
-                        cum += h[t];
-                        ++b;
-                    }
-                    s_prefix = prefix | ((uint32_t)(tid * 8 + b) << shift);
-                    s_mask = mask | (0xFFu << shift);
-                    s_kk = kk - cum;
-                }
-            }
-            __syncthreads();
-        }
-        tau = s_prefix;   // exactly the k-th smallest key (ties included by the <= below)
-    }
-    // ---- gather: one warp per qualifying slab, lane = row of the slab
-    const int warp = tid / 32, lane = tid % 32;
+    if (S > k) tau = ss_radix_kth(skey, S, k);
+    // ---- the qualifying slabs, then their rows: thread t takes row t % 32 of listed slab t / 32
+    for (int i = tid; i < S; i += SS_THREADS)
+        if (skey[i] <= tau) qlist[atomicAdd(&s_nq, 1u)] = (uint32_t)i;
+    __syncthreads();
+    const int nq_rows = (int)s_nq * 32;
     const float* dq = dist + (int64_t)q * cap;
-    for (int p = 0; p < probes; ++p) {
-        const int ns = s_off[p + 1] - s_off[p];
-        if (ns == 0) continue;
-        const int l = pl[p];
-        const int64_t lo = list_off[l], hi = list_off[l + 1];
-        const int64_t slab0 = lo >> 5;
-        for (int j = warp; j < ns; j += SS_THREADS / 32) {
-            if (skey[s_off[p] + j] > tau) continue;          // warp-uniform
-            const int64_t r = ((slab0 + j) << 5) + lane;
-            if (r >= lo && r < hi) {
-                const uint32_t pos = (uint32_t)(co[p] + (int32_t)(r - lo));
-                const uint32_t ok = orderable_key(dq[pos]);
-                if (ok <= tau) {
-                    const uint32_t slot = atomicAdd(&s_count, 1u);
-                    if (slot < (uint32_t)SS_CAND) cand[slot] = ((uint64_t)ok << 32) | pos;
-                }
+    for (int t = tid; t < nq_rows; t += SS_THREADS) {
+        const int i = (int)qlist[t >> 5];
+        int p = 0, hi_p = probes;                  // probe of slab i: s_off[p] <= i < s_off[p + 1]
+        while (hi_p - p > 1) {
+            const int mid = (p + hi_p) >> 1;
+            if (s_off[mid] <= i) p = mid;
+            else hi_p = mid;
+        }
+        while (p + 1 < probes && s_off[p + 1] <= i) ++p;      // empty probes share an offset
+        const int64_t lo = s_lo[p], hi = s_hi[p];
+        const int64_t r = (((lo >> 5) + (i - s_off[p])) << 5) + (t & 31);
+        if (r >= lo && r < hi) {
+            const uint32_t pos = (uint32_t)(s_co[p] + (int32_t)(r - lo));
+            const uint32_t ok = orderable_key(dq[pos]);
+            if (ok <= tau) {
+                const uint32_t slot = atomicAdd(&s_count, 1u);
+                if (slot < (uint32_t)SS_CAND) cand[slot] = ((uint64_t)ok << 32) | pos;
             }
         }
     }
@@ -165,12 +191,30 @@ __device__ __forceinline__ int slab_select_cta(const float* __restrict__ dist, c
     return (int)n;
 }
 
-// a short run (n <= SS_CAND candidates, e.g. the distances of one query to every centre): all of it, sorted
-__device__ __forceinline__ int direct_select_cta(const float* __restrict__ dq, int n, uint64_t* cand) {
-    for (int i = threadIdx.x; i < n; i += SS_THREADS) cand[i] = ((uint64_t)orderable_key(dq[i]) << 32) | (uint32_t)i;
+// a short run (n <= SS_CAND candidates, e.g. the distances of one query to every centre): the k-th smallest key is
+// radix-selected, the keys up to it gathered and sorted (a full sort of the run costs 50 k warp instructions per query).
+// `work`: n words of shared memory.  Returns the number gathered (>= min(k, n)), or -1 past SS_CAND (cannot happen: n <= SS_CAND).
+__device__ __forceinline__ int direct_select_cta(const float* __restrict__ dq, int n, int k, uint64_t* cand, void* work) {
+    __shared__ uint32_t s_cnt;
+    uint32_t* keys = reinterpret_cast<uint32_t*>(work);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < n; i += SS_THREADS) keys[i] = orderable_key(dq[i]);
+    if (tid == 0) s_cnt = 0;
     __syncthreads();
-    ss_sort_cand(cand, (uint32_t)n);
-    return n;
+    uint32_t tau = 0xFFFFFFFFu;
+    if (n > k) tau = ss_radix_kth(keys, n, k);
+    for (int i = tid; i < n; i += SS_THREADS) {
+        const uint32_t key = keys[i];
+        if (key <= tau) {
+            const uint32_t slot = atomicAdd(&s_cnt, 1u);
+            if (slot < (uint32_t)SS_CAND) cand[slot] = ((uint64_t)key << 32) | (uint32_t)i;
+        }
+    }
+    __syncthreads();
+    const uint32_t m = s_cnt;
+    if (m > (uint32_t)SS_CAND) return -1;
+    ss_sort_cand(cand, m);
+    return (int)m;
 }
 
 }  // namespace vb
