@@ -702,22 +702,35 @@ __global__ void __launch_bounds__(SS_THREADS) cta_refine_kernel(const uint8_t* _
     const float kth_approx = kth_key == ~0ull ? __int_as_float(0x7F800000) : key_to_float((uint32_t)(kth_key >> 32));
     const float T = kth_approx + 2.f * lc_eps(bound, qn[q]);
     const uint64_t thr = kp - 1 < have ? cand[kp - 1] : ~0ull;                    // the k'-th key
-    // ---- row address of every listed candidate (one per thread)
+    // ---- row address of every listed candidate (one per thread): position -> probe -> row.  After a slab selection the
+    // per-probe candidate offsets and list bounds are in shared memory already.
     const int32_t* co = cand_off + (int64_t)q * (probes + 1);
+    const SsWork W = ss_work_layout(work, cap_s, probes);
     for (int i = tid; i < kp; i += SS_THREADS) {
         exact[i] = __int_as_float(0x7F800000);
         rowp[i] = rows;
         if (i < have) {
             const int32_t ps = (int32_t)(uint32_t)cand[i];
-            int lo = 0, hi = probes;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (co[mid] <= ps) lo = mid;
-                else hi = mid;
+            if (smin) {
+                int lo = 0, hi = probes;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (W.co[mid] <= ps) lo = mid;
+                    else hi = mid;
+                }
+                // (empty lists share an offset with their successor: the search ends on the last of them, the non-empty one)
+                rowp[i] = rows + (size_t)(W.lo[lo] + (ps - W.co[lo])) * stride;
+            } else {
+                int lo = 0, hi = probes;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (co[mid] <= ps) lo = mid;
+                    else hi = mid;
+                }
+                while (lo + 1 < probes && co[lo + 1] <= ps) ++lo;   // empty lists share an offset
+                const int l = probe_lists[(int64_t)q * probes + lo];
+                rowp[i] = rows + (size_t)(list_off[l] + (ps - co[lo])) * stride;
             }
-            while (lo + 1 < probes && co[lo + 1] <= ps) ++lo;   // empty lists share an offset
-            const int l = probe_lists[(int64_t)q * probes + lo];
-            rowp[i] = rows + (size_t)(list_off[l] + (ps - co[lo])) * stride;
         }
     }
     __syncthreads();

@@ -97,6 +97,33 @@ __device__ __forceinline__ uint32_t ss_radix_kth(const uint32_t* keys, int S, in
     return s_prefix;   // exactly the k-th smallest key
 }
 
+// the probe whose run [off[p], off[p + 1]) holds entry i (off non-decreasing, off[0] = 0, i < off[probes]; empty probes share an offset)
+__device__ __forceinline__ int ss_probe_of(const int32_t* off, int probes, int i) {
+    int p = 0, hi = probes;
+    while (hi - p > 1) {
+        const int mid = (p + hi) >> 1;
+        if (off[mid] <= i) p = mid;
+        else hi = mid;
+    }
+    return p;
+}
+
+struct SsWork {
+    int64_t *lo, *hi;        // [probes] list bounds
+    uint32_t *skey, *qlist;  // [cap_s] orderable slab minima, qualifying slabs
+    int32_t *off, *co;       // [probes + 1] first slab of every probe, [probes] first candidate of every probe
+};
+__device__ __forceinline__ SsWork ss_work_layout(void* work, int64_t cap_s, int probes) {
+    SsWork w;
+    w.lo = reinterpret_cast<int64_t*>(work);
+    w.hi = w.lo + probes;
+    w.skey = reinterpret_cast<uint32_t*>(w.hi + probes);
+    w.qlist = w.skey + cap_s;
+    w.off = reinterpret_cast<int32_t*>(w.qlist + cap_s);
+    w.co = w.off + probes + 1;
+    return w;
+}
+
 // shared memory the selection needs beside cand[SS_CAND]: slab keys + the list of qualifying slabs (2 cap_s words), and
 // per probe: first slab (probes + 1), candidate offset, list bounds
 __host__ __device__ inline size_t ss_select_smem_bytes(int64_t cap_s, int probes) {
@@ -112,12 +139,10 @@ __device__ __forceinline__ int slab_select_cta(const float* __restrict__ dist, c
                                                const int64_t* __restrict__ list_off, int64_t cap, int64_t cap_s, int q, int k,
                                                uint64_t* cand, void* work) {
     __shared__ uint32_t s_count, s_nq;
-    int64_t* s_lo = reinterpret_cast<int64_t*>(work);                     // [probes] list bounds
-    int64_t* s_hi = s_lo + probes;
-    uint32_t* skey = reinterpret_cast<uint32_t*>(s_hi + probes);          // [cap_s] orderable slab minima
-    uint32_t* qlist = skey + cap_s;                                       // [cap_s] qualifying slabs
-    int32_t* s_off = reinterpret_cast<int32_t*>(qlist + cap_s);           // [probes + 1] first slab of every probe
-    int32_t* s_co = s_off + probes + 1;                                   // [probes] first candidate of every probe
+    const SsWork W = ss_work_layout(work, cap_s, probes);
+    int64_t *s_lo = W.lo, *s_hi = W.hi;
+    uint32_t *skey = W.skey, *qlist = W.qlist;
+    int32_t *s_off = W.off, *s_co = W.co;
     const int tid = threadIdx.x;
     const int32_t* co = cand_off + (int64_t)q * (probes + 1);
     const int32_t* pl = probe_lists + (int64_t)q * probes;
@@ -149,10 +174,10 @@ __device__ __forceinline__ int slab_select_cta(const float* __restrict__ dist, c
     }
     __syncthreads();
     const int S = s_off[probes];
-    for (int p = 0; p < probes; ++p) {
-        const int ns = s_off[p + 1] - s_off[p];
-        const float* sp = smin + slab_base(q, cap_s, s_co[p], p);
-        for (int j = tid; j < ns; j += SS_THREADS) skey[s_off[p] + j] = orderable_key(sp[j]);
+    // slab minima of all probes at once (one independent load per thread and step)
+    for (int i = tid; i < S; i += SS_THREADS) {
+        const int p = ss_probe_of(s_off, probes, i);
+        skey[i] = orderable_key(smin[slab_base(q, cap_s, s_co[p], p) + (i - s_off[p])]);
     }
     __syncthreads();
     // ---- tau: the k-th smallest slab minimum (everything when there are at most k slabs)
@@ -166,13 +191,7 @@ __device__ __forceinline__ int slab_select_cta(const float* __restrict__ dist, c
     const float* dq = dist + (int64_t)q * cap;
     for (int t = tid; t < nq_rows; t += SS_THREADS) {
         const int i = (int)qlist[t >> 5];
-        int p = 0, hi_p = probes;                  // probe of slab i: s_off[p] <= i < s_off[p + 1]
-        while (hi_p - p > 1) {
-            const int mid = (p + hi_p) >> 1;
-            if (s_off[mid] <= i) p = mid;
-            else hi_p = mid;
-        }
-        while (p + 1 < probes && s_off[p + 1] <= i) ++p;      // empty probes share an offset
+        const int p = ss_probe_of(s_off, probes, i);
         const int64_t lo = s_lo[p], hi = s_hi[p];
         const int64_t r = (((lo >> 5) + (i - s_off[p])) << 5) + (t & 31);
         if (r >= lo && r < hi) {
