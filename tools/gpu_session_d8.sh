@@ -3,7 +3,7 @@
 N=${1:-8}
 mkdir -p gpurun_out
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 420 $RUN --master-port 29513 bench.py --config D --gpus $N > gpurun_out/r2_bench_D_n$N.json 2> gpurun_out/r2_bench_D_n$N.err; echo "D exit $?"; tail -2 gpurun_out/r2_bench_D_n$N.err
+timeout 210 $RUN --master-port 29513 bench.py --config D --gpus $N > gpurun_out/r2_bench_D_n$N.json 2> gpurun_out/r2_bench_D_n$N.err; echo "D exit $?"; tail -2 gpurun_out/r2_bench_D_n$N.err
 python - <<PY
 import json
 try:
@@ -11,13 +11,4 @@ try:
     print("D n=$N rows/s", round(d["value"]), "ms/step", round(d["ms_per_step"],1), d["phases_s"], "recall", d["recall_at_10"], "roof", d["roofline"] and {k:d["roofline"].get(k) for k in ("achieved","frac","useful_tflops")})
 except Exception as e:
     print("D n=$N failed", e)
-PY
-timeout 300 $RUN --master-port 29512 bench.py --gpus $N --steps 100 --warmup 3 > gpurun_out/r2_bench_B_n$N.json 2> gpurun_out/r2_bench_B_n$N.err; echo "B exit $?"; tail -2 gpurun_out/r2_bench_B_n$N.err
-python - <<PY
-import json
-try:
-    d=json.load(open("gpurun_out/r2_bench_B_n$N.json"))
-    print("B sharded n=$N qps", round(d["value"]), "ms/step", round(d["ms_per_step"],4), "e2e", round(d["e2e"]["value"]), "replica", d.get("replica_mode"), json.dumps(d["roofline"].get("other_kernels_ms_per_step")), d["roofline"].get("avg_launch_ms"))
-except Exception as e:
-    print("B n=$N failed", e)
 PY
