@@ -175,6 +175,11 @@ __device__ __forceinline__ void load_query_image(const uint4* gq, int qvec, int 
 #ifndef VB_AB_NBRPF
 #define VB_AB_NBRPF 0
 #endif
+// rows of <= 96 words on a whole warp (LPR 32): W rows per pass with all three words per lane in flight (0 = the generic
+// two-steps-in-flight walk)
+#ifndef VB_AB_WIDE1
+#define VB_AB_WIDE1 0
+#endif
 // narrow rows: score all listed neighbours while their visited probes are in flight (see hnsw_search_layer).  Measured on
 // config E (10M x bit(1024), ef_search 200): 724 k queries/s with it, 758 k without -- the 60 % of wasted scorings cost more
 // than the overlapped round trip saves; kept as a switch (profiles/r2_ab_hnsw_spec.md)
@@ -223,6 +228,36 @@ __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* 
             return;
         }
     }
+#if VB_AB_WIDE1
+    if constexpr (LPR == 32) {
+        // rows of at most 96 words (768-d halfvec = 1536 bytes): the three words a lane owns of each of W1 rows are all
+        // requested before the first is used -- one round trip per pass instead of two (the generic path keeps two of the
+        // three steps in flight)
+        if (g.V <= 96) {
+            constexpr int W1 = VB_AB_WIDE1;
+            for (int b0 = 0; b0 < cnt; b0 += W1) {
+                Acc<ELEM, METRIC> acc[W1];
+                uint4 w[W1][3];
+#pragma unroll
+                for (int i = 0; i < W1; ++i) {
+                    const uint32_t e = bid[min(b0 + i, cnt - 1)] & 0x7fffffffu;
+                    const uint4* rp = reinterpret_cast<const uint4*>(g.rows + (size_t)e * g.stride);
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) w[i][t] = lane + 32 * t < g.V ? hnsw_row_ld(rp + lane + 32 * t) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int i = 0; i < W1; ++i) {
+#pragma unroll
+                    for (int t = 0; t < 3; ++t)
+                        if (lane + 32 * t < g.V) hnsw_acc_add<ELEM, METRIC>(acc[i], w[i][t], sq, lane + 32 * t);
+                    acc[i].template reduce<32>();
+                    if (lane == 0 && b0 + i < cnt) bkey[b0 + i] = orderable_key64(acc[i].value());
+                }
+            }
+            return;
+        }
+    }
+#endif
     for (int b0 = 0; b0 < cnt; b0 += GROUPS * RPI) {
         Acc<ELEM, METRIC> acc[RPI];
         const uint4* rp[RPI];
