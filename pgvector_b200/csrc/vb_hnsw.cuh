@@ -180,6 +180,10 @@ __device__ __forceinline__ void load_query_image(const uint4* gq, int qvec, int 
 #ifndef VB_AB_WIDE1
 #define VB_AB_WIDE1 0
 #endif
+// rows in flight per pass for whole-warp rows (LPR 32): 4 (fewer leave registers for more resident CTAs, see VB_HNSW_MINB)
+#ifndef VB_AB_RPI_WIDE
+#define VB_AB_RPI_WIDE 4
+#endif
 // narrow rows: score all listed neighbours while their visited probes are in flight (see hnsw_search_layer).  Measured on
 // config E (10M x bit(1024), ef_search 200): 724 k queries/s with it, 758 k without -- the 60 % of wasted scorings cost more
 // than the overlapped round trip saves; kept as a switch (profiles/r2_ab_hnsw_spec.md)
@@ -200,7 +204,7 @@ template <int ELEM, int METRIC, int LPR>
 __device__ __forceinline__ void hnsw_score_batch(const HnswDev& g, const uint4* sq, const uint32_t* bid, int cnt, uint64_t* bkey,
                                                  int lane) {
     constexpr int GROUPS = 32 / LPR;
-    constexpr int RPI = (LPR == 32) ? 4 : VB_AB_RPI_NARROW;   // (LPR 32: 8 in flight measured the same: 821 k vs 816 k queries/s, at 128 registers)
+    constexpr int RPI = (LPR == 32) ? VB_AB_RPI_WIDE : VB_AB_RPI_NARROW;   // (LPR 32: 8 in flight measured the same: 821 k vs 816 k queries/s, at 128 registers)
     const int grp = lane / LPR, gl = lane % LPR;
     if constexpr (LPR == 8) {
         // rows of at most 8 words (bit(1024) = 128 bytes): one word per lane and 8 rows per lane group, so the <= 32 rows of

@@ -20,5 +20,7 @@ ab base ""
 ab wide3 "VB_AB_WIDE1=3"
 ab wide4 "VB_AB_WIDE1=4"
 ab wide4_minb5 "VB_AB_WIDE1=4 VB_HNSW_MINB=5"
+ab rpi2_minb8 "VB_AB_RPI_WIDE=2 VB_HNSW_MINB=8"
+ab rpi3_minb7 "VB_AB_RPI_WIDE=3 VB_HNSW_MINB=7"
 touch pgvector_b200/csrc/vb_hnsw.cu pgvector_b200/csrc/vb_hnsw_iter.cu pgvector_b200/csrc/vb_hnsw_build.cu; python -m pgvector_b200.build > /dev/null 2>&1
 timeout 300 python tools/bench_extra.py sparse > $O/r2_extra_sparse.json 2> $O/r2_extra_sparse.err; cut -c1-900 $O/r2_extra_sparse.json; tail -2 $O/r2_extra_sparse.err
