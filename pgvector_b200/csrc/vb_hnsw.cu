@@ -49,7 +49,13 @@ __global__ void VB_HNSW_BOUNDS hnsw_search_kernel(HnswDev g, const uint8_t* __re
     const int nwarps = gridDim.x * HN_WARPS;
     uint32_t* vis = vis_all + (size_t)gwarp * vis_cap;
 
-    for (int64_t q = gwarp; q < nq; q += nwarps) {
+    // the first query of a warp is its own number; the following ones come from a counter (overflow[1], zeroed with the
+    // flag before the launch): a search takes 0.5x - 2x the mean, and a static split left a third of the warps idle
+    // through the tail of the launch
+#ifndef VB_AB_DYNQ
+#define VB_AB_DYNQ 1
+#endif
+    for (int64_t q = gwarp; q < nq;) {
         const uint4* gq = reinterpret_cast<const uint4*>(queries + (size_t)q * qstride);
         load_query_image<ELEM, METRIC>(gq, qvec, g.V, sq, lane);
         __syncwarp();
@@ -99,6 +105,13 @@ __global__ void VB_HNSW_BOUNDS hnsw_search_kernel(HnswDev g, const uint8_t* __re
         }
         if (out_ndist && lane == 0) out_ndist[q] = ndist;
         __syncwarp();
+#if VB_AB_DYNQ
+        int nxt = 0;
+        if (lane == 0) nxt = atomicAdd(overflow + 1, 1);
+        q = (int64_t)nwarps + __shfl_sync(0xffffffffu, nxt, 0);
+#else
+        q += nwarps;
+#endif
     }
 }
 
@@ -282,7 +295,7 @@ static int hnsw_search_impl(Hnsw& h, const void* queries, int64_t nq, int ef, in
             }
             h.vis_bytes = need;
         }
-        VB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
+        VB_CUDA(cudaMemsetAsync(d_flag, 0, 2 * sizeof(int), s));   // overflow flag, query counter
         if (c.hnsw_l2_persist) hnsw_l2_window(s, h.vis, need, true);
         prof_begin(VB_PROF_HNSW);
         const int lrc = hnsw_launch(h, g, qimg, qstride, nq, ef, k, h.vis, vis_cap, vis_upper, grid, d_ids, d_f, d_d, d_nd, (int*)d_flag);

@@ -89,6 +89,59 @@ __device__ __forceinline__ bool vis_insert(uint32_t* tab, uint32_t mask, uint32_
     }
 }
 
+// Bucketed variant (VB_AB_VISB): the table is an array of 8-slot buckets, one 32-byte sector each.  A probe is ONE load
+// round trip (two 16-byte loads of the same sector) instead of a chain of dependent atomicCAS round trips -- with linear
+// probing the warp waited for the longest probe sequence of its 32 lanes, 3 - 4 atomics at the load factors of a search.
+// The table belongs to one warp, so the only writers that can collide are lanes of the same call: they are arbitrated in
+// registers (__match_any_sync on the slot they want, lowest lane wins, the others take the bucket's next empty slot) and
+// the winners store plainly.  An id lives in the first bucket of its sequence that had an empty slot when it arrived;
+// buckets never lose entries, so a lookup stops at the first bucket that holds the id or still has an empty slot.
+// Warp-collective: every lane calls, lanes with want = true carry an id (< 2^31).  Returns true when the id was NOT in the
+// set (and inserts it); a second lane carrying the same id in the same call reports "visited", like a second CAS would.
+#ifndef VB_AB_VISB
+#define VB_AB_VISB 1
+#endif
+__device__ __forceinline__ bool vis_insert_warp(uint32_t* tab, uint32_t mask, bool want, uint32_t id, int lane) {
+    const uint32_t bmask = mask >> 3;
+    const unsigned same = __match_any_sync(0xffffffffu, want ? id : (0x80000000u | (uint32_t)lane));
+    bool pending = want && (__ffs(same) - 1 == lane);
+    bool fresh = false;
+    uint32_t b = hash_u32(id) & bmask;
+    while (__any_sync(0xffffffffu, pending)) {
+        unsigned empt = 0;
+        if (pending) {
+            const uint4* p = reinterpret_cast<const uint4*>(tab + ((size_t)b << 3));
+            const uint4 s0 = __ldcg(p), s1 = __ldcg(p + 1);
+            const bool found = s0.x == id || s0.y == id || s0.z == id || s0.w == id || s1.x == id || s1.y == id || s1.z == id || s1.w == id;
+            if (found) {
+                pending = false;
+            } else {
+                empt = (s0.x == VIS_EMPTY ? 1u : 0u) | (s0.y == VIS_EMPTY ? 2u : 0u) | (s0.z == VIS_EMPTY ? 4u : 0u) | (s0.w == VIS_EMPTY ? 8u : 0u) |
+                       (s1.x == VIS_EMPTY ? 16u : 0u) | (s1.y == VIS_EMPTY ? 32u : 0u) | (s1.z == VIS_EMPTY ? 64u : 0u) | (s1.w == VIS_EMPTY ? 128u : 0u);
+            }
+        }
+        bool claim = pending && empt != 0;
+        while (__any_sync(0xffffffffu, claim)) {
+            const uint32_t slot = (b << 3) + (uint32_t)(__ffs(empt) - 1);
+            const unsigned peers = __match_any_sync(0xffffffffu, claim ? slot : (0x80000000u | (uint32_t)lane));
+            if (claim) {
+                if (__ffs(peers) - 1 == lane) {
+                    __stcg(tab + slot, id);
+                    fresh = true;
+                    claim = false;
+                    pending = false;
+                } else {
+                    empt &= empt - 1;            // taken by a lane of this call
+                    if (empt == 0) claim = false; // the bucket filled up: on to the next one
+                }
+            }
+        }
+        if (pending) b = (b + 1) & bmask;
+        __syncwarp();   // the stores above are visible to the loads of the next pass (and of the next call)
+    }
+    return fresh;
+}
+
 __device__ __forceinline__ bool ent_less(uint64_t ka, uint32_t ia, uint64_t kb, uint32_t ib) {
     return ka < kb || (ka == kb && (ia & 0x7fffffffu) < (ib & 0x7fffffffu));
 }
@@ -564,14 +617,30 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
     const int vcn = (VB_AB_VCACHE && VB_AB_INPLACE) ? S.vcn : 0;
     for (int i = lane; i < vcn; i += 32) vc[i] = VIS_EMPTY;
     if (!ITER || init_visited) {
-        for (uint32_t i = lane; i < cap; i += 32) tab[i] = VIS_EMPTY;
+        {
+            uint4* t4 = reinterpret_cast<uint4*>(tab);   // (cap is a power of two >= 1024, tab 4 KB aligned)
+            const uint4 e4 = make_uint4(VIS_EMPTY, VIS_EMPTY, VIS_EMPTY, VIS_EMPTY);
+            for (uint32_t i = lane; i < cap / 4; i += 32) __stcg(t4 + i, e4);
+        }
         __syncwarp();
         // entry points: visited, unexpanded; they count towards `tuples` (src/hnswutils.c:866-873)
         if (S.len > efl) S.len = efl;   // ef shrinks only between an ef_construction layer and ... never; kept for safety
+#if VB_AB_VISB
+        for (int i0 = 0; i0 < S.len; i0 += 32) {
+            const int i = i0 + lane;
+            uint32_t id = 0;
+            if (i < S.len) {
+                id = S.ri[i] & 0x7fffffffu;
+                S.ri[i] = id;
+            }
+            vis_insert_warp(tab, mask, i < S.len, id, lane);
+        }
+#else
         for (int i = lane; i < S.len; i += 32) {
             S.ri[i] &= 0x7fffffffu;
             vis_insert(tab, mask, S.ri[i]);
         }
+#endif
         inserted += (uint32_t)S.len;
         if (ndist) *ndist += S.len;
         __syncwarp();
@@ -619,6 +688,7 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
                 known = vc[vslot] == (uint32_t)nid;
             }
             int cnt;
+            static_assert(!(VB_AB_SPEC && VB_AB_VISB), "the speculative path probes the linear table");
             if constexpr (VB_AB_SPEC && LPR <= 8) {
                 // Narrow rows (< 512 bytes; bit(1024) = 128): every listed neighbour is scored SPECULATIVELY while its visited
                 // probe is in flight -- the probe (a random atomic on a table that lives in L2 / DRAM) and the row gather
@@ -672,7 +742,11 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
                 }
                 __syncwarp();
             } else {
+#if VB_AB_VISB
+            bool fresh = vis_insert_warp(tab, mask, valid && !known, (uint32_t)nid, lane);
+#else
             bool fresh = valid && !known && vis_insert(tab, mask, (uint32_t)nid);
+#endif
             if (VB_AB_VCACHE && VB_AB_INPLACE && vcn > 0 && valid) vc[vslot] = (uint32_t)nid;
             inserted += (uint32_t)__popc(__ballot_sync(0xffffffffu, fresh));
             // elements below this layer are skipped (src/hnswutils.c:949-950)

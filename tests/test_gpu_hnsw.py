@@ -155,6 +155,57 @@ def test_empty_and_single_element_index(pv):
     assert list(ids[0]) == [0, -1, -1] and dist[0][0] == 1.0 and nd[0] == 1
 
 
+def test_visited_set_with_duplicate_neighbours_and_many_queries(pv):
+    """the per-warp visited table (bucketed, lanes of one expansion arbitrated in registers): neighbour lists that name the
+    same element twice (a second occurrence is "visited", src/hnswutils.c:907-921), every query of a batch much larger than
+    the resident warps (queries are handed out dynamically) -- ids, distances and the tuples counter equal the oracle's"""
+    x, _ = mixture(6000, 64, 40, seed=51)
+    q, _ = mixture(6000, 64, 40, seed=52)
+    rows, queries = O.binary_quantize(O.VECTOR, x), O.binary_quantize(O.VECTOR, q)
+    og0 = O.Hnsw(O.BIT, O.HAMMING, rows, m=16, ef_construction=64, seed=5, dim=64)
+    g = og0.export()
+    nbr0 = g["nbr0"].copy()
+    rng = np.random.default_rng(53)
+    for i in rng.choice(nbr0.shape[0], nbr0.shape[0] // 3, replace=False):
+        cnt = int((nbr0[i] >= 0).sum())
+        if cnt >= 3:
+            a, b = rng.choice(cnt, 2, replace=False)
+            nbr0[i, a] = nbr0[i, b]                     # the same neighbour twice in one list
+            if cnt >= 8:
+                nbr0[i, cnt - 1] = nbr0[i, 0]
+    g2 = dict(g, nbr0=nbr0)
+    erows = rows[g["elem_row"]]
+    og = O.Hnsw.from_export(O.BIT, O.HAMMING, erows, g2, dim=64)
+    gi = pv.HnswIndex("bit_hamming_ops", 64, m=16).load(erows, g["levels"], nbr0, g["upper_off"], g["upper"], g["entry"])
+    ids, dist, nd = gi.search(queries, k=10, ef_search=64)
+    wi, wd, wnd = og.search_batch(queries, 64, 10, ties=O.TIES_TOTAL, threads=8)
+    assert np.array_equal(dist, wd)
+    assert np.array_equal(ids, wi)
+    assert np.array_equal(nd, wnd)
+
+
+def test_visited_table_grows_when_a_search_fills_it(pv):
+    """a random graph (every list names 2m random elements, almost all of them fresh): a search visits ~32 elements per
+    expansion, the table sized from ef x m (4096 slots) fills beyond three quarters, the launch is repeated with a larger
+    one and the results are those of the oracle on the same graph"""
+    rows, _ = mixture(20000, 16, 20, seed=61)
+    queries, _ = mixture(64, 16, 20, seed=62)
+    n, m = rows.shape[0], 16
+    nbr0 = np.random.default_rng(63).integers(0, n, size=(n, 2 * m)).astype(np.int32)
+    g = dict(levels=np.zeros(n, np.int32), nbr0=nbr0, upper_off=np.full(n, -1, np.int64), upper=np.zeros((0, m), np.int32),
+             entry=0, entry_level=0, m=m)
+    og = O.Hnsw.from_export(O.VECTOR, O.L2_SQUARED, rows, g)
+    gi = pv.HnswIndex("vector_l2_ops", 16, m=m).load(rows, g["levels"], nbr0, g["upper_off"], g["upper"], 0)
+    for ef in (127, 100):      # (the grown size is remembered per ef_search: both calls go through the repeat)
+        ids, dist, nd = gi.search(queries, k=50, ef_search=ef)
+        wi, wd, wnd = og.search_batch(queries, ef, 50, ties=O.TIES_TOTAL, threads=8)
+        assert np.allclose(dist, wd, rtol=RTOL)
+        same_q = np.all(ids == wi, axis=1)
+        assert same_q.mean() > 0.9, same_q.mean()
+        assert np.array_equal(nd[same_q], wnd[same_q])
+        assert nd.max() > 3072        # (a search did outgrow 4096 slots, three quarters usable)
+
+
 # ------------------------------------------------------------------------------------------------ iterative scan
 
 def scan_all(gi, queries, ef, max_scan_tuples, max_batches=10 ** 6):
