@@ -236,4 +236,68 @@ __device__ __forceinline__ int direct_select_cta(const float* __restrict__ dq, i
     return (int)m;
 }
 
+// EXACTLY the min(k, n) smallest of keys[0 .. n) (shared memory, orderable keys) by (key, index), sorted, as composites
+// key << 32 | index in cand (capacity: the power of two >= max(2, min(k, n)); k <= SS_CAND).  Ties across the k-th place
+// are settled by index -- scan position / list number, this library's tie rule -- whatever their number (bit vectors put
+// thousands of rows at one Hamming distance): the index bound is found by bisection, a counting pass per step.
+// All SS_THREADS threads call it; keys must be complete (a __syncthreads() after the last write).
+__device__ __forceinline__ int select_exact_cta(const uint32_t* keys, int n, int k, uint64_t* cand) {
+    __shared__ uint32_t se_cnt, se_less, se_eq, se_tally;
+    const int tid = threadIdx.x;
+    if (n <= k) {
+        for (int i = tid; i < n; i += SS_THREADS) cand[i] = ((uint64_t)keys[i] << 32) | (uint32_t)i;
+        __syncthreads();
+        ss_sort_cand(cand, (uint32_t)n);
+        return n;
+    }
+    if (tid == 0) se_cnt = se_less = se_eq = 0;
+    const uint32_t tau = ss_radix_kth(keys, n, k);     // (its first barrier also publishes the zeros above)
+    {
+        uint32_t less = 0, eq = 0;
+        for (int i = tid; i < n; i += SS_THREADS) {
+            const uint32_t key = keys[i];
+            less += key < tau ? 1u : 0u;
+            eq += key == tau ? 1u : 0u;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            less += __shfl_xor_sync(0xffffffffu, less, o);
+            eq += __shfl_xor_sync(0xffffffffu, eq, o);
+        }
+        if ((tid & 31) == 0) {
+            if (less) atomicAdd(&se_less, less);
+            if (eq) atomicAdd(&se_eq, eq);
+        }
+    }
+    __syncthreads();
+    const uint32_t need = (uint32_t)k - se_less;       // 1 <= need <= se_eq: the equals that still fit
+    uint32_t plim = 0xFFFFFFFFu;                       // equals with index <= plim are taken
+    if (se_eq > need) {
+        uint32_t lo = 0, hi = (uint32_t)n - 1;         // the smallest P with #{i <= P : keys[i] == tau} >= need
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            __syncthreads();
+            if (tid == 0) se_tally = 0;
+            __syncthreads();
+            uint32_t c = 0;
+            for (int i = tid; i < n && (uint32_t)i <= mid; i += SS_THREADS) c += keys[i] == tau ? 1u : 0u;
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if ((tid & 31) == 0 && c) atomicAdd(&se_tally, c);
+            __syncthreads();
+            if (se_tally >= need) hi = mid;
+            else lo = mid + 1;
+        }
+        plim = lo;
+    }
+    for (int i = tid; i < n; i += SS_THREADS) {
+        const uint32_t key = keys[i];
+        if (key < tau || (key == tau && (uint32_t)i <= plim)) {
+            const uint32_t slot = atomicAdd(&se_cnt, 1u);
+            cand[slot] = ((uint64_t)key << 32) | (uint32_t)i;     // (exactly k of them)
+        }
+    }
+    __syncthreads();
+    ss_sort_cand(cand, (uint32_t)k);
+    return k;
+}
+
 }  // namespace vb
