@@ -714,11 +714,29 @@ def batch_sweep(env, args, ix, queries):
     for i in range(100):
         ix.search(qh[i:i + 1], k=k, probes=args.probes)
     one_call = (time.perf_counter() - t0) / 100 * 1e6
+    # the same two calls through the general path (nine launches, three memsets, four copies) for comparison
+    pv.set_option("one_query", 0)
+    try:
+        lat0 = []
+        for i in range(120):
+            t0 = time.perf_counter()
+            lists, _ = ix.scan_lists(qh[i], args.probes)
+            ix.scan_items(qh[i], lists[0], cap=k)
+            lat0.append(time.perf_counter() - t0)
+        lat0 = np.sort(np.array(lat0[20:])) * 1e6
+        t0 = time.perf_counter()
+        for i in range(100):
+            ix.search(qh[i:i + 1], k=k, probes=args.probes)
+        one_call0 = (time.perf_counter() - t0) / 100 * 1e6
+    finally:
+        pv.set_option("one_query", 1)
     return {"device_resident": out,
-            "single_query": {"calls": "vb_ivf_scan_lists + vb_ivf_scan_items (host buffers, synchronous)",
+            "single_query": {"calls": "vb_ivf_scan_lists + vb_ivf_scan_items (host buffers, synchronous, timed around the Python wrappers)",
+                             "kernels": "one_probe_kernel + one_scan_kernel (fused distance + select, csrc/vb_ivf_one.cu)",
                              "latency_us_p50": float(lat[len(lat) // 2]), "latency_us_p90": float(lat[int(len(lat) * 0.9)]),
                              "latency_us_mean": float(lat.mean()), "queries_per_s": float(1e6 / lat.mean()),
-                             "one_call_vb_ivf_search_latency_us": one_call}}
+                             "one_call_vb_ivf_search_latency_us": one_call,
+                             "general_path": {"latency_us_p50": float(lat0[len(lat0) // 2]), "one_call_vb_ivf_search_latency_us": one_call0}}}
 
 
 def north_star_kernel(env, args, ix, qbatches, cand_per_step_hint):

@@ -386,7 +386,9 @@ int64_t		vb_last_assign_rechecked(void);
  * tcgen05 distances, exact fp32 re-score of k' candidates, certificate, exact fallback) wherever it applies.
  * Every setting returns the same neighbours.  "tc_level1" (default 1): the tensor-core filter first reads only the
  * hi plane of the rows (half the HBM traffic, 2^-7 relative error bound) and repeats a batch with both planes when a
- * certificate fails.  "tensor_cores" as vb_set_tensor_cores.
+ * certificate fails.  "tensor_cores" as vb_set_tensor_cores.  "one_query" (default 1): calls with at most 16 queries --
+ * one backend's scan: vb_ivf_scan_lists, vb_ivf_scan_items, vb_ivf_search -- run as two fused distance + select
+ * kernels (the last CTA to finish selects; csrc/vb_ivf_one.cu) instead of the general launch sequence; 0 = general path.
  */
 int			vb_set_option(const char *name, int64_t value);
 

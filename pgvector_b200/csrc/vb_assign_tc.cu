@@ -361,6 +361,10 @@ int vb_set_option(const char* name, int64_t value) {
         vb::ctx().hnsw_l2_persist = value != 0;
         return VB_OK;
     }
+    if (!strcmp(name, "one_query")) {
+        vb::ctx().one_query = value != 0;
+        return VB_OK;
+    }
     if (!strcmp(name, "slab_select")) {
         vb::ctx().slab_select = value != 0;
         return VB_OK;

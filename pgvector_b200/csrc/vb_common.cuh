@@ -54,6 +54,7 @@ struct Context {
     int fused_refine = 3;              // tensor-core filter, after the k' select: 3 = select + exact re-score + certificate with one CTA per query,
                                        // 1 = re-score + certificate in one warp-per-query kernel fed by the selection kernel,
                                        // 0 = rescore_kernel + certify_kernel, 2 = the select runs inside the warp-per-query kernel too
+    int one_query = 1;                 // scans of at most 16 queries: two fused distance + select kernels (vb_ivf_one.cu); 0 = the general path
     int scan_impl = 2;                 // 0 = LDG variant (vb_scan.cu), 1 = bulk-copy / TMA variant (vb_scan_bulk.cu), 2 = by table size
     int hnsw_build_fraction = 64;      // HNSW build: a batch is at most 1/fraction of the elements already inserted
     int hnsw_build_batch = 16384;      // ... and at most this many elements
@@ -235,6 +236,16 @@ int launch_list_tc_cta_refine(const Table& rows, const ListTcImage& im, int key_
                               int k, int kp, int probes, const int32_t* d_lists, const int32_t* cand_off, const int64_t* d_list_off,
                               const float* dist, const float* smin, int64_t cap, int64_t cap_s, const int32_t* seg_len, const float* qn,
                               int32_t* out_pos, float* out_key, int* fail_dev, int level = 2);
+// vb_ivf_one.cu: the scan of one query (or a handful) as two fused distance + select kernels
+bool one_probe_fits(int lists, size_t qstride, int probes);
+bool one_scan_fits(int64_t cap, size_t qstride, int probes, int64_t k);
+int launch_one_probe(const Table& centres, int key_metric, const void* qimg, size_t qstride, int64_t nq, int probes, float* cdist,
+                     unsigned* ticket, int32_t* out_lists, float* out_ldist, int64_t* zero_me);
+int launch_one_scan(const Table& rows, int key_metric, int metric, const int64_t* list_off, const int64_t* ids,
+                    const int32_t* probe_lists, int probes, const void* qimg, size_t qstride, int64_t nq, int k, int64_t cap,
+                    float* dist, unsigned* ticket, int64_t* out_ids, float* out_f, double* out_d, int32_t* out_total,
+                    int64_t* cand_sum, bool cand_store);
+constexpr int ONE_MAX_Q = 16;   // queries per call the fused path takes
 int list_tile_rows();
 bool list_major_supported(int elem, int key_metric);
 int launch_list_major(const Table& rows, int key_metric, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists,

@@ -63,6 +63,7 @@ struct Ivf {
     void* q_buf[2] = {nullptr, nullptr};
     size_t q_bytes[2] = {0, 0};
     int64_t q_nq[2] = {0, 0};
+    unsigned* d_ticket = nullptr;     // 2 x ONE_MAX_Q arrival counters of the fused one-query kernels (zero between launches)
     int* d_tc_fail = nullptr;         // device counters of uncertified queries: [0] probe selection, [1] list scan
     bool defer_tc_check = false;      // batched search: counters are read once, with the results
     bool force_exact = false;         // re-run of a batch whose certificate failed
@@ -553,6 +554,75 @@ static int64_t ivf_batch_limit(const Ivf& ix, int probes) {
     return std::max<int64_t>(1, std::min<int64_t>(lim, 65535));
 }
 
+// ----------------------------------------------------------------------------- scans of one query (vb_ivf_one.cu)
+
+static size_t ivf_qstride(const Ivf& ix) {   // stride of the query image upload_queries() builds
+    const size_t pad = padded_row_bytes(ix.elem, ix.dim);
+    return ix.elem == VB_HALFVEC ? pad * 2 : pad;
+}
+
+static int ivf_tickets(Ivf& ix, unsigned** probe_t, unsigned** scan_t) {
+    if (!ix.d_ticket) {
+        VB_CUDA(cudaMalloc(&ix.d_ticket, 2 * ONE_MAX_Q * sizeof(unsigned)));
+        VB_CUDA(cudaMemsetAsync(ix.d_ticket, 0, 2 * ONE_MAX_Q * sizeof(unsigned), ctx().stream));
+    }
+    *probe_t = ix.d_ticket;
+    *scan_t = ix.d_ticket + ONE_MAX_Q;
+    return VB_OK;
+}
+
+// does a scan of nq queries (probes lists each, k results, at most cap candidates per query) take the fused kernels?
+static bool ivf_one_applies(const Ivf& ix, int64_t nq, int probes, int64_t k, int64_t cap) {
+    if (!ctx().one_query || nq < 1 || nq > ONE_MAX_Q || ix.rows.n <= 0) return false;
+    const size_t qs = ivf_qstride(ix);
+    return one_probe_fits(ix.lists, qs, probes) && one_scan_fits(cap, qs, probes, k);
+}
+
+// GetScanLists for nq <= ONE_MAX_Q query images: one launch
+static int ivf_one_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, int probes, int32_t** d_lists, float** d_ldist) {
+    void *d_cdist, *d_probe;
+    VB_TRY(workspace(WS_CDIST, sizeof(float) * (size_t)nq * ix.lists, &d_cdist));
+    VB_TRY(workspace(WS_PROBES, (sizeof(int32_t) + sizeof(float)) * (size_t)nq * probes, &d_probe));
+    int32_t* lists = (int32_t*)d_probe;
+    float* ldist = (float*)(lists + (size_t)nq * probes);
+    unsigned *tp, *ts;
+    VB_TRY(ivf_tickets(ix, &tp, &ts));
+    if (!ix.d_cand_sum) VB_CUDA(cudaMalloc(&ix.d_cand_sum, sizeof(int64_t)));
+    prof_begin(VB_PROF_SCAN_LISTS);
+    VB_TRY(launch_one_probe(ix.centers, key_metric(ix.metric), qimg, qstride, nq, probes, (float*)d_cdist, tp, lists, ldist, ix.d_cand_sum));
+    prof_end(VB_PROF_SCAN_LISTS);
+    *d_lists = lists;
+    *d_ldist = ldist;
+    return VB_OK;
+}
+
+// GetScanItems + sort for nq <= ONE_MAX_Q query images over device-resident probe lists: one launch
+static int ivf_one_items(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists, int probes, int k, int64_t cap,
+                         int64_t* out_ids_dev, float* out_f_dev, double* out_d_dev, bool cand_store) {
+    void* d_dist;
+    VB_TRY(workspace(WS_DIST, sizeof(float) * (size_t)nq * cap, &d_dist));
+    unsigned *tp, *ts;
+    VB_TRY(ivf_tickets(ix, &tp, &ts));
+    if (!ix.d_cand_sum) VB_CUDA(cudaMalloc(&ix.d_cand_sum, sizeof(int64_t)));
+    prof_begin(VB_PROF_SCAN_ITEMS);
+    VB_TRY(launch_one_scan(ix.rows, key_metric(ix.metric), ix.metric, ix.d_list_off, ix.d_ids, d_lists, probes, qimg, qstride, nq, k, cap,
+                           (float*)d_dist, ts, out_ids_dev, out_f_dev, out_d_dev, nullptr, ix.d_cand_sum, cand_store));
+    prof_end(VB_PROF_SCAN_ITEMS);
+    return VB_OK;
+}
+
+// results of a fused scan to host memory: ONE copy (ids and float8 distances are adjacent in the workspace) into the pinned
+// staging buffer, one synchronisation
+static int ivf_one_fetch(const void* d_out, int64_t n, int64_t* out_ids, double* out_d) {
+    void* pin;
+    VB_TRY(pinned_buffer2(16 * (size_t)n, &pin));
+    VB_CUDA(cudaMemcpyAsync(pin, d_out, 16 * (size_t)n, cudaMemcpyDeviceToHost, ctx().stream));
+    VB_CUDA(cudaStreamSynchronize(ctx().stream));
+    memcpy(out_ids, pin, 8 * (size_t)n);
+    memcpy(out_d, (const uint8_t*)pin + 8 * (size_t)n, 8 * (size_t)n);
+    return VB_OK;
+}
+
 }  // namespace vb
 
 using namespace vb;
@@ -948,6 +1018,7 @@ int vb_ivf_free(vb_ivf* h) {
     list_tc_release(&h->ix.ctc);
     if (h->ix.d_centre_off) cudaFree(h->ix.d_centre_off);
     if (h->ix.d_tc_fail) cudaFree(h->ix.d_tc_fail);
+    if (h->ix.d_ticket) cudaFree(h->ix.d_ticket);
     for (int i = 0; i < 2; ++i) {
         if (h->ix.q_buf[i]) cudaFree(h->ix.q_buf[i]);
         if (h->ix.q_ready[i]) cudaEventDestroy(h->ix.q_ready[i]);
@@ -979,6 +1050,25 @@ int vb_ivf_scan_lists(vb_ivf* h, const void* queries, int64_t nq, int max_probes
     VB_TRY(upload_queries(ix.elem, ix.dim, queries, nq, true, WS_QIMG, &qimg, &qstride));
     int32_t* d_lists;
     float* d_ldist;
+    if (c.one_query && nq <= ONE_MAX_Q && one_probe_fits(ix.lists, qstride, probes)) {
+        // one backend, one scan: distances to the centres and the selection in a single launch; list numbers and
+        // distances (adjacent in the workspace) come back with one copy
+        VB_TRY(ivf_one_probes(ix, qimg, qstride, nq, probes, &d_lists, &d_ldist));
+        void* pin;
+        const size_t np = (size_t)nq * probes;
+        VB_TRY(pinned_buffer2(8 * np, &pin));
+        VB_CUDA(cudaMemcpyAsync(pin, d_lists, 8 * np, cudaMemcpyDeviceToHost, c.stream));
+        VB_CUDA(cudaStreamSynchronize(c.stream));
+        const int32_t* pl = (const int32_t*)pin;
+        const float* pd = (const float*)(pl + np);
+        for (int64_t q = 0; q < nq; ++q)
+            for (int p = 0; p < max_probes; ++p) {
+                const bool have = p < probes;
+                out_lists[q * max_probes + p] = have ? pl[(size_t)(q * probes + p)] : -1;
+                if (out_dist) out_dist[q * max_probes + p] = have ? (double)pd[(size_t)(q * probes + p)] : INFINITY;
+            }
+        return VB_OK;
+    }
     VB_TRY(ivf_select_probes(ix, qimg, qstride, nq, probes, &d_lists, &d_ldist));
     std::vector<int32_t> hl((size_t)nq * probes);
     std::vector<float> hd((size_t)nq * probes);
@@ -1030,12 +1120,24 @@ int vb_ivf_scan_items(vb_ivf* h, const void* q, const int32_t* lists, int nlists
     VB_TRY(upload_queries(ix.elem, ix.dim, q, 1, true, WS_QIMG, &qimg, &qstride));
     void* d_misc;
     VB_TRY(workspace(WS_MISC, sizeof(int32_t) * (size_t)nlists, &d_misc));
-    VB_CUDA(cudaMemcpyAsync(d_misc, lists, sizeof(int32_t) * (size_t)nlists, cudaMemcpyHostToDevice, c.stream));
-    VB_CUDA(cudaStreamSynchronize(c.stream));
     void* d_out;
     VB_TRY(workspace(WS_OUT, (sizeof(int64_t) + sizeof(double)) * (size_t)k, &d_out));
     int64_t* o_ids = (int64_t*)d_out;
     double* o_d = (double*)(o_ids + k);
+    if (ivf_one_applies(ix, 1, nlists, k, total)) {
+        // distances, selection, heap ids and the operator's epilogue in one launch.  The list numbers go out through the
+        // second pinned buffer (no synchronisation), the results come back through it with one copy.
+        void* pin;
+        VB_TRY(pinned_buffer2(std::max(sizeof(int32_t) * (size_t)nlists, 16 * (size_t)k), &pin));
+        memcpy(pin, lists, sizeof(int32_t) * (size_t)nlists);
+        VB_CUDA(cudaMemcpyAsync(d_misc, pin, sizeof(int32_t) * (size_t)nlists, cudaMemcpyHostToDevice, c.stream));
+        VB_TRY(ivf_one_items(ix, qimg, qstride, 1, (const int32_t*)d_misc, nlists, (int)k, total, o_ids, nullptr, o_d, true));
+        ix.last_cand = -1;
+        ix.last_bytes = 1;
+        return ivf_one_fetch(d_out, k, out_ids, out_dist);
+    }
+    VB_CUDA(cudaMemcpyAsync(d_misc, lists, sizeof(int32_t) * (size_t)nlists, cudaMemcpyHostToDevice, c.stream));
+    VB_CUDA(cudaStreamSynchronize(c.stream));
     // capacity bound must cover these particular lists
     std::vector<int64_t> saved = ix.sorted_len;
     ix.sorted_len.assign(1, total);
@@ -1059,6 +1161,29 @@ static int ivf_search_impl(vb_ivf* h, const void* queries, int64_t nq, int probe
     probes = std::min(probes, ix.lists);
     if (nq <= 0) return VB_OK;
     const size_t rawq = raw_row_bytes(ix.elem, ix.dim);
+    if (ivf_one_applies(ix, nq, probes, k, ivf_cap(ix, probes))) {
+        // a handful of queries (one backend's scan): two fused launches, no memsets, one copy back
+        const int64_t cap = ivf_cap(ix, probes);
+        void* qimg;
+        size_t qstride;
+        VB_TRY(upload_queries(ix.elem, ix.dim, queries, nq, q_host, WS_QIMG, &qimg, &qstride));
+        int32_t* d_lists;
+        float* d_ldist;
+        VB_TRY(ivf_one_probes(ix, qimg, qstride, nq, probes, &d_lists, &d_ldist));
+        if (host) {
+            void* d_out;
+            VB_TRY(workspace(WS_OUT, (sizeof(int64_t) + sizeof(double)) * (size_t)nq * k, &d_out));
+            int64_t* o_ids = (int64_t*)d_out;
+            double* o_d = (double*)(o_ids + (size_t)nq * k);
+            VB_TRY(ivf_one_items(ix, qimg, qstride, nq, d_lists, probes, k, cap, o_ids, nullptr, o_d, false));
+            VB_TRY(ivf_one_fetch(d_out, nq * k, out_ids, out_d));
+        } else {
+            VB_TRY(ivf_one_items(ix, qimg, qstride, nq, d_lists, probes, k, cap, out_ids, out_f, nullptr, false));
+        }
+        ix.last_cand = -1;
+        ix.last_bytes = nq;
+        return VB_OK;
+    }
     const int64_t bq = ivf_batch_limit(ix, probes);
     if (!ix.d_cand_sum) VB_CUDA(cudaMalloc(&ix.d_cand_sum, sizeof(int64_t)));
     VB_CUDA(cudaMemsetAsync(ix.d_cand_sum, 0, sizeof(int64_t), c.stream));

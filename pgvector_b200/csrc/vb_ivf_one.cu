@@ -90,6 +90,7 @@ struct OneProbeArgs {
     unsigned* ticket;      // [nq], zero between launches
     int32_t* out_lists;    // [nq][probes]
     float* out_ldist;      // [nq][probes]
+    unsigned long long* zero_me;   // the scan's running candidate total, reset here (or null)
 };
 
 // GetScanLists (src/ivfscan.c:47-118) for query blockIdx.y
@@ -117,7 +118,10 @@ __global__ void __launch_bounds__(ONE_THREADS) one_probe_kernel(OneProbeArgs a) 
         a.out_lists[(size_t)q * a.probes + p] = have ? (int32_t)(uint32_t)cand[p] : -1;
         a.out_ldist[(size_t)q * a.probes + p] = have ? key_to_float((uint32_t)(cand[p] >> 32)) : __int_as_float(0x7F800000);
     }
-    if (threadIdx.x == 0) a.ticket[q] = 0;
+    if (threadIdx.x == 0) {
+        a.ticket[q] = 0;
+        if (q == 0 && a.zero_me) *a.zero_me = 0;
+    }
 }
 
 struct OneScanArgs {
@@ -139,6 +143,7 @@ struct OneScanArgs {
     double* out_d;                // [nq][k] or null
     int32_t* out_total;           // [nq] candidates scanned, or null
     unsigned long long* cand_sum; // running total of candidates scanned, or null
+    int cand_store;               // 1: store this query's total instead of adding it (single query, no probe kernel before)
 };
 
 __device__ __forceinline__ double one_finish_value(int metric, float key) {
@@ -219,7 +224,10 @@ __global__ void __launch_bounds__(ONE_THREADS) one_scan_kernel(OneScanArgs a) {
     if (threadIdx.x == 0) {
         a.ticket[q] = 0;
         if (a.out_total) a.out_total[q] = total;
-        if (a.cand_sum) atomicAdd(a.cand_sum, (unsigned long long)total);
+        if (a.cand_sum) {
+            if (a.cand_store) *a.cand_sum = (unsigned long long)total;
+            else atomicAdd(a.cand_sum, (unsigned long long)total);
+        }
     }
 }
 
@@ -324,7 +332,7 @@ static int one_scan_t(const OneScanArgs& a, int64_t nq) {
     } while (0)
 
 int launch_one_probe(const Table& centres, int km, const void* qimg, size_t qstride, int64_t nq, int probes, float* cdist,
-                     unsigned* ticket, int32_t* out_lists, float* out_ldist) {
+                     unsigned* ticket, int32_t* out_lists, float* out_ldist, int64_t* zero_me) {
     OneProbeArgs a{};
     a.centres = centres.d;
     a.stride = centres.stride;
@@ -338,12 +346,13 @@ int launch_one_probe(const Table& centres, int km, const void* qimg, size_t qstr
     a.ticket = ticket;
     a.out_lists = out_lists;
     a.out_ldist = out_ldist;
+    a.zero_me = (unsigned long long*)zero_me;
     VB_ONE_DISPATCH(one_probe_t, centres.elem, km, a, nq);
 }
 
 int launch_one_scan(const Table& rows, int km, int metric, const int64_t* list_off, const int64_t* ids, const int32_t* probe_lists,
                     int probes, const void* qimg, size_t qstride, int64_t nq, int k, int64_t cap, float* dist, unsigned* ticket,
-                    int64_t* out_ids, float* out_f, double* out_d, int32_t* out_total, int64_t* cand_sum) {
+                    int64_t* out_ids, float* out_f, double* out_d, int32_t* out_total, int64_t* cand_sum, bool cand_store) {
     OneScanArgs a{};
     a.rows = rows.d;
     a.stride = rows.stride;
@@ -365,6 +374,7 @@ int launch_one_scan(const Table& rows, int km, int metric, const int64_t* list_o
     a.out_d = out_d;
     a.out_total = out_total;
     a.cand_sum = (unsigned long long*)cand_sum;
+    a.cand_store = cand_store ? 1 : 0;
     VB_ONE_DISPATCH(one_scan_t, rows.elem, km, a, nq);
 }
 
