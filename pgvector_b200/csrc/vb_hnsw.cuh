@@ -243,6 +243,14 @@ __device__ __forceinline__ void load_query_image(const uint4* gq, int qvec, int 
 #ifndef VB_AB_SPEC
 #define VB_AB_SPEC 0
 #endif
+// layer 0: while the neighbours of the nearest unexpanded element are processed, the neighbour list of the SECOND nearest
+// unexpanded element is requested -- it is the next one to be expanded unless this expansion admits something nearer --
+// and, for rows of at most 256 bytes, the rows it names are prefetched into L2.  Data movement only: the walk, the
+// visited set and the `tuples` counter are untouched.  (Two of the three dependent round trips of an expansion -- list,
+// visited bucket, rows -- leave the critical path when the guess holds.)
+#ifndef VB_AB_NEXTPF
+#define VB_AB_NEXTPF 0
+#endif
 __device__ __forceinline__ uint4 hnsw_row_ld(const uint4* p) {
 #if VB_HNSW_EVICT_FIRST
     return ldg_gather(p);
@@ -649,8 +657,25 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
     }
 
     bool ok = true;
+    uint32_t pre_c = VIS_EMPTY;   // VB_AB_NEXTPF: the element whose list sits in pre_nid
+    int pre_nid = -1;
     for (;;) {
         // nearest unexpanded element of R
+#if VB_AB_NEXTPF
+        int first = -1, second = -1;
+        for (int j0 = 0; j0 < S.len && second < 0; j0 += 32) {
+            const int j = j0 + lane;
+            unsigned um = __ballot_sync(0xffffffffu, j < S.len && !(S.ri[j] & 0x80000000u));
+            if (um && first < 0) {
+                first = j0 + __ffs(um) - 1;
+                um &= um - 1;
+            }
+            if (um) second = j0 + __ffs(um) - 1;
+            if (lc != 0 && first >= 0) break;
+        }
+        if (first < 0) break;
+        const uint32_t next_c = (lc == 0 && second >= 0) ? (S.ri[second] & 0x7fffffffu) : VIS_EMPTY;
+#else
         int first = 0x7fffffff;
         for (int i = lane; i < S.len; i += 32)
             if (!(S.ri[i] & 0x80000000u)) {
@@ -660,6 +685,7 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
         if (first == 0x7fffffff) break;
+#endif
         const uint32_t c = S.ri[first] & 0x7fffffffu;
         __syncwarp();
         if (lane == 0) S.ri[first] = c | 0x80000000u;
@@ -672,7 +698,17 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
         if (nb == nullptr) continue;
 
         for (int off = 0; off < lm; off += 32) {
+#if VB_AB_NEXTPF
+            int nid;
+            if (off == 0 && pre_c == c) nid = pre_nid;           // requested one expansion ago
+            else nid = (off + lane < lm) ? nb[off + lane] : -1;
+            if (off == 0) {
+                pre_c = next_c;
+                if (next_c != VIS_EMPTY) pre_nid = lane < lm ? __ldg(g.nbr0 + (size_t)next_c * lm + lane) : -1;
+            }
+#else
             int nid = (off + lane < lm) ? nb[off + lane] : -1;
+#endif
             bool valid = nid >= 0;
             // an invalid TID terminates the list (src/hnswutils.c:809-810)
             unsigned vmask = __ballot_sync(0xffffffffu, valid);
@@ -744,6 +780,18 @@ __device__ __forceinline__ bool hnsw_search_layer(const HnswDev& g, const uint4*
             } else {
 #if VB_AB_VISB
             bool fresh = vis_insert_warp(tab, mask, valid && !known, (uint32_t)nid, lane);
+#if VB_AB_NEXTPF
+            // (the list requested above has arrived behind the bucket loads) the visited buckets its elements hash to, and
+            // -- narrow rows only: the rows of already visited elements are wasted traffic -- their rows, go to L2 now
+            if (off == 0 && pre_c != VIS_EMPTY && pre_nid >= 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(tab + ((size_t)(hash_u32((uint32_t)pre_nid) & (mask >> 3)) << 3)));
+                if (g.stride <= 256) {
+                    const uint8_t* pr = g.rows + (size_t)pre_nid * g.stride;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pr));
+                    if (g.stride > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + 128));
+                }
+            }
+#endif
 #else
             bool fresh = valid && !known && vis_insert(tab, mask, (uint32_t)nid);
 #endif

@@ -71,8 +71,14 @@ def test_search_of_a_few_queries_equals_the_general_path_and_the_oracle(pv, opcl
     gix, oix = make_index(pv, opclass, rows, centers, dim=dim)
     for nq, probes, k in [(1, 4, 10), (3, 1, 5), (16, 20, 40), (1, 7, 1)]:
         (ids, dist), (gi, gd) = both_paths(pv, lambda: gix.search(queries[:nq], k=k, probes=probes))
-        assert np.array_equal(ids, gi), (nq, probes, k)
-        assert np.array_equal(dist, gd), (nq, probes, k)
+        if nq * probes < 256 or elem == O.BIT:
+            # the general path scans query by query below 256 (query, list) pairs: the same per-row arithmetic
+            assert np.array_equal(ids, gi), (nq, probes, k)
+            assert np.array_equal(dist, gd), (nq, probes, k)
+        else:
+            # (list-major there: another summation order)
+            assert np.allclose(dist, gd, rtol=RTOL, atol=1e-6)
+            assert_same_neighbours(ids, dist, gi, gd, RTOL, min_positional=0.98)
         wi, wd = oix.search_batch(queries[:nq], probes, k, threads=8)
         if elem == O.BIT:
             assert np.array_equal(dist, wd)
