@@ -72,7 +72,15 @@ def main():
         sys.exit("no SASS page in the report (profile with --import-source on / --set full)")
     k = ks[min(a.launch, len(ks) - 1)]
     h = {n: i for i, n in enumerate(k["header"])}
-    fn, lm = line_map(a.lib, a.kernel)
+    want = a.kernel
+    if "ILi" not in want:
+        # the report names the instantiation ("kernel<(int)2, (int)4, (int)8>"): match it, not the first one of the library
+        mm = re.search(r"<([^>]*)>", k["name"])
+        if mm:
+            args = re.findall(r"\(int\)(-?\d+)", mm.group(1))
+            if args:
+                want = a.kernel + "I" + "".join(f"Li{v}E" if not v.startswith("-") else f"Lin{v[1:]}E" for v in args) + "E"
+    fn, lm = line_map(a.lib, want)
     if not lm:
         sys.exit(f"no function matching {a.kernel} in {a.lib}")
     base = int(k["rows"][0][h["Address"]], 16)
