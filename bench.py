@@ -1091,6 +1091,15 @@ def run_hnsw(args):
     if cfg == "C":
         qh = [x.view(np.uint16) for x in qh]
     ms_h = timed_steps(env, lambda i: ix.search(qh[i % len(qh)], k=k, ef_search=ef), args.steps, args.warmup)
+    # one query per scan (what one backend does: hnswgettuple's first call -> one vb_hnsw_search with host buffers, synchronous)
+    lat = []
+    for i in range(120):
+        t0 = time.perf_counter()
+        ix.search(qh[0][i:i + 1], k=k, ef_search=ef)
+        lat.append(time.perf_counter() - t0)
+    lat = np.sort(np.array(lat[20:])) * 1e6
+    single = {"calls": "vb_hnsw_search, one query, host buffers, synchronous (timed around the Python wrapper); one warp walks the graph",
+              "latency_us_p50": float(lat[len(lat) // 2]), "latency_us_p90": float(lat[int(len(lat) * 0.9)])}
     clocks = sampler.stop() if env.rank == 0 else None
     if env.rank != 0:
         env.close()
@@ -1135,6 +1144,7 @@ def run_hnsw(args):
             "cpu_baseline": cpu_base,
             "e2e": {"value": env.world * args.steps * B / (ms_h / 1000), "unit": "queries/s", "h2d_bytes_per_step": B * row_bytes, "d2h_bytes_per_step": B * (k * 16 + 8),
                     "ms_per_step": ms_h / args.steps, "call": "vb_hnsw_search"},
+            "single_query": single,
             "gpu_launches": int(launches), "clocks": clocks,
             "build": {"seconds": build_s, "rows_per_s": args.rows / build_s, "mean_degree_layer0": float((g["nbr0"] >= 0).sum(axis=1).mean()),
                       "duplicates_folded": int((g["dup_of"] >= 0).sum()), "max_level": int(g["levels"].max())}}

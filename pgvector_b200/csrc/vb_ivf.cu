@@ -572,10 +572,12 @@ static int ivf_tickets(Ivf& ix, unsigned** probe_t, unsigned** scan_t) {
 }
 
 // does a scan of nq queries (probes lists each, k results, at most cap candidates per query) take the fused kernels?
+static int64_t one_cap(int64_t cap) { return (cap + 3) & ~(int64_t)3; }   // stride of a query's distance run: 16-byte aligned runs
+
 static bool ivf_one_applies(const Ivf& ix, int64_t nq, int probes, int64_t k, int64_t cap) {
     if (!ctx().one_query || nq < 1 || nq > ONE_MAX_Q || ix.rows.n <= 0) return false;
     const size_t qs = ivf_qstride(ix);
-    return one_probe_fits(ix.lists, qs, probes) && one_scan_fits(cap, qs, probes, k);
+    return one_probe_fits(ix.lists, qs, probes) && one_scan_fits(one_cap(cap), qs, probes, k);
 }
 
 // GetScanLists for nq <= ONE_MAX_Q query images: one launch
@@ -599,6 +601,7 @@ static int ivf_one_probes(Ivf& ix, const void* qimg, size_t qstride, int64_t nq,
 // GetScanItems + sort for nq <= ONE_MAX_Q query images over device-resident probe lists: one launch
 static int ivf_one_items(Ivf& ix, const void* qimg, size_t qstride, int64_t nq, const int32_t* d_lists, int probes, int k, int64_t cap,
                          int64_t* out_ids_dev, float* out_f_dev, double* out_d_dev, bool cand_store) {
+    cap = one_cap(cap);
     void* d_dist;
     VB_TRY(workspace(WS_DIST, sizeof(float) * (size_t)nq * cap, &d_dist));
     unsigned *tp, *ts;

@@ -198,7 +198,19 @@ __global__ void __launch_bounds__(ONE_THREADS) one_scan_kernel(OneScanArgs a) {
         }
     }
     if (!one_last_cta(a.ticket + q)) return;
-    for (int i = threadIdx.x; i < total; i += ONE_THREADS) keys[i] = orderable_key(__ldcg(dq + i));
+    {
+        // (cap is a multiple of 4 and the workspace 256-byte aligned: every query's run starts on a 16-byte boundary)
+        const int t4 = total >> 2;
+        const uint4* d4 = reinterpret_cast<const uint4*>(dq);
+        for (int i = threadIdx.x; i < t4; i += ONE_THREADS) {
+            const uint4 v = __ldcg(d4 + i);
+            keys[4 * i] = orderable_key(__uint_as_float(v.x));
+            keys[4 * i + 1] = orderable_key(__uint_as_float(v.y));
+            keys[4 * i + 2] = orderable_key(__uint_as_float(v.z));
+            keys[4 * i + 3] = orderable_key(__uint_as_float(v.w));
+        }
+        for (int i = (t4 << 2) + threadIdx.x; i < total; i += ONE_THREADS) keys[i] = orderable_key(__ldcg(dq + i));
+    }
     __syncthreads();
     const int m = select_exact_cta(keys, total, a.k, cand);
     for (int i = threadIdx.x; i < a.k; i += ONE_THREADS) {
