@@ -139,8 +139,10 @@ __global__ void ivf_finish_kernel(int metric, int64_t nq, int k, int probes, con
     int64_t q = i / k;
     int32_t ps = pos[i];
     int64_t id = -1;
-    if (ps >= 0) {
-        const int32_t* co = cand_off + q * (probes + 1);
+    const int32_t* co = cand_off + q * (probes + 1);
+    // (a query the tensor-core filter could not select or certify leaves its slots unwritten -- the batch is repeated --
+    // so a position is only trusted inside the query's candidate run)
+    if (ps >= 0 && ps < co[probes]) {
         int lo = 0, hi = probes;  // largest p with co[p] <= ps
         while (hi - lo > 1) {
             int mid = (lo + hi) >> 1;

@@ -693,6 +693,10 @@ __global__ void __launch_bounds__(SS_THREADS) cta_refine_kernel(const uint8_t* _
     if (n < 0) {
         // not selected here: the query reports as uncertified (outputs are rewritten by the repeat of the batch)
         if (tid == 0) atomicAdd(n_failed, 1);
+        for (int i = tid; i < k; i += SS_THREADS) {
+            out_pos[(int64_t)q * k + i] = -1;
+            out_key[(int64_t)q * k + i] = __int_as_float(0x7F800000);
+        }
         return;
     }
     const int have = min(n, kp);
