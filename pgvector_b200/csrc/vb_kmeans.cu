@@ -20,6 +20,7 @@
 
 namespace vb {
 
+enum { WSK_STATE = 26 };   // Lloyd state arena (kmeans_run)
 enum { WSK_QIMG = 0, WSK_DIST = 1, WSK_A = 2, WSK_B = 3, WSK_C = 4, WSK_D = 5, WSK_E = 6, WSK_F = 7, WSK_G = 12, WSK_H = 13, WSK_I = 14, WSK_J = 16 };
 
 // ----------------------------------------------------------------------------- exact assign
@@ -585,41 +586,42 @@ static int kmeans_run(const Table& X, int kmeans_metric, void* centers_host, int
     st.centers.elem = X.elem;
     st.centers.dim = X.dim;
     st.centers.stride = X.stride;
-    int rc = table_append_host(st.centers, centers_host, k);
     const int64_t n = X.n;
-    auto cleanup = [&]() {
-        table_free(st.centers);
-        cudaFree(st.closest);
-        cudaFree(st.prev);
-        cudaFree(st.counts);
-        cudaFree(st.start);
-        cudaFree(st.members);
-        cudaFree(st.agg);
-        cudaFree(st.changes);
-        cudaFree(st.scan_tmp);
-    };
-    if (rc != VB_OK) {
-        cleanup();
-        return rc;
+    // The state of a run lives in ONE grow-only arena (slot WSK_STATE; the sharded-scan / sparsevec slots it shares
+    // never run beside a k-means): nine cudaMalloc + cudaFree pairs per call cost more than the five Lloyd iterations of
+    // config D on a context that holds a 58 GB table (0.2 s of 0.25 s measured), and cudaFree synchronises the device.
+    size_t scan_tmp_bytes = 0;
+    VB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp_bytes, (int32_t*)nullptr, (int32_t*)nullptr, k, s));
+    st.scan_tmp_bytes = scan_tmp_bytes;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_cent = up(X.stride * (size_t)k + 16), b_n = up(sizeof(int32_t) * (size_t)std::max<int64_t>(n, 1)),
+                 b_k = up(sizeof(int32_t) * (size_t)k), b_agg = up(sizeof(float) * (size_t)k * X.dim), b_tmp = up(std::max<size_t>(scan_tmp_bytes, 16));
+    void* arena;
+    VB_TRY(workspace(WSK_STATE, b_cent + 3 * b_n + 2 * b_k + b_agg + 256 + b_tmp, &arena));
+    {
+        uint8_t* p = (uint8_t*)arena;
+        st.centers.d = p;                       // (table_append_host copies into it: capacity k, nothing to reserve)
+        st.centers.cap = k;
+        p += b_cent;
+        st.closest = (int32_t*)p;
+        p += b_n;
+        st.prev = (int32_t*)p;
+        p += b_n;
+        st.members = (int32_t*)p;
+        p += b_n;
+        st.counts = (int32_t*)p;
+        p += b_k;
+        st.start = (int32_t*)p;
+        p += b_k;
+        st.agg = (float*)p;
+        p += b_agg;
+        st.changes = (int*)p;
+        p += 256;
+        st.scan_tmp = p;
     }
-    cudaError_t e = cudaSuccess;
-    auto alloc = [&](void** p, size_t bytes) {
-        if (e == cudaSuccess) e = cudaMalloc(p, std::max<size_t>(bytes, 16));
-    };
-    alloc((void**)&st.closest, sizeof(int32_t) * (size_t)n);
-    alloc((void**)&st.prev, sizeof(int32_t) * (size_t)n);
-    alloc((void**)&st.counts, sizeof(int32_t) * (size_t)k);
-    alloc((void**)&st.start, sizeof(int32_t) * (size_t)k);
-    alloc((void**)&st.members, sizeof(int32_t) * (size_t)n);
-    alloc((void**)&st.agg, sizeof(float) * (size_t)k * X.dim);
-    alloc((void**)&st.changes, sizeof(int));
-    if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(nullptr, st.scan_tmp_bytes, st.counts, st.start, k, s);
-    alloc(&st.scan_tmp, st.scan_tmp_bytes);
-    if (e != cudaSuccess) {
-        set_error("k-means allocation failed: %s", cudaGetErrorString(e));
-        cleanup();
-        return VB_ENOMEM;
-    }
+    auto cleanup = [&]() {};   // (the arena stays with the context)
+    int rc = table_append_host(st.centers, centers_host, k);
+    if (rc != VB_OK) return rc;
 
     int iteration = 0;
     rc = VB_OK;
@@ -928,6 +930,7 @@ __global__ void pp_fill_f64_kernel(double* p, int64_t n, double v) {
 }
 
 enum { WSK_XB = 27, WSK_FLT = 28, WSK_CENT = 29 };
+
 
 static bool pp_filter_applies(const Table& X, int kmeans_metric, int k) {
     // the filters pay off once the sample table is much larger than L2 and there are enough rounds to amortise the bf16 copy
