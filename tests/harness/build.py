@@ -8,10 +8,10 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference/src"
 EXT = os.path.join(ROOT, "pgvector_b200", "ext")
 OUT = os.path.join(HERE, "_build")
-SRCS = [os.path.join(HERE, f) for f in ("harness_common.c", "harness_ivf.c", "harness_hnsw.c")] + \
-       [os.path.join(EXT, f) for f in ("vb_ivfflat_scan.c", "vb_ivfflat_build.c", "vb_hnsw_scan.c", "vb_hnsw_build.c")] + \
+SRCS = [os.path.join(HERE, f) for f in ("harness_common.c", "harness_ivf.c", "harness_hnsw.c", "harness_broker.c")] + \
+       [os.path.join(EXT, f) for f in ("vb_ivfflat_scan.c", "vb_ivfflat_build.c", "vb_hnsw_scan.c", "vb_hnsw_build.c", "vb_broker.c")] + \
        [os.path.join(EXT, "pgstub", "pgstub_runtime.c")]
-FLAGS = ["-std=gnu11", "-O1", "-g", "-fPIC", "-shared", "-Wall", "-Werror", "-Wno-unused-function", "-Wno-comment",
+FLAGS = ["-std=gnu11", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-Wall", "-Werror", "-Wno-unused-function", "-Wno-comment",
          "-I" + os.path.join(EXT, "pgstub"), "-I" + REF, "-I" + os.path.join(ROOT, "include"), "-I" + EXT, "-I" + HERE]
 
 
@@ -24,7 +24,7 @@ def build(force=False):
     if not os.path.isdir(REF):
         return os.path.exists(mock), os.path.exists(real)
     os.makedirs(OUT, exist_ok=True)
-    deps = SRCS + [os.path.join(HERE, f) for f in ("mock_abi.c", "harness_common.h")] + [os.path.join(EXT, "vb_glue.h"),
+    deps = SRCS + [os.path.join(HERE, f) for f in ("mock_abi.c", "harness_common.h")] + [os.path.join(EXT, "vb_glue.h"), os.path.join(EXT, "vb_broker.h"),
                                                                                         os.path.join(EXT, "pgstub", "postgres.h"),
                                                                                         os.path.join(ROOT, "include", "vecb200.h")]
     newest = max(os.path.getmtime(d) for d in deps)

@@ -143,6 +143,39 @@ vb_ivf_scan_items(vb_ivf *h, const void *q, const int32_t *lists, int nlists, in
 	return VB_OK;
 }
 
+/* the first batch of ivfflatgettuple for nq queries: probes lists each, the k nearest (what vb_ivf_search returns) */
+static int	mock_search_calls = 0;
+int			mock_ivf_search_calls(void) { return mock_search_calls; }
+
+int
+vb_ivf_search(vb_ivf *h, const void *queries, int64_t nq, int probes, int k, int64_t *out_ids, double *out_dist)
+{
+	size_t		rb = pgv_row_bytes(h->ix.elem, h->ix.dim);
+
+	__atomic_add_fetch(&mock_search_calls, 1, __ATOMIC_RELAXED);
+	if (probes > h->ix.lists)
+		probes = h->ix.lists;
+	for (int64_t q = 0; q < nq; q++)
+	{
+		const char *qv = (const char *) queries + rb * (size_t) q;
+		int32_t    *lists = malloc(sizeof(int32_t) * (size_t) probes);
+		int64_t		n = 0;
+		int			rc = vb_ivf_scan_lists(h, qv, 1, probes, lists, NULL);
+
+		for (int i = 0; i < k; i++)
+		{
+			out_ids[q * k + i] = -1;
+			out_dist[q * k + i] = 1.0 / 0.0;
+		}
+		if (rc == VB_OK)
+			rc = vb_ivf_scan_items(h, qv, lists, probes, k, out_ids + q * k, out_dist + q * k, &n);
+		free(lists);
+		if (rc != VB_OK)
+			return rc;
+	}
+	return VB_OK;
+}
+
 /* ---- hnsw ---- */
 struct vb_hnsw
 {
