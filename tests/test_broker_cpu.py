@@ -25,6 +25,7 @@ def lib():
     L.vb_ivf_search.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.hb_broker_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p]
+    L.hb_broker_run_fork.argtypes = L.hb_broker_run.argtypes
     L.mock_ivf_search_calls.restype = C.c_int
     return L
 
@@ -53,11 +54,12 @@ def direct(lib, h, queries, probes, k):
     return ids, dist
 
 
-def through_broker(lib, h, queries, threads, probes, k, max_batch, window_us):
+def through_broker(lib, h, queries, threads, probes, k, max_batch, window_us, processes=False):
     ids = np.full((len(queries), k), -7, dtype=np.int64)
     dist = np.full((len(queries), k), np.nan)
     stats = np.zeros(4, dtype=np.int64)
-    rc = lib.hb_broker_run(h, queries.ctypes.data_as(C.c_void_p), len(queries), queries.shape[1] * 4, threads, probes, k, max_batch,
+    run = lib.hb_broker_run_fork if processes else lib.hb_broker_run
+    rc = run(h, queries.ctypes.data_as(C.c_void_p), len(queries), queries.shape[1] * 4, threads, probes, k, max_batch,
                            window_us, ids.ctypes.data_as(C.c_void_p), dist.ctypes.data_as(C.c_void_p), stats.ctypes.data_as(C.c_void_p))
     assert rc == 0
     return ids, dist, dict(requests=int(stats[0]), batches=int(stats[1]), largest=int(stats[2]), failed=int(stats[3]))
@@ -100,3 +102,21 @@ def test_k_larger_than_the_candidates_pads_like_the_library(lib, index):
     ids, dist, st = through_broker(lib, h, queries[:40], 8, 1, 600, 8, 100)
     assert np.array_equal(ids, want_i) and np.array_equal(dist, want_d)
     assert (ids == -1).any() and np.isinf(dist[ids == -1]).all()
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("procs,max_batch,window_us", [(1, 8, 0), (6, 64, 500), (12, 4, 0)])
+def test_requesters_in_other_processes(lib, index, procs, max_batch, window_us):
+    """backends are processes: the request block sits in shared memory, the requesters are forked children that never
+    touch the library; only the broker (this process) does"""
+    h, queries = index
+    q = queries[:240]
+    want_i, want_d = direct(lib, h, q, 3, 10)
+    before = lib.mock_ivf_search_calls()
+    ids, dist, st = through_broker(lib, h, q, procs, 3, 10, max_batch, window_us, processes=True)
+    assert np.array_equal(ids, want_i) and np.array_equal(dist, want_d)
+    assert st["requests"] == len(q) and st["failed"] == 0
+    assert lib.mock_ivf_search_calls() - before == st["batches"]       # every library call was made by the broker, here
+    assert 1 <= st["largest"] <= min(max_batch, procs)
+    if procs >= 6 and window_us > 0:
+        assert st["batches"] < len(q)
